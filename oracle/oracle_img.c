@@ -1,0 +1,176 @@
+/* oracle/oracle_img.c — scalar restatement of the OpenCV 8-bit primitives on the
+ * backscrub hot path.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * OpenCV is a system dependency of the reference (CMakeLists.txt:31) and its
+ * source is not under /root/reference, so these follow OpenCV's published
+ * fixed-point algorithms and are pinned bit-for-bit against the in-container
+ * cv2 4.13.0 by tests/test_oracle_img.py (call sites: lib/libbackscrub.cc:
+ * 285-302,366-371; app/deepseg.cc:87-134; app/background.cc:178-194).
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline uint8_t sat_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+/* BORDER_REFLECT_101: -1 -> 1, -2 -> 2, n -> n-2, n+1 -> n-3 (single reflection; n >= 3 here) */
+static inline int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) { if (p < 0) p = -p; else p = 2 * n - 2 - p; }
+  return p;
+}
+
+/* cv::resize INTER_LINEAR, CV_8U: 11-bit fixed-point coefficients (INTER_RESIZE_COEF_BITS),
+ * horizontal pass into int32 (scale 2^11), vertical pass with the >>4, >>16, +2, >>2
+ * descale; when both scale factors are exactly 2 OpenCV switches to INTER_AREA
+ * (2x2 mean, (sum+2)>>2). */
+void or_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstride,
+                         uint8_t* dst, int dw, int dh, size_t dstride, int cn) {
+  if (sw == dw * 2 && sh == dh * 2) {
+    for (int y = 0; y < dh; ++y)
+      for (int x = 0; x < dw; ++x)
+        for (int c = 0; c < cn; ++c) {
+          const uint8_t* s0 = src + (size_t)(2 * y) * sstride + (size_t)(2 * x) * cn + c;
+          const uint8_t* s1 = s0 + sstride;
+          dst[(size_t)y * dstride + (size_t)x * cn + c] = (uint8_t)((s0[0] + s0[cn] + s1[0] + s1[cn] + 2) >> 2);
+        }
+    return;
+  }
+  const double inv_scale_x = (double)dw / sw, inv_scale_y = (double)dh / sh;
+  const double scale_x = 1.0 / inv_scale_x, scale_y = 1.0 / inv_scale_y;
+  int* xofs = (int*)malloc(sizeof(int) * (size_t)dw);
+  short* ialpha = (short*)malloc(sizeof(short) * 2 * (size_t)dw);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    xofs[dx] = sx;
+    ialpha[2 * dx] = (short)lrintf((1.f - fx) * 2048.f);
+    ialpha[2 * dx + 1] = (short)lrintf(fx * 2048.f);
+  }
+  int* row0 = (int*)malloc(sizeof(int) * (size_t)dw * cn);
+  int* row1 = (int*)malloc(sizeof(int) * (size_t)dw * cn);
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= (float)sy;
+    const short b0 = (short)lrintf((1.f - fy) * 2048.f), b1 = (short)lrintf(fy * 2048.f);
+    const int r0 = clampi(sy, 0, sh - 1), r1 = clampi(sy + 1, 0, sh - 1);
+    const uint8_t* s0 = src + (size_t)r0 * sstride;
+    const uint8_t* s1 = src + (size_t)r1 * sstride;
+    for (int dx = 0; dx < dw; ++dx) {
+      const int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+      const int a0 = ialpha[2 * dx], a1 = ialpha[2 * dx + 1];
+      for (int c = 0; c < cn; ++c) {
+        row0[dx * cn + c] = s0[sx * cn + c] * a0 + s0[sx1 * cn + c] * a1;
+        row1[dx * cn + c] = s1[sx * cn + c] * a0 + s1[sx1 * cn + c] * a1;
+      }
+    }
+    uint8_t* d = dst + (size_t)dy * dstride;
+    for (int i = 0; i < dw * cn; ++i)
+      d[i] = sat_u8((((b0 * (row0[i] >> 4)) >> 16) + ((b1 * (row1[i] >> 4)) >> 16) + 2) >> 2);
+  }
+  free(xofs); free(ialpha); free(row0); free(row1);
+}
+
+/* cv::bilateralFilter(8UC3, d = 5): radius 2, taps with sqrt(i^2+j^2) <= 2 in (i, j)
+ * raster order, float LUT weights, BORDER_REFLECT_101, result cvRound(sum * (1/wsum)).
+ * Per-tap accumulation is `sum = fmaf(v, w, sum)` in tap order (matches OpenCV's
+ * v_muladd SIMD body on FMA hardware; see tests for the measured agreement). */
+void or_bilateral_d5_u8c3(const uint8_t* src, uint8_t* dst, int w, int h, double sigma_color, double sigma_space) {
+  const int radius = 2;
+  const double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+  float* color_w = (float*)malloc(sizeof(float) * 256 * 3);
+  for (int i = 0; i < 256 * 3; ++i) color_w[i] = (float)exp((double)i * i * gc);
+  float space_w[25]; int oi[25], oj[25]; int maxk = 0;
+  for (int i = -radius; i <= radius; ++i)
+    for (int j = -radius; j <= radius; ++j) {
+      double r = sqrt((double)i * i + (double)j * j);
+      if (r > radius) continue;
+      space_w[maxk] = (float)exp(r * r * gs);
+      oi[maxk] = i; oj[maxk] = j; ++maxk;
+    }
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const uint8_t* p0 = src + ((size_t)y * w + x) * 3;
+      const int b0 = p0[0], g0 = p0[1], r0 = p0[2];
+      float wsum = 0.f, sb = 0.f, sg = 0.f, sr = 0.f;
+      for (int k = 0; k < maxk; ++k) {
+        const int yy = reflect101(y + oi[k], h), xx = reflect101(x + oj[k], w);
+        const uint8_t* p = src + ((size_t)yy * w + xx) * 3;
+        const int b = p[0], g = p[1], r = p[2];
+        const float wk = space_w[k] * color_w[abs(b - b0) + abs(g - g0) + abs(r - r0)];
+        wsum += wk;
+        sb = fmaf((float)b, wk, sb);
+        sg = fmaf((float)g, wk, sg);
+        sr = fmaf((float)r, wk, sr);
+      }
+      const float inv = 1.f / wsum;
+      uint8_t* d = dst + ((size_t)y * w + x) * 3;
+      d[0] = sat_u8((int)lrintf(sb * inv));
+      d[1] = sat_u8((int)lrintf(sg * inv));
+      d[2] = sat_u8((int)lrintf(sr * inv));
+    }
+  free(color_w);
+}
+
+/* Mat::convertTo(CV_32F, alpha, beta) from CV_8U: (float)v * (float)alpha + (float)beta as
+ * one fused multiply-add (OpenCV's v_fma body on FMA hardware). */
+void or_convert_u8_f32(const uint8_t* src, float* dst, size_t n, float alpha, float beta) {
+  for (size_t i = 0; i < n; ++i) dst[i] = fmaf((float)src[i], alpha, beta);
+}
+
+/* cv::blur 5x5 normalised box, CV_8UC1, BORDER_REFLECT_101: integer window sum S,
+ * result cvRound(S * (1.0/25)) == (S + 12) / 25 (no exact .5 ties since 25 is odd). */
+void or_box_blur5_u8(const uint8_t* src, size_t sstride, uint8_t* dst, size_t dstride, int w, int h) {
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int s = 0;
+      for (int dy = -2; dy <= 2; ++dy) {
+        const uint8_t* row = src + (size_t)reflect101(y + dy, h) * sstride;
+        for (int dx = -2; dx <= 2; ++dx) s += row[reflect101(x + dx, w)];
+      }
+      dst[(size_t)y * dstride + x] = (uint8_t)lrint((double)s * (1.0 / 25));
+    }
+}
+
+/* cv::cvtColor(COLOR_RGB2YUV), CV_8U: 14-bit fixed point (yuv_shift), channel 0 = "R". */
+void or_rgb2yuv_u8(const uint8_t* src, uint8_t* dst, size_t npix) {
+  for (size_t i = 0; i < npix; ++i) {
+    const int R = src[3 * i], G = src[3 * i + 1], B = src[3 * i + 2];
+    const int Y = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
+    const int U = ((B - Y) * 8061 + (128 << 14) + 8192) >> 14;
+    const int V = ((R - Y) * 14369 + (128 << 14) + 8192) >> 14;
+    dst[3 * i] = sat_u8(Y); dst[3 * i + 1] = sat_u8(U); dst[3 * i + 2] = sat_u8(V);
+  }
+}
+
+/* app/deepseg.cc:87-106 convert_rgb_to_yuyv: RGB2YUV, then per pixel pair of the
+ * flattened image [Y0, (V0+V1)/2, Y1, (U0+U1)/2] (V before U, truncating average). */
+void or_convert_rgb_to_yuyv(const uint8_t* src, uint8_t* dst_yuyv, int w, int h) {
+  const size_t npix = (size_t)w * h;
+  uint8_t* yuv = (uint8_t*)malloc(npix * 3);
+  or_rgb2yuv_u8(src, yuv, npix);
+  for (size_t i = 0; i + 1 < npix; i += 2) {
+    const int u = ((int)yuv[3 * i + 1] + (int)yuv[3 * (i + 1) + 1]) / 2;
+    const int v = ((int)yuv[3 * i + 2] + (int)yuv[3 * (i + 1) + 2]) / 2;
+    dst_yuyv[2 * i + 0] = yuv[3 * i];
+    dst_yuyv[2 * i + 1] = (uint8_t)v;
+    dst_yuyv[2 * i + 2] = yuv[3 * (i + 1)];
+    dst_yuyv[2 * i + 3] = (uint8_t)u;
+  }
+  free(yuv);
+}
+
+/* app/deepseg.cc:108-134 alpha_blend: out = (a*m + b*(255-m)) / 255, C int division. */
+void or_alpha_blend(const uint8_t* srca, const uint8_t* srcb, const uint8_t* mask, uint8_t* out, size_t npix) {
+  for (size_t p = 0; p < npix; ++p) {
+    const int aw = mask[p], bw = 255 - aw;
+    for (int c = 0; c < 3; ++c)
+      out[3 * p + c] = (uint8_t)(((int)srca[3 * p + c] * aw + (int)srcb[3 * p + c] * bw) / 255);
+  }
+}
