@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's interface for the per-frame path.
+
+Names follow the reference: `bs_maskgen_new / bs_maskgen_process / bs_maskgen_delete /
+bs_tensorflow_version` (lib/libbackscrub.h:13-39), `alpha_blend`, `convert_rgb_to_yuyv`
+(app/deepseg.cc:87-134), `load_background / grab_background` (app/background.h:14-23);
+numpy arrays stand in for cv::Mat.  Everything computes on the GPU through the C ABI
+(include/backscrub_b200.h); there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _binding as B
+
+
+class BackscrubError(RuntimeError):
+    pass
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class MaskGen:
+    """One mask-generation context == one video stream (holds the temporal IIR state).
+
+    `lib` is the bound shared library (the product library by default)."""
+
+    def __init__(self, lib, modelname: str, width: int, height: int, *, threads: int = 2, device: int = 0,
+                 max_batch: int = 1, flags: int = 0, ondebug=None, onprep=None, oninfer=None, onmask=None):
+        self._lib = lib
+        self._msgs = []
+        self._user_debug = ondebug
+
+        def _dbg(_ctx, msg):
+            text = msg.decode("utf-8", "replace")
+            self._msgs.append(text)
+            if self._user_debug:
+                self._user_debug(text)
+
+        mk = lambda f: B.STAGE_CB(lambda _c: f()) if f else C.cast(None, B.STAGE_CB)
+        self._cbs = (B.DEBUG_CB(_dbg), mk(onprep), mk(oninfer), mk(onmask))  # keep alive
+        self._h = lib.bsb_maskgen_new_ex(modelname.encode(), width, height, device, max_batch, flags, *self._cbs, None)
+        if not self._h:
+            raise BackscrubError("".join(self._msgs).strip() or lib.bsb_last_error().decode())
+        self.width, self.height, self.max_batch, self.device = width, height, max_batch, device
+        r, i, o = (C.c_int * 4)(), (C.c_int * 4)(), (C.c_int * 4)()
+        ih, oh = (C.c_int * 3)(), (C.c_int * 3)()
+        lib.bsb_geometry(self._h, r, i, o, ih, oh)
+        self.roidim, self.in_roidim, self.out_roidim = list(r), list(i), list(o)
+        self.in_hwc, self.out_hwc = list(ih), list(oh)
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bsb_maskgen_delete(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _fail(self, what):
+        raise BackscrubError(f"{what}: {self._lib.bsb_last_error().decode()}")
+
+    # -- the reference's calls
+    def process(self, frame: np.ndarray) -> np.ndarray:
+        """bs_maskgen_process: BGR u8 H x W x 3 -> mask u8 H x W (255 = background)."""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        if frame.shape != (self.height, self.width, 3):
+            raise BackscrubError(f"frame shape {frame.shape} != {(self.height, self.width, 3)}")
+        mp, pitch = B.u8p(), C.c_size_t()
+        if not self._lib.bsb_maskgen_process(self._h, _ptr(frame), self.width * 3, C.byref(mp), C.byref(pitch)):
+            self._fail("bs_maskgen_process")
+        return np.ctypeslib.as_array(mp, shape=(self.height, pitch.value))[:, : self.width].copy()
+
+    def set_background(self, bg_raw: np.ndarray):
+        bg_raw = np.ascontiguousarray(bg_raw, np.uint8)
+        if not self._lib.bsb_set_background(self._h, _ptr(bg_raw), bg_raw.shape[1], bg_raw.shape[0], bg_raw.shape[1] * 3):
+            self._fail("bsb_set_background")
+
+    def background(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 3), np.uint8)
+        if not self._lib.bsb_get_background(self._h, _ptr(out), self.width * 3):
+            self._fail("bsb_get_background")
+        return out
+
+    def composite(self, frames: np.ndarray, want_out=True, want_yuyv=True, want_mask=True):
+        """Fused path on HOST buffers: frames [n, H, W, 3] (or [H, W, 3]) -> (out, yuyv, mask)."""
+        single = frames.ndim == 3
+        frames = np.ascontiguousarray(frames[None] if single else frames, np.uint8)
+        n = frames.shape[0]
+        if frames.shape[1:] != (self.height, self.width, 3):
+            raise BackscrubError(f"frame shape {frames.shape[1:]} != {(self.height, self.width, 3)}")
+        fb, npx = self.height * self.width * 3, self.height * self.width
+        out = np.empty((n, self.height, self.width, 3), np.uint8) if want_out else None
+        yuyv = np.empty((n, self.height, self.width, 2), np.uint8) if want_yuyv else None
+        mask = np.empty((n, self.height, self.width), np.uint8) if want_mask else None
+        ok = self._lib.bsb_composite(self._h, n, _ptr(frames), self.width * 3, fb,
+                                     _ptr(out) if want_out else None, self.width * 3, fb,
+                                     _ptr(yuyv) if want_yuyv else None, npx * 2,
+                                     _ptr(mask) if want_mask else None, npx)
+        if not ok:
+            self._fail("bsb_composite")
+        pick = (lambda a: a[0] if single and a is not None else a)
+        return pick(out), pick(yuyv), pick(mask)
+
+    def composite_into(self, frames: np.ndarray, out=None, yuyv=None, mask=None):
+        """bsb_composite into caller-provided (e.g. pinned) host arrays; frames [n, H, W, 3]."""
+        n = frames.shape[0]
+        fb, npx = self.height * self.width * 3, self.height * self.width
+        ok = self._lib.bsb_composite(self._h, n, _ptr(frames), self.width * 3, fb,
+                                     _ptr(out) if out is not None else None, self.width * 3, fb,
+                                     _ptr(yuyv) if yuyv is not None else None, npx * 2,
+                                     _ptr(mask) if mask is not None else None, npx)
+        if not ok:
+            self._fail("bsb_composite")
+
+    def composite_device(self, n, d_frames, d_out=0, d_yuyv=0, d_mask=0, sync=False):
+        """Fused path on DEVICE pointers (ints, e.g. torch.Tensor.data_ptr()); tightly packed frames."""
+        fb, npx = self.height * self.width * 3, self.height * self.width
+        if not self._lib.bsb_composite_device(self._h, n, d_frames, fb, d_out or None, fb, d_yuyv or None, npx * 2,
+                                              d_mask or None, npx, int(sync)):
+            self._fail("bsb_composite_device")
+
+    def synchronize(self):
+        if not self._lib.bsb_synchronize(self._h):
+            self._fail("bsb_synchronize")
+
+    @property
+    def stream(self) -> int:
+        return self._lib.bsb_stream(self._h) or 0
+
+    # -- introspection
+    def infer(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        n = 1 if x.ndim == 3 else x.shape[0]
+        out = np.empty((n, *self.out_hwc), np.float32)
+        if not self._lib.bsb_infer(self._h, n, _ptr(x), _ptr(out)):
+            self._fail("bsb_infer")
+        return out[0] if x.ndim == 3 else out
+
+    def tensor(self, index: int, count: int):
+        buf = np.empty(count, np.float32)
+        n = self._lib.bsb_get_tensor(self._h, index, _ptr(buf), count)
+        if n < 0:
+            self._fail("bsb_get_tensor")
+        return buf[:n] if n else None
+
+    def stage_u8(self, which: int, frame: int = 0) -> np.ndarray:
+        shape = self.in_hwc if which in (0, 1) else self.out_hwc[:2]
+        buf = np.empty(int(np.prod(shape)), np.uint8)
+        n = self._lib.bsb_get_stage_u8(self._h, which, frame, _ptr(buf), buf.size)
+        if n < 0:
+            self._fail("bsb_get_stage_u8")
+        return buf.reshape(shape)
+
+    def reset_state(self):
+        if not self._lib.bsb_reset_state(self._h):
+            self._fail("bsb_reset_state")
+
+    def time_stage(self, stage: int, n_frames: int, iters: int) -> float:
+        """ms per run of one stage (0 pre, 1 cnn, 2 decision, 3 post, 4 all) on device-resident buffers."""
+        ms = self._lib.bsb_time_stage(self._h, stage, n_frames, iters)
+        if ms < 0:
+            self._fail("bsb_time_stage")
+        return ms
+
+    @property
+    def launches_per_call(self) -> int:
+        return self._lib.bsb_launches_per_call(self._h, 1)
+
+    @property
+    def flops(self) -> float:
+        return self._lib.bsb_model_flops(self._h)
+
+
+def alpha_blend(lib, srca, srcb, mask, device=0):
+    """app/deepseg.cc:108-134 (srca weight = mask, srcb weight = 255 - mask)."""
+    srca, srcb, mask = (np.ascontiguousarray(a, np.uint8) for a in (srca, srcb, mask))
+    out = np.empty_like(srca)
+    if not lib.bsb_alpha_blend(device, _ptr(srca), _ptr(srcb), _ptr(mask), _ptr(out), mask.size):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return out
+
+
+def convert_rgb_to_yuyv(lib, rgb, device=0):
+    """app/deepseg.cc:87-106."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    h, w, _ = rgb.shape
+    out = np.empty((h, w, 2), np.uint8)
+    if not lib.bsb_convert_rgb_to_yuyv(device, _ptr(rgb), _ptr(out), w, h):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return out
+
+
+def resize_u8c3(lib, src, dw, dh, device=0):
+    """cv::resize(src, Size(dw, dh)) — what grab_background does (app/background.cc:178-194)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    out = np.empty((dh, dw, 3), np.uint8)
+    if not lib.bsb_resize_u8c3(device, _ptr(src), src.shape[1], src.shape[0], _ptr(out), dw, dh):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return out

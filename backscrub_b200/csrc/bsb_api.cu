@@ -1,0 +1,314 @@
+// backscrub_b200/csrc/bsb_api.cu — extern "C" entry points declared in include/backscrub_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/backscrub_b200.h"
+#include "engine.h"
+
+using bsb::Engine;
+
+struct bsb_ctx {
+  Engine* eng = nullptr;
+  bsb::Callbacks cb;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// lib/libbackscrub.cc:72-83 (_dbg): message to the ondebug callback, else stderr
+void report(const bsb::Callbacks* cb, const std::string& msg) {
+  g_last_error = msg;
+  std::string line = msg;
+  if (line.empty() || line.back() != '\n') line += "\n";
+  if (cb && cb->ondebug) cb->ondebug(cb->caller_ctx, line.c_str());
+  else std::fputs(line.c_str(), stderr);
+}
+
+bool check_ctx(bsb_ctx* ctx) {
+  if (!ctx || !ctx->eng) { g_last_error = "null context"; return false; }
+  return true;
+}
+
+#define API_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) { report(cbp, std::string("error: CUDA: ") + cudaGetErrorString(_e) + " at " #expr); return 0; } \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char* bsb_version(void) { return "backscrub-b200 0.1 (sm_100a CUDA; TFLite schema v3 graph runtime)"; }
+
+const char* bsb_last_error(void) { return g_last_error.c_str(); }
+
+int bsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+bsb_ctx* bsb_maskgen_new_ex(const char* modelname, size_t width, size_t height, int device, int max_batch, unsigned flags,
+                            bsb_debug_cb ondebug, bsb_stage_cb onprep, bsb_stage_cb oninfer, bsb_stage_cb onmask, void* caller_ctx) {
+  bsb::Callbacks cb;
+  cb.ondebug = ondebug; cb.onprep = onprep; cb.oninfer = oninfer; cb.onmask = onmask; cb.caller_ctx = caller_ctx;
+  if (!modelname) { report(&cb, "error: null model name"); return nullptr; }
+  std::string err;
+  Engine* e = Engine::create(modelname, (int)width, (int)height, device, max_batch, flags, cb, &err);
+  if (!e) { report(&cb, "error: " + err); return nullptr; }
+  bsb_ctx* c = new bsb_ctx();
+  c->eng = e; c->cb = cb;
+  g_last_error.clear();
+  return c;
+}
+
+bsb_ctx* bsb_maskgen_new(const char* modelname, size_t threads, size_t width, size_t height, bsb_debug_cb ondebug,
+                         bsb_stage_cb onprep, bsb_stage_cb oninfer, bsb_stage_cb onmask, void* caller_ctx) {
+  (void)threads;  // advisory in the reference as well (SetNumThreads after AllocateTensors, lib/libbackscrub.cc:217,224)
+  return bsb_maskgen_new_ex(modelname, width, height, 0, 1, 0, ondebug, onprep, oninfer, onmask, caller_ctx);
+}
+
+void bsb_maskgen_delete(bsb_ctx* ctx) {
+  if (!ctx) return;
+  delete ctx->eng;
+  delete ctx;
+}
+
+int bsb_maskgen_process(bsb_ctx* ctx, const uint8_t* frame, size_t frame_pitch, const uint8_t** mask, size_t* mask_pitch) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+  Engine* e = ctx->eng;
+  if (!frame || frame_pitch < (size_t)e->W() * 3) { report(cbp, "error: invalid frame"); return 0; }
+  API_CUDA(cudaSetDevice(e->device()));
+  const size_t row = (size_t)e->W() * 3;
+  API_CUDA(cudaMemcpy2DAsync(e->d_frames(), row, frame, frame_pitch, row, (size_t)e->H(), cudaMemcpyHostToDevice, e->stream()));
+  std::string err;
+  if (!e->run(1, e->d_frames(), row, row * e->H(), nullptr, 0, nullptr, 0, e->d_mask(), (size_t)e->W() * e->H(), true, &err)) {
+    report(cbp, "error: failed to interpret video frame: " + err); return 0;
+  }
+  API_CUDA(cudaMemcpyAsync(e->h_mask(), e->d_mask(), (size_t)e->W() * e->H(), cudaMemcpyDeviceToHost, e->stream()));
+  API_CUDA(cudaStreamSynchronize(e->stream()));
+  if (mask) *mask = e->h_mask();
+  if (mask_pitch) *mask_pitch = (size_t)e->W();
+  return 1;
+}
+
+int bsb_set_background(bsb_ctx* ctx, const uint8_t* bg_raw, int bg_w, int bg_h, size_t bg_pitch) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->set_background(bg_raw, bg_w, bg_h, bg_pitch, &err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+int bsb_get_background(bsb_ctx* ctx, uint8_t* out, size_t out_pitch) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+  Engine* e = ctx->eng;
+  if (!out || out_pitch < (size_t)e->W() * 3) { report(cbp, "error: invalid output buffer"); return 0; }
+  if (!e->has_background()) { report(cbp, "error: no background set"); return 0; }
+  API_CUDA(cudaSetDevice(e->device()));
+  API_CUDA(cudaStreamSynchronize(e->stream()));
+  const size_t row = (size_t)e->W() * 3;
+  for (int y = 0; y < e->H(); ++y) API_CUDA(cudaMemcpy(out + (size_t)y * out_pitch, e->d_bg() + (size_t)y * row, row, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+int bsb_composite(bsb_ctx* ctx, int n_frames, const uint8_t* frames, size_t frame_pitch, size_t frame_stride,
+                  uint8_t* out, size_t out_pitch, size_t out_stride, uint8_t* out_yuyv, size_t yuyv_stride,
+                  uint8_t* out_mask, size_t mask_stride) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+  Engine* e = ctx->eng;
+  const size_t row = (size_t)e->W() * 3, fbytes = row * e->H(), npix = (size_t)e->W() * e->H();
+  if (n_frames < 1 || n_frames > e->max_batch()) { report(cbp, "error: n_frames out of range (1..max_batch)"); return 0; }
+  if (!frames || frame_pitch < row) { report(cbp, "error: invalid frame"); return 0; }
+  if (out && out_pitch < row) { report(cbp, "error: invalid output pitch"); return 0; }
+  if (!e->has_background() && (out || out_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  if (out_yuyv && (e->W() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
+  API_CUDA(cudaSetDevice(e->device()));
+  if (frame_pitch == row && frame_stride == fbytes) {
+    API_CUDA(cudaMemcpyAsync(e->d_frames(), frames, fbytes * n_frames, cudaMemcpyHostToDevice, e->stream()));
+  } else {
+    for (int b = 0; b < n_frames; ++b)
+      API_CUDA(cudaMemcpy2DAsync(e->d_frames() + b * fbytes, row, frames + (size_t)b * frame_stride, frame_pitch, row, (size_t)e->H(),
+                                 cudaMemcpyHostToDevice, e->stream()));
+  }
+  std::string err;
+  if (!e->run(n_frames, e->d_frames(), row, fbytes, out ? e->d_out() : nullptr, fbytes, out_yuyv ? e->d_yuyv() : nullptr, npix * 2,
+              out_mask ? e->d_mask() : nullptr, npix, false, &err)) {
+    report(cbp, "error: failed to process video frame: " + err); return 0;
+  }
+  if (out) {
+    if (out_pitch == row && out_stride == fbytes) API_CUDA(cudaMemcpyAsync(out, e->d_out(), fbytes * n_frames, cudaMemcpyDeviceToHost, e->stream()));
+    else for (int b = 0; b < n_frames; ++b)
+      API_CUDA(cudaMemcpy2DAsync(out + (size_t)b * out_stride, out_pitch, e->d_out() + b * fbytes, row, row, (size_t)e->H(), cudaMemcpyDeviceToHost, e->stream()));
+  }
+  if (out_yuyv) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * npix * 2, npix * 2, cudaMemcpyDeviceToHost, e->stream()));
+  if (out_mask) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out_mask + (size_t)b * mask_stride, e->d_mask() + b * npix, npix, cudaMemcpyDeviceToHost, e->stream()));
+  API_CUDA(cudaStreamSynchronize(e->stream()));
+  API_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int bsb_composite_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_frames, size_t frame_stride, uint8_t* d_out, size_t out_stride,
+                         uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, int sync) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+  Engine* e = ctx->eng;
+  if (!d_frames) { report(cbp, "error: invalid frame"); return 0; }
+  if (!e->has_background() && (d_out || d_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  std::string err;
+  if (!e->run(n_frames, d_frames, (size_t)e->W() * 3, frame_stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, false, &err)) {
+    report(cbp, "error: " + err); return 0;
+  }
+  if (sync) { API_CUDA(cudaStreamSynchronize(e->stream())); API_CUDA(cudaGetLastError()); }
+  return 1;
+}
+
+int bsb_synchronize(bsb_ctx* ctx) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->sync(&err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+void* bsb_stream(bsb_ctx* ctx) { return check_ctx(ctx) ? (void*)ctx->eng->stream() : nullptr; }
+
+// ---- stand-alone stages -------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; }
+  uint8_t* u8() const { return static_cast<uint8_t*>(p); }
+};
+bool stage_begin(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { g_last_error = "no CUDA device available (this library has no CPU path)"; return false; }
+  if (device < 0 || device >= n || cudaSetDevice(device) != cudaSuccess) { g_last_error = "invalid CUDA device"; return false; }
+  return true;
+}
+bool stage_end() {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+}  // namespace
+
+int bsb_alpha_blend(int device, const uint8_t* srca, const uint8_t* srcb, const uint8_t* mask, uint8_t* out, size_t npix) {
+  if (!srca || !srcb || !mask || !out) { g_last_error = "null buffer"; return 0; }
+  if (!stage_begin(device)) return 0;
+  DevBuf a, b, m, o;
+  if (!a.alloc(npix * 3) || !b.alloc(npix * 3) || !m.alloc(npix) || !o.alloc(npix * 3)) { g_last_error = "cudaMalloc failed"; return 0; }
+  cudaMemcpy(a.p, srca, npix * 3, cudaMemcpyHostToDevice); cudaMemcpy(b.p, srcb, npix * 3, cudaMemcpyHostToDevice);
+  cudaMemcpy(m.p, mask, npix, cudaMemcpyHostToDevice);
+  if (npix) bsb::launch_alpha_blend(nullptr, a.u8(), b.u8(), m.u8(), o.u8(), npix);
+  if (!stage_end()) return 0;
+  cudaMemcpy(out, o.p, npix * 3, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+int bsb_convert_rgb_to_yuyv(int device, const uint8_t* rgb, uint8_t* yuyv, int width, int height) {
+  if (!rgb || !yuyv || width < 0 || height < 0) { g_last_error = "invalid argument"; return 0; }
+  const size_t npix = (size_t)width * height;
+  if (npix & 1) { g_last_error = "YUYV needs an even number of pixels"; return 0; }
+  if (!stage_begin(device)) return 0;
+  DevBuf a, o;
+  if (!a.alloc(npix * 3) || !o.alloc(npix * 2)) { g_last_error = "cudaMalloc failed"; return 0; }
+  cudaMemcpy(a.p, rgb, npix * 3, cudaMemcpyHostToDevice);
+  if (npix) bsb::launch_rgb_to_yuyv(nullptr, a.u8(), o.u8(), npix);
+  if (!stage_end()) return 0;
+  cudaMemcpy(yuyv, o.p, npix * 2, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) {
+  if (!src || !dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) { g_last_error = "invalid argument"; return 0; }
+  if (!stage_begin(device)) return 0;
+  const bsb::HostResizeTab h = bsb::build_resize_tab(sw, sh, dw, dh);
+  DevBuf a, o, t0, t1, t2, t3, t4;
+  const size_t sb = (size_t)sw * sh * 3, db = (size_t)dw * dh * 3;
+  if (!a.alloc(sb) || !o.alloc(db) || !t0.alloc(dw * 4) || !t1.alloc(dw * 4) || !t2.alloc(dh * 4) || !t3.alloc(dh * 4) || !t4.alloc(dh * 4)) {
+    g_last_error = "cudaMalloc failed"; return 0;
+  }
+  cudaMemcpy(a.p, src, sb, cudaMemcpyHostToDevice);
+  cudaMemcpy(t0.p, h.xofs.data(), (size_t)dw * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(t1.p, h.xw.data(), (size_t)dw * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(t2.p, h.yofs0.data(), (size_t)dh * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(t3.p, h.yofs1.data(), (size_t)dh * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(t4.p, h.yw.data(), (size_t)dh * 4, cudaMemcpyHostToDevice);
+  bsb::ResizeTab tab{(const int*)t0.p, (const short*)t1.p, (const int*)t2.p, (const int*)t3.p, (const short*)t4.p};
+  bsb::launch_resize_u8c3(nullptr, a.u8(), sw, sh, (size_t)sw * 3, o.u8(), dw, dh, (size_t)dw * 3, tab, h.area2x2);
+  if (!stage_end()) return 0;
+  cudaMemcpy(dst, o.p, db, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+// ---- introspection ----------------------------------------------------------------
+int bsb_geometry(bsb_ctx* ctx, int roidim[4], int in_roidim[4], int out_roidim[4], int in_hwc[3], int out_hwc[3]) {
+  if (!check_ctx(ctx)) return 0;
+  Engine* e = ctx->eng;
+  if (roidim) std::memcpy(roidim, e->roidim(), 16);
+  if (in_roidim) std::memcpy(in_roidim, e->in_roidim(), 16);
+  if (out_roidim) std::memcpy(out_roidim, e->out_roidim(), 16);
+  if (in_hwc) e->in_hwc(in_hwc);
+  if (out_hwc) e->out_hwc(out_hwc);
+  return 1;
+}
+
+int bsb_infer(bsb_ctx* ctx, int n_frames, const float* input, float* output) {
+  if (!check_ctx(ctx)) return 0;
+  if (!input || !output) { report(&ctx->cb, "error: null buffer"); return 0; }
+  std::string err;
+  if (!ctx->eng->infer(n_frames, input, output, &err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+long bsb_get_tensor(bsb_ctx* ctx, int tensor_index, float* out, long capacity) {
+  if (!check_ctx(ctx)) return -1;
+  std::string err;
+  long n = ctx->eng->get_tensor(tensor_index, out, capacity, &err);
+  if (n < 0) report(&ctx->cb, "error: " + err);
+  return n;
+}
+
+long bsb_get_stage_u8(bsb_ctx* ctx, int which, int frame, uint8_t* out, long capacity) {
+  if (!check_ctx(ctx)) return -1;
+  std::string err;
+  long n = ctx->eng->get_stage_u8(which, frame, out, capacity, &err);
+  if (n < 0) report(&ctx->cb, "error: " + err);
+  return n;
+}
+
+int bsb_reset_state(bsb_ctx* ctx) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->reset_state(&err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+int bsb_launches_per_call(bsb_ctx* ctx, int n_frames) {
+  (void)n_frames;
+  return check_ctx(ctx) ? ctx->eng->launches_per_call() : 0;
+}
+
+double bsb_time_stage(bsb_ctx* ctx, int stage, int n_frames, int iters) {
+  if (!check_ctx(ctx)) return -1.0;
+  std::string err;
+  double ms = ctx->eng->time_stage(stage, n_frames, iters, &err);
+  if (ms < 0) report(&ctx->cb, "error: " + err);
+  return ms;
+}
+
+long bsb_total_launches(void) { return bsb::launch_count(); }
+
+double bsb_model_flops(bsb_ctx* ctx) { return check_ctx(ctx) ? ctx->eng->flops() : 0.0; }
+
+}  // extern "C"

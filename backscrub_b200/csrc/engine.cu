@@ -1,0 +1,687 @@
+// backscrub_b200/csrc/engine.cu — planner + per-stream engine (see engine.h).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace bsb {
+
+#define CUDA_OK(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      if (err) *err = std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr; \
+      return false;                                                                        \
+    }                                                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// OpenCV INTER_LINEAR 8-bit tables (cv::resize; formulas pinned in oracle/oracle_img.c)
+// ---------------------------------------------------------------------------
+HostResizeTab build_resize_tab(int sw, int sh, int dw, int dh) {
+  HostResizeTab t;
+  t.area2x2 = (sw == dw * 2 && sh == dh * 2);
+  const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+  t.xofs.resize(dw); t.xw.resize(2 * (size_t)dw);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)std::floor(fx);
+    fx -= (float)sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    t.xofs[dx] = sx;
+    t.xw[2 * dx] = (short)std::lrintf((1.f - fx) * 2048.f);
+    t.xw[2 * dx + 1] = (short)std::lrintf(fx * 2048.f);
+  }
+  t.yofs0.resize(dh); t.yofs1.resize(dh); t.yw.resize(2 * (size_t)dh);
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)std::floor(fy);
+    fy -= (float)sy;
+    t.yofs0[dy] = std::min(std::max(sy, 0), sh - 1);
+    t.yofs1[dy] = std::min(std::max(sy + 1, 0), sh - 1);
+    t.yw[2 * dy] = (short)std::lrintf((1.f - fy) * 2048.f);
+    t.yw[2 * dy + 1] = (short)std::lrintf(fy * 2048.f);
+  }
+  return t;
+}
+
+static bool upload_tab(const HostResizeTab& h, DevResizeTab* d, std::string* err) {
+  const size_t nx = h.xofs.size(), ny = h.yofs0.size();
+  auto al = [](size_t n) { return (n + 15) / 16 * 16; };
+  const size_t o_xofs = 0, o_y0 = o_xofs + al(nx * 4), o_y1 = o_y0 + al(ny * 4), o_xw = o_y1 + al(ny * 4), o_yw = o_xw + al(nx * 4);
+  const size_t total = o_yw + al(ny * 4);
+  std::vector<uint8_t> blob(total, 0);
+  std::memcpy(blob.data() + o_xofs, h.xofs.data(), nx * 4);
+  std::memcpy(blob.data() + o_y0, h.yofs0.data(), ny * 4);
+  std::memcpy(blob.data() + o_y1, h.yofs1.data(), ny * 4);
+  std::memcpy(blob.data() + o_xw, h.xw.data(), nx * 4);
+  std::memcpy(blob.data() + o_yw, h.yw.data(), ny * 4);
+  if (d->blob) { cudaFree(d->blob); d->blob = nullptr; }
+  CUDA_OK(cudaMalloc(&d->blob, blob.size()));
+  CUDA_OK(cudaMemcpy(d->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  uint8_t* b = static_cast<uint8_t*>(d->blob);
+  d->tab.xofs = reinterpret_cast<const int*>(b + o_xofs);
+  d->tab.yofs0 = reinterpret_cast<const int*>(b + o_y0);
+  d->tab.yofs1 = reinterpret_cast<const int*>(b + o_y1);
+  d->tab.xw = reinterpret_cast<const short*>(b + o_xw);
+  d->tab.yw = reinterpret_cast<const short*>(b + o_yw);
+  d->area2x2 = h.area2x2;
+  return true;
+}
+
+// TF SAME/VALID output size + leading pad (reference kernels/padding.h:23-82)
+static void conv_geom(int in, int k, int stride, int dil, int padding, int* out, int* pad_before) {
+  const int eff = (k - 1) * dil + 1;
+  const int o = padding == 0 ? (in + stride - 1) / stride : (in + stride - eff) / stride;
+  int total = (o - 1) * stride + eff - in;
+  if (total < 0) total = 0;
+  *out = o; *pad_before = total / 2;
+}
+
+static int unary_act(int kind) {
+  switch (kind) {
+    case OP_HARD_SWISH: return ACT_HARD_SWISH;
+    case OP_RELU: return ACT_RELU;
+    case OP_RELU6: return ACT_RELU6;
+    case OP_LOGISTIC: return ACT_LOGISTIC;
+    default: return -1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Planner: TFLite op list -> fused steps + arena layout
+// ---------------------------------------------------------------------------
+bool Engine::plan(std::string* err) {
+  const int nt = (int)g_.tensors.size(), nops = (int)g_.ops.size();
+  std::vector<std::vector<int>> consumers(nt);
+  std::vector<int> produced_at(nt, -1);
+  for (int i = 0; i < nops; ++i) {
+    const GOp& O = g_.ops[i];
+    if (O.kind == OP_DEQUANTIZE) continue;
+    for (int t : O.in) if (t >= 0 && !g_.tensors[t].is_const) consumers[t].push_back(i);
+    if (O.out >= 0) produced_at[O.out] = i;
+  }
+  tinfo_.assign(nt, TensorInfo());
+  for (int t = 0; t < nt; ++t) {
+    const GTensor& T = g_.tensors[t];
+    if (T.is_const || T.dtype != 0) continue;
+    if (T.dim4(0) != 1) { *err = "tensor '" + T.name + "': batch dimension must be 1"; return false; }
+    TensorInfo& I = tinfo_[t];
+    I.h = T.dim4(1); I.w = T.dim4(2); I.c = T.dim4(3); I.ld = I.c;
+    I.frame_elems = (size_t)I.h * I.w * I.ld;
+  }
+  auto is_pw = [&](const GOp& O) {
+    if (O.kind != OP_CONV_2D) return false;
+    const GTensor& w = g_.tensors[O.in[1]];
+    return w.shape.size() == 4 && w.shape[1] == 1 && w.shape[2] == 1 && O.stride_w == 1 && O.stride_h == 1;
+  };
+  auto add_blob = [&](const std::vector<float>& v) {
+    size_t off = (wblob_h_.size() + 63) / 64 * 64;
+    wblob_h_.resize(off + v.size(), 0.f);
+    std::copy(v.begin(), v.end(), wblob_h_.begin() + off);
+    return off;
+  };
+  struct Fold { int x, s, add; };
+  std::map<int, Fold> prologue;      // tensor consumed by a PW conv -> (x, scale, add)
+  std::vector<char> done(nops, 0);
+
+  auto fold_unary = [&](int i, Step& st) {  // fold a single-consumer unary op after op i
+    const int t = st.out;
+    if (consumers[t].size() != 1) return;
+    const int j = consumers[t][0];
+    const int a = unary_act(g_.ops[j].kind);
+    if (a < 0 || done[j] || j <= i) return;
+    st.act2 = a; done[j] = 1; st.out = g_.ops[j].out;
+  };
+  auto fold_add = [&](int i, Step& st) {    // fold a single-consumer residual ADD
+    const int t = st.out;
+    if (t == g_.output || consumers[t].size() != 1) return;
+    const int j = consumers[t][0];
+    const GOp& A = g_.ops[j];
+    if (A.kind != OP_ADD || done[j] || j <= i || A.in.size() != 2) return;
+    const int other = A.in[0] == t ? A.in[1] : A.in[0];
+    if (other == t || g_.tensors[other].is_const) return;
+    if (g_.tensors[other].count() != g_.tensors[t].count()) return;
+    if (other != g_.input && !(produced_at[other] >= 0 && produced_at[other] < i)) return;
+    if (prologue.count(other)) return;
+    st.residual = other; st.act3 = A.act; done[j] = 1; st.out = A.out;
+  };
+  auto pack_pw_weights = [&](const GTensor& w, int N, int K, Step& st) {
+    st.K = K; st.N = N; st.n4 = (N + 3) / 4 * 4;
+    std::vector<float> wt((size_t)K * st.n4, 0.f);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) wt[(size_t)k * st.n4 + n] = w.f32[(size_t)n * K + k];
+    st.w_off = add_blob(wt);
+  };
+
+  for (int i = 0; i < nops; ++i) {
+    const GOp& O = g_.ops[i];
+    if (done[i] || O.kind == OP_DEQUANTIZE) continue;
+    Step st; st.op_index = i;
+    auto need = [&](bool c, const char* what) { if (!c) { *err = std::string("unsupported model construct: ") + what; } return c; };
+    switch (O.kind) {
+      case OP_CONV_2D: {
+        if (!need(O.in.size() >= 2 && g_.tensors[O.in[1]].is_const, "CONV_2D with non-constant weights")) return false;
+        const GTensor& w = g_.tensors[O.in[1]];
+        const int oc = w.shape[0], kh = w.shape[1], kw = w.shape[2], ic = w.shape[3];
+        st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
+        if (O.in.size() > 2 && O.in[2] >= 0) { st.has_bias = true; st.b_off = add_blob(g_.tensors[O.in[2]].f32); }
+        if (is_pw(O)) {
+          st.kind = Step::PW;
+          pack_pw_weights(w, oc, ic, st);
+          auto it = prologue.find(st.in);
+          if (it != prologue.end()) { st.in = it->second.x; st.scale = it->second.s; st.in_add = it->second.add; }
+        } else {
+          st.kind = Step::CONV;
+          st.kh = kh; st.kw = kw; st.sh = O.stride_h; st.sw = O.stride_w; st.dh = O.dil_h; st.dw = O.dil_w;
+          st.K = ic; st.N = oc; st.n4 = (oc + 3) / 4 * 4;
+          int o_h, o_w;
+          conv_geom(tinfo_[st.in].h, kh, st.sh, st.dh, O.padding, &o_h, &st.pt);
+          conv_geom(tinfo_[st.in].w, kw, st.sw, st.dw, O.padding, &o_w, &st.pl);
+          if (!need(o_h == tinfo_[O.out].h && o_w == tinfo_[O.out].w, "CONV_2D output shape")) return false;
+          if (!need((size_t)kh * kw * ic * st.n4 * 4 <= 96 * 1024, "dense KxK conv too large for the direct kernel")) return false;
+          std::vector<float> wt((size_t)kh * kw * ic * st.n4, 0.f);   // [kh][kw][ic][oc4]
+          for (int o = 0; o < oc; ++o) for (int y = 0; y < kh; ++y) for (int x = 0; x < kw; ++x) for (int c = 0; c < ic; ++c)
+            wt[(((size_t)y * kw + x) * ic + c) * st.n4 + o] = w.f32[(((size_t)o * kh + y) * kw + x) * ic + c];
+          st.w_off = add_blob(wt);
+        }
+        fold_unary(i, st); fold_add(i, st);
+        break;
+      }
+      case OP_FULLY_CONNECTED: {
+        if (!need(O.in.size() >= 2 && g_.tensors[O.in[1]].is_const, "FULLY_CONNECTED with non-constant weights")) return false;
+        const GTensor& w = g_.tensors[O.in[1]];
+        st.kind = Step::PW; st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
+        const int out_depth = w.shape[w.shape.size() - 2], in_depth = w.shape[w.shape.size() - 1];
+        if (!need(tinfo_[st.in].c == in_depth, "FULLY_CONNECTED over flattened spatial dims")) return false;
+        pack_pw_weights(w, out_depth, in_depth, st);
+        if (O.in.size() > 2 && O.in[2] >= 0) { st.has_bias = true; st.b_off = add_blob(g_.tensors[O.in[2]].f32); }
+        fold_unary(i, st);
+        break;
+      }
+      case OP_DEPTHWISE_CONV_2D: {
+        if (!need(O.depth_mult == 1, "depthwise multiplier != 1")) return false;
+        const GTensor& w = g_.tensors[O.in[1]];
+        st.kind = Step::DW; st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
+        st.kh = w.shape[1]; st.kw = w.shape[2]; st.sh = O.stride_h; st.sw = O.stride_w; st.dh = O.dil_h; st.dw = O.dil_w;
+        int o_h, o_w;
+        conv_geom(tinfo_[st.in].h, st.kh, st.sh, st.dh, O.padding, &o_h, &st.pt);
+        conv_geom(tinfo_[st.in].w, st.kw, st.sw, st.dw, O.padding, &o_w, &st.pl);
+        if (!need(o_h == tinfo_[O.out].h && o_w == tinfo_[O.out].w, "DEPTHWISE_CONV_2D output shape")) return false;
+        st.w_off = add_blob(w.f32);
+        if (O.in.size() > 2 && O.in[2] >= 0) { st.has_bias = true; st.b_off = add_blob(g_.tensors[O.in[2]].f32); }
+        fold_unary(i, st); fold_add(i, st);
+        break;
+      }
+      case OP_AVERAGE_POOL_2D: {
+        st.kind = Step::POOL; st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
+        if (!need(O.filter_h == tinfo_[st.in].h && O.filter_w == tinfo_[st.in].w && tinfo_[O.out].h == 1 && tinfo_[O.out].w == 1,
+                  "AVERAGE_POOL_2D that is not global")) return false;
+        if (!need((size_t)tinfo_[st.in].h * tinfo_[st.in].c * 4 <= 160 * 1024, "global pool row buffer")) return false;
+        break;
+      }
+      case OP_RESIZE_BILINEAR: {
+        st.kind = Step::RESIZE; st.in = O.in[0]; st.out = O.out; st.align_corners = O.align_corners; st.half_pixel = O.half_pixel;
+        const GTensor& sz = g_.tensors[O.in[1]];
+        if (!need(sz.is_const && sz.i32.size() == 2 && sz.i32[0] == tinfo_[O.out].h && sz.i32[1] == tinfo_[O.out].w, "RESIZE_BILINEAR size")) return false;
+        break;
+      }
+      case OP_CUSTOM: {
+        if (!need(O.custom == "Convolution2DTransposeBias", "unknown custom op")) return false;
+        const GTensor& w = g_.tensors[O.in[1]];
+        if (!need(w.shape[1] == 2 && w.shape[2] == 2 && O.stride_w == 2 && O.stride_h == 2 && O.tconv_same &&
+                  tinfo_[O.out].h == 2 * tinfo_[O.in[0]].h && tinfo_[O.out].w == 2 * tinfo_[O.in[0]].w,
+                  "Convolution2DTransposeBias other than k2 s2 SAME on even sizes")) return false;
+        st.kind = Step::TCONV; st.in = O.in[0]; st.out = O.out; st.N = w.shape[0]; st.K = w.shape[3];
+        st.w_off = add_blob(w.f32); st.has_bias = true; st.b_off = add_blob(g_.tensors[O.in[2]].f32);
+        fold_unary(i, st);
+        break;
+      }
+      case OP_MUL: {
+        if (!need(O.in.size() == 2, "MUL arity")) return false;
+        int x = O.in[0], s = O.in[1];
+        if (g_.tensors[x].count() < g_.tensors[s].count()) std::swap(x, s);
+        const bool bcast = g_.tensors[s].count() != g_.tensors[x].count();
+        if (bcast && !need((int)g_.tensors[s].count() == tinfo_[x].c && !g_.tensors[s].is_const, "MUL broadcast other than per-channel")) return false;
+        if (bcast && O.act == ACT_NONE && consumers[O.out].size() == 1 && O.out != g_.output) {
+          const int j = consumers[O.out][0];
+          const GOp& C = g_.ops[j];
+          if (is_pw(C) && C.in[0] == O.out) { prologue[O.out] = Fold{x, s, -1}; done[i] = 1; continue; }
+          if (C.kind == OP_ADD && C.act == ACT_NONE && C.in.size() == 2 && consumers[C.out].size() == 1 && C.out != g_.output) {
+            const int other = C.in[0] == O.out ? C.in[1] : C.in[0];
+            const GOp& P = g_.ops[consumers[C.out][0]];
+            if (other != O.out && !g_.tensors[other].is_const && g_.tensors[other].count() == g_.tensors[x].count() &&
+                is_pw(P) && P.in[0] == C.out && !prologue.count(other)) {
+              prologue[C.out] = Fold{x, s, other}; done[i] = 1; done[j] = 1; continue;
+            }
+          }
+        }
+        st.kind = Step::ELT; st.in = x; st.out = O.out; st.act1 = O.act;
+        if (bcast) { st.elt_mode = 3; st.scale = s; } else { st.elt_mode = 2; st.in2 = s; }
+        break;
+      }
+      case OP_ADD: {
+        if (!need(O.in.size() == 2 && g_.tensors[O.in[0]].count() == g_.tensors[O.in[1]].count(), "ADD with broadcasting")) return false;
+        st.kind = Step::ELT; st.elt_mode = 1; st.in = O.in[0]; st.in2 = O.in[1]; st.out = O.out; st.act1 = O.act;
+        break;
+      }
+      case OP_HARD_SWISH: case OP_RELU: case OP_RELU6: case OP_LOGISTIC:
+        st.kind = Step::ELT; st.elt_mode = 0; st.in = O.in[0]; st.out = O.out; st.act1 = unary_act(O.kind);
+        break;
+      case OP_CONCATENATION: {
+        const int rank = (int)g_.tensors[O.out].shape.size();
+        const int axis = O.axis < 0 ? O.axis + rank : O.axis;
+        if (!need(axis == rank - 1 && O.act == ACT_NONE, "CONCATENATION not on the channel axis")) return false;
+        int off = 0;
+        for (int t : O.in) {
+          Step c; c.op_index = i; c.kind = Step::COPY; c.in = t; c.out = O.out; c.copy_off = off;
+          off += tinfo_[t].c;
+          steps_.push_back(c);
+        }
+        continue;
+      }
+      default:
+        *err = "unsupported TFLite operator code " + std::to_string(O.kind);
+        return false;
+    }
+    steps_.push_back(st);
+  }
+
+  // ---- liveness + arena (floats; every tensor is max_batch frames) ----
+  const int ns = (int)steps_.size();
+  auto use = [&](int t, int s) { if (t >= 0) tinfo_[t].last_use = std::max(tinfo_[t].last_use, s); };
+  tinfo_[g_.input].materialized = true; tinfo_[g_.input].first_def = -1;
+  for (int s = 0; s < ns; ++s) {
+    const Step& st = steps_[s];
+    use(st.in, s); use(st.in2, s); use(st.scale, s); use(st.in_add, s); use(st.residual, s);
+    tinfo_[st.out].materialized = true;
+    tinfo_[st.out].first_def = std::min(tinfo_[st.out].first_def, s);
+    use(st.out, s);
+  }
+  tinfo_[g_.output].last_use = 1 << 30;
+  tinfo_[g_.input].last_use = std::max(tinfo_[g_.input].last_use, 0);
+  if (!tinfo_[g_.output].materialized) { *err = "graph output is never produced"; return false; }
+  for (const Step& st : steps_)
+    for (int t : {st.in, st.in2, st.scale, st.in_add, st.residual})
+      if (t >= 0 && !tinfo_[t].materialized) { *err = "planner: step reads a tensor that was folded away"; return false; }
+
+  struct Free { size_t off, size; };
+  std::vector<Free> free_list;
+  size_t top = 0;
+  auto alloc = [&](size_t n) {
+    n = (n + 63) / 64 * 64;
+    for (size_t k = 0; k < free_list.size(); ++k)
+      if (free_list[k].size >= n) {
+        size_t off = free_list[k].off;
+        free_list[k].off += n; free_list[k].size -= n;
+        if (!free_list[k].size) free_list.erase(free_list.begin() + k);
+        return off;
+      }
+    size_t off = top; top += n; return off;
+  };
+  auto release = [&](size_t off, size_t n) {
+    n = (n + 63) / 64 * 64;
+    free_list.push_back({off, n});
+    std::sort(free_list.begin(), free_list.end(), [](const Free& a, const Free& b) { return a.off < b.off; });
+    for (size_t k = 0; k + 1 < free_list.size();)
+      if (free_list[k].off + free_list[k].size == free_list[k + 1].off) { free_list[k].size += free_list[k + 1].size; free_list.erase(free_list.begin() + k + 1); }
+      else ++k;
+  };
+  const bool keep = (flags_ & 1u) != 0;
+  std::vector<char> allocated(nt, 0);
+  tinfo_[g_.input].offset = alloc(tinfo_[g_.input].frame_elems * max_batch_); allocated[g_.input] = 1;
+  for (int s = 0; s < ns; ++s) {
+    const int o = steps_[s].out;
+    if (!allocated[o]) { tinfo_[o].offset = alloc(tinfo_[o].frame_elems * max_batch_); allocated[o] = 1; }
+    if (keep) continue;
+    for (int t = 0; t < nt; ++t)
+      if (allocated[t] == 1 && tinfo_[t].materialized && tinfo_[t].last_use == s) { release(tinfo_[t].offset, tinfo_[t].frame_elems * max_batch_); allocated[t] = 2; }
+  }
+  arena_elems_ = top;
+
+  // algorithmic FLOPs (2*MAC of conv / depthwise / fc / tconv), SURVEY.md Appendix A
+  flops_ = 0;
+  for (const GOp& O : g_.ops) {
+    if (O.out < 0 || O.in.size() < 2) continue;
+    const GTensor& out = g_.tensors[O.out]; const GTensor& w = g_.tensors[O.in[1]];
+    if (O.kind == OP_CONV_2D) flops_ += 2.0 * out.count() * w.shape[1] * w.shape[2] * w.shape[3];
+    else if (O.kind == OP_DEPTHWISE_CONV_2D) flops_ += 2.0 * out.count() * w.shape[1] * w.shape[2];
+    else if (O.kind == OP_FULLY_CONNECTED) flops_ += 2.0 * out.count() * w.shape.back();
+    else if (O.kind == OP_CUSTOM) flops_ += 2.0 * out.count() * w.shape[3];
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------
+Engine* Engine::create(const std::string& model_path, int width, int height, int device, int max_batch,
+                       unsigned flags, const Callbacks& cb, std::string* err) {
+  Engine* e = new Engine();
+  e->cb_ = cb; e->W_ = width; e->H_ = height; e->device_ = device; e->max_batch_ = std::max(1, max_batch); e->flags_ = flags;
+  auto fail = [&](const std::string& m) { *err = m; delete e; return (Engine*)nullptr; };
+  if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return fail("invalid frame size");
+  if (!load_tflite(model_path, &e->g_, err)) { delete e; return nullptr; }
+  // lib/libbackscrub.cc:194-200
+  e->model_type_ = model_type_from_name(model_path);
+  if (e->model_type_ == MODEL_UNKNOWN) return fail("unknown model type '" + model_path + "'.");
+  // lib/libbackscrub.cc:132-148
+  if (e->model_type_ == MODEL_DEEPLAB) { e->scaling_ = (float)(1 / 127.5); e->offset_ = -1.f; }
+  else { e->scaling_ = (float)(1 / 255.0); e->offset_ = 0.f; }
+  const GTensor& in = e->g_.tensors[e->g_.input]; const GTensor& out = e->g_.tensors[e->g_.output];
+  // lib/libbackscrub.cc:85-112: float32, batch 1
+  if (in.dtype != 0 || out.dtype != 0) return fail("error: input/output tensor is not float32 type");
+  if (in.shape.size() != 4 || out.shape.size() != 4 || in.shape[0] != 1 || out.shape[0] != 1) return fail("error: input/output tensor is not single vector");
+  e->mh_ = in.shape[1]; e->mw_ = in.shape[2];
+  if (in.shape[3] != 3) return fail("model input must have 3 channels");
+  e->oh_ = out.shape[1]; e->ow_ = out.shape[2]; e->oc_ = out.shape[3];
+  const int need_oc = e->model_type_ == MODEL_DEEPLAB ? 21 : (e->model_type_ == MODEL_MEET ? 2 : 1);
+  if (e->oc_ != need_oc) return fail("model output channel count does not match the model family");
+  // lib/libbackscrub.cc:231-246 (float arithmetic, truncating conversion)
+  const float ratio = (float)e->mh_ / (float)e->mw_, frameratio = (float)height / (float)width;
+  if (frameratio < ratio) {
+    e->roidim_[0] = (int)(((float)width - (float)height / ratio) / 2); e->roidim_[1] = 0;
+    e->roidim_[2] = (int)((float)height / ratio); e->roidim_[3] = height;
+    e->in_roidim_[0] = 0; e->in_roidim_[1] = 0; e->in_roidim_[2] = e->mw_; e->in_roidim_[3] = e->mh_;
+  } else {
+    e->roidim_[0] = 0; e->roidim_[1] = 0; e->roidim_[2] = width; e->roidim_[3] = height;
+    e->in_roidim_[0] = (int)(((float)e->mw_ - (float)e->mh_ / frameratio) / 2); e->in_roidim_[1] = 0;
+    e->in_roidim_[2] = (int)((float)e->mh_ / frameratio); e->in_roidim_[3] = e->mh_;
+  }
+  // documented deviation for models whose output grid differs from the input grid (body-pix):
+  // the reference slices ofinal with in_roidim and throws; scale the rectangle by out/in.
+  if (e->oh_ == e->mh_ && e->ow_ == e->mw_) std::memcpy(e->out_roidim_, e->in_roidim_, sizeof(e->in_roidim_));
+  else {
+    e->out_roidim_[0] = e->in_roidim_[0] * e->ow_ / e->mw_; e->out_roidim_[1] = e->in_roidim_[1] * e->oh_ / e->mh_;
+    e->out_roidim_[2] = e->in_roidim_[2] * e->ow_ / e->mw_; e->out_roidim_[3] = e->in_roidim_[3] * e->oh_ / e->mh_;
+  }
+  for (int k = 2; k < 4; ++k)
+    if (e->roidim_[k] <= 0 || e->in_roidim_[k] <= 0 || e->out_roidim_[k] <= 0) return fail("degenerate ROI for this frame size");
+  if (e->roidim_[0] < 0 || e->roidim_[0] + e->roidim_[2] > width || e->in_roidim_[0] < 0 || e->in_roidim_[0] + e->in_roidim_[2] > e->mw_)
+    return fail("ROI outside the frame");
+  if (!e->plan(err)) { delete e; return nullptr; }
+  if (!e->upload(err)) { delete e; return nullptr; }
+  return e;
+}
+
+bool Engine::upload(std::string* err) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { *err = "no CUDA device available (this library has no CPU path)"; return false; }
+  if (device_ < 0 || device_ >= ndev) { *err = "CUDA device ordinal out of range"; return false; }
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  const size_t B = (size_t)max_batch_;
+  CUDA_OK(cudaMalloc((void**)&wblob_, std::max<size_t>(wblob_h_.size(), 64) * 4));
+  CUDA_OK(cudaMemcpy(wblob_, wblob_h_.data(), wblob_h_.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc((void**)&arena_, std::max<size_t>(arena_elems_, 64) * 4));
+  CUDA_OK(cudaMemset(arena_, 0, std::max<size_t>(arena_elems_, 64) * 4));
+  // bilateral LUTs (cv::bilateralFilter d=5, sigma 100/100; oracle_img.c:or_bilateral_d5_u8c3)
+  {
+    std::vector<float> lut(768 + 16, 0.f);
+    const double gc = -0.5 / (100.0 * 100.0), gs = -0.5 / (100.0 * 100.0);
+    for (int i = 0; i < 768; ++i) lut[i] = (float)std::exp((double)i * i * gc);
+    int k = 0;
+    for (int i = -2; i <= 2; ++i) for (int j = -2; j <= 2; ++j) {
+      const double r = std::sqrt((double)i * i + (double)j * j);
+      if (r > 2) continue;
+      lut[768 + k++] = (float)std::exp(r * r * gs);
+    }
+    CUDA_OK(cudaMalloc((void**)&lut_, lut.size() * 4));
+    CUDA_OK(cudaMemcpy(lut_, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
+  }
+  const size_t in_px = (size_t)mh_ * mw_, out_px = (size_t)oh_ * ow_, fpx = (size_t)W_ * H_;
+  CUDA_OK(cudaMalloc((void**)&in_u8_, B * in_px * 3));
+  CUDA_OK(cudaMemset(in_u8_, 0, B * in_px * 3));      // zero padding outside in_roidim stays zero
+  if (flags_ & 1u) { CUDA_OK(cudaMalloc((void**)&filt_u8_, B * in_px * 3)); }
+  CUDA_OK(cudaMalloc((void**)&state_, out_px));
+  CUDA_OK(cudaMemset(state_, 0, out_px));
+  CUDA_OK(cudaMalloc((void**)&ofinal_, B * out_px));
+  CUDA_OK(cudaMemset(ofinal_, 0, B * out_px));
+  CUDA_OK(cudaMalloc((void**)&d_frames_, B * fpx * 3));
+  CUDA_OK(cudaMalloc((void**)&d_out_, B * fpx * 3));
+  CUDA_OK(cudaMalloc((void**)&d_yuyv_, B * fpx * 2));
+  CUDA_OK(cudaMalloc((void**)&d_mask_, B * fpx));
+  CUDA_OK(cudaMalloc((void**)&d_bg_, fpx * 3));
+  CUDA_OK(cudaMemset(d_bg_, 0, fpx * 3));
+  CUDA_OK(cudaMallocHost((void**)&h_mask_, fpx));
+  if (!upload_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
+  if (!upload_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
+  if (tab_up_.area2x2) { *err = "mask upsample degenerated to a 2x down-scale"; return false; }
+  CUDA_OK(cudaDeviceSynchronize());
+  return true;
+}
+
+Engine::~Engine() {
+#ifndef BSB_EMU
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+#endif
+  if (stream_) { cudaStreamSynchronize(stream_); }
+  for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
+                  (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_,
+                  tab_in_.blob, tab_up_.blob, tab_bg_.blob})
+    if (p) cudaFree(p);
+  if (h_mask_) cudaFreeHost(h_mask_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+// ---------------------------------------------------------------------------
+// enqueue: the per-call kernel sequence (captured into a CUDA graph by run())
+// ---------------------------------------------------------------------------
+void Engine::enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride) {
+  launch_resize_roi_swap(stream_, n, d_frames, stride, pitch, roidim_[0], roidim_[1], roidim_[2], roidim_[3], tab_in_.tab,
+                         in_u8_, mw_, mh_, in_roidim_[0], in_roidim_[1], in_roidim_[2], in_roidim_[3], tab_in_.area2x2);
+  launch_bilateral_norm(stream_, n, in_u8_, mw_, mh_, lut_, lut_ + 768, scaling_, offset_, tptr(g_.input), filt_u8_);
+}
+
+void Engine::enqueue_cnn(int n) {
+  for (const Step& st : steps_) {
+    const TensorInfo& I = tinfo_[st.in];
+    const TensorInfo& O = tinfo_[st.out];
+    Epilogue e;
+    e.bias = st.has_bias ? wblob_ + st.b_off : nullptr;
+    e.act1 = st.act1; e.act2 = st.act2; e.act3 = st.act3;
+    if (st.residual >= 0) { e.residual = tptr(st.residual); e.ld_res = tinfo_[st.residual].ld; }
+    switch (st.kind) {
+      case Step::CONV:
+        launch_conv_direct(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, wblob_ + st.w_off, st.N, st.kh, st.kw, st.sh, st.sw,
+                           st.dh, st.dw, st.pt, st.pl, tptr(st.out), O.h, O.w, O.ld, e);
+        break;
+      case Step::PW:
+        launch_pointwise(stream_, n * I.h * I.w, st.K, st.N, tptr(st.in), I.ld, wblob_ + st.w_off, st.n4, tptr(st.out), O.ld, e,
+                         st.scale >= 0 ? tptr(st.scale) : nullptr, I.h * I.w,
+                         st.in_add >= 0 ? tptr(st.in_add) : nullptr, st.in_add >= 0 ? tinfo_[st.in_add].ld : 0);
+        break;
+      case Step::DW:
+        launch_depthwise(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, wblob_ + st.w_off, st.kh, st.kw, st.sh, st.sw, st.dh, st.dw,
+                         st.pt, st.pl, tptr(st.out), O.h, O.w, O.ld, e);
+        break;
+      case Step::POOL:
+        launch_global_avgpool(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, tptr(st.out), O.ld, st.act1);
+        break;
+      case Step::RESIZE:
+        launch_resize_bilinear(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, tptr(st.out), O.h, O.w, O.ld, st.align_corners, st.half_pixel);
+        break;
+      case Step::TCONV:
+        launch_tconv2x2(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, wblob_ + st.w_off, wblob_ + st.b_off, st.N, tptr(st.out), O.h, O.w, O.ld, st.act2);
+        break;
+      case Step::ELT:
+        launch_eltwise(stream_, st.elt_mode, n, I.h * I.w, I.c, tptr(st.in), I.ld, st.in2 >= 0 ? tptr(st.in2) : nullptr,
+                       st.in2 >= 0 ? tinfo_[st.in2].ld : 0, st.scale >= 0 ? tptr(st.scale) : nullptr, tptr(st.out), O.ld, st.act1);
+        break;
+      case Step::COPY:
+        launch_copy_channels(stream_, n * I.h * I.w, I.c, tptr(st.in), I.ld, tptr(st.out) + st.copy_off, O.ld);
+        break;
+    }
+  }
+}
+
+void Engine::enqueue_decision(int n) {
+  launch_decision_iir(stream_, model_type_, n, tptr(g_.output), oh_, ow_, oc_, state_, ofinal_);
+}
+
+void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                          uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride) {
+  PostArgs a{};
+  a.B = n; a.W = W_; a.H = H_;
+  a.frames = d_frames; a.frame_pitch = pitch; a.frame_stride = stride;
+  a.bg = d_bg_; a.bg_pitch = (size_t)W_ * 3; a.bg_stride = 0;
+  a.ofinal = ofinal_; a.ow = ow_; a.oh = oh_;
+  a.out_x = out_roidim_[0]; a.out_y = out_roidim_[1]; a.out_w = out_roidim_[2]; a.out_h = out_roidim_[3];
+  a.roi_x = roidim_[0]; a.roi_y = roidim_[1]; a.roi_w = roidim_[2]; a.roi_h = roidim_[3];
+  a.tab = tab_up_.tab; a.area2x2 = false;
+  a.out = d_out; a.out_pitch = (size_t)W_ * 3; a.out_stride = out_stride;
+  a.yuyv = d_yuyv; a.yuyv_stride = yuyv_stride;
+  a.mask = d_mask; a.mask_stride = mask_stride;
+  launch_post(stream_, a);
+}
+
+bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                 uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err) {
+  if (n < 1 || n > max_batch_) { *err = "n_frames out of range (1..max_batch)"; return false; }
+  CUDA_OK(cudaSetDevice(device_));
+  const bool cbs = use_callbacks && (cb_.onprep || cb_.oninfer || cb_.onmask);
+  bool eager = cbs || (flags_ & 2u);
+#ifdef BSB_EMU
+  eager = true;
+#endif
+  if (eager) {
+    enqueue_pre(n, d_frames, pitch, stride);
+    if (cbs && cb_.onprep) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onprep(cb_.caller_ctx); }
+    enqueue_cnn(n);
+    if (cbs && cb_.oninfer) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.oninfer(cb_.caller_ctx); }
+    enqueue_decision(n);
+    if (cbs && cb_.onmask) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onmask(cb_.caller_ctx); }
+    enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride);
+    CUDA_OK(cudaGetLastError());
+    return true;
+  }
+#ifndef BSB_EMU
+  const GraphKey key{n, d_frames, pitch, stride, d_out, d_yuyv, d_mask};
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    if (graphs_.size() >= 64) { for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second); graphs_.clear(); }
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    enqueue_pre(n, d_frames, pitch, stride);
+    enqueue_cnn(n);
+    enqueue_decision(n);
+    enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride);
+    CUDA_OK(cudaStreamEndCapture(stream_, &graph));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = graphs_.emplace(key, exec).first;
+  }
+  CUDA_OK(cudaGraphLaunch(it->second, stream_));
+#endif
+  return true;
+}
+
+bool Engine::infer(int n, const float* h_in, float* h_out, std::string* err) {
+  if (n < 1 || n > max_batch_) { *err = "n_frames out of range (1..max_batch)"; return false; }
+  CUDA_OK(cudaSetDevice(device_));
+  const TensorInfo& I = tinfo_[g_.input]; const TensorInfo& O = tinfo_[g_.output];
+  CUDA_OK(cudaMemcpyAsync(tptr(g_.input), h_in, (size_t)n * I.frame_elems * 4, cudaMemcpyHostToDevice, stream_));
+  enqueue_cnn(n);
+  CUDA_OK(cudaMemcpyAsync(h_out, tptr(g_.output), (size_t)n * O.frame_elems * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  CUDA_OK(cudaGetLastError());
+  return true;
+}
+
+bool Engine::set_background(const uint8_t* bg_raw, int bw, int bh, size_t pitch, std::string* err) {
+  if (!bg_raw || bw <= 0 || bh <= 0 || pitch < (size_t)bw * 3) { *err = "invalid background"; return false; }
+  CUDA_OK(cudaSetDevice(device_));
+  const size_t need = (size_t)bw * bh * 3;
+  if (need > bg_raw_cap_) {
+    if (d_bg_raw_) cudaFree(d_bg_raw_);
+    d_bg_raw_ = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d_bg_raw_, need));
+    bg_raw_cap_ = need;
+  }
+  if (bw != bg_w_ || bh != bg_h_) {
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    if (!upload_tab(build_resize_tab(bw, bh, W_, H_), &tab_bg_, err)) return false;
+    bg_w_ = bw; bg_h_ = bh;
+  }
+  CUDA_OK(cudaMemcpy2DAsync(d_bg_raw_, (size_t)bw * 3, bg_raw, pitch, (size_t)bw * 3, (size_t)bh, cudaMemcpyHostToDevice, stream_));
+  // app/background.cc:178-194: cv::resize(raw, out, Size(width, height))
+  launch_resize_u8c3(stream_, d_bg_raw_, bw, bh, (size_t)bw * 3, d_bg_, W_, H_, (size_t)W_ * 3, tab_bg_.tab, tab_bg_.area2x2);
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  CUDA_OK(cudaGetLastError());
+  has_bg_ = true;
+  return true;
+}
+
+bool Engine::sync(std::string* err) {
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  CUDA_OK(cudaGetLastError());
+  return true;
+}
+
+bool Engine::reset_state(std::string* err) {
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaMemsetAsync(state_, 0, (size_t)oh_ * ow_, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  return true;
+}
+
+double Engine::time_stage(int stage, int n, int iters, std::string* err) {
+  if (n < 1 || n > max_batch_ || iters < 1 || stage < 0 || stage > 4) { *err = "bad arguments"; return -1.0; }
+  if (cudaSetDevice(device_) != cudaSuccess) { *err = "cudaSetDevice failed"; return -1.0; }
+  const size_t row = (size_t)W_ * 3, fbytes = row * H_, npix = (size_t)W_ * H_;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto once = [&]() {
+    if (stage == 0 || stage == 4) enqueue_pre(n, d_frames_, row, fbytes);
+    if (stage == 1 || stage == 4) enqueue_cnn(n);
+    if (stage == 2 || stage == 4) enqueue_decision(n);
+    if (stage == 3 || stage == 4) enqueue_post(n, d_frames_, row, fbytes, d_out_, fbytes, d_yuyv_, npix * 2, d_mask_, npix);
+  };
+  once();                                   // warm-up (instruction cache, tables)
+  cudaStreamSynchronize(stream_);
+  cudaEventRecord(e0, stream_);
+  for (int i = 0; i < iters; ++i) once();
+  cudaEventRecord(e1, stream_);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess) { *err = "CUDA error while timing"; return -1.0; }
+  return (double)ms / iters;
+}
+
+long Engine::get_tensor(int t, float* out, long cap, std::string* err) {
+  if (!(flags_ & 1u)) { *err = "bsb_get_tensor needs BSB_FLAG_KEEP_TENSORS"; return -1; }
+  if (t < 0 || t >= (int)tinfo_.size()) { *err = "tensor index out of range"; return -1; }
+  const TensorInfo& I = tinfo_[t];
+  if (!I.materialized) return 0;
+  const long n = (long)I.h * I.w * I.c;
+  if (cap < n) { *err = "output buffer too small"; return -1; }
+  if (cudaSetDevice(device_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) { *err = "CUDA error in get_tensor"; return -1; }
+  if (I.ld == I.c) {
+    if (cudaMemcpy(out, tptr(t), (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "CUDA memcpy failed"; return -1; }
+  } else {
+    for (long p = 0; p < (long)I.h * I.w; ++p)
+      if (cudaMemcpy(out + p * I.c, tptr(t) + p * I.ld, (size_t)I.c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "CUDA memcpy failed"; return -1; }
+  }
+  return n;
+}
+
+long Engine::get_stage_u8(int which, int frame, uint8_t* out, long cap, std::string* err) {
+  if (frame < 0 || frame >= max_batch_) { *err = "frame index out of range"; return -1; }
+  const uint8_t* src = nullptr; long n = 0;
+  if (which == 0) { n = (long)mh_ * mw_ * 3; src = in_u8_ + (size_t)frame * n; }
+  else if (which == 1) { n = (long)mh_ * mw_ * 3; src = filt_u8_ ? filt_u8_ + (size_t)frame * n : nullptr; }
+  else if (which == 2) { n = (long)oh_ * ow_; src = ofinal_ + (size_t)frame * n; }
+  if (!src) { *err = which == 1 ? "stage buffer needs BSB_FLAG_KEEP_TENSORS" : "unknown stage"; return -1; }
+  if (cap < n) { *err = "output buffer too small"; return -1; }
+  if (cudaSetDevice(device_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess ||
+      cudaMemcpy(out, src, (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "CUDA error in get_stage_u8"; return -1; }
+  return n;
+}
+
+}  // namespace bsb

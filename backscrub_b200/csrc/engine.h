@@ -1,0 +1,154 @@
+// backscrub_b200/csrc/engine.h — per-stream context: model plan, HBM layout, CUDA graph.
+//
+// Host-side equivalent of backscrub_ctx_t + bs_maskgen_new/process
+// (lib/libbackscrub.cc:28-54,161-376), re-designed for one GPU per process:
+//   * the .tflite graph is planned once into a short list of fused kernel launches
+//     (unary ops, residual ADDs, SE channel scales folded into producers/consumers),
+//   * activations live in one liveness-packed arena sized for `max_batch` frames so a
+//     whole batch stays L2-resident between layers,
+//   * a whole call (pre-proc -> CNN -> decision/IIR -> mask upsample/blur/blend/YUYV) is
+//     captured once per batch size into a CUDA graph and replayed with one launch.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tflite_model.h"
+
+namespace bsb {
+
+struct TensorInfo {
+  int h = 1, w = 1, c = 1, ld = 1;
+  size_t frame_elems = 0;     // h*w*ld floats per frame
+  size_t offset = 0;          // float offset inside the arena
+  bool materialized = false;
+  int first_def = 1 << 30, last_use = -1;
+};
+
+struct Step {
+  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY } kind = ELT;
+  int op_index = -1;
+  int in = -1, in2 = -1, out = -1, scale = -1, in_add = -1, residual = -1;
+  size_t w_off = 0, b_off = 0; bool has_bias = false;
+  int act1 = 0, act2 = 0, act3 = 0;
+  int K = 0, N = 0, n4 = 0;
+  int kh = 1, kw = 1, sh = 1, sw = 1, dh = 1, dw = 1, pt = 0, pl = 0;
+  int elt_mode = 0;
+  bool align_corners = false, half_pixel = false;
+  int copy_off = 0;
+};
+
+struct HostResizeTab {
+  std::vector<int> xofs, yofs0, yofs1;
+  std::vector<short> xw, yw;
+  bool area2x2 = false;
+};
+// OpenCV INTER_LINEAR 8-bit coefficient tables for sw x sh -> dw x dh
+HostResizeTab build_resize_tab(int sw, int sh, int dw, int dh);
+
+struct DevResizeTab { void* blob = nullptr; ResizeTab tab{}; bool area2x2 = false; };
+
+struct Callbacks {
+  void (*ondebug)(void*, const char*) = nullptr;
+  void (*onprep)(void*) = nullptr;
+  void (*oninfer)(void*) = nullptr;
+  void (*onmask)(void*) = nullptr;
+  void* caller_ctx = nullptr;
+};
+
+class Engine {
+ public:
+  static Engine* create(const std::string& model_path, int width, int height, int device, int max_batch,
+                        unsigned flags, const Callbacks& cb, std::string* err);
+  ~Engine();
+
+  // frames on device: n frames, row pitch / frame stride in bytes.  Any output may be null.
+  bool run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+           uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err);
+  bool infer(int n, const float* h_in, float* h_out, std::string* err);
+  bool set_background(const uint8_t* bg_raw, int bw, int bh, size_t pitch, std::string* err);
+  bool sync(std::string* err);
+  bool reset_state(std::string* err);
+  double time_stage(int stage, int n, int iters, std::string* err);
+
+  // accessors
+  int W() const { return W_; }
+  int H() const { return H_; }
+  int max_batch() const { return max_batch_; }
+  int device() const { return device_; }
+  cudaStream_t stream() const { return stream_; }
+  const int* roidim() const { return roidim_; }
+  const int* in_roidim() const { return in_roidim_; }
+  const int* out_roidim() const { return out_roidim_; }
+  void in_hwc(int* v) const { v[0] = mh_; v[1] = mw_; v[2] = 3; }
+  void out_hwc(int* v) const { v[0] = oh_; v[1] = ow_; v[2] = oc_; }
+  double flops() const { return flops_; }
+  int launches_per_call() const { return (int)steps_.size() + 4; }
+  long get_tensor(int t, float* out, long cap, std::string* err);
+  long get_stage_u8(int which, int frame, uint8_t* out, long cap, std::string* err);
+
+  // device staging owned by the context (host-buffer API)
+  uint8_t* d_frames() const { return d_frames_; }
+  uint8_t* d_out() const { return d_out_; }
+  uint8_t* d_yuyv() const { return d_yuyv_; }
+  uint8_t* d_mask() const { return d_mask_; }
+  uint8_t* d_bg() const { return d_bg_; }
+  uint8_t* h_mask() const { return h_mask_; }
+  bool has_background() const { return has_bg_; }
+
+ private:
+  Engine() = default;
+  bool plan(std::string* err);
+  bool upload(std::string* err);
+  void enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride);
+  void enqueue_cnn(int n);
+  void enqueue_decision(int n);
+  void enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                    uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride);
+  float* tptr(int t) const { return arena_ + tinfo_[t].offset; }
+
+  Graph g_;
+  int model_type_ = 0;
+  float scaling_ = 0.f, offset_ = 0.f;
+  int W_ = 0, H_ = 0, device_ = 0, max_batch_ = 1;
+  unsigned flags_ = 0;
+  Callbacks cb_;
+  int mh_ = 0, mw_ = 0, oh_ = 0, ow_ = 0, oc_ = 0;
+  int roidim_[4] = {0, 0, 0, 0}, in_roidim_[4] = {0, 0, 0, 0}, out_roidim_[4] = {0, 0, 0, 0};
+  double flops_ = 0;
+
+  std::vector<TensorInfo> tinfo_;
+  std::vector<Step> steps_;
+  std::vector<float> wblob_h_;
+  size_t arena_elems_ = 0;
+
+  // device memory
+  cudaStream_t stream_ = nullptr;
+  float* wblob_ = nullptr;
+  float* arena_ = nullptr;
+  float* lut_ = nullptr;             // color_w[768] + space_w[16]
+  uint8_t* in_u8_ = nullptr;         // [B][mh][mw][3] zero outside in_roidim
+  uint8_t* filt_u8_ = nullptr;       // [B][mh][mw][3] (KEEP_TENSORS only)
+  uint8_t* state_ = nullptr;         // [oh*ow] IIR state
+  uint8_t* ofinal_ = nullptr;        // [B][oh*ow]
+  uint8_t* d_frames_ = nullptr, *d_out_ = nullptr, *d_yuyv_ = nullptr, *d_mask_ = nullptr, *d_bg_ = nullptr, *d_bg_raw_ = nullptr;
+  size_t bg_raw_cap_ = 0;
+  uint8_t* h_mask_ = nullptr;        // pinned host W*H
+  bool has_bg_ = false;
+  DevResizeTab tab_in_, tab_up_, tab_bg_;
+  int bg_w_ = 0, bg_h_ = 0;
+
+  struct GraphKey {
+    int n; const void* f; size_t pitch, stride; const void* o; const void* y; const void* m;
+    bool operator<(const GraphKey& r) const {
+      if (n != r.n) return n < r.n; if (f != r.f) return f < r.f; if (pitch != r.pitch) return pitch < r.pitch;
+      if (stride != r.stride) return stride < r.stride; if (o != r.o) return o < r.o; if (y != r.y) return y < r.y; return m < r.m;
+    }
+  };
+#ifndef BSB_EMU
+  std::map<GraphKey, cudaGraphExec_t> graphs_;
+#endif
+};
+
+}  // namespace bsb

@@ -1,0 +1,114 @@
+// backscrub_b200/csrc/kernels.h — host-side launchers of the sm_100a kernels.
+// All activations are fp32 NHWC with an explicit per-pixel channel stride (`ld`, in
+// floats) so producers can write straight into a concatenated buffer; a batch of B
+// frames is B consecutive images.
+#pragma once
+#include "bsb_common.h"
+
+namespace bsb {
+
+// Epilogue shared by conv / pointwise / depthwise kernels, in graph order:
+//   v = act1(total + bias)   (TFLite fused activation)
+//   v = act2(v)              (following stand-alone unary op, folded by the planner)
+//   v = act3(v + residual)   (following ADD, folded by the planner)
+struct Epilogue {
+  const float* bias = nullptr;
+  int act1 = ACT_NONE, act2 = ACT_NONE, act3 = ACT_NONE;
+  const float* residual = nullptr;  // same N/H/W/C as the output
+  int ld_res = 0;
+};
+
+// ---- CNN ---------------------------------------------------------------------
+// Dense KxK convolution, small Cin (the 3x3 s2 stems).  w_t: [kh][kw][ic][oc4] (oc padded to 4).
+void launch_conv_direct(cudaStream_t s, int B, const float* in, int ih, int iw, int ic, int ld_in,
+                        const float* w_t, int oc, int kh, int kw, int stride_h, int stride_w,
+                        int dil_h, int dil_w, int pad_t, int pad_l,
+                        float* out, int oh, int ow, int ld_out, const Epilogue& e);
+
+// 1x1 convolution / fully-connected as a GEMM: out[M][N] = A[M][K] * w_kn[K][N4] (+ epilogue).
+// in_scale (optional): [B][K] per-frame channel scale applied to A on load (folded SE MUL);
+// in_add (optional): tensor added after the scale (folded ADD), same layout as A.
+void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int ld_a,
+                      const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
+                      const float* in_scale, int rows_per_frame, const float* in_add, int ld_add);
+
+// Depthwise KxK (depth multiplier 1).  w: [kh][kw][C].
+void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
+                      const float* w, int kh, int kw, int stride_h, int stride_w, int dil_h, int dil_w,
+                      int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e);
+
+// Global average pool: out[B][C] = (sum over rows of (sum over x)) / (H*W), act applied.
+void launch_global_avgpool(cudaStream_t s, int B, const float* in, int h, int w, int c, int ld_in,
+                           float* out, int ld_out, int act);
+
+// RESIZE_BILINEAR (reference resize_bilinear.h:29-117 float path)
+void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
+                            float* out, int oh, int ow, int ld_out, bool align_corners, bool half_pixel);
+
+// Convolution2DTransposeBias k2x2 s2 (lib/transpose_conv_bias.cc:37-114).  w: OHWI [oc][2][2][ic].
+void launch_tconv2x2(cudaStream_t s, int B, const float* in, int ih, int iw, int ic, int ld_in,
+                     const float* w, const float* bias, int oc, float* out, int oh, int ow, int ld_out, int act2);
+
+// Element-wise: mode 0 unary act(a); 1 act(a + b); 2 act(a * b); 3 act(a * scale[b][c]) (channel broadcast);
+// 4: act(a * scale[b][c] + b2) (MUL then ADD, two roundings).
+void launch_eltwise(cudaStream_t s, int mode, int B, int hw, int c, const float* a, int ld_a,
+                    const float* b, int ld_b, const float* scale, float* out, int ld_out, int act);
+
+// Strided channel copy (CONCATENATION fallback): out[..., off:off+c] = in
+void launch_copy_channels(cudaStream_t s, int rows, int c, const float* in, int ld_in, float* out, int ld_out);
+
+// ---- image stages ---------------------------------------------------------------
+struct ResizeTab {        // OpenCV INTER_LINEAR 8-bit tables (device pointers)
+  const int* xofs;        // [dw] source column
+  const short* xw;        // [dw][2] weights (scale 2^11)
+  const int* yofs0;       // [dh] clamped row r0
+  const int* yofs1;       // [dh] clamped row r1
+  const short* yw;        // [dh][2]
+};
+
+// lib/libbackscrub.cc:285-290: ROI crop -> cv::resize(INTER_LINEAR) -> BGR2RGB, into the
+// zero-padded model-sized u8 image.  frames: B x (H x W x 3, stride bytes).
+void launch_resize_roi_swap(cudaStream_t s, int B, const uint8_t* frames, size_t frame_stride, size_t frame_pitch,
+                            int roi_x, int roi_y, int roi_w, int roi_h, ResizeTab tab,
+                            uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h, bool area2x2);
+
+// lib/libbackscrub.cc:295-302: bilateralFilter(5,100,100) + convertTo(CV_32F, scale, offset)
+void launch_bilateral_norm(cudaStream_t s, int B, const uint8_t* in_u8, int mw, int mh,
+                           const float* color_w, const float* space_w, float scale, float offset,
+                           float* out_f32, uint8_t* out_u8_dbg);
+
+// lib/libbackscrub.cc:314-361: decision + 3-tap bit-shift IIR over B consecutive frames.
+// state: [oh*ow] persistent; ofinal: [B][oh*ow] state after each frame.
+void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
+                         uint8_t* state, uint8_t* ofinal);
+
+// lib/libbackscrub.cc:366-371 + app/deepseg.cc:108-134,87-106 fused:
+// mask = blur5x5(resize(ofinal(out_roi) -> roi)) inside roidim, 255 outside;
+// out = (bg*mask + frame*(255-mask))/255; optional YUYV of out; optional mask store.
+struct PostArgs {
+  int B, W, H;
+  const uint8_t* frames; size_t frame_pitch, frame_stride;   // row pitch / per-frame stride (bytes)
+  const uint8_t* bg; size_t bg_pitch, bg_stride;             // bg_stride 0 => one static background
+  const uint8_t* ofinal; int ow, oh;                          // [B][oh*ow]
+  int out_x, out_y, out_w, out_h;                              // out_roidim inside ofinal
+  int roi_x, roi_y, roi_w, roi_h;                              // roidim inside the frame
+  ResizeTab tab;                                               // out_roi -> roi upsample tables
+  bool area2x2;
+  uint8_t* out; size_t out_pitch, out_stride;                  // may be null
+  uint8_t* yuyv; size_t yuyv_stride;                           // may be null (W*2 bytes per row)
+  uint8_t* mask; size_t mask_stride;                           // may be null (W bytes per row)
+};
+void launch_post(cudaStream_t s, const PostArgs& a);
+
+// app/background.cc:178-194: cv::resize(raw -> W x H), 3 channels
+void launch_resize_u8c3(cudaStream_t s, const uint8_t* src, int sw, int sh, size_t spitch,
+                        uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2);
+
+// stand-alone stage kernels (exported through the C-ABI for stage-level parity tests)
+void launch_alpha_blend(cudaStream_t s, const uint8_t* a, const uint8_t* b, const uint8_t* mask, uint8_t* out, size_t npix);
+void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix);
+
+// number of kernel launches issued through the launchers above (bench gpu_launches)
+long launch_count();
+
+}  // namespace bsb

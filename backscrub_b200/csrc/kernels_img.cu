@@ -1,0 +1,364 @@
+// backscrub_b200/csrc/kernels_img.cu — integer image stages of the hot path (sm_100a).
+//
+// Replaces the OpenCV calls of lib/libbackscrub.cc:285-302 (ROI resize, BGR2RGB,
+// bilateralFilter, convertTo), :314-361 (decision + IIR), :366-371 (mask upsample + 5x5
+// blur) and app/deepseg.cc:108-134 (alpha_blend), :87-106 (convert_rgb_to_yuyv),
+// app/background.cc:178-194 (background resize).  All integer arithmetic is OpenCV's
+// fixed-point arithmetic restated (see oracle/oracle_img.c for the formulas and their
+// cv2 pins); results are bit-exact against the oracle.
+#include "kernels.h"
+
+namespace bsb {
+
+void count_launch();
+
+// cv::resize INTER_LINEAR 8-bit, one output sample: horizontal taps at scale 2^11, vertical
+// descale ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
+BSB_D int lin_h(const uint8_t* row, int sx, int sx1, int cn, int c, int a0, int a1) {
+  return (int)row[sx * cn + c] * a0 + (int)row[sx1 * cn + c] * a1;
+}
+BSB_D uint8_t lin_v(int h0, int h1, int b0, int b1) {
+  return bsb_sat_u8((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// ---------------------------------------------------------------------------
+// ROI crop -> resize -> BGR2RGB into the zero-padded model-sized image.
+// One thread = one destination pixel (3 channels).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize_roi_swap(int B, const uint8_t* frames, size_t frame_stride, size_t pitch,
+                                                         int roi_x, int roi_y, int roi_w, int roi_h, ResizeTab t,
+                                                         uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h,
+                                                         bool area2x2) {
+  const long total = (long)B * in_w * in_h;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int dx = (int)(idx % in_w), dy = (int)((idx / in_w) % in_h), b = (int)(idx / ((long)in_w * in_h));
+  const uint8_t* roi = frames + (size_t)b * frame_stride + (size_t)roi_y * pitch + (size_t)roi_x * 3;
+  uint8_t px[3];
+  if (area2x2) {
+    const uint8_t* s0 = roi + (size_t)(2 * dy) * pitch + (size_t)(2 * dx) * 3;
+    const uint8_t* s1 = s0 + pitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) px[c] = (uint8_t)((s0[c] + s0[3 + c] + s1[c] + s1[3 + c] + 2) >> 2);
+  } else {
+    const int sx = __ldg(t.xofs + dx), sx1 = min(sx + 1, roi_w - 1);
+    const int a0 = __ldg(t.xw + 2 * dx), a1 = __ldg(t.xw + 2 * dx + 1);
+    const int b0 = __ldg(t.yw + 2 * dy), b1 = __ldg(t.yw + 2 * dy + 1);
+    const uint8_t* r0 = roi + (size_t)__ldg(t.yofs0 + dy) * pitch;
+    const uint8_t* r1 = roi + (size_t)__ldg(t.yofs1 + dy) * pitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) px[c] = lin_v(lin_h(r0, sx, sx1, 3, c, a0, a1), lin_h(r1, sx, sx1, 3, c, a0, a1), b0, b1);
+  }
+  uint8_t* d = in_u8 + ((size_t)b * mh * mw + (size_t)(in_y + dy) * mw + (in_x + dx)) * 3;
+  d[0] = px[2]; d[1] = px[1]; d[2] = px[0];   // BGR -> RGB
+}
+
+void launch_resize_roi_swap(cudaStream_t s, int B, const uint8_t* frames, size_t frame_stride, size_t frame_pitch,
+                            int roi_x, int roi_y, int roi_w, int roi_h, ResizeTab tab,
+                            uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h, bool area2x2) {
+  const long total = (long)B * in_w * in_h;
+  BSB_LAUNCH(k_resize_roi_swap, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, frames, frame_stride, frame_pitch,
+             roi_x, roi_y, roi_w, roi_h, tab, in_u8, mw, mh, in_x, in_y, in_w, in_h, area2x2);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// cv::bilateralFilter(d=5, sigma 100/100) + convertTo(CV_32F, scale, offset).
+// 13 taps (i^2+j^2 <= 4) in raster order, weights = space_w[k] * color_w[|db|+|dg|+|dr|],
+// per-tap fmaf accumulation, cvRound(sum * (1/wsum)), BORDER_REFLECT_101.
+// One thread = one pixel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bilateral_norm(int B, const uint8_t* in_u8, int mw, int mh,
+                                                        const float* color_w, const float* space_w,
+                                                        float scale, float offset, float* out_f32, uint8_t* out_u8) {
+  __shared__ float cw[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) cw[i] = __ldg(color_w + i);
+  __syncthreads();
+  const long total = (long)B * mw * mh;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % mw), y = (int)((idx / mw) % mh), b = (int)(idx / ((long)mw * mh));
+  const uint8_t* img = in_u8 + (size_t)b * mh * mw * 3;
+  const uint8_t* p0 = img + ((size_t)y * mw + x) * 3;
+  const int c0 = p0[0], c1 = p0[1], c2 = p0[2];
+  float wsum = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  int k = 0;
+  for (int i = -2; i <= 2; ++i) {
+    const int yy = bsb_reflect101(y + i, mh);
+    for (int j = -2; j <= 2; ++j) {
+      if (i * i + j * j > 4) continue;
+      const int xx = bsb_reflect101(x + j, mw);
+      const uint8_t* p = img + ((size_t)yy * mw + xx) * 3;
+      const int v0 = p[0], v1 = p[1], v2 = p[2];
+      const float w = __ldg(space_w + k) * cw[abs(v0 - c0) + abs(v1 - c1) + abs(v2 - c2)];
+      ++k;
+      wsum = wsum + w;
+      s0 = fmaf((float)v0, w, s0);
+      s1 = fmaf((float)v1, w, s1);
+      s2 = fmaf((float)v2, w, s2);
+    }
+  }
+  const float inv = 1.f / wsum;
+  const int r0 = bsb_sat_u8(__float2int_rn(s0 * inv)), r1 = bsb_sat_u8(__float2int_rn(s1 * inv)), r2 = bsb_sat_u8(__float2int_rn(s2 * inv));
+  float* o = out_f32 + (size_t)idx * 3;
+  o[0] = fmaf((float)r0, scale, offset);
+  o[1] = fmaf((float)r1, scale, offset);
+  o[2] = fmaf((float)r2, scale, offset);
+  if (out_u8) { uint8_t* u = out_u8 + (size_t)idx * 3; u[0] = (uint8_t)r0; u[1] = (uint8_t)r1; u[2] = (uint8_t)r2; }
+}
+
+void launch_bilateral_norm(cudaStream_t s, int B, const uint8_t* in_u8, int mw, int mh,
+                           const float* color_w, const float* space_w, float scale, float offset,
+                           float* out_f32, uint8_t* out_u8_dbg) {
+  const long total = (long)B * mw * mh;
+  BSB_LAUNCH(k_bilateral_norm, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, in_u8, mw, mh, color_w, space_w,
+             scale, offset, out_f32, out_u8_dbg);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// Decision + temporal IIR, lib/libbackscrub.cc:314-361.  One thread = one model-output
+// pixel, looping over the B consecutive frames of the batch so the 3-tap state
+// out = (val & 0xE0) | (out >> 3) advances in frame order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_decision_iir(int model_type, int B, const float* out_f, int npix, int oc,
+                                                      uint8_t* state, uint8_t* ofinal) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= npix) return;
+  unsigned st = state[n];
+  for (int b = 0; b < B; ++b) {
+    const float* t = out_f + ((size_t)b * npix + n) * oc;
+    unsigned val;
+    if (model_type == MODEL_DEEPLAB) {
+      float maxval = -10000.f; int maxpos = 0;
+      for (int i = 0; i < 21; ++i) { const float v = __ldg(t + i); if (v > maxval) { maxval = v; maxpos = i; } }
+      val = (maxpos == 15) ? 0u : 255u;
+    } else if (model_type == MODEL_MEET) {
+      const float e0 = bsb_expf(__ldg(t)), e1 = bsb_expf(__ldg(t + 1));
+      const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
+      val = (p0 < p1) ? 0u : 255u;
+    } else {
+      // `tmp[n] > 0.65` compares float with the double literal; equivalent to > 0.65f
+      // (0.65 lies strictly between two adjacent floats) — SURVEY.md Appendix A
+      val = (__ldg(t) > 0.65f) ? 0u : 255u;
+    }
+    st = (val & 0xE0u) | (st >> 3);
+    ofinal[(size_t)b * npix + n] = (uint8_t)st;
+  }
+  state[n] = (uint8_t)st;
+}
+
+void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
+                         uint8_t* state, uint8_t* ofinal) {
+  const int npix = oh * ow;
+  BSB_LAUNCH(k_decision_iir, dim3((unsigned)ceil_div(npix, 256)), dim3(256), 0, s, model_type, B, model_out, npix, oc, state, ofinal);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// Fused post stage: mask upsample (cv::resize 8UC1) + cv::blur 5x5 (REFLECT_101 inside the
+// ROI) + alpha_blend + optional RGB->YUYV + optional mask store.
+//
+// Block = 256 threads = one 128 x 32 pixel tile; thread = 16 consecutive pixels of one row
+// (48 B per 3-channel array: three 16-byte vector accesses).  Shared memory holds the
+// upsampled tile with a 2-pixel halo (u8) and its vertical 5-sums (u16); box sums are
+// integer, so the separable evaluation is exact.
+// ---------------------------------------------------------------------------
+constexpr int PT_W = 128, PT_H = 32, PT_PX = 16;
+constexpr int PT_UW = PT_W + 4, PT_UH = PT_H + 4, PT_US = PT_UW + 4;   // smem row stride (bytes)
+
+struct Px16 { uint4 v[3]; };
+
+BSB_D void load48(const uint8_t* p, bool fast, Px16& r) {
+  if (fast) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    r.v[0] = __ldg(q); r.v[1] = __ldg(q + 1); r.v[2] = __ldg(q + 2);
+  } else {
+    uint8_t* d = reinterpret_cast<uint8_t*>(&r);
+    for (int i = 0; i < 48; ++i) d[i] = p[i];
+  }
+}
+
+BSB_D void rgb2yuv(int R, int G, int Bc, int& Y, int& U, int& V) {
+  // cv::cvtColor(COLOR_RGB2YUV) 8-bit, 14-bit fixed point (oracle_img.c:or_rgb2yuv_u8)
+  Y = (4899 * R + 9617 * G + 1868 * Bc + 8192) >> 14;
+  U = ((Bc - Y) * 8061 + (128 << 14) + 8192) >> 14;
+  V = ((R - Y) * 14369 + (128 << 14) + 8192) >> 14;
+  Y = Y > 255 ? 255 : Y;
+  U = U < 0 ? 0 : (U > 255 ? 255 : U);
+  V = V < 0 ? 0 : (V > 255 ? 255 : V);
+}
+
+__global__ void __launch_bounds__(256) k_post(PostArgs a) {
+  __shared__ __align__(16) uint8_t Us[PT_UH * PT_US];
+  __shared__ __align__(16) unsigned short Vs[PT_H * PT_UW];
+  const int b = blockIdx.z;
+  const int tx0 = blockIdx.x * PT_W, ty0 = blockIdx.y * PT_H;
+  const int tid = threadIdx.x;
+  const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + PT_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PT_H > a.roi_y;
+
+  if (hits_roi) {
+    // ---- A: upsampled mask tile with halo, reflect-101 at the ROI border ----
+    const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
+    for (int i = tid; i < PT_UH * PT_UW; i += 256) {
+      const int uy = i / PT_UW, ux = i % PT_UW;
+      const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
+      const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + ux, a.roi_w);
+      const int sx = __ldg(a.tab.xofs + gx), sx1 = min(sx + 1, a.out_w - 1);
+      const int a0 = __ldg(a.tab.xw + 2 * gx), a1 = __ldg(a.tab.xw + 2 * gx + 1);
+      const int b0 = __ldg(a.tab.yw + 2 * gy), b1 = __ldg(a.tab.yw + 2 * gy + 1);
+      const uint8_t* r0 = src + (size_t)__ldg(a.tab.yofs0 + gy) * a.ow;
+      const uint8_t* r1 = src + (size_t)__ldg(a.tab.yofs1 + gy) * a.ow;
+      Us[uy * PT_US + ux] = lin_v(lin_h(r0, sx, sx1, 1, 0, a0, a1), lin_h(r1, sx, sx1, 1, 0, a0, a1), b0, b1);
+    }
+    __syncthreads();
+    // ---- B: vertical 5-sums ----
+    for (int i = tid; i < PT_H * PT_UW; i += 256) {
+      const int y = i / PT_UW, x = i % PT_UW;
+      const uint8_t* u = Us + y * PT_US + x;
+      Vs[i] = (unsigned short)(u[0] + u[PT_US] + u[2 * PT_US] + u[3 * PT_US] + u[4 * PT_US]);
+    }
+    __syncthreads();
+  }
+
+  const int lx = (tid % (PT_W / PT_PX)) * PT_PX, ly = tid / (PT_W / PT_PX);
+  const int x0 = tx0 + lx, y = ty0 + ly;
+  if (y >= a.H || x0 >= a.W) return;
+  const int npx = min(PT_PX, a.W - x0);
+
+  // ---- C: horizontal 5-sums -> mask ----
+  uint8_t m[PT_PX];
+  const bool row_in = hits_roi && y >= a.roi_y && y < a.roi_y + a.roi_h;
+#pragma unroll
+  for (int i = 0; i < PT_PX; ++i) {
+    const int x = x0 + i;
+    unsigned mv = 255u;
+    if (row_in && x >= a.roi_x && x < a.roi_x + a.roi_w) {
+      const unsigned short* v = Vs + ly * PT_UW + lx + i;
+      mv = bsb_box25((unsigned)v[0] + v[1] + v[2] + v[3] + v[4]);
+    }
+    m[i] = (uint8_t)mv;
+  }
+
+  // ---- D: blend (+ YUYV, + mask) ----
+  const size_t fo = (size_t)b * a.frame_stride + (size_t)y * a.frame_pitch + (size_t)x0 * 3;
+  const size_t bo = (size_t)b * a.bg_stride + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
+  const bool full = npx == PT_PX;
+  const bool fast_in = full && ((reinterpret_cast<uintptr_t>(a.frames + fo) | reinterpret_cast<uintptr_t>(a.bg + bo)) & 15) == 0;
+  Px16 f, g, o;
+  if (full) { load48(a.frames + fo, fast_in, f); load48(a.bg + bo, fast_in, g); }
+  else {
+    uint8_t* fd = reinterpret_cast<uint8_t*>(&f); uint8_t* gd = reinterpret_cast<uint8_t*>(&g);
+    for (int i = 0; i < npx * 3; ++i) { fd[i] = a.frames[fo + i]; gd[i] = a.bg[bo + i]; }
+  }
+  const uint8_t* fb = reinterpret_cast<const uint8_t*>(&f);
+  const uint8_t* gb = reinterpret_cast<const uint8_t*>(&g);
+  uint8_t* ob = reinterpret_cast<uint8_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < PT_PX; ++i) {
+    const unsigned aw = m[i], bw = 255u - aw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ob[3 * i + c] = (uint8_t)bsb_div255((unsigned)gb[3 * i + c] * aw + (unsigned)fb[3 * i + c] * bw);
+  }
+  if (a.out) {
+    uint8_t* op = a.out + (size_t)b * a.out_stride + (size_t)y * a.out_pitch + (size_t)x0 * 3;
+    if (full && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+      uint4* q = reinterpret_cast<uint4*>(op); q[0] = o.v[0]; q[1] = o.v[1]; q[2] = o.v[2];
+    } else for (int i = 0; i < npx * 3; ++i) op[i] = ob[i];
+  }
+  if (a.mask) {
+    uint8_t* mp = a.mask + (size_t)b * a.mask_stride + (size_t)y * a.W + x0;
+    if (full && (reinterpret_cast<uintptr_t>(mp) & 15) == 0) *reinterpret_cast<uint4*>(mp) = *reinterpret_cast<const uint4*>(m);
+    else for (int i = 0; i < npx; ++i) mp[i] = m[i];
+  }
+  if (a.yuyv) {
+    // pairs are taken over the flattened image (app/deepseg.cc:97-104); W even => pairs never straddle rows
+    __align__(16) uint8_t yy[PT_PX * 2];
+#pragma unroll
+    for (int i = 0; i < PT_PX; i += 2) {
+      int Y0, U0, V0, Y1, U1, V1;
+      rgb2yuv(ob[3 * i], ob[3 * i + 1], ob[3 * i + 2], Y0, U0, V0);
+      rgb2yuv(ob[3 * i + 3], ob[3 * i + 4], ob[3 * i + 5], Y1, U1, V1);
+      yy[2 * i] = (uint8_t)Y0; yy[2 * i + 1] = (uint8_t)((V0 + V1) / 2);
+      yy[2 * i + 2] = (uint8_t)Y1; yy[2 * i + 3] = (uint8_t)((U0 + U1) / 2);
+    }
+    uint8_t* yp = a.yuyv + (size_t)b * a.yuyv_stride + ((size_t)y * a.W + x0) * 2;
+    if (full && (reinterpret_cast<uintptr_t>(yp) & 15) == 0) {
+      uint4* q = reinterpret_cast<uint4*>(yp); const uint4* sv = reinterpret_cast<const uint4*>(yy); q[0] = sv[0]; q[1] = sv[1];
+    } else for (int i = 0; i < (npx & ~1) * 2; ++i) yp[i] = yy[i];
+  }
+}
+
+void launch_post(cudaStream_t s, const PostArgs& a) {
+  dim3 grid((unsigned)ceil_div(a.W, PT_W), (unsigned)ceil_div(a.H, PT_H), (unsigned)a.B);
+  BSB_LAUNCH(k_post, grid, dim3(256), 0, s, a);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// cv::resize(src -> dst) 8UC3 (background provider).  One thread = one dst pixel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize_u8c3(const uint8_t* src, int sw, int sh, size_t spitch,
+                                                     uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab t, bool area2x2) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)dw * dh) return;
+  const int dx = (int)(idx % dw), dy = (int)(idx / dw);
+  uint8_t* d = dst + (size_t)dy * dpitch + (size_t)dx * 3;
+  if (area2x2) {
+    const uint8_t* s0 = src + (size_t)(2 * dy) * spitch + (size_t)(2 * dx) * 3;
+    const uint8_t* s1 = s0 + spitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = (uint8_t)((s0[c] + s0[3 + c] + s1[c] + s1[3 + c] + 2) >> 2);
+    return;
+  }
+  const int sx = __ldg(t.xofs + dx), sx1 = min(sx + 1, sw - 1);
+  const int a0 = __ldg(t.xw + 2 * dx), a1 = __ldg(t.xw + 2 * dx + 1);
+  const int b0 = __ldg(t.yw + 2 * dy), b1 = __ldg(t.yw + 2 * dy + 1);
+  const uint8_t* r0 = src + (size_t)__ldg(t.yofs0 + dy) * spitch;
+  const uint8_t* r1 = src + (size_t)__ldg(t.yofs1 + dy) * spitch;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) d[c] = lin_v(lin_h(r0, sx, sx1, 3, c, a0, a1), lin_h(r1, sx, sx1, 3, c, a0, a1), b0, b1);
+  (void)sh;
+}
+
+void launch_resize_u8c3(cudaStream_t s, const uint8_t* src, int sw, int sh, size_t spitch,
+                        uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2) {
+  const long total = (long)dw * dh;
+  BSB_LAUNCH(k_resize_u8c3, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, sw, sh, spitch, dst, dw, dh, dpitch, tab, area2x2);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone alpha_blend / convert_rgb_to_yuyv (stage-level parity through the C-ABI).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_alpha_blend(const uint8_t* a, const uint8_t* b, const uint8_t* mask, uint8_t* out, size_t npix) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const unsigned aw = mask[p], bw = 255u - aw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[3 * p + c] = (uint8_t)bsb_div255((unsigned)a[3 * p + c] * aw + (unsigned)b[3 * p + c] * bw);
+}
+
+void launch_alpha_blend(cudaStream_t s, const uint8_t* a, const uint8_t* b, const uint8_t* mask, uint8_t* out, size_t npix) {
+  BSB_LAUNCH(k_alpha_blend, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, s, a, b, mask, out, npix);
+  count_launch();
+}
+
+__global__ void __launch_bounds__(256) k_rgb_to_yuyv(const uint8_t* rgb, uint8_t* yuyv, size_t npairs) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const uint8_t* s = rgb + 6 * p;
+  int Y0, U0, V0, Y1, U1, V1;
+  rgb2yuv(s[0], s[1], s[2], Y0, U0, V0);
+  rgb2yuv(s[3], s[4], s[5], Y1, U1, V1);
+  uint8_t* d = yuyv + 4 * p;
+  d[0] = (uint8_t)Y0; d[1] = (uint8_t)((V0 + V1) / 2); d[2] = (uint8_t)Y1; d[3] = (uint8_t)((U0 + U1) / 2);
+}
+
+void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix) {
+  const size_t npairs = npix / 2;
+  BSB_LAUNCH(k_rgb_to_yuyv, dim3((unsigned)((npairs + 255) / 256)), dim3(256), 0, s, rgb, yuyv, npairs);
+  count_launch();
+}
+
+}  // namespace bsb

@@ -1,0 +1,150 @@
+/* include/backscrub_b200.h — C ABI of the B200-native backscrub hot path.
+ *
+ * This is the drop-in boundary for the reference's per-frame path.  The reference exposes
+ * a C++ API (std::string, cv::Mat&) — lib/libbackscrub.h:13-39 — plus two free functions
+ * compiled into the app (app/deepseg.cc:87-134) and the background provider
+ * (app/background.h:14-23).  Everything below is plain C (pointers + sizes, no C++ or
+ * torch types); include/libbackscrub.h and include/background.h are the header-only
+ * cv::Mat shims that map the reference's signatures onto it, and INTEGRATION.md shows
+ * the binding a maintainer adds.
+ *
+ * Conventions (same as the reference):
+ *   - frames are 8-bit 3-channel, in the channel order the camera delivers (BGR in
+ *     backscrub), row pitch given in bytes; W x H fixed at bsb_maskgen_new;
+ *   - masks are 8-bit 1-channel W x H, 255 = background, 0 = person;
+ *   - errors: NULL / negative return + message via the ondebug callback (or stderr) and
+ *     bsb_last_error(); no exceptions cross the boundary;
+ *   - one context is used by one thread at a time; contexts are independent (one per
+ *     stream / GPU); the library has no global mutable state except the error string.
+ *   - There is NO CPU fallback: every entry point that computes requires a CUDA device
+ *     and fails loudly without one.
+ */
+#ifndef BACKSCRUB_B200_H
+#define BACKSCRUB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSB_API __attribute__((visibility("default")))
+
+typedef struct bsb_ctx bsb_ctx;
+
+/* Optional callbacks, as in lib/libbackscrub.h:21-33.  onprep / oninfer / onmask fire in
+ * this order, once per bsb_maskgen_process() call, on the calling thread, after the GPU
+ * work of that stage has been *enqueued and completed* (the call synchronises the stage
+ * boundary only when the callback is non-NULL). */
+typedef void (*bsb_debug_cb)(void* caller_ctx, const char* msg);
+typedef void (*bsb_stage_cb)(void* caller_ctx);
+
+/* flags for bsb_maskgen_new_ex */
+enum {
+  BSB_FLAG_KEEP_TENSORS = 1,  /* keep every intermediate activation (tests / debugging) */
+  BSB_FLAG_NO_GRAPH = 2,      /* launch kernels eagerly instead of one CUDA graph per batch */
+  BSB_FLAG_TENSOR_CORES = 4   /* allow tcgen05 3xTF32 pointwise convs (not bit-exact vs the oracle) */
+};
+
+/* replaces bs_tensorflow_version() (lib/libbackscrub.h:13, lib/libbackscrub.cc:150):
+ * a static string naming the inference runtime. */
+BSB_API const char* bsb_version(void);
+
+/* Thread-local text of the last error raised by any entry point ("" if none). */
+BSB_API const char* bsb_last_error(void);
+
+/* Number of CUDA devices visible (0 => nothing below can run). */
+BSB_API int bsb_device_count(void);
+
+/* replaces bs_maskgen_new (lib/libbackscrub.h:16-34, lib/libbackscrub.cc:161-259).
+ * Model family is chosen by file-name substring (body-pix / deeplab / segm_ / selfie),
+ * lib/libbackscrub.cc:116-130.  `threads` is accepted and ignored (advisory in the
+ * reference too).  Returns NULL after reporting through ondebug. */
+BSB_API bsb_ctx* bsb_maskgen_new(const char* modelname, size_t threads, size_t width, size_t height,
+                                 bsb_debug_cb ondebug, bsb_stage_cb onprep, bsb_stage_cb oninfer,
+                                 bsb_stage_cb onmask, void* caller_ctx);
+
+/* Same, with the GPU-side knobs: CUDA device ordinal, maximum frames per launch
+ * (consecutive frames of ONE stream; the IIR advances in order), flags above. */
+BSB_API bsb_ctx* bsb_maskgen_new_ex(const char* modelname, size_t width, size_t height, int device,
+                                    int max_batch, unsigned flags, bsb_debug_cb ondebug, bsb_stage_cb onprep,
+                                    bsb_stage_cb oninfer, bsb_stage_cb onmask, void* caller_ctx);
+
+/* replaces bs_maskgen_delete (lib/libbackscrub.h:37, lib/libbackscrub.cc:261-277); NULL-safe. */
+BSB_API void bsb_maskgen_delete(bsb_ctx* ctx);
+
+/* replaces bs_maskgen_process (lib/libbackscrub.h:39, lib/libbackscrub.cc:279-376).
+ * frame: host pointer, W x H x 3, `frame_pitch` bytes per row (never written).
+ * *mask / *mask_pitch receive a pointer to context-owned HOST storage holding the W x H
+ * mask — valid until the next process call on this context (the reference returns a
+ * cv::Mat header aliasing ctx.mask the same way, lib/libbackscrub.cc:374).
+ * Returns 1 on success, 0 on error (the reference returns bool). */
+BSB_API int bsb_maskgen_process(bsb_ctx* ctx, const uint8_t* frame, size_t frame_pitch,
+                                const uint8_t** mask, size_t* mask_pitch);
+
+/* ---- background provider (app/background.h:14-23, app/background.cc:178-194) ----
+ * Decoding stays on the host (cv::VideoCapture / imread in the shim); the library takes
+ * the decoded raw frame and performs grab_background's cv::resize(raw -> W x H) on the
+ * GPU.  Call again whenever the decoded frame changes (video backgrounds). */
+BSB_API int bsb_set_background(bsb_ctx* ctx, const uint8_t* bg_raw, int bg_w, int bg_h, size_t bg_pitch);
+/* the resized background (what grab_background hands back), copied to host */
+BSB_API int bsb_get_background(bsb_ctx* ctx, uint8_t* out, size_t out_pitch);
+
+/* ---- fused per-frame path: one CUDA-graph launch per call ---------------------------
+ * mask generation (bs_maskgen_process) + alpha_blend(bg, frame, mask)
+ * (app/deepseg.cc:108-134, :661) + convert_rgb_to_yuyv (app/deepseg.cc:87-106, :681).
+ * HOST buffers; n_frames consecutive frames of the stream (1 <= n <= max_batch), laid out
+ * `frame_stride` bytes apart.  Any of out / out_yuyv / out_mask may be NULL. */
+BSB_API int bsb_composite(bsb_ctx* ctx, int n_frames, const uint8_t* frames, size_t frame_pitch, size_t frame_stride,
+                          uint8_t* out, size_t out_pitch, size_t out_stride,
+                          uint8_t* out_yuyv, size_t yuyv_stride, uint8_t* out_mask, size_t mask_stride);
+
+/* Same with DEVICE pointers (frames already resident in HBM; tightly packed W*3 / W*2 / W
+ * rows).  Asynchronous on the context's stream unless `sync` is non-zero. */
+BSB_API int bsb_composite_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_frames, size_t frame_stride,
+                                 uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
+                                 uint8_t* d_mask, size_t mask_stride, int sync);
+BSB_API int bsb_synchronize(bsb_ctx* ctx);
+/* the context's cudaStream_t (for event timing on the launching stream) */
+BSB_API void* bsb_stream(bsb_ctx* ctx);
+
+/* ---- stand-alone stages (stage-level parity; HOST buffers, tightly packed) -----------
+ * app/deepseg.cc:108-134 */
+BSB_API int bsb_alpha_blend(int device, const uint8_t* srca, const uint8_t* srcb, const uint8_t* mask,
+                            uint8_t* out, size_t npix);
+/* app/deepseg.cc:87-106 */
+BSB_API int bsb_convert_rgb_to_yuyv(int device, const uint8_t* rgb, uint8_t* yuyv, int width, int height);
+/* cv::resize(src, dst, Size(dw, dh)) 8UC3 (app/background.cc:178-194) */
+BSB_API int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
+
+/* ---- introspection (tests, bench) -------------------------------------------------- */
+/* geometry: roidim / in_roidim / out_roidim as x,y,w,h (lib/libbackscrub.cc:234-246);
+ * model input / output dims as h,w,c */
+BSB_API int bsb_geometry(bsb_ctx* ctx, int roidim[4], int in_roidim[4], int out_roidim[4], int in_hwc[3], int out_hwc[3]);
+/* run only the CNN on a caller-provided fp32 NHWC input batch (host), output to host */
+BSB_API int bsb_infer(bsb_ctx* ctx, int n_frames, const float* input, float* output);
+/* copy an intermediate activation (frame 0) to host; needs BSB_FLAG_KEEP_TENSORS.
+ * Returns the element count, 0 if the tensor was folded away, -1 on error. */
+BSB_API long bsb_get_tensor(bsb_ctx* ctx, int tensor_index, float* out, long capacity);
+/* stage buffers of the last call, frame `frame`: which = 0 model-sized RGB u8 (after resize +
+ * BGR2RGB), 1 bilateral-filtered u8, 2 ofinal (IIR state after that frame) */
+BSB_API long bsb_get_stage_u8(bsb_ctx* ctx, int which, int frame, uint8_t* out, long capacity);
+/* reset the temporal IIR state to zero (start of a new stream) */
+BSB_API int bsb_reset_state(bsb_ctx* ctx);
+/* kernel launches per n-frame call (graph nodes) and launches issued so far by this process */
+BSB_API int bsb_launches_per_call(bsb_ctx* ctx, int n_frames);
+BSB_API long bsb_total_launches(void);
+/* Average device time (ms, CUDA events on the context's stream) of one stage of the per-call
+ * kernel sequence, run `iters` times back to back on the context-owned device buffers:
+ * stage 0 = pre-proc (resize+bilateral+normalise), 1 = CNN, 2 = decision+IIR,
+ * 3 = post (mask upsample + blur + blend + YUYV), 4 = whole call.  Returns < 0 on error.
+ * Measurement aid for bench.py's roofline block; it advances the IIR state. */
+BSB_API double bsb_time_stage(bsb_ctx* ctx, int stage, int n_frames, int iters);
+/* algorithmic FLOPs of one CNN frame (2*MAC) */
+BSB_API double bsb_model_flops(bsb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

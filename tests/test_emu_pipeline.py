@@ -1,0 +1,68 @@
+"""CUDA kernel / planner / C-ABI logic on the GPU-less box: the product's .cu sources
+compiled against tests/emu/cuemu.h (a test-only kernel-logic emulator) must reproduce the
+oracle bit for bit.  This guards indexing, fusion and host logic before the `-m gpu`
+parity tests run the real sm_100a build on a B200."""
+import numpy as np
+import pytest
+
+from tests import parity_common as pc
+from tests.emu.emu_lib import emu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu()
+
+
+@pytest.mark.parametrize("key,W,H", [("mlkit", 640, 480), ("meet_full", 640, 480), ("meet_lite", 640, 480),
+                                     ("bodypix", 640, 480), ("meet_full", 1280, 720)])
+def test_pipeline_bit_exact(lib, key, W, H):
+    person = pc.check_pipeline(lib, key, W, H, n_frames=3, batch=2, tensors=True)
+    assert 0.05 < person < 0.6
+
+
+@pytest.mark.slow
+def test_pipeline_deeplab(lib):
+    pc.check_pipeline(lib, "deeplab", 640, 480, n_frames=2, batch=2)
+
+
+@pytest.mark.parametrize("kind", ["noise", "const"])
+def test_pipeline_edge_streams(lib, kind):
+    pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=2, frame_kind=kind)
+
+
+def test_pipeline_ragged_geometry(lib):
+    """odd sizes: ROI not tile-aligned, width not a multiple of 16, letter-boxed model input."""
+    pc.check_pipeline(lib, "meet_lite", 324, 250, n_frames=2)
+    pc.check_pipeline(lib, "mlkit", 322, 182, n_frames=1)
+
+
+@pytest.mark.parametrize("key", ["mlkit", "meet_full", "bodypix"])
+def test_every_tensor_bit_exact(lib, key):
+    assert pc.check_tensors(lib, key) > 20
+
+
+def test_infer_batch(lib):
+    pc.check_infer_batch(lib, "meet_lite", n=3)
+
+
+def test_stage_functions(lib):
+    pc.check_stage_functions(lib)
+
+
+def test_mask_only_and_callbacks(lib):
+    pc.check_mask_only_and_callbacks(lib, "meet_lite")
+
+
+def test_errors(lib, tmp_path):
+    pc.check_errors(lib, tmp_path)
+
+
+def test_planner_fuses(lib):
+    """launch counts: fused plan is far below one-kernel-per-TFLite-op (136 / 131 / 70 / 28 ops)."""
+    from backscrub_b200 import api
+    from tests.conftest import model_path
+    for key, max_launches in [("mlkit", 80), ("meet_full", 84), ("deeplab", 70), ("bodypix", 33)]:
+        g = api.MaskGen(lib, model_path(key), 640, 480)
+        assert g.launches_per_call <= max_launches, (key, g.launches_per_call)
+        g.close()

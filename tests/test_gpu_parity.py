@@ -1,0 +1,94 @@
+"""GPU parity tests proper (`-m gpu`): the sm_100a library, called through the C ABI,
+vs the CPU oracle on the same seeded inputs — bit-exact for every integer stage and,
+because the kernels keep the oracle's accumulation order, for every CNN activation too."""
+import numpy as np
+import pytest
+
+from tests import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import backscrub_b200 as bs
+    L = bs.lib()
+    assert L.bsb_device_count() > 0, "no CUDA device: the gpu tests must run on the B200 box"
+    return L
+
+
+@pytest.mark.parametrize("key,W,H", [("mlkit", 640, 480), ("meet_full", 640, 480), ("meet_lite", 640, 480),
+                                     ("bodypix", 640, 480), ("meet_full", 1280, 720), ("deeplab", 640, 480)])
+def test_pipeline_bit_exact(lib, key, W, H):
+    person = pc.check_pipeline(lib, key, W, H, n_frames=4, batch=3, tensors=True)
+    assert 0.05 < person < 0.6
+
+
+def test_pipeline_deeplab_720p(lib):          # BASELINE config 3
+    pc.check_pipeline(lib, "deeplab", 1280, 720, n_frames=2, batch=2)
+
+
+@pytest.mark.parametrize("kind", ["noise", "const"])
+def test_pipeline_edge_streams(lib, kind):
+    pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=3, frame_kind=kind)
+
+
+def test_pipeline_ragged_geometry(lib):
+    pc.check_pipeline(lib, "meet_lite", 324, 250, n_frames=2)
+    pc.check_pipeline(lib, "mlkit", 322, 182, n_frames=2)
+    pc.check_pipeline(lib, "meet_full", 720, 1280, n_frames=1)     # portrait: letter-boxed input
+
+
+def test_graph_and_eager_agree(lib):
+    pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=2, flags=2)  # BSB_FLAG_NO_GRAPH
+
+
+@pytest.mark.parametrize("key", ["mlkit", "meet_full", "meet_lite", "deeplab", "bodypix"])
+def test_every_tensor_bit_exact(lib, key):
+    assert pc.check_tensors(lib, key) > 20
+
+
+@pytest.mark.parametrize("key", ["mlkit", "meet_full", "deeplab"])
+def test_infer_batch(lib, key):
+    pc.check_infer_batch(lib, key, n=4)
+
+
+def test_stage_functions(lib):
+    pc.check_stage_functions(lib)
+
+
+def test_mask_only_and_callbacks(lib):
+    pc.check_mask_only_and_callbacks(lib, "mlkit")
+
+
+def test_errors(lib, tmp_path):
+    pc.check_errors(lib, tmp_path)
+
+
+def test_large_batch_stream_consistency(lib):
+    """Size-independent property at full batch: one 32-frame launch == 32 single-frame launches
+    (same stream, IIR advancing in order), and batches of different streams are independent."""
+    from backscrub_b200 import api
+    from tests import synth
+    from tests.conftest import model_path
+    W, H, n = 1280, 720, 32
+    frames = np.stack([synth.frame(W, H, t=t) for t in range(n)])
+    bg = synth.background()
+    a = api.MaskGen(lib, model_path("meet_full"), W, H, max_batch=n)
+    b = api.MaskGen(lib, model_path("meet_full"), W, H, max_batch=1)
+    a.set_background(bg); b.set_background(bg)
+    out_a, yuyv_a, mask_a = a.composite(frames)
+    for t in range(n):
+        o, y, m = b.composite(frames[t])
+        assert np.array_equal(out_a[t], o) and np.array_equal(yuyv_a[t], y) and np.array_equal(mask_a[t], m), t
+    # outside roidim nothing but background; mask extremes blend exactly
+    assert (mask_a[:, :, :] <= 255).all()
+    sel = mask_a == 255
+    assert np.array_equal(out_a[sel], np.broadcast_to(a.background(), out_a.shape)[sel])
+    sel0 = mask_a == 0
+    assert np.array_equal(out_a[sel0], frames[sel0])
+    a.close(); b.close()
+
+
+def test_4k_bodypix(lib):                     # BASELINE config 5 geometry (documented out_roidim deviation)
+    pc.check_pipeline(lib, "bodypix", 3840, 2160, n_frames=1)
