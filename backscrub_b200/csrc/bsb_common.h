@@ -46,6 +46,17 @@ BSB_HD float bsb_bits_to_float(int i) {
 #endif
 }
 
+// IEEE-754 round-to-nearest division.  Spelled out because nvcc -ftz=true strength-reduces
+// `x / constant` into `x * (1/constant)` even with -prec-div=true (seen in SASS as
+// FMUL.FTZ by 0.16666667), which is not the correctly rounded quotient the oracle computes.
+BSB_HD float bsb_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+
 // exp(x): Cody-Waite reduction by ln2 (2 constants), degree-5 Horner polynomial in fmaf
 // form (Cephes expf coefficients), exact two-step power-of-two scaling.  Stands in for
 // std::exp in reference logistic.h:30-57 and expf in lib/libbackscrub.cc:350-351.
@@ -76,7 +87,7 @@ BSB_HD float bsb_expf(float x) {
 BSB_HD float bsb_logistic(float v) {
   if (v > 16.619047164916992188f) return 1.0f;
   if (v < -9.f) return bsb_expf(v);
-  return 1.f / (1.f + bsb_expf(-v));
+  return bsb_div(1.f, 1.f + bsb_expf(-v));
 }
 
 // reference hard_swish.h:45-56: x * min(6, max(0, x + 3)) / 6
@@ -84,7 +95,7 @@ BSB_HD float bsb_hard_swish(float x) {
   float t = x + 3.f;
   t = t < 0.f ? 0.f : t;
   t = t > 6.f ? 6.f : t;
-  return (x * t) / 6.f;
+  return bsb_div(x * t, 6.f);
 }
 
 BSB_HD float bsb_act(float x, int act) {

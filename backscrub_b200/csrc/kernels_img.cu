@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_bilateral_norm(int B, const uint8_t* in
       s2 = fmaf((float)v2, w, s2);
     }
   }
-  const float inv = 1.f / wsum;
+  const float inv = bsb_div(1.f, wsum);
   const int r0 = bsb_sat_u8(__float2int_rn(s0 * inv)), r1 = bsb_sat_u8(__float2int_rn(s1 * inv)), r2 = bsb_sat_u8(__float2int_rn(s2 * inv));
   float* o = out_f32 + (size_t)idx * 3;
   o[0] = fmaf((float)r0, scale, offset);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_decision_iir(int model_type, int B, con
       val = (maxpos == 15) ? 0u : 255u;
     } else if (model_type == MODEL_MEET) {
       const float e0 = bsb_expf(__ldg(t)), e1 = bsb_expf(__ldg(t + 1));
-      const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
+      const float p0 = bsb_div(e0, e0 + e1), p1 = bsb_div(e1, e0 + e1);
       val = (p0 < p1) ? 0u : 255u;
     } else {
       // `tmp[n] > 0.65` compares float with the double literal; equivalent to > 0.65f
@@ -289,7 +289,249 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path of the same fused stage (W % 16 == 0, tight 16-byte aligned rows).
+// The kernel is bound by integer instruction issue, not by HBM, so it is organised to
+// minimise instructions per pixel:
+//   A0  column / row interpolation parameters of the tile -> shared memory (once)
+//   A1  horizontal pass of cv::resize for the few source rows the tile touches (Hs, >>4)
+//   A2  vertical pass -> upsampled mask tile with halo (Us, u16)
+//   B   vertical 5-sums on packed u16x2 lanes with a sliding window (Vs)
+//   C   horizontal 5-sums on packed lanes -> mask = (S + 12) / 25 as a multiply-shift
+//   D   alpha blend with two channels per 32-bit IMAD (16-bit lanes share the pixel's
+//       mask) and one via DP4A, division by 255 on packed lanes, RGB->YUV with DP2A,
+//       16-byte streaming loads / stores.
+// ---------------------------------------------------------------------------
+constexpr int PF_W = 128, PF_H = 32, PF_PX = 16;
+constexpr int PF_UW = PF_W + 4, PF_UH = PF_H + 4, PF_US = 136, PF_RMAX = 40;
+
+BSB_D uint4 ldg_stream(const uint8_t* p) {
+#if defined(BSB_EMU)
+  return *reinterpret_cast<const uint4*>(p);
+#else
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+#endif
+}
+BSB_D void stg_stream(uint8_t* p, uint4 v) {
+#if defined(BSB_EMU)
+  *reinterpret_cast<uint4*>(p) = v;
+#else
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
+}
+
+struct PfCol { short sx, sx1, a0, a1; };
+struct PfRow { short r0, r1, b0, b1; };
+
+// one pixel: pair channels (two 16-bit lanes) + single channel; returns T = (c0, c1, c2, x) bytes
+template <int PAIR_SEL, int SINGLE_SEL, int T_SEL>
+BSB_D unsigned blend_px(unsigned g_pair_w, unsigned f_pair_w, unsigned g_single_w, unsigned f_single_w, unsigned m) {
+  const unsigned nm = 255u - m;
+  const unsigned gp = __byte_perm(g_pair_w, 0u, PAIR_SEL), fp = __byte_perm(f_pair_w, 0u, PAIR_SEL);
+  const unsigned x = gp * m + fp * nm;                                   // two lanes, each <= 65025
+  const unsigned y = x + __byte_perm(x, 0u, 0x4341) + 0x00010001u;       // (x + 1 + (x >> 8)) per lane; result in bytes 1, 3
+  const unsigned sw = __byte_perm(g_single_w, f_single_w, SINGLE_SEL);   // (g, f, g, f)
+  const unsigned xs = __dp4a(sw, m | (nm << 8), 0u);                     // g*m + f*(255-m)
+  const unsigned ys = xs + 1u + (xs >> 8);                               // result in byte 1
+  return __byte_perm(y, ys, T_SEL);
+}
+
+template <bool OUT, bool YUYV>
+__global__ void __launch_bounds__(256, 3) k_post_fast(PostArgs a) {
+  __shared__ __align__(16) unsigned short Hs[PF_RMAX * PF_US];
+  __shared__ __align__(16) unsigned short Us[PF_UH * PF_US];
+  __shared__ __align__(16) unsigned short Vs[PF_H * PF_US];
+  __shared__ PfCol cols[PF_UW];
+  __shared__ PfRow rows[PF_UH];
+  __shared__ int rrange[2];
+  const int b = blockIdx.z;
+  const int tx0 = blockIdx.x * PF_W, ty0 = blockIdx.y * PF_H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + PF_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+
+  if (hits_roi) {
+    // ---- A0: interpolation parameters ----
+    if (tid < PF_UW) {
+      const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + tid, a.roi_w);
+      const int sx = __ldg(a.tab.xofs + gx);
+      PfCol c; c.sx = (short)sx; c.sx1 = (short)min(sx + 1, a.out_w - 1);
+      c.a0 = __ldg(a.tab.xw + 2 * gx); c.a1 = __ldg(a.tab.xw + 2 * gx + 1);
+      cols[tid] = c;
+    } else if (tid >= 192 && tid < 192 + PF_UH) {
+      const int uy = tid - 192;
+      const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
+      PfRow r; r.r0 = (short)__ldg(a.tab.yofs0 + gy); r.r1 = (short)__ldg(a.tab.yofs1 + gy);
+      r.b0 = __ldg(a.tab.yw + 2 * gy); r.b1 = __ldg(a.tab.yw + 2 * gy + 1);
+      rows[uy] = r;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int lo = rows[lane].r0, hi = rows[lane].r1;
+      if (lane < PF_UH - 32) { lo = min(lo, (int)rows[32 + lane].r0); hi = max(hi, (int)rows[32 + lane].r1); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+      if (lane == 0) { rrange[0] = lo; rrange[1] = hi - lo + 1; }
+    }
+    __syncthreads();
+    const int rmin = rrange[0], nrows = rrange[1];
+    // ---- A1: horizontal pass for the touched source rows ----
+    const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
+    for (int r = warp; r < nrows; r += 8) {
+      const uint8_t* srow = src + (size_t)(rmin + r) * a.ow;
+      for (int ux = lane; ux < PF_UW; ux += 32) {
+        const PfCol c = cols[ux];
+        Hs[r * PF_US + ux] = (unsigned short)(((int)srow[c.sx] * c.a0 + (int)srow[c.sx1] * c.a1) >> 4);
+      }
+    }
+    __syncthreads();
+    // ---- A2: vertical pass -> upsampled tile ----
+    for (int uy = warp; uy < PF_UH; uy += 8) {
+      const PfRow rp = rows[uy];
+      const unsigned short* h0 = Hs + (rp.r0 - rmin) * PF_US;
+      const unsigned short* h1 = Hs + (rp.r1 - rmin) * PF_US;
+      for (int ux = lane; ux < PF_UW; ux += 32)
+        Us[uy * PF_US + ux] = (unsigned short)(((((int)rp.b0 * (int)h0[ux]) >> 16) + (((int)rp.b1 * (int)h1[ux]) >> 16) + 2) >> 2);
+    }
+    __syncthreads();
+    // ---- B: vertical 5-sums, two columns per 32-bit word, sliding window over 8 rows ----
+    for (int it = tid; it < (PF_UW / 2) * 4; it += 256) {
+      const int pair = it % (PF_UW / 2), seg = it / (PF_UW / 2);
+      const unsigned* up = reinterpret_cast<const unsigned*>(Us + (seg * 8) * PF_US) + pair;
+      unsigned* vp = reinterpret_cast<unsigned*>(Vs + (seg * 8) * PF_US) + pair;
+      unsigned u[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) u[k] = up[k * (PF_US / 2)];
+      unsigned v = u[0] + u[1] + u[2] + u[3] + u[4];
+      vp[0] = v;
+#pragma unroll
+      for (int k = 1; k < 8; ++k) { v = v + u[k + 4] - u[k - 1]; vp[k * (PF_US / 2)] = v; }
+    }
+    __syncthreads();
+  }
+
+  const int lx = (tid & 7) * PF_PX, ly = tid >> 3;
+  const int x0 = tx0 + lx, y = ty0 + ly;
+  if (y >= a.H || x0 >= a.W) return;
+
+  // ---- issue the streaming loads early ----
+  unsigned f[12], g[12];
+  if (OUT || YUYV) {
+    const uint8_t* fp = a.frames + (size_t)b * a.frame_stride + (size_t)y * a.frame_pitch + (size_t)x0 * 3;
+    const uint8_t* gp = a.bg + (size_t)b * a.bg_stride + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint4 t = ldg_stream(fp + 16 * k);
+      f[4 * k] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
+      const uint4 s = __ldg(reinterpret_cast<const uint4*>(gp + 16 * k));
+      g[4 * k] = s.x; g[4 * k + 1] = s.y; g[4 * k + 2] = s.z; g[4 * k + 3] = s.w;
+    }
+  }
+
+  // ---- C: horizontal 5-sums on packed lanes -> 16 mask values ----
+  unsigned m[PF_PX];
+  const bool row_in = hits_roi && y >= a.roi_y && y < a.roi_y + a.roi_h;
+  if (row_in) {
+    const uint4* vq = reinterpret_cast<const uint4*>(Vs + ly * PF_US + lx);
+    const uint4 q0 = vq[0], q1 = vq[1];
+    const uint2 q2 = *reinterpret_cast<const uint2*>(vq + 2);
+    const unsigned w[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+    unsigned c[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = __byte_perm(w[k], w[k + 1], 0x5432);
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      const unsigned s = w[k - 1] + w[k] + w[k + 1] + c[k - 1] + c[k];
+      m[2 * (k - 1)] = ((s & 0xffffu) * 5243u + 62916u) >> 17;          // (S + 12) / 25
+      m[2 * (k - 1) + 1] = ((s >> 16) * 5243u + 62916u) >> 17;
+    }
+    if (x0 < a.roi_x || x0 + PF_PX > a.roi_x + a.roi_w) {
+#pragma unroll
+      for (int i = 0; i < PF_PX; ++i) if (x0 + i < a.roi_x || x0 + i >= a.roi_x + a.roi_w) m[i] = 255u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PF_PX; ++i) m[i] = 255u;
+  }
+
+  if (a.mask) {
+    uint4 mv;
+    mv.x = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+    mv.y = m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
+    mv.z = m[8] | (m[9] << 8) | (m[10] << 16) | (m[11] << 24);
+    mv.w = m[12] | (m[13] << 8) | (m[14] << 16) | (m[15] << 24);
+    stg_stream(a.mask + (size_t)b * a.mask_stride + (size_t)y * a.W + x0, mv);
+  }
+  if (!(OUT || YUYV)) return;
+
+  // ---- D: blend, 4 pixels = 3 words at a time ----
+  unsigned o[12], yy[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const unsigned fA = f[3 * q], fB = f[3 * q + 1], fC = f[3 * q + 2];
+    const unsigned gA = g[3 * q], gB = g[3 * q + 1], gC = g[3 * q + 2];
+    // T = (c0, c1, c2, -) per pixel
+    const unsigned T0 = blend_px<0x4140, 0x6262, 0x0531>(gA, fA, gA, fA, m[4 * q]);          // A.b0 A.b1 | A.b2
+    const unsigned T1 = blend_px<0x4140, 0x7373, 0x0315>(gB, fB, gA, fA, m[4 * q + 1]);      // B.b0 B.b1 | A.b3 (c0)
+    const unsigned T2 = blend_px<0x4342, 0x4040, 0x0531>(gB, fB, gC, fC, m[4 * q + 2]);      // B.b2 B.b3 | C.b0
+    const unsigned T3 = blend_px<0x4241, 0x7373, 0x0531>(gC, fC, gC, fC, m[4 * q + 3]);      // C.b1 C.b2 | C.b3
+    if (OUT) {
+      o[3 * q] = __byte_perm(T0, T1, 0x4210);
+      o[3 * q + 1] = __byte_perm(T1, T2, 0x5421);
+      o[3 * q + 2] = __byte_perm(T2, T3, 0x6542);
+    }
+    if (YUYV) {
+      const unsigned T[4] = {T0, T1, T2, T3};
+      unsigned Y[4], U[4]; int V[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned y14 = __dp2a_hi(1868u, T[j], __dp2a_lo(4899u | (9617u << 16), T[j], 8192u));
+        Y[j] = y14 >> 14;
+        U[j] = __dp2a_hi(8061u, T[j], 2105344u - 8061u * Y[j]) >> 14;
+        V[j] = (int)__dp2a_lo(14369u, T[j], 2105344u - 14369u * Y[j]) >> 14;
+        V[j] = min(max(V[j], 0), 255);
+      }
+      yy[2 * q] = Y[0] | ((unsigned)((V[0] + V[1]) >> 1) << 8) | (Y[1] << 16) | (((U[0] + U[1]) >> 1) << 24);
+      yy[2 * q + 1] = Y[2] | ((unsigned)((V[2] + V[3]) >> 1) << 8) | (Y[3] << 16) | (((U[2] + U[3]) >> 1) << 24);
+    }
+  }
+  if (OUT) {
+    uint8_t* op = a.out + (size_t)b * a.out_stride + (size_t)y * a.out_pitch + (size_t)x0 * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) stg_stream(op + 16 * k, make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+  }
+  if (YUYV) {
+    uint8_t* yp = a.yuyv + (size_t)b * a.yuyv_stride + ((size_t)y * a.W + x0) * 2;
+    stg_stream(yp, make_uint4(yy[0], yy[1], yy[2], yy[3]));
+    stg_stream(yp + 16, make_uint4(yy[4], yy[5], yy[6], yy[7]));
+  }
+}
+
+static bool post_fast_ok(const PostArgs& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.W % 16 != 0) return false;
+  if (!al16(a.frames) || !al16(a.bg) || a.frame_pitch % 16 || a.frame_stride % 16 || a.bg_pitch % 16 || a.bg_stride % 16) return false;
+  if (a.out && (!al16(a.out) || a.out_pitch % 16 || a.out_stride % 16)) return false;
+  if (a.yuyv && (!al16(a.yuyv) || a.yuyv_stride % 16)) return false;
+  if (a.mask && (!al16(a.mask) || a.mask_stride % 16)) return false;
+  if (a.ow > 32000 || a.oh > 32000) return false;
+  // source rows touched by one 36-row tile must fit the Hs buffer: ceil(36 * scale) + 2
+  const double scale_y = (double)a.out_h / (double)a.roi_h;
+  if ((int)(PF_UH * scale_y) + 3 > PF_RMAX) return false;
+  return true;
+}
+
 void launch_post(cudaStream_t s, const PostArgs& a) {
+  if (post_fast_ok(a)) {
+    dim3 grid((unsigned)ceil_div(a.W, PF_W), (unsigned)ceil_div(a.H, PF_H), (unsigned)a.B);
+    if (a.yuyv && a.out) { auto k = k_post_fast<true, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else if (a.yuyv) { auto k = k_post_fast<false, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else if (a.out) { auto k = k_post_fast<true, false>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else { auto k = k_post_fast<false, false>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    count_launch();
+    return;
+  }
   dim3 grid((unsigned)ceil_div(a.W, PT_W), (unsigned)ceil_div(a.H, PT_H), (unsigned)a.B);
   BSB_LAUNCH(k_post, grid, dim3(256), 0, s, a);
   count_launch();

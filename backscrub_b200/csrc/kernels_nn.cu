@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) k_global_avgpool(const float* in, int h, 
     float t = 0.f;
     for (int y = 0; y < h; ++y) t = t + rows[y * c + ch];
     const float count = (float)(h * w);
-    out[(size_t)b * ld_out + ch] = bsb_act(t / count, act);
+    out[(size_t)b * ld_out + ch] = bsb_act(bsb_div(t, count), act);
   }
 }
 

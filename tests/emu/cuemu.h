@@ -107,6 +107,8 @@ static inline int __dp4a(unsigned a, unsigned b, int c) {  // unsigned x unsigne
   for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 0xff) * (int)((b >> (8 * i)) & 0xff); return c; }
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
   for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff); return c; }
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
+static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * ((b >> 16) & 0xffu) + (a >> 16) * ((b >> 24) & 0xffu); }
 template <typename T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
