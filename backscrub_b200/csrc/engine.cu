@@ -126,6 +126,10 @@ bool Engine::plan(std::string* err) {
   };
   struct Fold { int x, s, add; };
   std::map<int, Fold> prologue;      // tensor consumed by a PW conv -> (x, scale, add)
+  std::map<int, std::pair<int, int>> concat_for_pool;
+  std::map<int, int> producer_step;  // tensor -> index in steps_ of the step that writes it
+  std::map<int, std::vector<int>> aliased_into;
+  std::vector<int> concat_virtual;
   std::vector<char> done(nops, 0);
 
   auto fold_unary = [&](int i, Step& st) {  // fold a single-consumer unary op after op i
@@ -217,9 +221,38 @@ bool Engine::plan(std::string* err) {
       }
       case OP_AVERAGE_POOL_2D: {
         st.kind = Step::POOL; st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
-        if (!need(O.filter_h == tinfo_[st.in].h && O.filter_w == tinfo_[st.in].w && tinfo_[O.out].h == 1 && tinfo_[O.out].w == 1,
+        int ph = tinfo_[st.in].h, pw = tinfo_[st.in].w, pc = tinfo_[st.in].c;
+        if (!need(O.filter_h == ph && O.filter_w == pw && tinfo_[O.out].h == 1 && tinfo_[O.out].w == 1,
                   "AVERAGE_POOL_2D that is not global")) return false;
-        if (!need((size_t)tinfo_[st.in].h * tinfo_[st.in].c * 4 <= 160 * 1024, "global pool row buffer")) return false;
+        if (!need(pc <= 512, "global pool over more than 512 channels")) return false;
+        auto cp = concat_for_pool.find(st.in);
+        if (cp != concat_for_pool.end()) { st.in = cp->second.first; st.in2 = cp->second.second; }
+        rowsum_elems_ = std::max(rowsum_elems_, (size_t)ph * pc);
+        // fold the squeeze-excite FC chain: pool -> {1x1 conv | FC} (+unary) [-> {1x1 conv | FC} (+unary)]
+        int cur = st.out;
+        while (st.n_fc < 2 && cur != g_.output && consumers[cur].size() == 1) {
+          const int j = consumers[cur][0];
+          const GOp& F = g_.ops[j];
+          if (done[j] || j <= i || F.in.empty() || F.in[0] != cur || F.in.size() < 2 || !g_.tensors[F.in[1]].is_const) break;
+          const GTensor& w = g_.tensors[F.in[1]];
+          int K, N;
+          if (is_pw(F)) { N = w.shape[0]; K = w.shape[3]; }
+          else if (F.kind == OP_FULLY_CONNECTED) { N = w.shape[w.shape.size() - 2]; K = w.shape[w.shape.size() - 1]; }
+          else break;
+          if (K != tinfo_[cur].c || K > 512 || N > 512 || tinfo_[F.out].h != 1 || tinfo_[F.out].w != 1) break;
+          Step tmp;
+          pack_pw_weights(w, N, K, tmp);
+          Step::Fc& fc = st.fc[st.n_fc++];
+          fc.w_off = tmp.w_off; fc.K = K; fc.N = N; fc.n4 = tmp.n4; fc.act1 = F.act;
+          if (F.in.size() > 2 && F.in[2] >= 0) { fc.has_bias = true; fc.b_off = add_blob(g_.tensors[F.in[2]].f32); }
+          done[j] = 1; cur = F.out;
+          if (consumers[cur].size() == 1) {
+            const int u = consumers[cur][0];
+            const int ua = unary_act(g_.ops[u].kind);
+            if (ua >= 0 && !done[u] && u > j) { fc.act2 = ua; done[u] = 1; cur = g_.ops[u].out; }
+          }
+        }
+        st.out = cur;
         break;
       }
       case OP_RESIZE_BILINEAR: {
@@ -274,11 +307,32 @@ bool Engine::plan(std::string* err) {
         const int rank = (int)g_.tensors[O.out].shape.size();
         const int axis = O.axis < 0 ? O.axis + rank : O.axis;
         if (!need(axis == rank - 1 && O.act == ACT_NONE, "CONCATENATION not on the channel axis")) return false;
+        // (1) a concatenation that only feeds a global pool is never materialised: the pool's
+        //     row-sum kernel reads both sources (pool(concat(a,b)) == concat(pool(a),pool(b)) exactly)
+        if (O.in.size() == 2 && O.out != g_.output && consumers[O.out].size() == 1 &&
+            g_.ops[consumers[O.out][0]].kind == OP_AVERAGE_POOL_2D && !prologue.count(O.in[0]) && !prologue.count(O.in[1])) {
+          concat_for_pool[O.out] = std::make_pair(O.in[0], O.in[1]);
+          continue;
+        }
+        // (2) otherwise producers write straight into the concatenated buffer when they can
         int off = 0;
         for (int t : O.in) {
-          Step c; c.op_index = i; c.kind = Step::COPY; c.in = t; c.out = O.out; c.copy_off = off;
+          const bool can_alias = t != g_.input && consumers[t].size() == 1 && producer_step.count(t) && tinfo_[t].alias_parent < 0 &&
+                                 off % 4 == 0 && tinfo_[O.out].c % 4 == 0 && !prologue.count(t);
+          if (can_alias) {
+            tinfo_[t].alias_parent = O.out; tinfo_[t].alias_off = off; tinfo_[t].ld = tinfo_[O.out].ld;
+            tinfo_[t].frame_elems = tinfo_[O.out].frame_elems;
+            aliased_into[O.out].push_back(t);
+          } else {
+            Step c; c.op_index = i; c.kind = Step::COPY; c.in = t; c.out = O.out; c.copy_off = off;
+            steps_.push_back(c);
+          }
           off += tinfo_[t].c;
-          steps_.push_back(c);
+        }
+        if (aliased_into.count(O.out)) {   // a no-op marker step so the buffer counts as produced here
+          bool any_copy = false;
+          for (const Step& c : steps_) any_copy = any_copy || (c.kind == Step::COPY && c.out == O.out);
+          if (!any_copy) concat_virtual.push_back(O.out);
         }
         continue;
       }
@@ -286,21 +340,25 @@ bool Engine::plan(std::string* err) {
         *err = "unsupported TFLite operator code " + std::to_string(O.kind);
         return false;
     }
+    producer_step[st.out] = (int)steps_.size();
     steps_.push_back(st);
   }
 
   // ---- liveness + arena (floats; every tensor is max_batch frames) ----
   const int ns = (int)steps_.size();
-  auto use = [&](int t, int s) { if (t >= 0) tinfo_[t].last_use = std::max(tinfo_[t].last_use, s); };
+  auto root = [&](int t) { return tinfo_[t].alias_parent >= 0 ? tinfo_[t].alias_parent : t; };
+  auto use = [&](int t, int s) { if (t >= 0) { const int r = root(t); tinfo_[r].last_use = std::max(tinfo_[r].last_use, s); } };
   tinfo_[g_.input].materialized = true; tinfo_[g_.input].first_def = -1;
   for (int s = 0; s < ns; ++s) {
     const Step& st = steps_[s];
     use(st.in, s); use(st.in2, s); use(st.scale, s); use(st.in_add, s); use(st.residual, s);
     tinfo_[st.out].materialized = true;
-    tinfo_[st.out].first_def = std::min(tinfo_[st.out].first_def, s);
+    const int r = root(st.out);
+    tinfo_[r].materialized = true;
+    tinfo_[r].first_def = std::min(tinfo_[r].first_def, s);
     use(st.out, s);
   }
-  tinfo_[g_.output].last_use = 1 << 30;
+  tinfo_[root(g_.output)].last_use = 1 << 30;
   tinfo_[g_.input].last_use = std::max(tinfo_[g_.input].last_use, 0);
   if (!tinfo_[g_.output].materialized) { *err = "graph output is never produced"; return false; }
   for (const Step& st : steps_)
@@ -333,11 +391,13 @@ bool Engine::plan(std::string* err) {
   std::vector<char> allocated(nt, 0);
   tinfo_[g_.input].offset = alloc(tinfo_[g_.input].frame_elems * max_batch_); allocated[g_.input] = 1;
   for (int s = 0; s < ns; ++s) {
-    const int o = steps_[s].out;
+    const int o = root(steps_[s].out);
     if (!allocated[o]) { tinfo_[o].offset = alloc(tinfo_[o].frame_elems * max_batch_); allocated[o] = 1; }
     if (keep) continue;
     for (int t = 0; t < nt; ++t)
-      if (allocated[t] == 1 && tinfo_[t].materialized && tinfo_[t].last_use == s) { release(tinfo_[t].offset, tinfo_[t].frame_elems * max_batch_); allocated[t] = 2; }
+      if (allocated[t] == 1 && tinfo_[t].alias_parent < 0 && tinfo_[t].materialized && tinfo_[t].last_use == s) {
+        release(tinfo_[t].offset, tinfo_[t].frame_elems * max_batch_); allocated[t] = 2;
+      }
   }
   arena_elems_ = top;
 
@@ -417,6 +477,7 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMemcpy(wblob_, wblob_h_.data(), wblob_h_.size() * 4, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc((void**)&arena_, std::max<size_t>(arena_elems_, 64) * 4));
   CUDA_OK(cudaMemset(arena_, 0, std::max<size_t>(arena_elems_, 64) * 4));
+  CUDA_OK(cudaMalloc((void**)&rowsum_, std::max<size_t>(rowsum_elems_ * B, 64) * 4));
   // bilateral LUTs (cv::bilateralFilter d=5, sigma 100/100; oracle_img.c:or_bilateral_d5_u8c3)
   {
     std::vector<float> lut(768 + 16, 0.f);
@@ -458,7 +519,7 @@ Engine::~Engine() {
   for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
 #endif
   if (stream_) { cudaStreamSynchronize(stream_); }
-  for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
+  for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)rowsum_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
                   (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_,
                   tab_in_.blob, tab_up_.blob, tab_bg_.blob})
     if (p) cudaFree(p);
@@ -497,9 +558,17 @@ void Engine::enqueue_cnn(int n) {
         launch_depthwise(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, wblob_ + st.w_off, st.kh, st.kw, st.sh, st.sw, st.dh, st.dw,
                          st.pt, st.pl, tptr(st.out), O.h, O.w, O.ld, e);
         break;
-      case Step::POOL:
-        launch_global_avgpool(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, tptr(st.out), O.ld, st.act1);
+      case Step::POOL: {
+        FcLayer fc[2];
+        for (int k = 0; k < st.n_fc; ++k) {
+          fc[k].w = wblob_ + st.fc[k].w_off; fc[k].bias = st.fc[k].has_bias ? wblob_ + st.fc[k].b_off : nullptr;
+          fc[k].K = st.fc[k].K; fc[k].N = st.fc[k].N; fc[k].n4 = st.fc[k].n4; fc[k].act1 = st.fc[k].act1; fc[k].act2 = st.fc[k].act2;
+        }
+        const bool two = st.in2 >= 0;
+        launch_pool_fc(stream_, n, tptr(st.in), I.c, I.ld, two ? tptr(st.in2) : nullptr, two ? tinfo_[st.in2].c : 0,
+                       two ? tinfo_[st.in2].ld : 0, I.h, I.w, rowsum_, st.act1, nullptr, st.n_fc, fc, tptr(st.out), O.ld);
         break;
+      }
       case Step::RESIZE:
         launch_resize_bilinear(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, tptr(st.out), O.h, O.w, O.ld, st.align_corners, st.half_pixel);
         break;

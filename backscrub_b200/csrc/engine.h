@@ -22,6 +22,8 @@ struct TensorInfo {
   int h = 1, w = 1, c = 1, ld = 1;
   size_t frame_elems = 0;     // h*w*ld floats per frame
   size_t offset = 0;          // float offset inside the arena
+  int alias_parent = -1;      // >= 0: lives inside that tensor's buffer (in-place CONCATENATION)
+  int alias_off = 0;          // channel offset inside the parent
   bool materialized = false;
   int first_def = 1 << 30, last_use = -1;
 };
@@ -37,6 +39,11 @@ struct Step {
   int elt_mode = 0;
   bool align_corners = false, half_pixel = false;
   int copy_off = 0;
+  // POOL: optional fused fully-connected chain (squeeze-excite) after the global average pool
+  struct Fc { size_t w_off = 0, b_off = 0; bool has_bias = false; int K = 0, N = 0, n4 = 0, act1 = 0, act2 = 0; };
+  int n_fc = 0;
+  Fc fc[2];
+  int launches() const { return kind == POOL ? 2 : 1; }
 };
 
 struct HostResizeTab {
@@ -84,7 +91,7 @@ class Engine {
   void in_hwc(int* v) const { v[0] = mh_; v[1] = mw_; v[2] = 3; }
   void out_hwc(int* v) const { v[0] = oh_; v[1] = ow_; v[2] = oc_; }
   double flops() const { return flops_; }
-  int launches_per_call() const { return (int)steps_.size() + 4; }
+  int launches_per_call() const { int n = 4; for (const Step& s : steps_) n += s.launches(); return n; }
   long get_tensor(int t, float* out, long cap, std::string* err);
   long get_stage_u8(int which, int frame, uint8_t* out, long cap, std::string* err);
 
@@ -106,7 +113,10 @@ class Engine {
   void enqueue_decision(int n);
   void enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
                     uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride);
-  float* tptr(int t) const { return arena_ + tinfo_[t].offset; }
+  float* tptr(int t) const {
+    const TensorInfo& I = tinfo_[t];
+    return I.alias_parent >= 0 ? arena_ + tinfo_[I.alias_parent].offset + I.alias_off : arena_ + I.offset;
+  }
 
   Graph g_;
   int model_type_ = 0;
@@ -128,6 +138,8 @@ class Engine {
   float* wblob_ = nullptr;
   float* arena_ = nullptr;
   float* lut_ = nullptr;             // color_w[768] + space_w[16]
+  float* rowsum_ = nullptr;          // scratch of the global-average-pool row sums
+  size_t rowsum_elems_ = 0;
   uint8_t* in_u8_ = nullptr;         // [B][mh][mw][3] zero outside in_roidim
   uint8_t* filt_u8_ = nullptr;       // [B][mh][mw][3] (KEEP_TENSORS only)
   uint8_t* state_ = nullptr;         // [oh*ow] IIR state

@@ -37,9 +37,16 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
                       const float* w, int kh, int kw, int stride_h, int stride_w, int dil_h, int dil_w,
                       int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e);
 
-// Global average pool: out[B][C] = (sum over rows of (sum over x)) / (H*W), act applied.
-void launch_global_avgpool(cudaStream_t s, int B, const float* in, int h, int w, int c, int ld_in,
-                           float* out, int ld_out, int act);
+// Global average pool (+ optional squeeze-excite FC chain), two launches:
+//   1. row sums: rowsum[b][y][c] = sum_x in[b][y][x][c]   (x ascending; many blocks)
+//      — the input may be the channel concatenation of two tensors (inA | inB);
+//   2. one block per frame: total = sum_y rowsum (y ascending), avg = total / (H*W), pool
+//      activation, then up to two fully-connected layers (w: [K][N4], k ascending fmaf,
+//      + bias, activations) — the SE "squeeze" path of MobileNetV3-style blocks.
+struct FcLayer { const float* w = nullptr; const float* bias = nullptr; int K = 0, N = 0, n4 = 0, act1 = 0, act2 = 0; };
+void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, const float* inB, int cB, int ldB,
+                    int h, int w, float* rowsum_scratch, int pool_act, float* pooled_out /*may be null*/,
+                    int n_fc, const FcLayer* fc, float* out, int ld_out);
 
 // RESIZE_BILINEAR (reference resize_bilinear.h:29-117 float path)
 void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,

@@ -187,22 +187,76 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
   }
 }
 
+// Row-streaming variant for small K x N (the high-resolution MobileNet layers, K, N <= 64):
+// the whole weight matrix sits in shared memory; a thread owns 4 output channels of one
+// pixel and walks K in ascending order (float4 loads of the pixel row are shared by the
+// CT threads of that pixel through the L1 broadcast path).  Memory-bound by design.
+__global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
+  BSB_DYN_SMEM(smem_raw);
+  float* Ws = reinterpret_cast<float*>(smem_raw);            // [K][n4]
+  for (int i = threadIdx.x * 4; i < a.K * a.n4; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(Ws + i) = __ldg(reinterpret_cast<const float4*>(a.w + i));
+  __syncthreads();
+  const int rows_per_block = 256 / ct;
+  const int tx = threadIdx.x % ct, tr = threadIdx.x / ct;
+  if (tr >= rows_per_block) return;
+  const int n0 = tx * 4;
+  for (long gm = (long)blockIdx.x * rows_per_block + tr; gm < a.M; gm += (long)gridDim.x * rows_per_block) {
+    const float* ap = a.A + (size_t)gm * a.ld_a;
+    const float* sp = a.in_scale ? a.in_scale + (size_t)(gm / a.rows_per_frame) * a.K : nullptr;
+    const float* dp = a.in_add ? a.in_add + (size_t)gm * a.ld_add : nullptr;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    for (int k = 0; k < a.K; k += 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(ap + k));
+      if (sp) { const float4 sc = __ldg(reinterpret_cast<const float4*>(sp + k)); v.x = v.x * sc.x; v.y = v.y * sc.y; v.z = v.z * sc.z; v.w = v.w * sc.w; }
+      if (dp) { const float4 ad = __ldg(reinterpret_cast<const float4*>(dp + k)); v.x = v.x + ad.x; v.y = v.y + ad.y; v.z = v.z + ad.z; v.w = v.w + ad.w; }
+      const float av[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(Ws + (k + j) * a.n4 + n0);
+        acc0 = fmaf(av[j], w4.x, acc0); acc1 = fmaf(av[j], w4.y, acc1);
+        acc2 = fmaf(av[j], w4.z, acc2); acc3 = fmaf(av[j], w4.w, acc3);
+      }
+    }
+    float* op = a.out + (size_t)gm * a.ld_out + n0;
+    const float r0 = epilogue(acc0, n0, (size_t)gm, a.e);
+    if (n0 + 3 < a.N && (a.ld_out & 3) == 0) {
+      *reinterpret_cast<float4*>(op) = make_float4(r0, epilogue(acc1, n0 + 1, (size_t)gm, a.e), epilogue(acc2, n0 + 2, (size_t)gm, a.e),
+                                                   epilogue(acc3, n0 + 3, (size_t)gm, a.e));
+    } else {
+      op[0] = r0;
+      if (n0 + 1 < a.N) op[1] = epilogue(acc1, n0 + 1, (size_t)gm, a.e);
+      if (n0 + 2 < a.N) op[2] = epilogue(acc2, n0 + 2, (size_t)gm, a.e);
+      if (n0 + 3 < a.N) op[3] = epilogue(acc3, n0 + 3, (size_t)gm, a.e);
+    }
+  }
+}
+
 void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int ld_a,
                       const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
                       const float* in_scale, int rows_per_frame, const float* in_add, int ld_add) {
   PWArgs a{A, w_kn, out, in_scale, in_add, M, K, N, n4, ld_a, ld_out, rows_per_frame > 0 ? rows_per_frame : 1, ld_add, to_dev(e)};
+  if (K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 4096) {
+    const int ct = n4 / 4, rows_per_block = 256 / ct;
+    long blocks = ((long)M + rows_per_block - 1) / rows_per_block;
+    if (blocks > 148L * 16) blocks = 148L * 16;             // grid-stride: a few waves of 148 SMs
+    BSB_LAUNCH(k_pointwise_rows, dim3((unsigned)blocks), dim3(256), sizeof(float) * (size_t)K * n4, s, a, ct);
+    count_launch();
+    return;
+  }
   // choose the N tile that wastes the fewest columns; ties go to the wider tile
   const int pad16 = (N + 15) / 16 * 16, pad32 = (N + 31) / 32 * 32, pad64 = (N + 63) / 64 * 64;
   int bn = 64;
   if (pad32 < pad64) bn = 32;
   if (pad16 < (bn == 64 ? pad64 : pad32)) bn = 16;
-  if (bn == 64) {
-    BSB_LAUNCH((k_pointwise<64, 4>), dim3((unsigned)ceil_div(M, 64), (unsigned)ceil_div(N, 64)), dim3(256), 0, s, a);
-  } else if (bn == 32) {
-    BSB_LAUNCH((k_pointwise<32, 4>), dim3((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 32)), dim3(256), 0, s, a);
-  } else {
-    BSB_LAUNCH((k_pointwise<16, 4>), dim3((unsigned)ceil_div(M, 256), (unsigned)ceil_div(N, 16)), dim3(256), 0, s, a);
-  }
+  // small problems: one row per thread (TM = 1) gives 4x more blocks to spread over the 148 SMs
+  const int rt = 256 / (bn / 4);
+  const bool small = (long)ceil_div(M, rt * 4) * ceil_div(N, bn) < 2 * 148;
+  const int bm = small ? rt : rt * 4;
+  dim3 grid((unsigned)ceil_div(M, bm), (unsigned)ceil_div(N, bn));
+  if (bn == 64) { if (small) { auto k = k_pointwise<64, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<64, 4>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+  else if (bn == 32) { if (small) { auto k = k_pointwise<32, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<32, 4>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+  else { if (small) { auto k = k_pointwise<16, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<16, 4>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
   count_launch();
 }
 
@@ -266,35 +320,76 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
 }
 
 // ---------------------------------------------------------------------------
-// Global average pool.  Summation order (shared with the oracle): each row left to
-// right, then the row sums top to bottom; total / (float)(H*W).
-// One block per frame; row sums in shared memory.
+// Global average pool + SE fully-connected chain.  Summation order (shared with the
+// oracle): each row left to right, then the row sums top to bottom; total / (float)(H*W).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_global_avgpool(const float* in, int h, int w, int c, int ld_in,
-                                                        float* out, int ld_out, int act) {
-  BSB_DYN_SMEM(smem_raw);
-  float* rows = reinterpret_cast<float*>(smem_raw);   // [h][c]
-  const int b = blockIdx.x;
-  const float* inb = in + (size_t)b * h * w * ld_in;
-  for (int i = threadIdx.x; i < h * c; i += blockDim.x) {
-    const int y = i / c, ch = i % c;
-    const float* p = inb + (size_t)y * w * ld_in + ch;
-    float r = 0.f;
-    for (int x = 0; x < w; ++x) r = r + __ldg(p + (size_t)x * ld_in);
-    rows[i] = r;
+__global__ void __launch_bounds__(256) k_rowsum(int B, const float* inA, int cA, int ldA, const float* inB, int cB, int ldB,
+                                                int h, int w, float* rowsum) {
+  const int C = cA + cB;
+  const long total = (long)B * h * C;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % C);
+  const long row = idx / C;                       // b * h + y
+  const float* p; int ld;
+  if (ch < cA) { p = inA + (size_t)row * w * ldA + ch; ld = ldA; }
+  else { p = inB + (size_t)row * w * ldB + (ch - cA); ld = ldB; }
+  float r = 0.f;
+  int x = 0;
+  for (; x + 8 <= w; x += 8) {                    // loads first (independent), adds in x order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (size_t)(x + j) * ld);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r = r + v[j];
   }
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+  for (; x < w; ++x) r = r + __ldg(p + (size_t)x * ld);
+  rowsum[idx] = r;
+}
+
+struct FcDev { const float* w; const float* bias; int K, N, n4, act1, act2; };
+
+__global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int C, float count, int pool_act, float* pooled_out,
+                                                 int n_fc, FcDev f0, FcDev f1, float* out, int ld_out) {
+  __shared__ float v0[512];
+  __shared__ float v1[512];
+  const int b = blockIdx.x;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const float* p = rowsum + (size_t)b * h * C + ch;
     float t = 0.f;
-    for (int y = 0; y < h; ++y) t = t + rows[y * c + ch];
-    const float count = (float)(h * w);
-    out[(size_t)b * ld_out + ch] = bsb_act(bsb_div(t, count), act);
+    for (int y = 0; y < h; ++y) t = t + __ldg(p + (size_t)y * C);
+    const float a = bsb_act(bsb_div(t, count), pool_act);
+    v0[ch] = a;
+    if (pooled_out) pooled_out[(size_t)b * C + ch] = a;
+    if (n_fc == 0) out[(size_t)b * ld_out + ch] = a;
+  }
+  if (n_fc == 0) return;
+  __syncthreads();
+  for (int n = threadIdx.x; n < f0.N; n += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < f0.K; ++k) acc = fmaf(v0[k], __ldg(f0.w + (size_t)k * f0.n4 + n), acc);
+    float r = bsb_act(bsb_act(acc + (f0.bias ? __ldg(f0.bias + n) : 0.f), f0.act1), f0.act2);
+    if (n_fc == 1) out[(size_t)b * ld_out + n] = r; else v1[n] = r;
+  }
+  if (n_fc == 1) return;
+  __syncthreads();
+  for (int n = threadIdx.x; n < f1.N; n += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < f1.K; ++k) acc = fmaf(v1[k], __ldg(f1.w + (size_t)k * f1.n4 + n), acc);
+    out[(size_t)b * ld_out + n] = bsb_act(bsb_act(acc + (f1.bias ? __ldg(f1.bias + n) : 0.f), f1.act1), f1.act2);
   }
 }
 
-void launch_global_avgpool(cudaStream_t s, int B, const float* in, int h, int w, int c, int ld_in,
-                           float* out, int ld_out, int act) {
-  BSB_LAUNCH(k_global_avgpool, dim3((unsigned)B), dim3(256), sizeof(float) * (size_t)h * c, s, in, h, w, c, ld_in, out, ld_out, act);
+void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, const float* inB, int cB, int ldB,
+                    int h, int w, float* rowsum_scratch, int pool_act, float* pooled_out,
+                    int n_fc, const FcLayer* fc, float* out, int ld_out) {
+  const int C = cA + cB;
+  const long total = (long)B * h * C;
+  BSB_LAUNCH(k_rowsum, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, inA, cA, ldA, inB, cB, ldB, h, w, rowsum_scratch);
+  count_launch();
+  FcDev f[2] = {{nullptr, nullptr, 0, 0, 0, 0, 0}, {nullptr, nullptr, 0, 0, 0, 0, 0}};
+  for (int i = 0; i < n_fc && i < 2; ++i) f[i] = FcDev{fc[i].w, fc[i].bias, fc[i].K, fc[i].N, fc[i].n4, fc[i].act1, fc[i].act2};
+  BSB_LAUNCH(k_pool_fc, dim3((unsigned)B), dim3(256), 0, s, rowsum_scratch, h, C, (float)(h * w), pool_act, pooled_out, n_fc, f[0], f[1], out, ld_out);
   count_launch();
 }
 
