@@ -121,29 +121,41 @@ void launch_bilateral_norm(cudaStream_t s, int B, const uint8_t* in_u8, int mw, 
 // pixel, looping over the B consecutive frames of the batch so the 3-tap state
 // out = (val & 0xE0) | (out >> 3) advances in frame order.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_decision_iir(int model_type, int B, const float* out_f, int npix, int oc,
+BSB_D unsigned decide(int model_type, const float* t) {
+  if (model_type == MODEL_DEEPLAB) {
+    float maxval = -10000.f; int maxpos = 0;
+    for (int i = 0; i < 21; ++i) { const float v = __ldg(t + i); if (v > maxval) { maxval = v; maxpos = i; } }
+    return (maxpos == 15) ? 0u : 1u;
+  }
+  if (model_type == MODEL_MEET) {
+    const float e0 = bsb_expf(__ldg(t)), e1 = bsb_expf(__ldg(t + 1));
+    const float p0 = bsb_div(e0, e0 + e1), p1 = bsb_div(e1, e0 + e1);
+    return (p0 < p1) ? 0u : 1u;
+  }
+  // `tmp[n] > 0.65` compares float with the double literal; equivalent to > 0.65f
+  // (0.65 lies strictly between two adjacent floats) — SURVEY.md Appendix A
+  return (__ldg(t) > 0.65f) ? 0u : 1u;
+}
+
+// The per-frame decisions of a pixel are independent (computed 8 at a time so their loads
+// overlap); only the 3-tap state update is sequential, and it is pure ALU on a bit mask.
+__global__ void __launch_bounds__(128) k_decision_iir(int model_type, int B, const float* out_f, int npix, int oc,
                                                       uint8_t* state, uint8_t* ofinal) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= npix) return;
   unsigned st = state[n];
-  for (int b = 0; b < B; ++b) {
-    const float* t = out_f + ((size_t)b * npix + n) * oc;
-    unsigned val;
-    if (model_type == MODEL_DEEPLAB) {
-      float maxval = -10000.f; int maxpos = 0;
-      for (int i = 0; i < 21; ++i) { const float v = __ldg(t + i); if (v > maxval) { maxval = v; maxpos = i; } }
-      val = (maxpos == 15) ? 0u : 255u;
-    } else if (model_type == MODEL_MEET) {
-      const float e0 = bsb_expf(__ldg(t)), e1 = bsb_expf(__ldg(t + 1));
-      const float p0 = bsb_div(e0, e0 + e1), p1 = bsb_div(e1, e0 + e1);
-      val = (p0 < p1) ? 0u : 255u;
-    } else {
-      // `tmp[n] > 0.65` compares float with the double literal; equivalent to > 0.65f
-      // (0.65 lies strictly between two adjacent floats) — SURVEY.md Appendix A
-      val = (__ldg(t) > 0.65f) ? 0u : 255u;
-    }
-    st = (val & 0xE0u) | (st >> 3);
-    ofinal[(size_t)b * npix + n] = (uint8_t)st;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b0 + j < B) bits |= decide(model_type, out_f + ((size_t)(b0 + j) * npix + n) * oc) << j;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b0 + j < B) {
+        const unsigned val = ((bits >> j) & 1u) ? 255u : 0u;
+        st = (val & 0xE0u) | (st >> 3);
+        ofinal[(size_t)(b0 + j) * npix + n] = (uint8_t)st;
+      }
   }
   state[n] = (uint8_t)st;
 }
@@ -151,7 +163,7 @@ __global__ void __launch_bounds__(256) k_decision_iir(int model_type, int B, con
 void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
                          uint8_t* state, uint8_t* ofinal) {
   const int npix = oh * ow;
-  BSB_LAUNCH(k_decision_iir, dim3((unsigned)ceil_div(npix, 256)), dim3(256), 0, s, model_type, B, model_out, npix, oc, state, ofinal);
+  BSB_LAUNCH(k_decision_iir, dim3((unsigned)ceil_div(npix, 128)), dim3(128), 0, s, model_type, B, model_out, npix, oc, state, ofinal);
   count_launch();
 }
 
@@ -322,8 +334,6 @@ BSB_D void stg_stream(uint8_t* p, uint4 v) {
 #endif
 }
 
-struct PfCol { short sx, sx1, a0, a1; };
-struct PfRow { short r0, r1, b0, b1; };
 
 // one pixel: pair channels (two 16-bit lanes) + single channel; returns T = (c0, c1, c2, x) bytes
 template <int PAIR_SEL, int SINGLE_SEL, int T_SEL>
@@ -343,8 +353,7 @@ __global__ void __launch_bounds__(256, 3) k_post_fast(PostArgs a) {
   __shared__ __align__(16) unsigned short Hs[PF_RMAX * PF_US];
   __shared__ __align__(16) unsigned short Us[PF_UH * PF_US];
   __shared__ __align__(16) unsigned short Vs[PF_H * PF_US];
-  __shared__ PfCol cols[PF_UW];
-  __shared__ PfRow rows[PF_UH];
+  __shared__ __align__(16) uint4 rows[PF_UH];     // r0, r1, b0 << 16, b1 << 16
   __shared__ int rrange[2];
   const int b = blockIdx.z;
   const int tx0 = blockIdx.x * PF_W, ty0 = blockIdx.y * PF_H;
@@ -352,47 +361,51 @@ __global__ void __launch_bounds__(256, 3) k_post_fast(PostArgs a) {
   const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + PF_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
 
   if (hits_roi) {
-    // ---- A0: interpolation parameters ----
-    if (tid < PF_UW) {
-      const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + tid, a.roi_w);
-      const int sx = __ldg(a.tab.xofs + gx);
-      PfCol c; c.sx = (short)sx; c.sx1 = (short)min(sx + 1, a.out_w - 1);
-      c.a0 = __ldg(a.tab.xw + 2 * gx); c.a1 = __ldg(a.tab.xw + 2 * gx + 1);
-      cols[tid] = c;
-    } else if (tid >= 192 && tid < 192 + PF_UH) {
-      const int uy = tid - 192;
-      const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
-      PfRow r; r.r0 = (short)__ldg(a.tab.yofs0 + gy); r.r1 = (short)__ldg(a.tab.yofs1 + gy);
-      r.b0 = __ldg(a.tab.yw + 2 * gy); r.b1 = __ldg(a.tab.yw + 2 * gy + 1);
-      rows[uy] = r;
-    }
-    __syncthreads();
+    // ---- A0: row interpolation parameters + range of source rows the tile touches (warp 0) ----
     if (warp == 0) {
-      int lo = rows[lane].r0, hi = rows[lane].r1;
-      if (lane < PF_UH - 32) { lo = min(lo, (int)rows[32 + lane].r0); hi = max(hi, (int)rows[32 + lane].r1); }
+      int lo = 1 << 30, hi = -1;
+      for (int uy = lane; uy < PF_UH; uy += 32) {
+        const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
+        const int r0 = __ldg(a.tab.yofs0 + gy), r1 = __ldg(a.tab.yofs1 + gy);
+        rows[uy] = make_uint4((unsigned)r0, (unsigned)r1, (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
+        lo = min(lo, r0); hi = max(hi, r1);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
       if (lane == 0) { rrange[0] = lo; rrange[1] = hi - lo + 1; }
     }
     __syncthreads();
     const int rmin = rrange[0], nrows = rrange[1];
-    // ---- A1: horizontal pass for the touched source rows ----
-    const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
-    for (int r = warp; r < nrows; r += 8) {
-      const uint8_t* srow = src + (size_t)(rmin + r) * a.ow;
-      for (int ux = lane; ux < PF_UW; ux += 32) {
-        const PfCol c = cols[ux];
-        Hs[r * PF_US + ux] = (unsigned short)(((int)srow[c.sx] * c.a0 + (int)srow[c.sx1] * c.a1) >> 4);
+    // ---- A1: horizontal pass of cv::resize for the touched source rows: Hs = (s[sx]*a0 + s[sx1]*a1) >> 4.
+    //      A thread owns a column (parameters in registers) and walks every second source row. ----
+    {
+      const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
+      const int phase = tid >> 7;
+      for (int ux = tid & 127; ux < PF_UW; ux += 128) {
+        const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + ux, a.roi_w);
+        const int sx = __ldg(a.tab.xofs + gx), sx1 = min(sx + 1, a.out_w - 1);
+        const int a0 = __ldg(a.tab.xw + 2 * gx), a1 = __ldg(a.tab.xw + 2 * gx + 1);
+        const uint8_t* srow = src + (size_t)(rmin + phase) * a.ow;
+        unsigned short* hp = Hs + phase * PF_US + ux;
+        for (int r = phase; r < nrows; r += 2) {
+          *hp = (unsigned short)(((int)srow[sx] * a0 + (int)srow[sx1] * a1) >> 4);
+          srow += 2 * a.ow; hp += 2 * PF_US;
+        }
       }
     }
     __syncthreads();
-    // ---- A2: vertical pass -> upsampled tile ----
+    // ---- A2: vertical pass -> upsampled tile.  ((b*h) >> 16) is one IMAD.HI with b pre-shifted by 16.
+    //      A warp takes a row; each lane produces columns lane, lane+32, ... ----
     for (int uy = warp; uy < PF_UH; uy += 8) {
-      const PfRow rp = rows[uy];
-      const unsigned short* h0 = Hs + (rp.r0 - rmin) * PF_US;
-      const unsigned short* h1 = Hs + (rp.r1 - rmin) * PF_US;
-      for (int ux = lane; ux < PF_UW; ux += 32)
-        Us[uy * PF_US + ux] = (unsigned short)(((((int)rp.b0 * (int)h0[ux]) >> 16) + (((int)rp.b1 * (int)h1[ux]) >> 16) + 2) >> 2);
+      const uint4 rp = rows[uy];
+      const unsigned short* h0 = Hs + ((int)rp.x - rmin) * PF_US + lane;
+      const unsigned short* h1 = Hs + ((int)rp.y - rmin) * PF_US + lane;
+      unsigned short* up = Us + uy * PF_US + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        up[32 * k] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[32 * k]) + __umulhi(rp.w, (unsigned)h1[32 * k]) + 2u) >> 2);
+      if (lane < PF_UW - 128)
+        up[128] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[128]) + __umulhi(rp.w, (unsigned)h1[128]) + 2u) >> 2);
     }
     __syncthreads();
     // ---- B: vertical 5-sums, two columns per 32-bit word, sliding window over 8 rows ----

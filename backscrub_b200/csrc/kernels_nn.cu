@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
   const int n0 = tx * 4;
   for (long gm = (long)blockIdx.x * rows_per_block + tr; gm < a.M; gm += (long)gridDim.x * rows_per_block) {
     const float* ap = a.A + (size_t)gm * a.ld_a;
-    const float* sp = a.in_scale ? a.in_scale + (size_t)(gm / a.rows_per_frame) * a.K : nullptr;
+    const float* sp = a.in_scale ? a.in_scale + (size_t)((unsigned)gm / (unsigned)a.rows_per_frame) * a.K : nullptr;
     const float* dp = a.in_add ? a.in_add + (size_t)gm * a.ld_add : nullptr;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     for (int k = 0; k < a.K; k += 4) {
@@ -308,11 +308,79 @@ __global__ void __launch_bounds__(256) k_depthwise(DWArgs a) {
   for (int j = 0; j < VEC; ++j) op[j] = epilogue(acc[j], c0 + j, (size_t)pix, a.e);
 }
 
+// Strip variant (dilation 1, C % 4 == 0): a thread produces 4 consecutive output pixels x 4
+// channels, so each input row segment is loaded once and reused by the overlapping windows
+// (3x3 s1: 18 float4 loads for 4 outputs instead of 36).  Per output the taps are still
+// accumulated in (fy, fx) order and out-of-image taps are skipped, exactly like the oracle.
+BSB_D void fma4(float4& acc, const float4& v, const float4& w) {
+  acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+}
+
+template <int KS, int S>
+__global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
+  constexpr int CNT = 3 * S + KS;
+  const int groups = a.c / 4, strips = (a.ow + 3) / 4;
+  const long total = (long)a.B * a.oh * strips * groups;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % groups) * 4;
+  long t = idx / groups;
+  const int ox0 = (int)(t % strips) * 4; t /= strips;
+  const int oy = (int)(t % a.oh);
+  const int b = (int)(t / a.oh);
+  const float* inb = a.in + (size_t)b * a.ih * a.iw * a.ld_in + c0;
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ix0 = ox0 * S - a.pl;
+#pragma unroll
+  for (int fy = 0; fy < KS; ++fy) {
+    const int iy = oy * S - a.pt + fy;
+    if (iy < 0 || iy >= a.ih) continue;
+    const float* rowp = inb + (size_t)iy * a.iw * a.ld_in;
+    float4 v[CNT];
+#pragma unroll
+    for (int cidx = 0; cidx < CNT; ++cidx) {
+      const int ix = ix0 + cidx;
+      v[cidx] = (ix >= 0 && ix < a.iw) ? __ldg(reinterpret_cast<const float4*>(rowp + (size_t)ix * a.ld_in)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 wr[KS];
+#pragma unroll
+    for (int fx = 0; fx < KS; ++fx) wr[fx] = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(fy * KS + fx) * a.c + c0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int fx = 0; fx < KS; ++fx) {
+        const int ix = ix0 + j * S + fx;
+        if (ix >= 0 && ix < a.iw) fma4(acc[j], v[j * S + fx], wr[fx]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ox = ox0 + j;
+    if (ox >= a.ow) break;
+    const size_t pix = ((size_t)b * a.oh + oy) * a.ow + ox;
+    float* op = a.out + pix * a.ld_out + c0;
+    *reinterpret_cast<float4*>(op) = make_float4(epilogue(acc[j].x, c0, pix, a.e), epilogue(acc[j].y, c0 + 1, pix, a.e),
+                                                 epilogue(acc[j].z, c0 + 2, pix, a.e), epilogue(acc[j].w, c0 + 3, pix, a.e));
+  }
+}
+
 void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                       const float* w, int kh, int kw, int stride_h, int stride_w, int dil_h, int dil_w,
                       int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e) {
   DWArgs a{in, w, out, B, ih, iw, c, ld_in, kh, kw, stride_h, stride_w, dil_h, dil_w, pad_t, pad_l, oh, ow, ld_out, to_dev(e)};
   const bool vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0);
+  if (vec && dil_h == 1 && dil_w == 1 && kh == kw && stride_h == stride_w && (kh == 3 || kh == 5) && (stride_h == 1 || stride_h == 2)) {
+    const long nthreads = (long)B * oh * ((ow + 3) / 4) * (c / 4);
+    const dim3 grid((unsigned)((nthreads + 127) / 128)), block(128);
+    if (kh == 3 && stride_h == 1) { auto k = k_depthwise_strip<3, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    else if (kh == 3) { auto k = k_depthwise_strip<3, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    else if (stride_h == 1) { auto k = k_depthwise_strip<5, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    else { auto k = k_depthwise_strip<5, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    count_launch();
+    return;
+  }
   const long total = (long)B * oh * ow * (vec ? c / 4 : c);
   if (vec) BSB_LAUNCH(k_depthwise<4>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
   else BSB_LAUNCH(k_depthwise<1>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
@@ -349,6 +417,21 @@ __global__ void __launch_bounds__(256) k_rowsum(int B, const float* inA, int cA,
 
 struct FcDev { const float* w; const float* bias; int K, N, n4, act1, act2; };
 
+// dot(v[0..K), w[k*n4 + n]) with k ascending; loads issued 8 at a time (independent), FMAs in order
+BSB_D float fc_dot(const float* v, const float* w, int K, int n4) {
+  float acc = 0.f;
+  int k = 0;
+  for (; k + 8 <= K; k += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = __ldg(w + (size_t)(k + j) * n4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(v[k + j], t[j], acc);
+  }
+  for (; k < K; ++k) acc = fmaf(v[k], __ldg(w + (size_t)k * n4), acc);
+  return acc;
+}
+
 __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int C, float count, int pool_act, float* pooled_out,
                                                  int n_fc, FcDev f0, FcDev f1, float* out, int ld_out) {
   __shared__ float v0[512];
@@ -357,7 +440,15 @@ __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const float* p = rowsum + (size_t)b * h * C + ch;
     float t = 0.f;
-    for (int y = 0; y < h; ++y) t = t + __ldg(p + (size_t)y * C);
+    int y = 0;
+    for (; y + 8 <= h; y += 8) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __ldg(p + (size_t)(y + j) * C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t = t + r[j];
+    }
+    for (; y < h; ++y) t = t + __ldg(p + (size_t)y * C);
     const float a = bsb_act(bsb_div(t, count), pool_act);
     v0[ch] = a;
     if (pooled_out) pooled_out[(size_t)b * C + ch] = a;
@@ -366,16 +457,14 @@ __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int
   if (n_fc == 0) return;
   __syncthreads();
   for (int n = threadIdx.x; n < f0.N; n += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < f0.K; ++k) acc = fmaf(v0[k], __ldg(f0.w + (size_t)k * f0.n4 + n), acc);
-    float r = bsb_act(bsb_act(acc + (f0.bias ? __ldg(f0.bias + n) : 0.f), f0.act1), f0.act2);
+    const float acc = fc_dot(v0, f0.w + n, f0.K, f0.n4);
+    const float r = bsb_act(bsb_act(acc + (f0.bias ? __ldg(f0.bias + n) : 0.f), f0.act1), f0.act2);
     if (n_fc == 1) out[(size_t)b * ld_out + n] = r; else v1[n] = r;
   }
   if (n_fc == 1) return;
   __syncthreads();
   for (int n = threadIdx.x; n < f1.N; n += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < f1.K; ++k) acc = fmaf(v1[k], __ldg(f1.w + (size_t)k * f1.n4 + n), acc);
+    const float acc = fc_dot(v1, f1.w + n, f1.K, f1.n4);
     out[(size_t)b * ld_out + n] = bsb_act(bsb_act(acc + (f1.bias ? __ldg(f1.bias + n) : 0.f), f1.act1), f1.act2);
   }
 }

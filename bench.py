@@ -247,12 +247,13 @@ def run_b200(args, wl):
         hb = []
         for s in range(S):
             h_in = pin((B, H, W, 3)); h_in.numpy()[:] = rings[s]["host"]
-            hb.append(dict(inp=h_in.numpy(), out=pin((B, H, W, 3)).numpy(), yuyv=pin((B, H, W, 2)).numpy(), keep=h_in))
+            hb.append(dict(inp=h_in.numpy(), yuyv=pin((B, H, W, 2)).numpy(), keep=h_in))
         e_steps = max(3, args.steps // 2)
 
         def worker(s, n):
             for _ in range(n):
-                ctxs[s].composite_into(hb[s]["inp"], out=hb[s]["out"], yuyv=hb[s]["yuyv"])
+                # the frame deepseg.cc hands to the loopback device is the YUYV one (app/deepseg.cc:681-690)
+                ctxs[s].composite_into(hb[s]["inp"], yuyv=hb[s]["yuyv"])
 
         def run_threads(n):
             th = [threading.Thread(target=worker, args=(s, n)) for s in range(S)]
@@ -270,7 +271,8 @@ def run_b200(args, wl):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * fb,
-               "d2h_bytes_per_step": S * B * (fb + npx * 2), "steps": e_steps}
+               "d2h_bytes_per_step": S * B * npx * 2, "steps": e_steps,
+               "result": "YUYV frame (what app/deepseg.cc:681-690 writes to the v4l2 loopback device)"}
 
     # ---- per-stage device times + roofline of the HBM-bound blur+composite kernel ----
     stages = {}

@@ -14,8 +14,12 @@ if [ "${1:-}" = "ncu" ]; then
       python bench.py --steps 2 --warmup 1 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
   tail -3 gpurun_out/ncu_list.log
   echo "== ncu full: k_post"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_post -s 2 -c 2 -f -o gpurun_out/prof_post \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_post -s 2 -c 1 -f -o gpurun_out/prof_post \
       python bench.py --steps 2 --warmup 1 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_post.log 2>&1
-  tail -3 gpurun_out/ncu_post.log
+  tail -2 gpurun_out/ncu_post.log
+  echo "== ncu full: CNN kernels"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_pointwise_rows|k_depthwise_strip|k_conv_direct|k_tconv2x2|k_bilateral" -s 40 -c 12 -f -o gpurun_out/prof_cnn \
+      python bench.py --steps 2 --warmup 1 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_cnn.log 2>&1
+  tail -2 gpurun_out/ncu_cnn.log
 fi
 ls -la gpurun_out
