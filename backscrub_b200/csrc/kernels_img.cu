@@ -326,6 +326,14 @@ BSB_D uint4 ldg_stream(const uint8_t* p) {
   return r;
 #endif
 }
+BSB_D void prefetch_l2(const uint8_t* p) {
+#if !defined(BSB_EMU)
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 32));
+#else
+  (void)p;
+#endif
+}
 BSB_D void stg_stream(uint8_t* p, uint4 v) {
 #if defined(BSB_EMU)
   *reinterpret_cast<uint4*>(p) = v;
@@ -349,47 +357,59 @@ BSB_D unsigned blend_px(unsigned g_pair_w, unsigned f_pair_w, unsigned g_single_
 }
 
 template <bool OUT, bool YUYV>
-__global__ void __launch_bounds__(256, 3) k_post_fast(PostArgs a) {
+__global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   __shared__ __align__(16) unsigned short Hs[PF_RMAX * PF_US];
   __shared__ __align__(16) unsigned short Us[PF_UH * PF_US];
   __shared__ __align__(16) unsigned short Vs[PF_H * PF_US];
   __shared__ __align__(16) uint4 rows[PF_UH];     // r0, r1, b0 << 16, b1 << 16
-  __shared__ int rrange[2];
   const int b = blockIdx.z;
   const int tx0 = blockIdx.x * PF_W, ty0 = blockIdx.y * PF_H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + PF_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+  {
+    // pull this thread's 48 bytes of camera frame into L2 while the mask tile is being built
+    const int px0 = tx0 + (tid & 7) * PF_PX, py = ty0 + (tid >> 3);
+    if ((OUT || YUYV) && py < a.H && px0 < a.W) prefetch_l2(a.frames + (size_t)b * a.frame_stride + (size_t)py * a.frame_pitch + (size_t)px0 * 3);
+  }
 
   if (hits_roi) {
-    // ---- A0: row interpolation parameters + range of source rows the tile touches (warp 0) ----
-    if (warp == 0) {
-      int lo = 1 << 30, hi = -1;
-      for (int uy = lane; uy < PF_UH; uy += 32) {
-        const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
-        const int r0 = __ldg(a.tab.yofs0 + gy), r1 = __ldg(a.tab.yofs1 + gy);
-        rows[uy] = make_uint4((unsigned)r0, (unsigned)r1, (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
-        lo = min(lo, r0); hi = max(hi, r1);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-      if (lane == 0) { rrange[0] = lo; rrange[1] = hi - lo + 1; }
-    }
-    __syncthreads();
-    const int rmin = rrange[0], nrows = rrange[1];
-    // ---- A1: horizontal pass of cv::resize for the touched source rows: Hs = (s[sx]*a0 + s[sx1]*a1) >> 4.
-    //      A thread owns a column (parameters in registers) and walks every second source row. ----
+    // ---- A1: horizontal pass of cv::resize for the source rows this tile touches:
+    //      Hs = (s[sx]*a0 + s[sx1]*a1) >> 4.  yofs0/yofs1 are monotonic in gy, so the touched range
+    //      follows from the smallest / largest (reflected) gy of the tile — no reduction needed.
+    //      A thread owns a column (parameters in registers) and walks every second source row with all
+    //      of its loads in flight; 36 other threads fetch the row parameters for A2 meanwhile. ----
+    const int gy_lo = ty0 - a.roi_y - 2, gy_hi = gy_lo + PF_UH - 1;
+    const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
+    const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
+    const int rmin = __ldg(a.tab.yofs0 + gy_min);
+    const int nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
     {
       const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
       const int phase = tid >> 7;
+      if (tid >= 192 && tid < 192 + PF_UH) {
+        const int uy = tid - 192;
+        const int gy = bsb_reflect101(gy_lo + uy, a.roi_h);
+        rows[uy] = make_uint4((unsigned)__ldg(a.tab.yofs0 + gy), (unsigned)__ldg(a.tab.yofs1 + gy),
+                              (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
+      }
       for (int ux = tid & 127; ux < PF_UW; ux += 128) {
         const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + ux, a.roi_w);
         const int sx = __ldg(a.tab.xofs + gx), sx1 = min(sx + 1, a.out_w - 1);
         const int a0 = __ldg(a.tab.xw + 2 * gx), a1 = __ldg(a.tab.xw + 2 * gx + 1);
         const uint8_t* srow = src + (size_t)(rmin + phase) * a.ow;
         unsigned short* hp = Hs + phase * PF_US + ux;
-        for (int r = phase; r < nrows; r += 2) {
-          *hp = (unsigned short)(((int)srow[sx] * a0 + (int)srow[sx1] * a1) >> 4);
-          srow += 2 * a.ow; hp += 2 * PF_US;
+        for (int r0 = phase; r0 < nrows; r0 += 16) {
+          int p0[8], p1[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const bool ok = r0 + 2 * k < nrows;
+            p0[k] = ok ? (int)srow[(size_t)(2 * k) * a.ow + sx] : 0;
+            p1[k] = ok ? (int)srow[(size_t)(2 * k) * a.ow + sx1] : 0;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (r0 + 2 * k < nrows) hp[2 * k * PF_US] = (unsigned short)((p0[k] * a0 + p1[k] * a1) >> 4);
+          srow += (size_t)16 * a.ow; hp += 16 * PF_US;
         }
       }
     }

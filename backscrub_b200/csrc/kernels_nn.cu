@@ -236,7 +236,7 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
                       const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
                       const float* in_scale, int rows_per_frame, const float* in_add, int ld_add) {
   PWArgs a{A, w_kn, out, in_scale, in_add, M, K, N, n4, ld_a, ld_out, rows_per_frame > 0 ? rows_per_frame : 1, ld_add, to_dev(e)};
-  if (K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 4096) {
+  if (K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 65536) {
     const int ct = n4 / 4, rows_per_block = 256 / ct;
     long blocks = ((long)M + rows_per_block - 1) / rows_per_block;
     if (blocks > 148L * 16) blocks = 148L * 16;             // grid-stride: a few waves of 148 SMs
@@ -373,6 +373,7 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
   const bool vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0);
   if (vec && dil_h == 1 && dil_w == 1 && kh == kw && stride_h == stride_w && (kh == 3 || kh == 5) && (stride_h == 1 || stride_h == 2)) {
     const long nthreads = (long)B * oh * ((ow + 3) / 4) * (c / 4);
+    if (nthreads >= 148L * 1024) {   // enough strips to fill the GPU; small layers keep one pixel per thread
     const dim3 grid((unsigned)((nthreads + 127) / 128)), block(128);
     if (kh == 3 && stride_h == 1) { auto k = k_depthwise_strip<3, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
     else if (kh == 3) { auto k = k_depthwise_strip<3, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
@@ -380,6 +381,7 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
     else { auto k = k_depthwise_strip<5, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
     count_launch();
     return;
+    }
   }
   const long total = (long)B * oh * ow * (vec ? c / 4 : c);
   if (vec) BSB_LAUNCH(k_depthwise<4>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
