@@ -189,12 +189,14 @@ def run_b200(args, wl):
     fb, npx = W * H * 3, W * H
     R = 2                                     # ring slots per stream: S*R*B frames in + out exceed the 126 MB L2
     bg = synth.background()
+    from backscrub_b200 import sharding
+    my_streams = sharding.streams_for_rank(world * S, rank, world)      # stream ids served by this GPU
     ctxs, rings = [], []
     for s in range(S):
         c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B)
         c.set_background(bg)
         ctxs.append(c)
-        host = synthetic_frames(W, H, B, stream=rank * S + s)
+        host = synthetic_frames(W, H, B, stream=my_streams[s])
         slots = []
         for r in range(R):
             d_in = torch.from_numpy(host).to(f"cuda:{dev}")
@@ -233,12 +235,9 @@ def run_b200(args, wl):
     barrier()
     ms = max(ev0.elapsed_time(e) for e in ev1)
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{dev}")
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
-    frames_total = world * S * B * args.steps
-    value = frames_total / (ms * 1e-3)
+    frames_total, secs, value = sharding.reduce_throughput(S * B * args.steps, ms * 1e-3,
+                                                            torch.distributed if world > 1 else None, f"cuda:{dev}")
+    ms = secs * 1e3
 
     # ---- end to end through the host-buffer C-ABI call (H2D + graph + D2H every step) ----
     e2e = None
