@@ -244,7 +244,7 @@ int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst
   cudaMemcpy(t2.p, h.yofs0.data(), (size_t)dh * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(t3.p, h.yofs1.data(), (size_t)dh * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(t4.p, h.yw.data(), (size_t)dh * 4, cudaMemcpyHostToDevice);
-  bsb::ResizeTab tab{(const int*)t0.p, (const short*)t1.p, (const int*)t2.p, (const int*)t3.p, (const short*)t4.p};
+  bsb::ResizeTab tab{(const int*)t0.p, (const short*)t1.p, (const int*)t2.p, (const int*)t3.p, (const short*)t4.p, nullptr};
   bsb::launch_resize_u8c3(nullptr, a.u8(), sw, sh, (size_t)sw * 3, o.u8(), dw, dh, (size_t)dw * 3, tab, h.area2x2);
   if (!stage_end()) return 0;
   cudaMemcpy(dst, o.p, db, cudaMemcpyDeviceToHost);

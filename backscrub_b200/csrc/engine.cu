@@ -22,6 +22,7 @@ namespace bsb {
 // ---------------------------------------------------------------------------
 HostResizeTab build_resize_tab(int sw, int sh, int dw, int dh) {
   HostResizeTab t;
+  t.sw = sw;
   t.area2x2 = (sw == dw * 2 && sh == dh * 2);
   const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
   t.xofs.resize(dw); t.xw.resize(2 * (size_t)dw);
@@ -52,8 +53,18 @@ static bool upload_tab(const HostResizeTab& h, DevResizeTab* d, std::string* err
   const size_t nx = h.xofs.size(), ny = h.yofs0.size();
   auto al = [](size_t n) { return (n + 15) / 16 * 16; };
   const size_t o_xofs = 0, o_y0 = o_xofs + al(nx * 4), o_y1 = o_y0 + al(ny * 4), o_xw = o_y1 + al(ny * 4), o_yw = o_xw + al(nx * 4);
-  const size_t total = o_yw + al(ny * 4);
+  const size_t o_xcol = o_yw + al(ny * 4);
+  const size_t total = o_xcol + al(nx * 8);
   std::vector<uint8_t> blob(total, 0);
+  {
+    std::vector<uint32_t> xc(2 * nx);
+    for (size_t i = 0; i < nx; ++i) {
+      const int sx = h.xofs[i], sx1 = std::min(sx + 1, h.sw - 1);
+      xc[2 * i] = (uint32_t)sx | ((uint32_t)sx1 << 16);
+      xc[2 * i + 1] = (uint32_t)(uint16_t)h.xw[2 * i] | ((uint32_t)(uint16_t)h.xw[2 * i + 1] << 16);
+    }
+    std::memcpy(blob.data() + o_xcol, xc.data(), nx * 8);
+  }
   std::memcpy(blob.data() + o_xofs, h.xofs.data(), nx * 4);
   std::memcpy(blob.data() + o_y0, h.yofs0.data(), ny * 4);
   std::memcpy(blob.data() + o_y1, h.yofs1.data(), ny * 4);
@@ -68,6 +79,7 @@ static bool upload_tab(const HostResizeTab& h, DevResizeTab* d, std::string* err
   d->tab.yofs1 = reinterpret_cast<const int*>(b + o_y1);
   d->tab.xw = reinterpret_cast<const short*>(b + o_xw);
   d->tab.yw = reinterpret_cast<const short*>(b + o_yw);
+  d->tab.xcol = reinterpret_cast<const uint2*>(b + o_xcol);
   d->area2x2 = h.area2x2;
   return true;
 }
@@ -401,6 +413,11 @@ bool Engine::plan(std::string* err) {
   }
   arena_elems_ = top;
 
+  {
+    const Step& s0 = steps_[0];
+    stem_u8_ok_ = s0.kind == Step::CONV && s0.in == g_.input && s0.K == 3 && s0.N == 16 && s0.dh == 1 && s0.dw == 1 &&
+                  consumers[g_.input].size() == 1 && tinfo_[s0.out].ld % 4 == 0 && s0.residual < 0;
+  }
   // algorithmic FLOPs (2*MAC of conv / depthwise / fc / tconv), SURVEY.md Appendix A
   flops_ = 0;
   for (const GOp& O : g_.ops) {
@@ -495,7 +512,7 @@ bool Engine::upload(std::string* err) {
   const size_t in_px = (size_t)mh_ * mw_, out_px = (size_t)oh_ * ow_, fpx = (size_t)W_ * H_;
   CUDA_OK(cudaMalloc((void**)&in_u8_, B * in_px * 3));
   CUDA_OK(cudaMemset(in_u8_, 0, B * in_px * 3));      // zero padding outside in_roidim stays zero
-  if (flags_ & 1u) { CUDA_OK(cudaMalloc((void**)&filt_u8_, B * in_px * 3)); }
+  CUDA_OK(cudaMalloc((void**)&filt_u8_, B * in_px * 3));
   CUDA_OK(cudaMalloc((void**)&state_, out_px));
   CUDA_OK(cudaMemset(state_, 0, out_px));
   CUDA_OK(cudaMalloc((void**)&ofinal_, B * out_px));
@@ -533,11 +550,16 @@ Engine::~Engine() {
 void Engine::enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride) {
   launch_resize_roi_swap(stream_, n, d_frames, stride, pitch, roidim_[0], roidim_[1], roidim_[2], roidim_[3], tab_in_.tab,
                          in_u8_, mw_, mh_, in_roidim_[0], in_roidim_[1], in_roidim_[2], in_roidim_[3], tab_in_.area2x2);
-  launch_bilateral_norm(stream_, n, in_u8_, mw_, mh_, lut_, lut_ + 768, scaling_, offset_, tptr(g_.input), filt_u8_);
+  // with the fused stem the fp32 input tensor is only materialised for introspection (KEEP_TENSORS)
+  float* f32 = (stem_u8_ok_ && !(flags_ & 1u)) ? nullptr : tptr(g_.input);
+  launch_bilateral_norm(stream_, n, in_u8_, mw_, mh_, lut_, lut_ + 768, scaling_, offset_, f32, filt_u8_);
 }
 
-void Engine::enqueue_cnn(int n) {
+void Engine::enqueue_cnn(int n, bool from_u8) {
+  bool first = true;
   for (const Step& st : steps_) {
+    const bool fused_stem = first && from_u8 && stem_u8_ok_;
+    first = false;
     const TensorInfo& I = tinfo_[st.in];
     const TensorInfo& O = tinfo_[st.out];
     Epilogue e;
@@ -546,6 +568,11 @@ void Engine::enqueue_cnn(int n) {
     if (st.residual >= 0) { e.residual = tptr(st.residual); e.ld_res = tinfo_[st.residual].ld; }
     switch (st.kind) {
       case Step::CONV:
+        if (fused_stem) {
+          launch_stem_u8(stream_, n, filt_u8_, I.h, I.w, scaling_, offset_, wblob_ + st.w_off, st.kh, st.kw, st.sh, st.sw, st.pt, st.pl,
+                         tptr(st.out), O.h, O.w, O.ld, e);
+          break;
+        }
         launch_conv_direct(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, wblob_ + st.w_off, st.N, st.kh, st.kw, st.sh, st.sw,
                            st.dh, st.dw, st.pt, st.pl, tptr(st.out), O.h, O.w, O.ld, e);
         break;
@@ -618,7 +645,7 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
   if (eager) {
     enqueue_pre(n, d_frames, pitch, stride);
     if (cbs && cb_.onprep) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onprep(cb_.caller_ctx); }
-    enqueue_cnn(n);
+    enqueue_cnn(n, true);
     if (cbs && cb_.oninfer) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.oninfer(cb_.caller_ctx); }
     enqueue_decision(n);
     if (cbs && cb_.onmask) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onmask(cb_.caller_ctx); }
@@ -634,7 +661,7 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
     enqueue_pre(n, d_frames, pitch, stride);
-    enqueue_cnn(n);
+    enqueue_cnn(n, true);
     enqueue_decision(n);
     enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride);
     CUDA_OK(cudaStreamEndCapture(stream_, &graph));
@@ -653,7 +680,7 @@ bool Engine::infer(int n, const float* h_in, float* h_out, std::string* err) {
   CUDA_OK(cudaSetDevice(device_));
   const TensorInfo& I = tinfo_[g_.input]; const TensorInfo& O = tinfo_[g_.output];
   CUDA_OK(cudaMemcpyAsync(tptr(g_.input), h_in, (size_t)n * I.frame_elems * 4, cudaMemcpyHostToDevice, stream_));
-  enqueue_cnn(n);
+  enqueue_cnn(n, false);
   CUDA_OK(cudaMemcpyAsync(h_out, tptr(g_.output), (size_t)n * O.frame_elems * 4, cudaMemcpyDeviceToHost, stream_));
   CUDA_OK(cudaStreamSynchronize(stream_));
   CUDA_OK(cudaGetLastError());
@@ -706,7 +733,7 @@ double Engine::time_stage(int stage, int n, int iters, std::string* err) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto once = [&]() {
     if (stage == 0 || stage == 4) enqueue_pre(n, d_frames_, row, fbytes);
-    if (stage == 1 || stage == 4) enqueue_cnn(n);
+    if (stage == 1 || stage == 4) enqueue_cnn(n, true);
     if (stage == 2 || stage == 4) enqueue_decision(n);
     if (stage == 3 || stage == 4) enqueue_post(n, d_frames_, row, fbytes, d_out_, fbytes, d_yuyv_, npix * 2, d_mask_, npix);
   };

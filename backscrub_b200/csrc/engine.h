@@ -50,6 +50,7 @@ struct HostResizeTab {
   std::vector<int> xofs, yofs0, yofs1;
   std::vector<short> xw, yw;
   bool area2x2 = false;
+  int sw = 0;
 };
 // OpenCV INTER_LINEAR 8-bit coefficient tables for sw x sh -> dw x dh
 HostResizeTab build_resize_tab(int sw, int sh, int dw, int dh);
@@ -109,7 +110,7 @@ class Engine {
   bool plan(std::string* err);
   bool upload(std::string* err);
   void enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride);
-  void enqueue_cnn(int n);
+  void enqueue_cnn(int n, bool from_u8);
   void enqueue_decision(int n);
   void enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
                     uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride);
@@ -132,6 +133,7 @@ class Engine {
   std::vector<Step> steps_;
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
+  bool stem_u8_ok_ = false;          // step 0 is a 3->16 dense conv that is the only reader of the graph input
 
   // device memory
   cudaStream_t stream_ = nullptr;

@@ -25,6 +25,12 @@ void launch_conv_direct(cudaStream_t s, int B, const float* in, int ih, int iw, 
                         int dil_h, int dil_w, int pad_t, int pad_l,
                         float* out, int oh, int ow, int ld_out, const Epilogue& e);
 
+// Stem variant that reads the bilateral-filtered u8 image directly and applies convertTo's
+// fmaf(u8, scale, offset) on the fly (identical values, no fp32 input tensor round trip).  oc == 16, ic == 3.
+void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw, float scale, float offset,
+                    const float* w_t, int kh, int kw, int stride_h, int stride_w, int pad_t, int pad_l,
+                    float* out, int oh, int ow, int ld_out, const Epilogue& e);
+
 // 1x1 convolution / fully-connected as a GEMM: out[M][N] = A[M][K] * w_kn[K][N4] (+ epilogue).
 // in_scale (optional): [B][K] per-frame channel scale applied to A on load (folded SE MUL);
 // in_add (optional): tensor added after the scale (folded ADD), same layout as A.
@@ -71,6 +77,7 @@ struct ResizeTab {        // OpenCV INTER_LINEAR 8-bit tables (device pointers)
   const int* yofs0;       // [dh] clamped row r0
   const int* yofs1;       // [dh] clamped row r1
   const short* yw;        // [dh][2]
+  const uint2* xcol;      // [dw] packed {sx | sx1 << 16, a0 | a1 << 16} (sx1 = min(sx + 1, sw - 1))
 };
 
 // lib/libbackscrub.cc:285-290: ROI crop -> cv::resize(INTER_LINEAR) -> BGR2RGB, into the

@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(256) k_bilateral_norm(int B, const uint8_t* in
   }
   const float inv = bsb_div(1.f, wsum);
   const int r0 = bsb_sat_u8(__float2int_rn(s0 * inv)), r1 = bsb_sat_u8(__float2int_rn(s1 * inv)), r2 = bsb_sat_u8(__float2int_rn(s2 * inv));
-  float* o = out_f32 + (size_t)idx * 3;
-  o[0] = fmaf((float)r0, scale, offset);
-  o[1] = fmaf((float)r1, scale, offset);
-  o[2] = fmaf((float)r2, scale, offset);
+  if (out_f32) {
+    float* o = out_f32 + (size_t)idx * 3;
+    o[0] = fmaf((float)r0, scale, offset);
+    o[1] = fmaf((float)r1, scale, offset);
+    o[2] = fmaf((float)r2, scale, offset);
+  }
   if (out_u8) { uint8_t* u = out_u8 + (size_t)idx * 3; u[0] = (uint8_t)r0; u[1] = (uint8_t)r1; u[2] = (uint8_t)r2; }
 }
 
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
 //       16-byte streaming loads / stores.
 // ---------------------------------------------------------------------------
 constexpr int PF_W = 128, PF_H = 32, PF_PX = 16;
-constexpr int PF_UW = PF_W + 4, PF_UH = PF_H + 4, PF_US = 136, PF_RMAX = 40;
+constexpr int PF_UW = PF_W + 4, PF_UH = PF_H + 4, PF_US = 136, PF_RMAX = 40, PF_PS = 144;
 
 BSB_D uint4 ldg_stream(const uint8_t* p) {
 #if defined(BSB_EMU)
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   __shared__ __align__(16) unsigned short Us[PF_UH * PF_US];
   __shared__ __align__(16) unsigned short Vs[PF_H * PF_US];
   __shared__ __align__(16) uint4 rows[PF_UH];     // r0, r1, b0 << 16, b1 << 16
+  __shared__ __align__(16) uint8_t Ps[PF_RMAX * PF_PS];   // source patch of the small mask
   const int b = blockIdx.z;
   const int tx0 = blockIdx.x * PF_W, ty0 = blockIdx.y * PF_H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -373,43 +376,49 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   }
 
   if (hits_roi) {
-    // ---- A1: horizontal pass of cv::resize for the source rows this tile touches:
-    //      Hs = (s[sx]*a0 + s[sx1]*a1) >> 4.  yofs0/yofs1 are monotonic in gy, so the touched range
-    //      follows from the smallest / largest (reflected) gy of the tile — no reduction needed.
-    //      A thread owns a column (parameters in registers) and walks every second source row with all
-    //      of its loads in flight; 36 other threads fetch the row parameters for A2 meanwhile. ----
+    // yofs0/yofs1/xofs are monotonic, so the source patch this tile touches follows from the smallest /
+    // largest (reflected) destination coordinates of the tile — no reduction needed.
     const int gy_lo = ty0 - a.roi_y - 2, gy_hi = gy_lo + PF_UH - 1;
     const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
     const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
+    const int gx_lo = tx0 - a.roi_x - 2, gx_hi = gx_lo + PF_UW - 1;
+    const int gx_min = gx_lo < 0 ? 0 : min(gx_lo, a.roi_w - 1);
+    const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
     const int rmin = __ldg(a.tab.yofs0 + gy_min);
     const int nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
+    const int cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
+    const int ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
+    // ---- P: source patch of the small mask -> shared memory (coalesced); row parameters for A2 ----
     {
-      const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
-      const int phase = tid >> 7;
+      const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)(a.out_y + rmin) * a.ow + a.out_x + cmin;
+      for (int r = warp; r < nrows; r += 8)
+        for (int c = lane; c < ncols; c += 32) Ps[r * PF_PS + c] = src[(size_t)r * a.ow + c];
       if (tid >= 192 && tid < 192 + PF_UH) {
         const int uy = tid - 192;
-        const int gy = bsb_reflect101(gy_lo + uy, a.roi_h);
+        int gy = gy_lo + uy;
+        gy = gy < 0 ? -gy : gy; gy = gy >= a.roi_h ? 2 * a.roi_h - 2 - gy : gy;     // reflect-101 (single fold)
+        gy = min(max(gy, 0), a.roi_h - 1);
         rows[uy] = make_uint4((unsigned)__ldg(a.tab.yofs0 + gy), (unsigned)__ldg(a.tab.yofs1 + gy),
                               (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
       }
+    }
+    __syncthreads();
+    // ---- A1: horizontal pass of cv::resize on the patch rows: Hs = (s[sx]*a0 + s[sx1]*a1) >> 4.
+    //      A thread owns a column (parameters in registers) and walks every second patch row. ----
+    {
+      const int phase = tid >> 7;
       for (int ux = tid & 127; ux < PF_UW; ux += 128) {
-        const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + ux, a.roi_w);
-        const int sx = __ldg(a.tab.xofs + gx), sx1 = min(sx + 1, a.out_w - 1);
-        const int a0 = __ldg(a.tab.xw + 2 * gx), a1 = __ldg(a.tab.xw + 2 * gx + 1);
-        const uint8_t* srow = src + (size_t)(rmin + phase) * a.ow;
+        int gx = gx_lo + ux;
+        gx = gx < 0 ? -gx : gx; gx = gx >= a.roi_w ? 2 * a.roi_w - 2 - gx : gx;
+        gx = min(max(gx, 0), a.roi_w - 1);
+        const uint2 xc = __ldg(a.tab.xcol + gx);
+        const int sx = (int)(xc.x & 0xffffu) - cmin, sx1 = (int)(xc.x >> 16) - cmin;
+        const int a0 = (int)(short)(xc.y & 0xffffu), a1 = (int)(short)(xc.y >> 16);
+        const uint8_t* pr = Ps + phase * PF_PS;
         unsigned short* hp = Hs + phase * PF_US + ux;
-        for (int r0 = phase; r0 < nrows; r0 += 16) {
-          int p0[8], p1[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const bool ok = r0 + 2 * k < nrows;
-            p0[k] = ok ? (int)srow[(size_t)(2 * k) * a.ow + sx] : 0;
-            p1[k] = ok ? (int)srow[(size_t)(2 * k) * a.ow + sx1] : 0;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (r0 + 2 * k < nrows) hp[2 * k * PF_US] = (unsigned short)((p0[k] * a0 + p1[k] * a1) >> 4);
-          srow += (size_t)16 * a.ow; hp += 16 * PF_US;
+        for (int r = phase; r < nrows; r += 2) {
+          *hp = (unsigned short)(((int)pr[sx] * a0 + (int)pr[sx1] * a1) >> 4);
+          pr += 2 * PF_PS; hp += 2 * PF_US;
         }
       }
     }
@@ -498,21 +507,33 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   }
   if (!(OUT || YUYV)) return;
 
-  // ---- D: blend, 4 pixels = 3 words at a time ----
+  // ---- D: blend, 4 pixels = 3 words at a time.  Most 16-pixel runs are entirely background
+  //      (mask 255 -> out = bg) or entirely person (mask 0 -> out = frame): those skip the arithmetic. ----
   unsigned o[12], yy[8];
+  unsigned m_and = m[0], m_or = m[0];
+#pragma unroll
+  for (int i = 1; i < PF_PX; ++i) { m_and &= m[i]; m_or |= m[i]; }
+  const bool all_bg = m_and == 255u, all_fg = m_or == 0u;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const unsigned fA = f[3 * q], fB = f[3 * q + 1], fC = f[3 * q + 2];
     const unsigned gA = g[3 * q], gB = g[3 * q + 1], gC = g[3 * q + 2];
     // T = (c0, c1, c2, -) per pixel
-    const unsigned T0 = blend_px<0x4140, 0x6262, 0x0531>(gA, fA, gA, fA, m[4 * q]);          // A.b0 A.b1 | A.b2
-    const unsigned T1 = blend_px<0x4140, 0x7373, 0x0315>(gB, fB, gA, fA, m[4 * q + 1]);      // B.b0 B.b1 | A.b3 (c0)
-    const unsigned T2 = blend_px<0x4342, 0x4040, 0x0531>(gB, fB, gC, fC, m[4 * q + 2]);      // B.b2 B.b3 | C.b0
-    const unsigned T3 = blend_px<0x4241, 0x7373, 0x0531>(gC, fC, gC, fC, m[4 * q + 3]);      // C.b1 C.b2 | C.b3
-    if (OUT) {
-      o[3 * q] = __byte_perm(T0, T1, 0x4210);
-      o[3 * q + 1] = __byte_perm(T1, T2, 0x5421);
-      o[3 * q + 2] = __byte_perm(T2, T3, 0x6542);
+    unsigned T0, T1, T2, T3;
+    if (all_bg || all_fg) {
+      const unsigned sA = all_bg ? gA : fA, sB = all_bg ? gB : fB, sC = all_bg ? gC : fC;
+      T0 = sA; T1 = __byte_perm(sA, sB, 0x0543); T2 = __byte_perm(sB, sC, 0x0432); T3 = sC >> 8;
+      if (OUT) { o[3 * q] = sA; o[3 * q + 1] = sB; o[3 * q + 2] = sC; }
+    } else {
+      T0 = blend_px<0x4140, 0x6262, 0x0531>(gA, fA, gA, fA, m[4 * q]);          // A.b0 A.b1 | A.b2
+      T1 = blend_px<0x4140, 0x7373, 0x0315>(gB, fB, gA, fA, m[4 * q + 1]);      // B.b0 B.b1 | A.b3 (c0)
+      T2 = blend_px<0x4342, 0x4040, 0x0531>(gB, fB, gC, fC, m[4 * q + 2]);      // B.b2 B.b3 | C.b0
+      T3 = blend_px<0x4241, 0x7373, 0x0531>(gC, fC, gC, fC, m[4 * q + 3]);      // C.b1 C.b2 | C.b3
+      if (OUT) {
+        o[3 * q] = __byte_perm(T0, T1, 0x4210);
+        o[3 * q + 1] = __byte_perm(T1, T2, 0x5421);
+        o[3 * q + 2] = __byte_perm(T2, T3, 0x6542);
+      }
     }
     if (YUYV) {
       const unsigned T[4] = {T0, T1, T2, T3};
@@ -548,10 +569,12 @@ static bool post_fast_ok(const PostArgs& a) {
   if (a.out && (!al16(a.out) || a.out_pitch % 16 || a.out_stride % 16)) return false;
   if (a.yuyv && (!al16(a.yuyv) || a.yuyv_stride % 16)) return false;
   if (a.mask && (!al16(a.mask) || a.mask_stride % 16)) return false;
-  if (a.ow > 32000 || a.oh > 32000) return false;
+  if (a.ow > 32000 || a.oh > 32000 || a.roi_w < 8 || a.roi_h < 8) return false;
   // source rows touched by one 36-row tile must fit the Hs buffer: ceil(36 * scale) + 2
   const double scale_y = (double)a.out_h / (double)a.roi_h;
   if ((int)(PF_UH * scale_y) + 3 > PF_RMAX) return false;
+  const double scale_x = (double)a.out_w / (double)a.roi_w;
+  if ((int)(PF_UW * scale_x) + 4 > PF_PS || a.tab.xcol == nullptr) return false;
   return true;
 }
 

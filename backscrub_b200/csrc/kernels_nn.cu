@@ -95,6 +95,69 @@ void launch_conv_direct(cudaStream_t s, int B, const float* in, int ih, int iw, 
 }
 
 // ---------------------------------------------------------------------------
+// Stem conv on the u8 image: one thread = one output pixel x all 16 output channels.
+// Each tap value is fmaf((float)u8, scale, offset) — exactly what convertTo stores — and the
+// accumulation order is the reference's (fy, fx, c).
+// ---------------------------------------------------------------------------
+struct StemArgs {
+  const uint8_t* in; const float* w; float* out;
+  int B, ih, iw, kh, kw, sh, sw, pt, pl, oh, ow, ld_out;
+  float scale, offset;
+  EpiDev e;
+};
+
+__global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
+  BSB_DYN_SMEM(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw);     // [kh][kw][3][16]
+  const int wcount = a.kh * a.kw * 3 * 16;
+  for (int i = threadIdx.x; i < wcount; i += blockDim.x) ws[i] = __ldg(a.w + i);
+  __syncthreads();
+  const long total = (long)a.B * a.oh * a.ow;
+  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int ox = (int)(pix % a.ow), oy = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
+  const uint8_t* inb = a.in + (size_t)b * a.ih * a.iw * 3;
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+  const int iy0 = oy * a.sh - a.pt, ix0 = ox * a.sw - a.pl;
+  for (int fy = 0; fy < a.kh; ++fy) {
+    const int iy = iy0 + fy;
+    if (iy < 0 || iy >= a.ih) continue;
+    for (int fx = 0; fx < a.kw; ++fx) {
+      const int ix = ix0 + fx;
+      if (ix < 0 || ix >= a.iw) continue;
+      const uint8_t* ip = inb + ((size_t)iy * a.iw + ix) * 3;
+      const float* wp = ws + (fy * a.kw + fx) * 48;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = fmaf((float)ip[c], a.scale, a.offset);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + c * 16 + q * 4);
+          acc[4 * q] = fmaf(v, w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  float* op = a.out + (size_t)pix * a.ld_out;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<float4*>(op + 4 * q) = make_float4(epilogue(acc[4 * q], 4 * q, (size_t)pix, a.e), epilogue(acc[4 * q + 1], 4 * q + 1, (size_t)pix, a.e),
+                                                         epilogue(acc[4 * q + 2], 4 * q + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], 4 * q + 3, (size_t)pix, a.e));
+}
+
+void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw, float scale, float offset,
+                    const float* w_t, int kh, int kw, int stride_h, int stride_w, int pad_t, int pad_l,
+                    float* out, int oh, int ow, int ld_out, const Epilogue& e) {
+  StemArgs a{in_u8, w_t, out, B, ih, iw, kh, kw, stride_h, stride_w, pad_t, pad_l, oh, ow, ld_out, scale, offset, to_dev(e)};
+  const long total = (long)B * oh * ow;
+  BSB_LAUNCH(k_stem_u8, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * (size_t)kh * kw * 48, s, a);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
 // Pointwise (1x1) conv / fully connected as a shared-memory tiled FFMA GEMM.
 //   out[m][n] = epilogue( sum_k A'[m][k] * W[k][n] ),  A' = A (* scale[frame][k]) (+ add[m][k])
 // 256 threads; thread tile TM rows x 4 cols; K consumed in ascending chunks of 16 so each
@@ -545,33 +608,44 @@ void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int 
 // (the order in which lib/transpose_conv_bias.cc:80-108 scatters into one output).
 // One thread = one output pixel; weights in shared memory.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tconv2x2(const float* in, int B, int ih, int iw, int ic, int ld_in,
+// One thread = one INPUT pixel: its ic values are loaded once (float4) and produce the 2x2 x oc
+// outputs it alone determines.
+__global__ void __launch_bounds__(128) k_tconv2x2(const float* in, int B, int ih, int iw, int ic, int ld_in,
                                                   const float* w, const float* bias, int oc,
                                                   float* out, int oh, int ow, int ld_out, int act2) {
   BSB_DYN_SMEM(smem_raw);
   float* ws = reinterpret_cast<float*>(smem_raw);    // [oc][2][2][ic]
   for (int i = threadIdx.x; i < oc * 4 * ic; i += blockDim.x) ws[i] = __ldg(w + i);
   __syncthreads();
-  const long total = (long)B * oh * ow;
+  const long total = (long)B * ih * iw;
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total) return;
-  const int x = (int)(pix % ow), y = (int)((pix / ow) % oh), b = (int)(pix / ((long)ow * oh));
-  const int iy = y >> 1, ix = x >> 1, fy = y & 1, fx = x & 1;
-  if (iy >= ih || ix >= iw) return;
-  const float* ip = in + ((size_t)b * ih * iw + (size_t)iy * iw + ix) * ld_in;
-  float* op = out + (size_t)pix * ld_out;
-  for (int o = 0; o < oc; ++o) {
-    const float* wp = ws + ((o * 2 + fy) * 2 + fx) * ic;
-    float acc = __ldg(bias + o);
-    for (int c = 0; c < ic; ++c) acc = fmaf(__ldg(ip + c), wp[c], acc);
-    op[o] = bsb_act(acc, act2);
-  }
+  const int ix = (int)(pix % iw), iy = (int)((pix / iw) % ih), b = (int)(pix / ((long)iw * ih));
+  const float* ip = in + (size_t)pix * ld_in;
+  const bool vec = (ic % 4 == 0) && (ld_in % 4 == 0);
+  for (int fy = 0; fy < 2; ++fy)
+    for (int fx = 0; fx < 2; ++fx) {
+      float* op = out + (((size_t)b * oh + 2 * iy + fy) * ow + 2 * ix + fx) * ld_out;
+      for (int o = 0; o < oc; ++o) {
+        const float* wp = ws + ((o * 2 + fy) * 2 + fx) * ic;
+        float acc = __ldg(bias + o);
+        if (vec) {
+          for (int c = 0; c < ic; c += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(ip + c));
+            acc = fmaf(v.x, wp[c], acc); acc = fmaf(v.y, wp[c + 1], acc); acc = fmaf(v.z, wp[c + 2], acc); acc = fmaf(v.w, wp[c + 3], acc);
+          }
+        } else {
+          for (int c = 0; c < ic; ++c) acc = fmaf(__ldg(ip + c), wp[c], acc);
+        }
+        op[o] = bsb_act(acc, act2);
+      }
+    }
 }
 
 void launch_tconv2x2(cudaStream_t s, int B, const float* in, int ih, int iw, int ic, int ld_in,
                      const float* w, const float* bias, int oc, float* out, int oh, int ow, int ld_out, int act2) {
-  const long total = (long)B * oh * ow;
-  BSB_LAUNCH(k_tconv2x2, dim3((unsigned)((total + 255) / 256)), dim3(256), sizeof(float) * (size_t)oc * 4 * ic, s,
+  const long total = (long)B * ih * iw;
+  BSB_LAUNCH(k_tconv2x2, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * (size_t)oc * 4 * ic, s,
              in, B, ih, iw, ic, ld_in, w, bias, oc, out, oh, ow, ld_out, act2);
   count_launch();
 }
