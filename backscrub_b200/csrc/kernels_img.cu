@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   const int tx0 = blockIdx.x * PF_W, ty0 = blockIdx.y * PF_H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + PF_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+  int tile_const = -1;                       // 255 / 0 when the whole mask tile is known to be constant
   {
     // pull this thread's 48 bytes of camera frame into L2 while the mask tile is being built
     const int px0 = tx0 + (tid & 7) * PF_PX, py = ty0 + (tid >> 3);
@@ -388,11 +389,18 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
     const int nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
     const int cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
     const int ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
-    // ---- P: source patch of the small mask -> shared memory (coalesced); row parameters for A2 ----
+    // ---- P: source patch of the small mask -> shared memory (coalesced); row parameters for A2.
+    //      If every source pixel of the patch is 255 (or 0) the upsampled + blurred tile is 255 (or 0)
+    //      whatever the interpolation weights are (their sums are 2048 +- 1), so A1/A2/B are skipped. ----
+    unsigned p_and = 255u, p_or = 0u;
     {
       const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)(a.out_y + rmin) * a.ow + a.out_x + cmin;
       for (int r = warp; r < nrows; r += 8)
-        for (int c = lane; c < ncols; c += 32) Ps[r * PF_PS + c] = src[(size_t)r * a.ow + c];
+        for (int c = lane; c < ncols; c += 32) {
+          const unsigned v = src[(size_t)r * a.ow + c];
+          Ps[r * PF_PS + c] = (uint8_t)v;
+          p_and &= v; p_or |= v;
+        }
       if (tid >= 192 && tid < 192 + PF_UH) {
         const int uy = tid - 192;
         int gy = gy_lo + uy;
@@ -402,7 +410,10 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
                               (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
       }
     }
-    __syncthreads();
+    const int all_hi = __syncthreads_and(p_and == 255u);
+    const int all_lo = all_hi ? 0 : __syncthreads_and(p_or == 0u);
+    tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
+    if (tile_const < 0) {
     // ---- A1: horizontal pass of cv::resize on the patch rows: Hs = (s[sx]*a0 + s[sx1]*a1) >> 4.
     //      A thread owns a column (parameters in registers) and walks every second patch row. ----
     {
@@ -451,6 +462,7 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
       for (int k = 1; k < 8; ++k) { v = v + u[k + 4] - u[k - 1]; vp[k * (PF_US / 2)] = v; }
     }
     __syncthreads();
+    }
   }
 
   const int lx = (tid & 7) * PF_PX, ly = tid >> 3;
@@ -474,7 +486,14 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   // ---- C: horizontal 5-sums on packed lanes -> 16 mask values ----
   unsigned m[PF_PX];
   const bool row_in = hits_roi && y >= a.roi_y && y < a.roi_y + a.roi_h;
-  if (row_in) {
+  if (row_in && tile_const >= 0) {
+#pragma unroll
+    for (int i = 0; i < PF_PX; ++i) m[i] = (unsigned)tile_const;
+    if (x0 < a.roi_x || x0 + PF_PX > a.roi_x + a.roi_w) {
+#pragma unroll
+      for (int i = 0; i < PF_PX; ++i) if (x0 + i < a.roi_x || x0 + i >= a.roi_x + a.roi_w) m[i] = 255u;
+    }
+  } else if (row_in) {
     const uint4* vq = reinterpret_cast<const uint4*>(Vs + ly * PF_US + lx);
     const uint4 q0 = vq[0], q1 = vq[1];
     const uint2 q2 = *reinterpret_cast<const uint2*>(vq + 2);

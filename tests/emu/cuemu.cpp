@@ -33,6 +33,7 @@ struct Fiber {
   State state;
   uint3 tid;
   int lin;
+  int and_gen;
 };
 
 constexpr size_t kStack = 128 * 1024;
@@ -48,6 +49,7 @@ struct Worker {
   std::vector<unsigned> slots;      // per-thread shuffle slots
   std::vector<unsigned char> smem;  // dynamic shared memory
   int nthreads = 0;
+  int and_acc[4] = {1, 1, 1, 1};
 };
 thread_local Worker W;
 
@@ -69,6 +71,7 @@ void yield_to_sched() {
 void run_block_fibers(dim3 block, const std::function<void()>& body) {
   const int n = (int)(block.x * block.y * block.z);
   W.nthreads = n;
+  for (int q = 0; q < 4; ++q) W.and_acc[q] = 1;
   W.body = &body;
   W.fiber_mode = true;
   if ((int)W.fibers.size() < n) W.fibers.resize(n);
@@ -87,6 +90,7 @@ void run_block_fibers(dim3 block, const std::function<void()>& body) {
         f.state = READY;
         f.tid = uint3{x, y, z};
         f.lin = i;
+        f.and_gen = 0;
       }
   for (;;) {
     bool ran = false;
@@ -142,6 +146,18 @@ void syncthreads() {
   if (!W.fiber_mode) throw NeedFibers{};
   W.cur->state = WAIT_BLOCK;
   yield_to_sched();
+}
+
+int syncthreads_and(int pred) {
+  if (!W.fiber_mode) throw NeedFibers{};
+  // four rotating accumulators: a fiber can run at most one call ahead of the slowest one, so the
+  // slot two generations ahead can be reset while this generation is being read.
+  const int gen = W.cur->and_gen++;
+  if (!pred) W.and_acc[gen & 3] = 0;
+  syncthreads();
+  const int r = W.and_acc[gen & 3];
+  W.and_acc[(gen + 2) & 3] = 1;
+  return r;
 }
 
 void syncwarp() {

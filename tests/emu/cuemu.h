@@ -57,6 +57,7 @@ extern thread_local uint3 t_threadIdx, t_blockIdx;
 extern thread_local dim3 t_blockDim, t_gridDim;
 unsigned char* dyn_smem();
 void syncthreads();
+int syncthreads_and(int pred);
 void syncwarp();
 unsigned shfl_exchange(unsigned value, int src_lane_or_delta, int mode, int width);  // mode 0 idx,1 down,2 up,3 xor
 unsigned ballot(int pred);
@@ -72,6 +73,8 @@ static const int warpSize = 32;
 // ---- device intrinsics --------------------------------------------------------
 static inline void __syncthreads() { cuemu::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::syncwarp(); }
+static inline int __syncthreads_and(int pred) { return cuemu::syncthreads_and(pred); }
+static inline int __syncthreads_or(int pred) { return !cuemu::syncthreads_and(!pred); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int lane, int width = 32) {
   unsigned u; static_assert(sizeof(T) == 4, "32-bit shuffles only"); memcpy(&u, &v, 4);
