@@ -21,7 +21,7 @@ SYMBOLS = [
     "bsb_version", "bsb_last_error", "bsb_device_count", "bsb_maskgen_new", "bsb_maskgen_new_ex",
     "bsb_maskgen_delete", "bsb_maskgen_process", "bsb_set_background", "bsb_get_background",
     "bsb_composite", "bsb_composite_device", "bsb_synchronize", "bsb_stream", "bsb_alpha_blend",
-    "bsb_convert_rgb_to_yuyv", "bsb_resize_u8c3", "bsb_geometry", "bsb_infer", "bsb_get_tensor",
+    "bsb_convert_rgb_to_yuyv", "bsb_resize_u8c3", "bsb_pointwise", "bsb_geometry", "bsb_infer", "bsb_get_tensor",
     "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops",
 ]
 
@@ -54,6 +54,7 @@ def bind(path: str) -> C.CDLL:
     L.bsb_alpha_blend.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.bsb_convert_rgb_to_yuyv.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.bsb_resize_u8c3.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.bsb_pointwise.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.bsb_geometry.argtypes = [C.c_void_p, i32p, i32p, i32p, i32p, i32p]
     L.bsb_infer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.bsb_get_tensor.restype = C.c_long

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/backscrub_b200.h"
 #include "engine.h"
@@ -248,6 +249,44 @@ int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst
   bsb::launch_resize_u8c3(nullptr, a.u8(), sw, sh, (size_t)sw * 3, o.u8(), dw, dh, (size_t)dw * 3, tab, h.area2x2);
   if (!stage_end()) return 0;
   cudaMemcpy(dst, o.p, db, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+int bsb_pointwise(int device, int use_tc, int M, int K, int N, const float* A, const float* W, const float* bias, int act, float* out) {
+  if (!A || !W || !out || M <= 0 || K <= 0 || N <= 0) { g_last_error = "invalid argument"; return 0; }
+  if (!stage_begin(device)) return 0;
+  DevBuf dA, dW, dW2, dB, dO;
+  if (!dA.alloc((size_t)M * K * 4) || !dO.alloc((size_t)M * N * 4) || (bias && !dB.alloc((size_t)N * 4))) { g_last_error = "cudaMalloc failed"; return 0; }
+  cudaMemcpy(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice);
+  if (bias) cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
+  bsb::Epilogue e; e.bias = bias ? (const float*)dB.p : nullptr; e.act1 = act;
+  if (use_tc) {
+    const int bn = bsb::pointwise_tc_tile_n(N);
+    if (bn <= 0 || K % 4) { g_last_error = "shape not supported by the tensor-core kernel"; return 0; }
+    const int kpad = (K + 31) / 32 * 32, npad = (N + bn - 1) / bn * bn;
+    std::vector<float> hi((size_t)npad * kpad, 0.f), lo((size_t)npad * kpad, 0.f);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) {
+      const float v = W[(size_t)n * K + k];
+      uint32_t bits; std::memcpy(&bits, &v, 4); bits &= 0xffffe000u;
+      float h; std::memcpy(&h, &bits, 4);
+      hi[(size_t)n * kpad + k] = h; lo[(size_t)n * kpad + k] = v - h;
+    }
+    if (!dW.alloc(hi.size() * 4) || !dW2.alloc(lo.size() * 4)) { g_last_error = "cudaMalloc failed"; return 0; }
+    cudaMemcpy(dW.p, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW2.p, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice);
+    if (!bsb::launch_pointwise_tc(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, (const float*)dW2.p, kpad, npad, (float*)dO.p, N, e)) {
+      g_last_error = "tensor-core launch rejected the shape"; return 0;
+    }
+  } else {
+    const int n4 = (N + 3) / 4 * 4;
+    std::vector<float> wt((size_t)K * n4, 0.f);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) wt[(size_t)k * n4 + n] = W[(size_t)n * K + k];
+    if (!dW.alloc(wt.size() * 4)) { g_last_error = "cudaMalloc failed"; return 0; }
+    cudaMemcpy(dW.p, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice);
+    bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+  }
+  if (!stage_end()) return 0;
+  cudaMemcpy(out, dO.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
   return 1;
 }
 

@@ -171,6 +171,20 @@ bool Engine::plan(std::string* err) {
     for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) wt[(size_t)k * st.n4 + n] = w.f32[(size_t)n * K + k];
     st.w_off = add_blob(wt);
   };
+  // 3xTF32 operand split for the tensor-core path: w = hi + lo, hi = w with the 13 low mantissa bits cleared
+  auto pack_tc_weights = [&](const GTensor& w, int N, int K, Step& st) {
+    const int bn = pointwise_tc_tile_n(N);
+    if (bn <= 0) return;
+    st.kpad = (K + 31) / 32 * 32; st.npad = (N + bn - 1) / bn * bn;
+    std::vector<float> hi((size_t)st.npad * st.kpad, 0.f), lo((size_t)st.npad * st.kpad, 0.f);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) {
+      const float v = w.f32[(size_t)n * K + k];
+      uint32_t bits; std::memcpy(&bits, &v, 4); bits &= 0xffffe000u;
+      float h; std::memcpy(&h, &bits, 4);
+      hi[(size_t)n * st.kpad + k] = h; lo[(size_t)n * st.kpad + k] = v - h;
+    }
+    st.tc_hi_off = add_blob(hi); st.tc_lo_off = add_blob(lo); st.use_tc = true;
+  };
 
   for (int i = 0; i < nops; ++i) {
     const GOp& O = g_.ops[i];
@@ -189,6 +203,10 @@ bool Engine::plan(std::string* err) {
           pack_pw_weights(w, oc, ic, st);
           auto it = prologue.find(st.in);
           if (it != prologue.end()) { st.in = it->second.x; st.scale = it->second.s; st.in_add = it->second.add; }
+          // tensor cores (opt-in): plain GEMM-shaped layers with enough rows and depth to fill a 128 x N x 32 tile pipeline
+          if ((flags_ & 4u) && st.scale < 0 && st.in_add < 0 && ic >= 32 && ic % 4 == 0 && oc >= 8 &&
+              tinfo_[st.in].h * tinfo_[st.in].w >= 1024 && tinfo_[st.in].ld % 4 == 0)
+            pack_tc_weights(w, oc, ic, st);
         } else {
           st.kind = Step::CONV;
           st.kh = kh; st.kw = kw; st.sh = O.stride_h; st.sw = O.stride_w; st.dh = O.dil_h; st.dw = O.dil_w;
@@ -577,6 +595,9 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
                            st.dh, st.dw, st.pt, st.pl, tptr(st.out), O.h, O.w, O.ld, e);
         break;
       case Step::PW:
+        if (st.use_tc && launch_pointwise_tc(stream_, n * I.h * I.w, st.K, st.N, tptr(st.in), I.ld, wblob_ + st.tc_hi_off, wblob_ + st.tc_lo_off,
+                                             st.kpad, st.npad, tptr(st.out), O.ld, e))
+          break;
         launch_pointwise(stream_, n * I.h * I.w, st.K, st.N, tptr(st.in), I.ld, wblob_ + st.w_off, st.n4, tptr(st.out), O.ld, e,
                          st.scale >= 0 ? tptr(st.scale) : nullptr, I.h * I.w,
                          st.in_add >= 0 ? tptr(st.in_add) : nullptr, st.in_add >= 0 ? tinfo_[st.in_add].ld : 0);

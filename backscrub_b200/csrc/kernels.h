@@ -38,6 +38,13 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
                       const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
                       const float* in_scale, int rows_per_frame, const float* in_add, int ld_add);
 
+// Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators) — kernels_tc.cu.
+// w_hi / w_lo: [npad][kpad] zero-padded copies of W[N][K] split as w = hi + lo with hi tf32-representable;
+// kpad % 32 == 0, npad % pointwise_tc_tile_n(N) == 0.  Returns false if the shape is not supported.
+int pointwise_tc_tile_n(int N);
+bool launch_pointwise_tc(cudaStream_t s, int M, int K, int N, const float* A, int ld_a, const float* w_hi, const float* w_lo,
+                         int kpad, int npad, float* out, int ld_out, const Epilogue& e);
+
 // Depthwise KxK (depth multiplier 1).  w: [kh][kw][C].
 void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                       const float* w, int kh, int kw, int stride_h, int stride_w, int dil_h, int dil_w,
