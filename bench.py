@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--workload", default="meet720", choices=list(WORKLOADS))
     ap.add_argument("--streams", type=int, default=2, help="independent streams (contexts) per GPU")
     ap.add_argument("--batch", type=int, default=32, help="consecutive frames per stream per step")
+    ap.add_argument("--tensor-cores", action="store_true", help="tcgen05 3xTF32 pointwise convs (not bit-exact; IoU-validated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -193,7 +194,7 @@ def run_b200(args, wl):
     my_streams = sharding.streams_for_rank(world * S, rank, world)      # stream ids served by this GPU
     ctxs, rings = [], []
     for s in range(S):
-        c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B)
+        c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=4 if args.tensor_cores else 0)
         c.set_background(bg)
         ctxs.append(c)
         host = synthetic_frames(W, H, B, stream=my_streams[s])
@@ -321,7 +322,7 @@ def run_b200(args, wl):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "batch": B, "frames_per_step": world * S * B,
-                       "outputs": "RGB composite + YUYV + mask", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                       "outputs": "RGB composite + YUYV + mask", "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                        "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (2 * fb + 3 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
             "gpu_launches": args.steps * S * c0.launches_per_call,
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stages": stages,
