@@ -102,24 +102,39 @@ __device__ __forceinline__ float tc_epilogue(float total, int ch, size_t pix, co
   return v;
 }
 
-// One CTA = one 128 x BN output tile.  256 threads stage the operands (and build the lo parts),
-// thread 0 issues the MMAs, all 8 warps drain TMEM (warp w reads lane quadrant w % 4, column half w / 4).
+// One CTA = one 128 x BN output tile (BN <= 128).  256 threads.  Three shared-memory stages fed by
+// cp.async (16-byte copies land directly at their swizzled position, two K chunks in flight ahead of the
+// tensor core); per chunk the threads split the A tile in place into hi / lo, thread 0 issues the twelve
+// tcgen05.mma (3 products x 4 K steps) and commits to the stage's mbarrier.  All 8 warps drain TMEM
+// (warp w reads lane quadrant w % 4, column half w / 4) with 16-byte stores.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
+  const int sz = valid ? 16 : 0;                      // src-size 0 => 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 template <int BN>
 __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  constexpr int NS = 3;
   constexpr int A_BYTES = 128 * 128;            // 128 rows x 32 fp32
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bar_free[2];
+  __shared__ __align__(8) uint64_t bar_free[NS];
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
 
-  if (tid == 0) { tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1); tc::mbar_init(&bar_done, 1); tc::fence_barrier_init(); }
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) tc::mbar_init(&bar_free[i], 1);
+    tc::mbar_init(&bar_done, 1);
+    tc::fence_barrier_init();
+  }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
@@ -129,47 +144,66 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const int nchunks = a.kpad / 32;
+  const uint32_t sbase = tc::smem_u32(base);
 
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    uint8_t* sA_hi = base + s * STAGE;
-    uint8_t* sA_lo = sA_hi + A_BYTES;
-    uint8_t* sB_hi = sA_lo + A_BYTES;
-    uint8_t* sB_lo = sB_hi + B_BYTES;
-    if (c >= 2) { tc::mbar_wait(&bar_free[s], (uint32_t)(((c >> 1) - 1) & 1)); tc::tc_fence_after(); }
+  auto issue_loads = [&](int c) {           // global -> shared for K chunk c (A raw, W hi, W lo)
+    const uint32_t st = sbase + (uint32_t)((c % NS) * STAGE);
     const int k0 = c * 32;
-    // ---- A chunk: 128 rows x 8 x 16 B; hi = raw fp32 (the tensor core reads the tf32 bits), lo = a - tf32(a) ----
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int q = tid + 256 * i;
-      const int row = q >> 3, c16 = q & 7;
+      const int q = tid + 256 * i, row = q >> 3, c16 = q & 7;
       const int gm = m0 + row, gk = k0 + c16 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gm < a.M && gk < a.K) v = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)gm * a.ld_a + gk));   // K % 4 == 0
-      float4 hi, lo;                       // hi is made exactly tf32-representable; lo = a - hi is exact in fp32
-      hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
-      hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
-      hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
-      hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
-      const uint32_t off = tc::swz(row, c16);
-      *reinterpret_cast<float4*>(sA_hi + off) = hi;
-      *reinterpret_cast<float4*>(sA_lo + off) = lo;
+      const bool ok = gm < a.M && gk < a.K;
+      cp_async16(st + tc::swz(row, c16), ok ? (const void*)(a.A + (size_t)gm * a.ld_a + gk) : (const void*)a.A, ok);
     }
-    // ---- W chunk: BN rows x 8 x 16 B from the pre-split, zero-padded weight copies ----
     for (int q = tid; q < BN * 8; q += 256) {
       const int row = q >> 3, c16 = q & 7;
       const size_t g = (size_t)(n0 + row) * a.kpad + k0 + c16 * 4;
       const uint32_t off = tc::swz(row, c16);
-      *reinterpret_cast<float4*>(sB_hi + off) = __ldg(reinterpret_cast<const float4*>(a.w_hi + g));
-      *reinterpret_cast<float4*>(sB_lo + off) = __ldg(reinterpret_cast<const float4*>(a.w_lo + g));
+      cp_async16(st + 2 * A_BYTES + off, a.w_hi + g, true);
+      cp_async16(st + 2 * A_BYTES + B_BYTES + off, a.w_lo + g, true);
     }
-    tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  };
+
+  // prologue: two chunks in flight
+  issue_loads(0); cp_async_commit();
+  if (nchunks > 1) issue_loads(1);
+  cp_async_commit();
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % NS;
+    // refill the stage that chunk c+2 will use (last read by the MMAs of chunk c-1)
+    if (c + 2 < nchunks) {
+      if (c >= 1) { tc::mbar_wait(&bar_free[(c + 2) % NS], (uint32_t)(((c - 1) / NS) & 1)); tc::tc_fence_after(); }
+      issue_loads(c + 2);
+    }
+    cp_async_commit();
+    cp_async_wait<2>();                      // this thread's copies of chunk c have landed
+    __syncthreads();                         // ... and everybody else's
+    uint8_t* sA_hi = base + s * STAGE;
+    uint8_t* sA_lo = sA_hi + A_BYTES;
+    // split the A tile in place: hi = tf32-representable part, lo = a - hi (exact)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = tid + 256 * i;
+      const uint32_t off = tc::swz(q >> 3, q & 7);
+      const float4 v = *reinterpret_cast<const float4*>(sA_hi + off);
+      float4 hi, lo;
+      hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+      hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+      hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+      hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+      *reinterpret_cast<float4*>(sA_hi + off) = hi;
+      *reinterpret_cast<float4*>(sA_lo + off) = lo;
+    }
+    tc::fence_proxy_async();                 // generic-proxy smem writes (cp.async + split) -> async proxy (tensor core)
     tc::tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc::tc_fence_after();
-      const uint64_t dA_hi = tc::make_desc(tc::smem_u32(sA_hi)), dA_lo = tc::make_desc(tc::smem_u32(sA_lo));
-      const uint64_t dB_hi = tc::make_desc(tc::smem_u32(sB_hi)), dB_lo = tc::make_desc(tc::smem_u32(sB_lo));
+      const uint32_t st = sbase + (uint32_t)(s * STAGE);
+      const uint64_t dA_hi = tc::make_desc(st), dA_lo = tc::make_desc(st + A_BYTES);
+      const uint64_t dB_hi = tc::make_desc(st + 2 * A_BYTES), dB_lo = tc::make_desc(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {                      // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (>>4) address field
         const uint64_t adv = (uint64_t)(ks * 2);
@@ -181,25 +215,30 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
       if (c == nchunks - 1) tc::mma_commit(&bar_done);
     }
   }
-  // ---- epilogue: TMEM -> registers -> bias / activation / residual -> global ----
+  // ---- epilogue: TMEM -> registers -> bias / activation / residual -> global (16-byte stores) ----
   tc::mbar_wait(&bar_done, 0);
   tc::tc_fence_after();
   {
     const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const int gm = m0 + row;
-    constexpr int COLS_PER_HALF = BN / 2 < 32 ? 32 : BN / 2;
-    constexpr int NHALVES = BN / 2 < 32 ? 1 : 2;
-    if (half < NHALVES) {
-      for (int cc = half * COLS_PER_HALF; cc < (half + 1) * COLS_PER_HALF && cc < BN; cc += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)cc, v);
-        if (gm < a.M) {
-          float* op = a.out + (size_t)gm * a.ld_out;
+    const int gm = m0 + quad * 32 + lane;
+    constexpr int NCH = (BN + 31) / 32;                       // 32-column chunks in the tile
+    const bool vec = (a.ld_out & 3) == 0;
+    for (int ci = half; ci < NCH; ci += 2) {
+      const int cc = ci * 32;
+      float v[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)cc, v);
+      if (gm < a.M) {
+        float* op = a.out + (size_t)gm * a.ld_out + n0 + cc;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ch = n0 + cc + j;
-            if (cc + j < BN && ch < a.N) op[ch] = tc_epilogue(v[j], ch, (size_t)gm, a.e);
+        for (int j = 0; j < 32; j += 4) {
+          const int ch = n0 + cc + j;
+          if (cc + j + 3 < BN && ch + 3 < a.N && vec) {
+            *reinterpret_cast<float4*>(op + j) = make_float4(tc_epilogue(v[j], ch, (size_t)gm, a.e), tc_epilogue(v[j + 1], ch + 1, (size_t)gm, a.e),
+                                                             tc_epilogue(v[j + 2], ch + 2, (size_t)gm, a.e), tc_epilogue(v[j + 3], ch + 3, (size_t)gm, a.e));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (cc + j + t < BN && ch + t < a.N) op[j + t] = tc_epilogue(v[j + t], ch + t, (size_t)gm, a.e);
           }
         }
       }
@@ -212,7 +251,7 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
 
 template <int BN>
 static void launch_tc_bn(cudaStream_t s, const TcArgs& a, int npad) {
-  const size_t smem = 2 * (2 * 128 * 128 + 2 * BN * 128) + 1024;
+  const size_t smem = 3 * (2 * 128 * 128 + 2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(k_pointwise_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)(npad / BN));
@@ -223,9 +262,8 @@ int pointwise_tc_tile_n(int N) {       // tile width the launcher will use for t
   if (N <= 16) return 16;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  if (N <= 256 && N % 16 == 0 && N > 192) return 256;
-  if (N == 480) return 240;
+  if (N <= 96) return 96;
+  if (N == 160 || N == 240 || N == 480) return 80;
   return 128;
 }
 
@@ -239,9 +277,9 @@ bool launch_pointwise_tc(cudaStream_t s, int M, int K, int N, const float* A, in
     case 16: launch_tc_bn<16>(s, a, npad); break;
     case 32: launch_tc_bn<32>(s, a, npad); break;
     case 64: launch_tc_bn<64>(s, a, npad); break;
+    case 80: launch_tc_bn<80>(s, a, npad); break;
+    case 96: launch_tc_bn<96>(s, a, npad); break;
     case 128: launch_tc_bn<128>(s, a, npad); break;
-    case 240: launch_tc_bn<240>(s, a, npad); break;
-    case 256: launch_tc_bn<256>(s, a, npad); break;
     default: return false;
   }
   count_launch();
