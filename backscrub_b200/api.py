@@ -117,12 +117,39 @@ class MaskGen:
         if not ok:
             self._fail("bsb_composite")
 
+    def composite_yuyv_into(self, yuyv_frames: np.ndarray, out=None, yuyv=None, mask=None):
+        """bsb_composite_yuyv: camera YUYV frames [n, H, W, 2] in, results into caller-provided host arrays."""
+        n = yuyv_frames.shape[0]
+        fb, npx = self.height * self.width * 3, self.height * self.width
+        ok = self._lib.bsb_composite_yuyv(self._h, n, _ptr(yuyv_frames), npx * 2,
+                                          _ptr(out) if out is not None else None, fb,
+                                          _ptr(yuyv) if yuyv is not None else None, npx * 2,
+                                          _ptr(mask) if mask is not None else None, npx)
+        if not ok:
+            self._fail("bsb_composite_yuyv")
+
+    def composite_yuyv(self, yuyv_frames: np.ndarray):
+        yuyv_frames = np.ascontiguousarray(yuyv_frames, np.uint8)
+        n = yuyv_frames.shape[0]
+        out = np.empty((n, self.height, self.width, 3), np.uint8)
+        yuyv = np.empty((n, self.height, self.width, 2), np.uint8)
+        mask = np.empty((n, self.height, self.width), np.uint8)
+        self.composite_yuyv_into(yuyv_frames, out, yuyv, mask)
+        return out, yuyv, mask
+
     def composite_device(self, n, d_frames, d_out=0, d_yuyv=0, d_mask=0, sync=False):
         """Fused path on DEVICE pointers (ints, e.g. torch.Tensor.data_ptr()); tightly packed frames."""
         fb, npx = self.height * self.width * 3, self.height * self.width
         if not self._lib.bsb_composite_device(self._h, n, d_frames, fb, d_out or None, fb, d_yuyv or None, npx * 2,
                                               d_mask or None, npx, int(sync)):
             self._fail("bsb_composite_device")
+
+    def composite_yuyv_device(self, n, d_yuyv_in, d_out=0, d_yuyv=0, d_mask=0, sync=False):
+        """Fused path from DEVICE-resident camera YUYV frames (tightly packed)."""
+        fb, npx = self.height * self.width * 3, self.height * self.width
+        if not self._lib.bsb_composite_yuyv_device(self._h, n, d_yuyv_in, d_out or None, fb, d_yuyv or None, npx * 2,
+                                                   d_mask or None, npx, int(sync)):
+            self._fail("bsb_composite_yuyv_device")
 
     def synchronize(self):
         if not self._lib.bsb_synchronize(self._h):
@@ -211,5 +238,15 @@ def pointwise(lib, A, W, bias=None, act=0, use_tc=False, device=0):
     b = np.ascontiguousarray(bias, np.float32) if bias is not None else None
     out = np.empty((M, N), np.float32)
     if not lib.bsb_pointwise(device, int(use_tc), M, K, N, _ptr(A), _ptr(W), _ptr(b) if b is not None else None, act, _ptr(out)):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return out
+
+
+def convert_yuyv_to_bgr(lib, yuyv, device=0):
+    """cv::cvtColor(COLOR_YUV2BGR_YUYV) — the camera-frame ingest conversion."""
+    yuyv = np.ascontiguousarray(yuyv, np.uint8)
+    h, w, _ = yuyv.shape
+    out = np.empty((h, w, 3), np.uint8)
+    if not lib.bsb_convert_yuyv_to_bgr(device, _ptr(yuyv), _ptr(out), w, h):
         raise BackscrubError(lib.bsb_last_error().decode())
     return out

@@ -172,6 +172,51 @@ int bsb_composite_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_frames, si
   return 1;
 }
 
+int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_frames, size_t in_stride, uint8_t* out, size_t out_stride,
+                       uint8_t* out_yuyv, size_t yuyv_stride, uint8_t* out_mask, size_t mask_stride) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+  Engine* e = ctx->eng;
+  const size_t npix = (size_t)e->W() * e->H(), fbytes = npix * 3;
+  if (n_frames < 1 || n_frames > e->max_batch()) { report(cbp, "error: n_frames out of range (1..max_batch)"); return 0; }
+  if (!yuyv_frames || in_stride < npix * 2) { report(cbp, "error: invalid frame"); return 0; }
+  if (!e->has_background() && (out || out_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  API_CUDA(cudaSetDevice(e->device()));
+  if (in_stride == npix * 2) API_CUDA(cudaMemcpyAsync(e->d_yuyv_in(), yuyv_frames, npix * 2 * n_frames, cudaMemcpyHostToDevice, e->stream()));
+  else for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(e->d_yuyv_in() + b * npix * 2, yuyv_frames + (size_t)b * in_stride, npix * 2, cudaMemcpyHostToDevice, e->stream()));
+  std::string err;
+  if (!e->run_yuyv(n_frames, e->d_yuyv_in(), out ? e->d_out() : nullptr, fbytes, out_yuyv ? e->d_yuyv() : nullptr, npix * 2,
+                   out_mask ? e->d_mask() : nullptr, npix, &err)) {
+    report(cbp, "error: failed to process video frame: " + err); return 0;
+  }
+  if (out) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out + (size_t)b * out_stride, e->d_out() + b * fbytes, fbytes, cudaMemcpyDeviceToHost, e->stream()));
+  if (out_yuyv) {
+    if (yuyv_stride == npix * 2) API_CUDA(cudaMemcpyAsync(out_yuyv, e->d_yuyv(), npix * 2 * n_frames, cudaMemcpyDeviceToHost, e->stream()));
+    else for (int b = 0; b < n_frames; ++b)
+      API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * npix * 2, npix * 2, cudaMemcpyDeviceToHost, e->stream()));
+  }
+  if (out_mask) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out_mask + (size_t)b * mask_stride, e->d_mask() + b * npix, npix, cudaMemcpyDeviceToHost, e->stream()));
+  API_CUDA(cudaStreamSynchronize(e->stream()));
+  API_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int bsb_composite_yuyv_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_yuyv_frames, uint8_t* d_out, size_t out_stride,
+                              uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, int sync) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+  Engine* e = ctx->eng;
+  if (!d_yuyv_frames) { report(cbp, "error: invalid frame"); return 0; }
+  if (!e->has_background() && (d_out || d_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  std::string err;
+  if (!e->run_yuyv(n_frames, d_yuyv_frames, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, &err)) { report(cbp, "error: " + err); return 0; }
+  if (sync) { API_CUDA(cudaStreamSynchronize(e->stream())); API_CUDA(cudaGetLastError()); }
+  return 1;
+}
+
 int bsb_synchronize(bsb_ctx* ctx) {
   if (!check_ctx(ctx)) return 0;
   std::string err;
@@ -227,6 +272,20 @@ int bsb_convert_rgb_to_yuyv(int device, const uint8_t* rgb, uint8_t* yuyv, int w
   if (npix) bsb::launch_rgb_to_yuyv(nullptr, a.u8(), o.u8(), npix);
   if (!stage_end()) return 0;
   cudaMemcpy(yuyv, o.p, npix * 2, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+int bsb_convert_yuyv_to_bgr(int device, const uint8_t* yuyv, uint8_t* bgr, int width, int height) {
+  if (!yuyv || !bgr || width < 0 || height < 0) { g_last_error = "invalid argument"; return 0; }
+  const size_t npix = (size_t)width * height;
+  if (npix & 1) { g_last_error = "YUYV needs an even number of pixels"; return 0; }
+  if (!stage_begin(device)) return 0;
+  DevBuf a, o;
+  if (!a.alloc(npix * 2) || !o.alloc(npix * 3)) { g_last_error = "cudaMalloc failed"; return 0; }
+  cudaMemcpy(a.p, yuyv, npix * 2, cudaMemcpyHostToDevice);
+  if (npix) bsb::launch_yuyv_to_bgr(nullptr, a.u8(), o.u8(), npix);
+  if (!stage_end()) return 0;
+  cudaMemcpy(bgr, o.p, npix * 3, cudaMemcpyDeviceToHost);
   return 1;
 }
 

@@ -539,6 +539,7 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMalloc((void**)&d_out_, B * fpx * 3));
   CUDA_OK(cudaMalloc((void**)&d_yuyv_, B * fpx * 2));
   CUDA_OK(cudaMalloc((void**)&d_mask_, B * fpx));
+  CUDA_OK(cudaMalloc((void**)&d_yuyv_in_, B * fpx * 2));
   CUDA_OK(cudaMalloc((void**)&d_bg_, fpx * 3));
   CUDA_OK(cudaMemset(d_bg_, 0, fpx * 3));
   CUDA_OK(cudaMallocHost((void**)&h_mask_, fpx));
@@ -555,7 +556,7 @@ Engine::~Engine() {
 #endif
   if (stream_) { cudaStreamSynchronize(stream_); }
   for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)rowsum_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
-                  (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_,
+                  (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_, (void*)d_yuyv_in_,
                   tab_in_.blob, tab_up_.blob, tab_bg_.blob})
     if (p) cudaFree(p);
   if (h_mask_) cudaFreeHost(h_mask_);
@@ -655,8 +656,10 @@ void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t s
 }
 
 bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
-                 uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err) {
+                 uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err,
+                 const uint8_t* d_yuyv_in) {
   if (n < 1 || n > max_batch_) { *err = "n_frames out of range (1..max_batch)"; return false; }
+  if (d_yuyv_in && (W_ & 1)) { *err = "YUYV ingest needs an even width"; return false; }
   CUDA_OK(cudaSetDevice(device_));
   const bool cbs = use_callbacks && (cb_.onprep || cb_.oninfer || cb_.onmask);
   bool eager = cbs || (flags_ & 2u);
@@ -664,6 +667,7 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
   eager = true;
 #endif
   if (eager) {
+    if (d_yuyv_in) launch_yuyv_to_bgr(stream_, d_yuyv_in, const_cast<uint8_t*>(d_frames), (size_t)n * W_ * H_);
     enqueue_pre(n, d_frames, pitch, stride);
     if (cbs && cb_.onprep) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onprep(cb_.caller_ctx); }
     enqueue_cnn(n, true);
@@ -675,12 +679,13 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
     return true;
   }
 #ifndef BSB_EMU
-  const GraphKey key{n, d_frames, pitch, stride, d_out, d_yuyv, d_mask};
+  const GraphKey key{n, d_frames, pitch, stride, d_out, d_yuyv, d_mask, d_yuyv_in};
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
     if (graphs_.size() >= 64) { for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second); graphs_.clear(); }
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    if (d_yuyv_in) launch_yuyv_to_bgr(stream_, d_yuyv_in, const_cast<uint8_t*>(d_frames), (size_t)n * W_ * H_);
     enqueue_pre(n, d_frames, pitch, stride);
     enqueue_cnn(n, true);
     enqueue_decision(n);
@@ -694,6 +699,12 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
   CUDA_OK(cudaGraphLaunch(it->second, stream_));
 #endif
   return true;
+}
+
+bool Engine::run_yuyv(int n, const uint8_t* d_yuyv_in, uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
+                      uint8_t* d_mask, size_t mask_stride, std::string* err) {
+  const size_t row = (size_t)W_ * 3;
+  return run(n, d_frames_, row, row * H_, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, false, err, d_yuyv_in);
 }
 
 bool Engine::infer(int n, const float* h_in, float* h_out, std::string* err) {

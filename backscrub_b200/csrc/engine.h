@@ -74,7 +74,11 @@ class Engine {
 
   // frames on device: n frames, row pitch / frame stride in bytes.  Any output may be null.
   bool run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
-           uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err);
+           uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err,
+           const uint8_t* d_yuyv_in = nullptr);
+  // same, from camera YUYV frames (tightly packed W*2 rows): converted to BGR into the context staging first
+  bool run_yuyv(int n, const uint8_t* d_yuyv_in, uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
+                uint8_t* d_mask, size_t mask_stride, std::string* err);
   bool infer(int n, const float* h_in, float* h_out, std::string* err);
   bool set_background(const uint8_t* bg_raw, int bw, int bh, size_t pitch, std::string* err);
   bool sync(std::string* err);
@@ -103,6 +107,7 @@ class Engine {
   uint8_t* d_yuyv() const { return d_yuyv_; }
   uint8_t* d_mask() const { return d_mask_; }
   uint8_t* d_bg() const { return d_bg_; }
+  uint8_t* d_yuyv_in() const { return d_yuyv_in_; }
   uint8_t* h_mask() const { return h_mask_; }
   bool has_background() const { return has_bg_; }
 
@@ -147,7 +152,7 @@ class Engine {
   uint8_t* filt_u8_ = nullptr;       // [B][mh][mw][3] (KEEP_TENSORS only)
   uint8_t* state_ = nullptr;         // [oh*ow] IIR state
   uint8_t* ofinal_ = nullptr;        // [B][oh*ow]
-  uint8_t* d_frames_ = nullptr, *d_out_ = nullptr, *d_yuyv_ = nullptr, *d_mask_ = nullptr, *d_bg_ = nullptr, *d_bg_raw_ = nullptr;
+  uint8_t* d_frames_ = nullptr, *d_out_ = nullptr, *d_yuyv_ = nullptr, *d_mask_ = nullptr, *d_bg_ = nullptr, *d_bg_raw_ = nullptr, *d_yuyv_in_ = nullptr;
   size_t bg_raw_cap_ = 0;
   uint8_t* h_mask_ = nullptr;        // pinned host W*H
   bool has_bg_ = false;
@@ -155,10 +160,10 @@ class Engine {
   int bg_w_ = 0, bg_h_ = 0;
 
   struct GraphKey {
-    int n; const void* f; size_t pitch, stride; const void* o; const void* y; const void* m;
+    int n; const void* f; size_t pitch, stride; const void* o; const void* y; const void* m; const void* yin = nullptr;
     bool operator<(const GraphKey& r) const {
       if (n != r.n) return n < r.n; if (f != r.f) return f < r.f; if (pitch != r.pitch) return pitch < r.pitch;
-      if (stride != r.stride) return stride < r.stride; if (o != r.o) return o < r.o; if (y != r.y) return y < r.y; return m < r.m;
+      if (stride != r.stride) return stride < r.stride; if (o != r.o) return o < r.o; if (y != r.y) return y < r.y; if (m != r.m) return m < r.m; return yin < r.yin;
     }
   };
 #ifndef BSB_EMU

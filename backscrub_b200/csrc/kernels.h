@@ -125,6 +125,10 @@ void launch_post(cudaStream_t s, const PostArgs& a);
 void launch_resize_u8c3(cudaStream_t s, const uint8_t* src, int sw, int sh, size_t spitch,
                         uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2);
 
+// cv::cvtColor(COLOR_YUV2BGR_YUYV): camera YUYV frames -> BGR (what cv::VideoCapture does for the
+// reference, app/deepseg.cc:553).  n frames of W x H, tightly packed.
+void launch_yuyv_to_bgr(cudaStream_t s, const uint8_t* yuyv, uint8_t* bgr, size_t npix_total);
+
 // stand-alone stage kernels (exported through the C-ABI for stage-level parity tests)
 void launch_alpha_blend(cudaStream_t s, const uint8_t* a, const uint8_t* b, const uint8_t* mask, uint8_t* out, size_t npix);
 void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix);

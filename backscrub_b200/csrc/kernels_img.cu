@@ -646,6 +646,43 @@ void launch_resize_u8c3(cudaStream_t s, const uint8_t* src, int sw, int sh, size
 }
 
 // ---------------------------------------------------------------------------
+// YUYV -> BGR ingest (cv::cvtColor COLOR_YUV2BGR_YUYV, BT.601 limited range, 20-bit fixed point).
+// One thread = 8 pixels: one 16-byte load, 24 bytes out.
+// ---------------------------------------------------------------------------
+BSB_D void yuv2bgr_px(int y, int ruv, int guv, int buv, uint8_t* o) {
+  const int yy = max(y - 16, 0) * 1220542;
+  o[0] = bsb_sat_u8((yy + buv) >> 20); o[1] = bsb_sat_u8((yy + guv) >> 20); o[2] = bsb_sat_u8((yy + ruv) >> 20);
+}
+
+__global__ void __launch_bounds__(256) k_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, size_t ngroups, size_t npix) {
+  const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= ngroups) return;
+  const size_t p0 = gidx * 8;
+  __align__(16) uint8_t in[16];
+  __align__(8) uint8_t out[24];
+  const int n = (npix - p0) < 8 ? (int)(npix - p0) : 8;
+  if (n == 8) *reinterpret_cast<uint4*>(in) = __ldg(reinterpret_cast<const uint4*>(yuyv + 2 * p0));
+  else for (int i = 0; i < 2 * n; ++i) in[i] = yuyv[2 * p0 + i];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (2 * k >= n) break;
+    const int u = (int)in[4 * k + 1] - 128, v = (int)in[4 * k + 3] - 128;
+    const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
+    yuv2bgr_px(in[4 * k], ruv, guv, buv, out + 6 * k);
+    yuv2bgr_px(in[4 * k + 2], ruv, guv, buv, out + 6 * k + 3);
+  }
+  uint8_t* d = bgr + 3 * p0;
+  if (n == 8) { uint2* q = reinterpret_cast<uint2*>(d); const uint2* sv = reinterpret_cast<const uint2*>(out); q[0] = sv[0]; q[1] = sv[1]; q[2] = sv[2]; }
+  else for (int i = 0; i < 3 * n; ++i) d[i] = out[i];
+}
+
+void launch_yuyv_to_bgr(cudaStream_t s, const uint8_t* yuyv, uint8_t* bgr, size_t npix_total) {
+  const size_t ngroups = (npix_total + 7) / 8;
+  BSB_LAUNCH(k_yuyv_to_bgr, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, s, yuyv, bgr, ngroups, npix_total);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
 // Stand-alone alpha_blend / convert_rgb_to_yuyv (stage-level parity through the C-ABI).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_alpha_blend(const uint8_t* a, const uint8_t* b, const uint8_t* mask, uint8_t* out, size_t npix) {

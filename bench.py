@@ -78,10 +78,13 @@ def cpu_path_fps(wl, threads, frames_per_thread, warm=1):
     gens = [po.MaskGen(model, W, H) for _ in range(threads)]
     frames = [synthetic_frames(W, H, frames_per_thread + warm, s) for s in range(min(threads, 4))]
 
+    # camera frames arrive as YUYV (the reference lets cv::VideoCapture convert them, app/deepseg.cc:553)
+    frames = [np.stack([po.convert_rgb_to_yuyv(f) for f in fr]) for fr in frames]
+
     def work(i, lo, hi):
         g, fr = gens[i], frames[i % len(frames)]
         for t in range(lo, hi):
-            g.composite(fr[t], bg, want_yuyv=True)
+            g.composite(po.yuyv_to_bgr(fr[t]), bg, want_yuyv=True)
 
     def run(lo, hi):
         th = [threading.Thread(target=work, args=(i, lo, hi)) for i in range(threads)]
@@ -197,7 +200,8 @@ def run_b200(args, wl):
         c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=4 if args.tensor_cores else 0)
         c.set_background(bg)
         ctxs.append(c)
-        host = synthetic_frames(W, H, B, stream=my_streams[s])
+        from oracle import pyoracle as _po        # only to synthesise camera-format (YUYV) input frames
+        host = np.stack([_po.convert_rgb_to_yuyv(f) for f in synthetic_frames(W, H, B, stream=my_streams[s])])
         slots = []
         for r in range(R):
             d_in = torch.from_numpy(host).to(f"cuda:{dev}")
@@ -211,7 +215,7 @@ def run_b200(args, wl):
         r = i % R
         for s, c in enumerate(ctxs):
             sl = rings[s]["slots"][r]
-            c.composite_device(B, sl["d_in"].data_ptr(), sl["d_out"].data_ptr(), sl["d_yuyv"].data_ptr(), sl["d_mask"].data_ptr())
+            c.composite_yuyv_device(B, sl["d_in"].data_ptr(), sl["d_out"].data_ptr(), sl["d_yuyv"].data_ptr(), sl["d_mask"].data_ptr())
 
     def barrier():
         torch.cuda.synchronize()
@@ -245,14 +249,14 @@ def run_b200(args, wl):
         pin = lambda shape: torch.empty(shape, dtype=torch.uint8).pin_memory()
         hb = []
         for s in range(S):
-            h_in = pin((B, H, W, 3)); h_in.numpy()[:] = rings[s]["host"]
+            h_in = pin((B, H, W, 2)); h_in.numpy()[:] = rings[s]["host"]
             hb.append(dict(inp=h_in.numpy(), yuyv=pin((B, H, W, 2)).numpy(), keep=h_in))
         e_steps = max(3, args.steps // 2)
 
         def worker(s, n):
             for _ in range(n):
                 # the frame deepseg.cc hands to the loopback device is the YUYV one (app/deepseg.cc:681-690)
-                ctxs[s].composite_into(hb[s]["inp"], yuyv=hb[s]["yuyv"])
+                ctxs[s].composite_yuyv_into(hb[s]["inp"], yuyv=hb[s]["yuyv"])
 
         def run_threads(n):
             th = [threading.Thread(target=worker, args=(s, n)) for s in range(S)]
@@ -269,8 +273,9 @@ def run_b200(args, wl):
             t = torch.tensor([dt], device=f"cuda:{dev}")
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * fb,
+        e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * npx * 2,
                "d2h_bytes_per_step": S * B * npx * 2, "steps": e_steps,
+               "input": "camera YUYV frame in pinned host memory (GPU does the YUYV->BGR ingest of app/deepseg.cc:553)",
                "result": "YUYV frame (what app/deepseg.cc:681-690 writes to the v4l2 loopback device)"}
 
     if sampler:
@@ -322,8 +327,8 @@ def run_b200(args, wl):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "batch": B, "frames_per_step": world * S * B,
-                       "outputs": "RGB composite + YUYV + mask", "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
-                       "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (2 * fb + 3 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
+                       "input": "camera YUYV frames (YUYV->BGR ingest on the GPU)", "outputs": "RGB composite + YUYV + mask", "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                       "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
             "gpu_launches": args.steps * S * c0.launches_per_call,
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stages": stages,
             "cnn_mflop_per_frame": c0.flops / 1e6,

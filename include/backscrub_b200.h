@@ -105,6 +105,16 @@ BSB_API int bsb_composite(bsb_ctx* ctx, int n_frames, const uint8_t* frames, siz
 BSB_API int bsb_composite_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_frames, size_t frame_stride,
                                  uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
                                  uint8_t* d_mask, size_t mask_stride, int sync);
+/* Camera-format ingest: the same fused call fed with YUYV frames (W*2 bytes per row, tightly packed) — the
+ * YUYV -> BGR conversion cv::VideoCapture performs for the reference (CAP_PROP_CONVERT_RGB,
+ * app/deepseg.cc:553; cv::COLOR_YUV2BGR_YUYV) runs on the GPU ahead of the pipeline.  HOST buffers. */
+BSB_API int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_frames, size_t in_stride,
+                               uint8_t* out, size_t out_stride, uint8_t* out_yuyv, size_t yuyv_stride,
+                               uint8_t* out_mask, size_t mask_stride);
+/* DEVICE pointers, asynchronous unless `sync`. */
+BSB_API int bsb_composite_yuyv_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_yuyv_frames,
+                                      uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
+                                      uint8_t* d_mask, size_t mask_stride, int sync);
 BSB_API int bsb_synchronize(bsb_ctx* ctx);
 /* the context's cudaStream_t (for event timing on the launching stream) */
 BSB_API void* bsb_stream(bsb_ctx* ctx);
@@ -115,6 +125,8 @@ BSB_API int bsb_alpha_blend(int device, const uint8_t* srca, const uint8_t* srcb
                             uint8_t* out, size_t npix);
 /* app/deepseg.cc:87-106 */
 BSB_API int bsb_convert_rgb_to_yuyv(int device, const uint8_t* rgb, uint8_t* yuyv, int width, int height);
+/* cv::cvtColor(COLOR_YUV2BGR_YUYV) (camera ingest, app/deepseg.cc:553,725) */
+BSB_API int bsb_convert_yuyv_to_bgr(int device, const uint8_t* yuyv, uint8_t* bgr, int width, int height);
 /* cv::resize(src, dst, Size(dw, dh)) 8UC3 (app/background.cc:178-194) */
 BSB_API int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
 

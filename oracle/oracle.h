@@ -109,8 +109,8 @@ void or_rgb2yuv_u8(const uint8_t* src, uint8_t* dst, size_t npix);
 void or_convert_rgb_to_yuyv(const uint8_t* src, uint8_t* dst_yuyv, int w, int h);
 /* app/deepseg.cc:108-134 (srca = background, srcb = camera frame) */
 void or_alpha_blend(const uint8_t* srca, const uint8_t* srcb, const uint8_t* mask, uint8_t* out, size_t npix);
-/* cv::GaussianBlur(src, dst, Size(k,k), 0) 8UC3 (fixed-point path), BORDER_REFLECT_101 */
-void or_gaussian_blur_u8c3(const uint8_t* src, uint8_t* dst, int w, int h, int k);
+/* cv::cvtColor(COLOR_YUV2BGR_YUYV): the YUYV camera frame -> BGR conversion (app/deepseg.cc:553,725) */
+void or_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, int w, int h);
 
 /* ---- pipeline (lib/libbackscrub.cc:161-376 restated, deterministic) ---- */
 enum { OR_MODEL_UNKNOWN = 0, OR_MODEL_BODYPIX, OR_MODEL_DEEPLAB, OR_MODEL_MEET, OR_MODEL_MLKIT };

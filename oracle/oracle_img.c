@@ -174,3 +174,22 @@ void or_alpha_blend(const uint8_t* srca, const uint8_t* srcb, const uint8_t* mas
       out[3 * p + c] = (uint8_t)(((int)srca[3 * p + c] * aw + (int)srcb[3 * p + c] * bw) / 255);
   }
 }
+
+/* cv::cvtColor(COLOR_YUV2BGR_YUYV), CV_8UC2 -> CV_8UC3: ITU-R BT.601 limited range, 20-bit fixed point.
+ * This is the conversion OpenCV's V4L2 backend applies to YUYV camera frames when CAP_PROP_CONVERT_RGB is
+ * set (app/deepseg.cc:553) and that app/deepseg.cc:725 applies to the output frame; pinned bit-exact
+ * against cv2 in tests/test_oracle_img.py. */
+void or_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, int w, int h) {
+  const int CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527, SH = 20;
+  for (size_t i = 0; i + 1 < (size_t)w * h; i += 2) {
+    const int y0 = yuyv[2 * i], u = (int)yuyv[2 * i + 1] - 128, y1 = yuyv[2 * i + 2], v = (int)yuyv[2 * i + 3] - 128;
+    const int ruv = (1 << (SH - 1)) + CVR * v, guv = (1 << (SH - 1)) + CVG * v + CUG * u, buv = (1 << (SH - 1)) + CUB * u;
+    const int ys[2] = {y0, y1};
+    for (int k = 0; k < 2; ++k) {
+      const int yy = (ys[k] - 16 < 0 ? 0 : ys[k] - 16) * CY;
+      bgr[3 * (i + k) + 0] = sat_u8((yy + buv) >> SH);
+      bgr[3 * (i + k) + 1] = sat_u8((yy + guv) >> SH);
+      bgr[3 * (i + k) + 2] = sat_u8((yy + ruv) >> SH);
+    }
+  }
+}

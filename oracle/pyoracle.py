@@ -285,6 +285,14 @@ def convert_rgb_to_yuyv(src):
     return dst
 
 
+def yuyv_to_bgr(yuyv):
+    yuyv = _cu(yuyv)
+    h, w, _ = yuyv.shape
+    dst = np.empty((h, w, 3), np.uint8)
+    lib().or_yuyv_to_bgr(_u(yuyv), _u(dst), w, h)
+    return dst
+
+
 def alpha_blend(srca, srcb, mask):
     srca, srcb, mask = _cu(srca), _cu(srcb), _cu(mask)
     out = np.empty_like(srca)

@@ -92,6 +92,27 @@ def check_stage_functions(lib):
         assert np.array_equal(api.resize_u8c3(lib, s, dw, dh), po.resize_linear_u8(s, dw, dh)), (sw, sh, dw, dh)
 
 
+def check_yuyv_ingest(lib, key="meet_lite", W=640, H=480, n=2):
+    """Camera-format path: YUYV frames in -> (GPU YUYV->BGR) -> pipeline, vs oracle conversion + oracle pipeline."""
+    import cv2
+    g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+    o = po.MaskGen(model_path(key), W, H)
+    bg = synth.background()
+    g.set_background(bg)
+    bgr = np.stack([synth.frame(W, H, t=t) for t in range(n)])
+    yuyv_in = np.stack([po.convert_rgb_to_yuyv(f) for f in bgr])          # any valid YUYV camera frame will do
+    rng = np.random.default_rng(9)
+    yuyv_in[0, :8] = rng.integers(0, 256, (8, W, 2), dtype=np.uint8)       # include out-of-gamut / extreme codes
+    for b in range(n):
+        assert np.array_equal(api.convert_yuyv_to_bgr(lib, yuyv_in[b]), po.yuyv_to_bgr(yuyv_in[b]))
+    out, yuyv, mask = g.composite_yuyv(yuyv_in)
+    for b in range(n):
+        fr = po.yuyv_to_bgr(yuyv_in[b])
+        ro, ry, rm = o.composite(fr, bg)
+        assert np.array_equal(mask[b], rm) and np.array_equal(out[b], ro) and np.array_equal(yuyv[b], ry), b
+    g.close()
+
+
 def check_mask_only_and_callbacks(lib, key="mlkit", W=640, H=480):
     """bs_maskgen_process semantics: callbacks fire in order once per call; mask aliases
     context storage; consecutive calls advance the IIR like the oracle."""

@@ -50,6 +50,10 @@ def test_stage_functions(lib):
     pc.check_stage_functions(lib)
 
 
+def test_yuyv_ingest(lib):
+    pc.check_yuyv_ingest(lib)
+
+
 def test_mask_only_and_callbacks(lib):
     pc.check_mask_only_and_callbacks(lib, "meet_lite")
 

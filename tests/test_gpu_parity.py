@@ -57,6 +57,11 @@ def test_stage_functions(lib):
     pc.check_stage_functions(lib)
 
 
+def test_yuyv_ingest(lib):
+    pc.check_yuyv_ingest(lib, "meet_full", 1280, 720, n=3)
+    pc.check_yuyv_ingest(lib, "mlkit", 640, 480, n=2)
+
+
 def test_mask_only_and_callbacks(lib):
     pc.check_mask_only_and_callbacks(lib, "mlkit")
 

@@ -118,3 +118,18 @@ def test_bilateral_constant_and_border():
     assert np.array_equal(po.bilateral_d5(c), c)
     z = np.zeros((8, 8, 3), np.uint8)
     assert np.array_equal(po.bilateral_d5(z), z)
+
+
+def test_yuyv_to_bgr_bit_exact():
+    """cv::cvtColor(COLOR_YUV2BGR_YUYV) — the camera ingest conversion (app/deepseg.cc:553,725)."""
+    src = RNG.integers(0, 256, (48, 64, 2), dtype=np.uint8)
+    assert np.array_equal(po.yuyv_to_bgr(src), cv2.cvtColor(src, cv2.COLOR_YUV2BGR_YUYV))
+    # every (Y, U, V) combination on a coarse-but-complete grid of the extremes + all Y
+    y = np.arange(256, dtype=np.uint8)
+    for u in (0, 1, 16, 127, 128, 129, 240, 255):
+        for v in (0, 1, 16, 127, 128, 129, 240, 255):
+            row = np.empty((1, 256, 2), np.uint8)
+            row[0, :, 0] = y
+            row[0, 0::2, 1] = u
+            row[0, 1::2, 1] = v
+            assert np.array_equal(po.yuyv_to_bgr(row), cv2.cvtColor(row, cv2.COLOR_YUV2BGR_YUYV))
