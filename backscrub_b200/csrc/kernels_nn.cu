@@ -6,6 +6,7 @@
 // fully_connected}.h and lib/transpose_conv_bias.cc).  Every output element accumulates
 // its products with fmaf in the reference loop order (ky, kx, cin), so results are
 // bit-identical to the CPU oracle; parallelism comes from pixels x channels x frames.
+#include <algorithm>
 #include <atomic>
 
 #include "kernels.h"
@@ -482,26 +483,22 @@ __global__ void __launch_bounds__(256) k_rowsum(int B, const float* inA, int cA,
 
 struct FcDev { const float* w; const float* bias; int K, N, n4, act1, act2; };
 
-// dot(v[0..K), w[k*n4 + n]) with k ascending; loads issued 8 at a time (independent), FMAs in order
-BSB_D float fc_dot(const float* v, const float* w, int K, int n4) {
-  float acc = 0.f;
-  int k = 0;
-  for (; k + 8 <= K; k += 8) {
-    float t[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = __ldg(w + (size_t)(k + j) * n4);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(v[k + j], t[j], acc);
-  }
-  for (; k < K; ++k) acc = fmaf(v[k], __ldg(w + (size_t)k * n4), acc);
-  return acc;
+// One block per frame.  Each FC weight matrix ([K][n4], <= 64 KB) is first pulled into shared memory by
+// all 256 threads with every load in flight at once (one L2 round trip instead of K dependent ones);
+// the dot products then run out of shared memory with k ascending.
+BSB_D void stage_weights(float* ws, const float* w, int count) {
+  for (int i = threadIdx.x * 4; i < count; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(ws + i) = __ldg(reinterpret_cast<const float4*>(w + i));
 }
 
 __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int C, float count, int pool_act, float* pooled_out,
                                                  int n_fc, FcDev f0, FcDev f1, float* out, int ld_out) {
+  BSB_DYN_SMEM(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw);
   __shared__ float v0[512];
   __shared__ float v1[512];
   const int b = blockIdx.x;
+  if (n_fc > 0) stage_weights(ws, f0.w, f0.K * f0.n4);          // overlaps with the pooling reads below
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const float* p = rowsum + (size_t)b * h * C + ch;
     float t = 0.f;
@@ -522,14 +519,18 @@ __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int
   if (n_fc == 0) return;
   __syncthreads();
   for (int n = threadIdx.x; n < f0.N; n += blockDim.x) {
-    const float acc = fc_dot(v0, f0.w + n, f0.K, f0.n4);
+    float acc = 0.f;
+    for (int k = 0; k < f0.K; ++k) acc = fmaf(v0[k], ws[k * f0.n4 + n], acc);
     const float r = bsb_act(bsb_act(acc + (f0.bias ? __ldg(f0.bias + n) : 0.f), f0.act1), f0.act2);
     if (n_fc == 1) out[(size_t)b * ld_out + n] = r; else v1[n] = r;
   }
   if (n_fc == 1) return;
   __syncthreads();
+  stage_weights(ws, f1.w, f1.K * f1.n4);
+  __syncthreads();
   for (int n = threadIdx.x; n < f1.N; n += blockDim.x) {
-    const float acc = fc_dot(v1, f1.w + n, f1.K, f1.n4);
+    float acc = 0.f;
+    for (int k = 0; k < f1.K; ++k) acc = fmaf(v1[k], ws[k * f1.n4 + n], acc);
     out[(size_t)b * ld_out + n] = bsb_act(bsb_act(acc + (f1.bias ? __ldg(f1.bias + n) : 0.f), f1.act1), f1.act2);
   }
 }
@@ -543,7 +544,13 @@ void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, co
   count_launch();
   FcDev f[2] = {{nullptr, nullptr, 0, 0, 0, 0, 0}, {nullptr, nullptr, 0, 0, 0, 0, 0}};
   for (int i = 0; i < n_fc && i < 2; ++i) f[i] = FcDev{fc[i].w, fc[i].bias, fc[i].K, fc[i].N, fc[i].n4, fc[i].act1, fc[i].act2};
-  BSB_LAUNCH(k_pool_fc, dim3((unsigned)B), dim3(256), 0, s, rowsum_scratch, h, C, (float)(h * w), pool_act, pooled_out, n_fc, f[0], f[1], out, ld_out);
+  size_t wbytes = 16;
+  for (int i = 0; i < n_fc && i < 2; ++i) wbytes = std::max(wbytes, sizeof(float) * (size_t)f[i].K * f[i].n4);
+#ifndef BSB_EMU
+  static size_t configured = 48 * 1024;
+  if (wbytes > configured) { cudaFuncSetAttribute(k_pool_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes); configured = wbytes; }
+#endif
+  BSB_LAUNCH(k_pool_fc, dim3((unsigned)B), dim3(256), wbytes, s, rowsum_scratch, h, C, (float)(h * w), pool_act, pooled_out, n_fc, f[0], f[1], out, ld_out);
   count_launch();
 }
 
