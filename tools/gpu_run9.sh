@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 | tee gpurun_out/bench.json
+python bench.py --steps 10 --warmup 3 --streams 8 --batch 32 --no-cpu-baseline | tee gpurun_out/bench_s8.json
