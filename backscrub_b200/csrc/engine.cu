@@ -204,7 +204,7 @@ bool Engine::plan(std::string* err) {
           auto it = prologue.find(st.in);
           if (it != prologue.end()) { st.in = it->second.x; st.scale = it->second.s; st.in_add = it->second.add; }
           // tensor cores (opt-in): plain GEMM-shaped layers with enough rows and depth to fill a 128 x N x 32 tile pipeline
-          if ((flags_ & 4u) && st.scale < 0 && st.in_add < 0 && ic >= 64 && ic % 4 == 0 && oc >= 8 &&
+          if ((flags_ & 4u) && st.scale < 0 && st.in_add < 0 && ic >= 160 && ic % 4 == 0 && oc >= 8 &&
               tinfo_[st.in].h * tinfo_[st.in].w >= 1024 && tinfo_[st.in].ld % 4 == 0)
             pack_tc_weights(w, oc, ic, st);
         } else {

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_dyn;                      // 1024-byte aligned by declaration (SWIZZLE_128B atoms need it)
   __shared__ __align__(8) uint64_t bar_free[NS];
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t tmem_base_s;
@@ -178,8 +178,7 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
       issue_loads(c + 2);
     }
     cp_async_commit();
-    cp_async_wait<2>();                      // this thread's copies of chunk c have landed
-    __syncthreads();                         // ... and everybody else's
+    cp_async_wait<2>();                      // this thread's copies of chunk c have landed (it splits exactly those)
     uint8_t* sA_hi = base + s * STAGE;
     uint8_t* sA_lo = sA_hi + A_BYTES;
     // split the A tile in place: hi = tf32-representable part, lo = a - hi (exact)
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
 
 template <int BN>
 static void launch_tc_bn(cudaStream_t s, const TcArgs& a, int npad) {
-  const size_t smem = 3 * (2 * 128 * 128 + 2 * BN * 128) + 1024;
+  const size_t smem = 3 * (2 * 128 * 128 + 2 * BN * 128);
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(k_pointwise_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)(npad / BN));
