@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="meet720", choices=list(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=2, help="independent streams (contexts) per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="independent streams (contexts) per GPU")
     ap.add_argument("--batch", type=int, default=32, help="consecutive frames per stream per step")
     ap.add_argument("--tensor-cores", action="store_true", help="tcgen05 3xTF32 pointwise convs (not bit-exact; IoU-validated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
