@@ -374,6 +374,39 @@ bool Engine::plan(std::string* err) {
     steps_.push_back(st);
   }
 
+  // ---- fuse low-resolution inverted-residual blocks (expand -> depthwise -> SE -> project) into one kernel ----
+  if (!(flags_ & 1u)) {           // KEEP_TENSORS keeps every intermediate, so it keeps the stand-alone kernels
+    std::vector<int> readers(nt, 0);
+    for (const Step& st : steps_) for (int t : {st.in, st.in2, st.scale, st.in_add, st.residual}) if (t >= 0) ++readers[t];
+    std::vector<Step> fused;
+    for (size_t i = 0; i < steps_.size(); ++i) {
+      bool ok = i + 3 < steps_.size();
+      if (ok) {
+        const Step& e = steps_[i]; const Step& d = steps_[i + 1]; const Step& p = steps_[i + 2]; const Step& q = steps_[i + 3];
+        ok = e.kind == Step::PW && !e.use_tc && e.scale < 0 && e.in_add < 0 && e.residual < 0 && e.out != g_.output &&
+             d.kind == Step::DW && d.in == e.out && d.sh == 1 && d.sw == 1 && d.dh == 1 && d.dw == 1 && d.residual < 0 && d.kh == d.kw &&
+             p.kind == Step::POOL && p.in == d.out && p.in2 < 0 && p.n_fc == 2 &&
+             q.kind == Step::PW && !q.use_tc && q.in == d.out && q.scale == p.out && q.in_add < 0 && (q.residual < 0 || q.residual == e.in) &&
+             readers[e.out] == 1 && readers[d.out] == 2 && readers[p.out] == 1 && p.out != g_.output && d.out != g_.output;
+        if (ok) {
+          const TensorInfo& X = tinfo_[e.in]; const TensorInfo& D = tinfo_[d.out];
+          const int fc_max = std::max(std::max(p.fc[0].K * p.fc[0].n4, p.fc[1].K * p.fc[1].n4), q.K * q.n4);
+          ok = X.h == D.h && X.w == D.w && p.fc[0].K == e.N && p.fc[1].N == e.N && p.fc[0].N <= 128 && e.N <= 128 &&
+               (q.residual < 0 || X.c == q.N) && X.ld % 4 == 0 &&
+               mb_block_smem_bytes(X.h, X.w, X.c, e.N, q.N, fc_max) > 0;
+        }
+      }
+      if (!ok) { fused.push_back(steps_[i]); continue; }
+      Step b; b.kind = Step::BLOCK; b.op_index = steps_[i].op_index; b.in = steps_[i].in; b.out = steps_[i + 3].out;
+      b.residual = steps_[i + 3].residual; b.block = (int)blocks_.size();
+      blocks_.push_back(FusedBlock{steps_[i], steps_[i + 1], steps_[i + 2], steps_[i + 3]});
+      tinfo_[steps_[i].out].materialized = false; tinfo_[steps_[i + 1].out].materialized = false; tinfo_[steps_[i + 2].out].materialized = false;
+      fused.push_back(b);
+      i += 3;
+    }
+    steps_.swap(fused);
+  }
+
   // ---- liveness + arena (floats; every tensor is max_batch frames) ----
   const int ns = (int)steps_.size();
   auto root = [&](int t) { return tinfo_[t].alias_parent >= 0 ? tinfo_[t].alias_parent : t; };
@@ -628,6 +661,26 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
         launch_eltwise(stream_, st.elt_mode, n, I.h * I.w, I.c, tptr(st.in), I.ld, st.in2 >= 0 ? tptr(st.in2) : nullptr,
                        st.in2 >= 0 ? tinfo_[st.in2].ld : 0, st.scale >= 0 ? tptr(st.scale) : nullptr, tptr(st.out), O.ld, st.act1);
         break;
+      case Step::BLOCK: {
+        const FusedBlock& fb = blocks_[st.block];
+        MbBlockArgs a{};
+        a.x = tptr(st.in); a.ld_x = I.ld; a.y = tptr(st.out); a.ld_y = O.ld;
+        a.h = I.h; a.w = I.w; a.cin = I.c; a.cexp = fb.expand.N; a.cout = fb.project.N;
+        a.w1 = wblob_ + fb.expand.w_off; a.b1 = fb.expand.has_bias ? wblob_ + fb.expand.b_off : nullptr; a.n4_1 = fb.expand.n4;
+        a.a1a = fb.expand.act1; a.a1b = fb.expand.act2;
+        a.wd = wblob_ + fb.dw.w_off; a.bd = fb.dw.has_bias ? wblob_ + fb.dw.b_off : nullptr; a.k = fb.dw.kh; a.pt = fb.dw.pt; a.pl = fb.dw.pl;
+        a.ada = fb.dw.act1; a.adb = fb.dw.act2;
+        a.pool_act = fb.pool.act1;
+        FcLayer* fl[2] = {&a.f0, &a.f1};
+        for (int k = 0; k < 2; ++k) {
+          fl[k]->w = wblob_ + fb.pool.fc[k].w_off; fl[k]->bias = fb.pool.fc[k].has_bias ? wblob_ + fb.pool.fc[k].b_off : nullptr;
+          fl[k]->K = fb.pool.fc[k].K; fl[k]->N = fb.pool.fc[k].N; fl[k]->n4 = fb.pool.fc[k].n4; fl[k]->act1 = fb.pool.fc[k].act1; fl[k]->act2 = fb.pool.fc[k].act2;
+        }
+        a.w2 = wblob_ + fb.project.w_off; a.b2 = fb.project.has_bias ? wblob_ + fb.project.b_off : nullptr; a.n4_2 = fb.project.n4;
+        a.a2a = fb.project.act1; a.a2b = fb.project.act2; a.residual = fb.project.residual >= 0 ? 1 : 0; a.a3 = fb.project.act3;
+        launch_mb_block(stream_, n, a);
+        break;
+      }
       case Step::COPY:
         launch_copy_channels(stream_, n * I.h * I.w, I.c, tptr(st.in), I.ld, tptr(st.out) + st.copy_off, O.ld);
         break;

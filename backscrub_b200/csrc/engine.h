@@ -29,7 +29,8 @@ struct TensorInfo {
 };
 
 struct Step {
-  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY } kind = ELT;
+  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY, BLOCK } kind = ELT;
+  int block = -1;             // BLOCK: index into Engine::blocks_ (the four fused sub-steps)
   int op_index = -1;
   int in = -1, in2 = -1, out = -1, scale = -1, in_add = -1, residual = -1;
   size_t w_off = 0, b_off = 0; bool has_bias = false;
@@ -137,6 +138,8 @@ class Engine {
 
   std::vector<TensorInfo> tinfo_;
   std::vector<Step> steps_;
+  struct FusedBlock { Step expand, dw, pool, project; };
+  std::vector<FusedBlock> blocks_;
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
   bool stem_u8_ok_ = false;          // step 0 is a 3->16 dense conv that is the only reader of the graph input

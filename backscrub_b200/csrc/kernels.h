@@ -61,6 +61,22 @@ void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, co
                     int h, int w, float* rowsum_scratch, int pool_act, float* pooled_out /*may be null*/,
                     int n_fc, const FcLayer* fc, float* out, int ld_out);
 
+// Fused MobileNetV3 inverted-residual block at low resolution (<= 256 pixels per frame): 1x1 expand (+act) ->
+// depthwise k x k stride 1 (+act) -> global pool -> FC -> FC (squeeze-excite) -> channel scale -> 1x1 project
+// (+ residual).  One CTA per frame keeps every intermediate in shared memory; each stage accumulates in the
+// same order as the stand-alone kernels, so results are bit-identical to running them one after another.
+struct MbBlockArgs {
+  const float* x; int ld_x; float* y; int ld_y;
+  int h, w, cin, cexp, cout;
+  const float* w1; const float* b1; int n4_1, a1a, a1b;                    // expand  [cin][n4_1]
+  const float* wd; const float* bd; int k, pt, pl, ada, adb;               // depthwise [k][k][cexp]
+  int pool_act; FcLayer f0, f1;                                            // SE
+  const float* w2; const float* b2; int n4_2, a2a, a2b;                    // project [cexp][n4_2]
+  int residual, a3;                                                        // y += x (cin == cout)
+};
+size_t mb_block_smem_bytes(int h, int w, int cin, int cexp, int cout, int fc_max_floats);   // 0 if it does not fit
+void launch_mb_block(cudaStream_t s, int B, const MbBlockArgs& a);
+
 // RESIZE_BILINEAR (reference resize_bilinear.h:29-117 float path)
 void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                             float* out, int oh, int ow, int ld_out, bool align_corners, bool half_pixel);

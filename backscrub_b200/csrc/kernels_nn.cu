@@ -555,6 +555,151 @@ void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, co
 }
 
 // ---------------------------------------------------------------------------
+// Fused low-resolution inverted-residual block (see kernels.h).  Shared memory (floats):
+//   xs [P][cin] | es [P][32] (one 32-channel slice of the expanded tensor) | ds [P][cexp] | rs [h][cexp] | fw [fcw]
+// `fw` holds, one after another, the two SE weight matrices and the projection weights; when the whole
+// layout would not fit it overlaps xs|es, which are dead by then (the residual is re-read from global).
+// ---------------------------------------------------------------------------
+struct MbDev {
+  MbBlockArgs a; FcDev f0, f1;
+  int off_es, off_ds, off_rs, off_fw;
+};
+
+__global__ void __launch_bounds__(512) k_mb_block(MbDev m) {
+  BSB_DYN_SMEM(smem_raw);
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  const MbBlockArgs& a = m.a;
+  float* xs = sm; float* es = sm + m.off_es; float* ds = sm + m.off_ds; float* rs = sm + m.off_rs; float* fw = sm + m.off_fw;
+  __shared__ float v0[128];
+  __shared__ float v1[128];
+  __shared__ float sv[128];
+  __shared__ float w1s[64 * 32];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int P = a.h * a.w;
+  const int b = blockIdx.x;
+  const float* xg = a.x + (size_t)b * P * a.ld_x;
+  // ---- x -> shared ----
+  for (int i = tid; i < P * (a.cin / 4); i += T) {
+    const int p = i / (a.cin / 4), q = i % (a.cin / 4);
+    *reinterpret_cast<float4*>(xs + p * a.cin + 4 * q) = __ldg(reinterpret_cast<const float4*>(xg + (size_t)p * a.ld_x + 4 * q));
+  }
+  // ---- expand + depthwise, 32 channels at a time ----
+  for (int c0 = 0; c0 < a.cexp; c0 += 32) {
+    const int cw = min(32, a.cexp - c0);
+    __syncthreads();                                   // xs ready / previous slice fully consumed
+    for (int i = tid; i < a.cin * 32; i += T) {
+      const int kk = i >> 5, j = i & 31;
+      w1s[i] = j < cw ? __ldg(a.w1 + (size_t)kk * a.n4_1 + c0 + j) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < P * 32; i += T) {
+      const int p = i >> 5, j = i & 31;
+      if (j >= cw) continue;
+      float acc = 0.f;
+      const float* xp = xs + p * a.cin;
+      for (int kk = 0; kk < a.cin; ++kk) acc = fmaf(xp[kk], w1s[kk * 32 + j], acc);
+      float v = acc + (a.b1 ? __ldg(a.b1 + c0 + j) : 0.f);
+      es[i] = bsb_act(bsb_act(v, a.a1a), a.a1b);
+    }
+    __syncthreads();
+    for (int i = tid; i < P * 32; i += T) {
+      const int p = i >> 5, j = i & 31;
+      if (j >= cw) continue;
+      const int oy = p / a.w, ox = p - oy * a.w;
+      float acc = 0.f;
+      for (int fy = 0; fy < a.k; ++fy) {
+        const int iy = oy - a.pt + fy;
+        if (iy < 0 || iy >= a.h) continue;
+        for (int fx = 0; fx < a.k; ++fx) {
+          const int ix = ox - a.pl + fx;
+          if (ix < 0 || ix >= a.w) continue;
+          acc = fmaf(es[(iy * a.w + ix) * 32 + j], __ldg(a.wd + (size_t)(fy * a.k + fx) * a.cexp + c0 + j), acc);
+        }
+      }
+      float v = acc + (a.bd ? __ldg(a.bd + c0 + j) : 0.f);
+      ds[p * a.cexp + c0 + j] = bsb_act(bsb_act(v, a.ada), a.adb);
+    }
+  }
+  __syncthreads();
+  // ---- squeeze: row sums (x ascending), then rows (y ascending), / (h*w) ----
+  for (int i = tid; i < a.h * a.cexp; i += T) {
+    const int y = i / a.cexp, c = i - y * a.cexp;
+    const float* dp = ds + (size_t)(y * a.w) * a.cexp + c;
+    float r = 0.f;
+    for (int x = 0; x < a.w; ++x) r = r + dp[x * a.cexp];
+    rs[i] = r;
+  }
+  __syncthreads();                                     // also: xs / es are dead from here on
+  for (int i = tid * 4; i < m.f0.K * m.f0.n4; i += T * 4) *reinterpret_cast<float4*>(fw + i) = __ldg(reinterpret_cast<const float4*>(m.f0.w + i));
+  if (tid < a.cexp) {
+    float t = 0.f;
+    for (int y = 0; y < a.h; ++y) t = t + rs[y * a.cexp + tid];
+    v0[tid] = bsb_act(bsb_div(t, (float)(a.h * a.w)), a.pool_act);
+  }
+  __syncthreads();
+  if (tid < m.f0.N) {
+    float acc = 0.f;
+    for (int kk = 0; kk < m.f0.K; ++kk) acc = fmaf(v0[kk], fw[kk * m.f0.n4 + tid], acc);
+    v1[tid] = bsb_act(bsb_act(acc + (m.f0.bias ? __ldg(m.f0.bias + tid) : 0.f), m.f0.act1), m.f0.act2);
+  }
+  __syncthreads();
+  for (int i = tid * 4; i < m.f1.K * m.f1.n4; i += T * 4) *reinterpret_cast<float4*>(fw + i) = __ldg(reinterpret_cast<const float4*>(m.f1.w + i));
+  __syncthreads();
+  if (tid < m.f1.N) {
+    float acc = 0.f;
+    for (int kk = 0; kk < m.f1.K; ++kk) acc = fmaf(v1[kk], fw[kk * m.f1.n4 + tid], acc);
+    sv[tid] = bsb_act(bsb_act(acc + (m.f1.bias ? __ldg(m.f1.bias + tid) : 0.f), m.f1.act1), m.f1.act2);
+  }
+  __syncthreads();
+  // ---- excite + project (+ residual) ----
+  for (int i = tid * 4; i < a.cexp * a.n4_2; i += T * 4) *reinterpret_cast<float4*>(fw + i) = __ldg(reinterpret_cast<const float4*>(a.w2 + i));
+  __syncthreads();
+  float* yg = a.y + (size_t)b * P * a.ld_y;
+  const int cw2 = a.n4_2;                              // threads per pixel (output channels padded to 4)
+  for (int i = tid; i < P * cw2; i += T) {
+    const int p = i / cw2, n = i - p * cw2;
+    if (n >= a.cout) continue;
+    const float* dp = ds + (size_t)p * a.cexp;
+    float acc = 0.f;
+    for (int kk = 0; kk < a.cexp; ++kk) acc = fmaf(dp[kk] * sv[kk], fw[kk * a.n4_2 + n], acc);
+    float v = acc + (a.b2 ? __ldg(a.b2 + n) : 0.f);
+    v = bsb_act(bsb_act(v, a.a2a), a.a2b);
+    if (a.residual) v = bsb_act(v + __ldg(xg + (size_t)p * a.ld_x + n), a.a3);
+    yg[(size_t)p * a.ld_y + n] = v;
+  }
+}
+
+static void mb_layout(int h, int w, int cin, int cexp, int fc_max, int* off_es, int* off_ds, int* off_rs, int* off_fw, size_t* total) {
+  const int P = h * w;
+  *off_es = P * cin; *off_ds = *off_es + P * 32; *off_rs = *off_ds + P * cexp;
+  const int end = *off_rs + h * cexp;
+  if ((size_t)(end + fc_max) * 4 <= 200 * 1024) { *off_fw = end; *total = (size_t)(end + fc_max) * 4; }
+  else { *off_fw = 0; *total = (size_t)end * 4; if (fc_max > *off_ds) *total = 0; }      // overlap xs|es (dead by then)
+}
+
+size_t mb_block_smem_bytes(int h, int w, int cin, int cexp, int cout, int fc_max_floats) {
+  if (h * w > 256 || cin > 64 || cexp > 128 || cout > 64 || cin % 4 || cexp % 4) return 0;
+  int a, b, c, d; size_t total;
+  mb_layout(h, w, cin, cexp, fc_max_floats, &a, &b, &c, &d, &total);
+  return total <= 200 * 1024 ? total : 0;
+}
+
+void launch_mb_block(cudaStream_t s, int B, const MbBlockArgs& a) {
+  MbDev m; m.a = a;
+  m.f0 = FcDev{a.f0.w, a.f0.bias, a.f0.K, a.f0.N, a.f0.n4, a.f0.act1, a.f0.act2};
+  m.f1 = FcDev{a.f1.w, a.f1.bias, a.f1.K, a.f1.N, a.f1.n4, a.f1.act1, a.f1.act2};
+  const int fc_max = std::max(std::max(a.f0.K * a.f0.n4, a.f1.K * a.f1.n4), a.cexp * a.n4_2);
+  size_t total;
+  mb_layout(a.h, a.w, a.cin, a.cexp, fc_max, &m.off_es, &m.off_ds, &m.off_rs, &m.off_fw, &total);
+#ifndef BSB_EMU
+  static size_t configured = 48 * 1024;
+  if (total > configured) { cudaFuncSetAttribute(k_mb_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total); configured = total; }
+#endif
+  BSB_LAUNCH(k_mb_block, dim3((unsigned)B), dim3(512), total, s, m);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
 // RESIZE_BILINEAR, float, NHWC.  One thread = one output pixel x 4 channels.
 // ---------------------------------------------------------------------------
 BSB_D void interp(float value, float scale, bool half_pixel, int in_size, float* scaled, int* lo, int* hi) {
