@@ -375,7 +375,7 @@ bool Engine::plan(std::string* err) {
   }
 
   // ---- fuse low-resolution inverted-residual blocks (expand -> depthwise -> SE -> project) into one kernel ----
-  if (!(flags_ & 1u)) {           // KEEP_TENSORS keeps every intermediate, so it keeps the stand-alone kernels
+  if ((flags_ & 8u) && !(flags_ & 1u)) {   // opt-in (BSB_FLAG_FUSE_BLOCKS); KEEP_TENSORS keeps every intermediate -> stand-alone kernels
     std::vector<int> readers(nt, 0);
     for (const Step& st : steps_) for (int t : {st.in, st.in2, st.scale, st.in_add, st.residual}) if (t >= 0) ++readers[t];
     std::vector<Step> fused;

@@ -44,7 +44,8 @@ typedef void (*bsb_stage_cb)(void* caller_ctx);
 enum {
   BSB_FLAG_KEEP_TENSORS = 1,  /* keep every intermediate activation (tests / debugging) */
   BSB_FLAG_NO_GRAPH = 2,      /* launch kernels eagerly instead of one CUDA graph per batch */
-  BSB_FLAG_TENSOR_CORES = 4   /* allow tcgen05 3xTF32 pointwise convs (not bit-exact vs the oracle) */
+  BSB_FLAG_TENSOR_CORES = 4,  /* allow tcgen05 3xTF32 pointwise convs (not bit-exact vs the oracle) */
+  BSB_FLAG_FUSE_BLOCKS = 8    /* experimental: one-kernel inverted-residual blocks (bit-exact; currently slower) */
 };
 
 /* replaces bs_tensorflow_version() (lib/libbackscrub.h:13, lib/libbackscrub.cc:150):

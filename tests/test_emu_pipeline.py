@@ -31,6 +31,12 @@ def test_pipeline_edge_streams(lib, kind):
     pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=2, frame_kind=kind)
 
 
+def test_pipeline_fused_blocks(lib):
+    """BSB_FLAG_FUSE_BLOCKS: expand+depthwise+SE+project in one kernel must stay bit-exact."""
+    pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=2, flags=8)
+    pc.check_pipeline(lib, "meet_full", 640, 480, n_frames=2, flags=8)
+
+
 def test_pipeline_ragged_geometry(lib):
     """odd sizes: ROI not tile-aligned, width not a multiple of 16, letter-boxed model input."""
     pc.check_pipeline(lib, "meet_lite", 324, 250, n_frames=2)

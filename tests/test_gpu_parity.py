@@ -39,6 +39,11 @@ def test_pipeline_ragged_geometry(lib):
     pc.check_pipeline(lib, "meet_full", 720, 1280, n_frames=1)     # portrait: letter-boxed input
 
 
+def test_pipeline_fused_blocks(lib):
+    pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=3, flags=8)
+    pc.check_pipeline(lib, "meet_full", 1280, 720, n_frames=3, flags=8)
+
+
 def test_graph_and_eager_agree(lib):
     pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=2, flags=2)  # BSB_FLAG_NO_GRAPH
 
