@@ -275,6 +275,7 @@ def run_b200(args, wl):
             dt = float(t.item())
         e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * npx * 2,
                "d2h_bytes_per_step": S * B * npx * 2, "steps": e_steps,
+               "pcie_gbs_each_direction": world * S * B * e_steps * npx * 2 / dt / 1e9 / world,
                "input": "camera YUYV frame in pinned host memory (GPU does the YUYV->BGR ingest of app/deepseg.cc:553)",
                "result": "YUYV frame (what app/deepseg.cc:681-690 writes to the v4l2 loopback device)"}
 
