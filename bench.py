@@ -174,6 +174,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(torch, dev):
+    """Pin this rank (and the pinned buffers it is about to allocate) to the CPUs NVML reports as local to
+    its GPU, so host<->device copies do not cross the socket interconnect.  Returns the previous affinity."""
+    old = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(old) + 64) // 64)
+        cpus = {i * 64 + b for i, m in enumerate(words) for b in range(64) if (m >> b) & 1} & old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return old
+
+
 def run_b200(args, wl):
     import torch
 
@@ -186,6 +207,7 @@ def run_b200(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
+    full_affinity = bind_near_gpu(torch, dev)
     if bs.device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: backscrub_b200 has no CPU path")
     W, H, S, B = wl["W"], wl["H"], args.streams, args.batch
@@ -313,6 +335,7 @@ def run_b200(args, wl):
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, full_affinity)          # the CPU baseline may use every host core
         cores = host_cores()
         threads = max(1, min(cores, 64))
         fps1, _ = cpu_path_fps(wl, 1, 1, warm=1)
@@ -329,7 +352,7 @@ def run_b200(args, wl):
             "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "batch": B, "frames_per_step": world * S * B,
                        "input": "camera YUYV frames (YUYV->BGR ingest on the GPU)", "outputs": "RGB composite + YUYV + mask", "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
-                       "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
+                       "host_affinity_cpus": len(os.sched_getaffinity(0)) if cpu is None else None, "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
             "gpu_launches": args.steps * S * c0.launches_per_call,
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stages": stages,
             "cnn_mflop_per_frame": c0.flops / 1e6,
