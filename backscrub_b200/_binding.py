@@ -20,6 +20,8 @@ FLAG_KEEP_TENSORS, FLAG_NO_GRAPH, FLAG_TENSOR_CORES = 1, 2, 4
 SYMBOLS = [
     "bsb_version", "bsb_last_error", "bsb_device_count", "bsb_maskgen_new", "bsb_maskgen_new_ex",
     "bsb_maskgen_delete", "bsb_maskgen_process", "bsb_set_background", "bsb_get_background",
+    "bsb_set_background_ring", "bsb_set_background_cursor", "bsb_set_bgblur", "bsb_set_output", "bsb_output_size",
+    "bsb_gaussian_blur", "bsb_gaussian_taps", "bsb_flip",
     "bsb_composite", "bsb_composite_device", "bsb_composite_yuyv", "bsb_composite_yuyv_device", "bsb_convert_yuyv_to_bgr", "bsb_synchronize", "bsb_stream", "bsb_alpha_blend",
     "bsb_convert_rgb_to_yuyv", "bsb_resize_u8c3", "bsb_pointwise", "bsb_geometry", "bsb_infer", "bsb_get_tensor",
     "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops",
@@ -44,6 +46,14 @@ def bind(path: str) -> C.CDLL:
     L.bsb_maskgen_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(u8p), C.POINTER(C.c_size_t)]
     L.bsb_set_background.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
     L.bsb_get_background.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.bsb_set_background_ring.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int]
+    L.bsb_set_background_cursor.argtypes = [C.c_void_p, C.c_int]
+    L.bsb_set_bgblur.argtypes = [C.c_void_p, C.c_int]
+    L.bsb_set_output.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.bsb_output_size.argtypes = [C.c_void_p, i32p, i32p]
+    L.bsb_gaussian_blur.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.bsb_gaussian_taps.argtypes = [C.c_int, i32p]
+    L.bsb_flip.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.bsb_composite.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     L.bsb_composite_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,

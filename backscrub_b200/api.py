@@ -46,6 +46,7 @@ class MaskGen:
         if not self._h:
             raise BackscrubError("".join(self._msgs).strip() or lib.bsb_last_error().decode())
         self.width, self.height, self.max_batch, self.device = width, height, max_batch, device
+        self.out_width, self.out_height = width, height
         r, i, o = (C.c_int * 4)(), (C.c_int * 4)(), (C.c_int * 4)()
         ih, oh = (C.c_int * 3)(), (C.c_int * 3)()
         lib.bsb_geometry(self._h, r, i, o, ih, oh)
@@ -80,6 +81,31 @@ class MaskGen:
         if not self._lib.bsb_set_background(self._h, _ptr(bg_raw), bg_raw.shape[1], bg_raw.shape[0], bg_raw.shape[1] * 3):
             self._fail("bsb_set_background")
 
+    def set_background_ring(self, frames: np.ndarray, advance: int = 1):
+        """Animated background: frames [count, bh, bw, 3] -> device-resident ring (app/background.cc video branch)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        c, bh, bw, _ = frames.shape
+        if not self._lib.bsb_set_background_ring(self._h, _ptr(frames), c, bw, bh, bw * 3, bh * bw * 3, int(advance)):
+            self._fail("bsb_set_background_ring")
+
+    def set_background_cursor(self, index: int):
+        if not self._lib.bsb_set_background_cursor(self._h, int(index)):
+            self._fail("bsb_set_background_cursor")
+
+    def set_bgblur(self, ksize: int):
+        """`-p bgblur:k` (app/deepseg.cc:657-658); 0 = off."""
+        if not self._lib.bsb_set_bgblur(self._h, int(ksize)):
+            self._fail("bsb_set_bgblur")
+
+    def set_output(self, flip_h=False, flip_v=False, out_size=None):
+        """cv::flip + cv::resize to the virtual-camera size (app/deepseg.cc:667-679); out_size = (w, h)."""
+        ow, oh = out_size if out_size else (0, 0)
+        if not self._lib.bsb_set_output(self._h, int(bool(flip_h)), int(bool(flip_v)), int(ow), int(oh)):
+            self._fail("bsb_set_output")
+        w, h = C.c_int(), C.c_int()
+        self._lib.bsb_output_size(self._h, C.byref(w), C.byref(h))
+        self.out_width, self.out_height = w.value, h.value
+
     def background(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), np.uint8)
         if not self._lib.bsb_get_background(self._h, _ptr(out), self.width * 3):
@@ -94,12 +120,13 @@ class MaskGen:
         if frames.shape[1:] != (self.height, self.width, 3):
             raise BackscrubError(f"frame shape {frames.shape[1:]} != {(self.height, self.width, 3)}")
         fb, npx = self.height * self.width * 3, self.height * self.width
-        out = np.empty((n, self.height, self.width, 3), np.uint8) if want_out else None
-        yuyv = np.empty((n, self.height, self.width, 2), np.uint8) if want_yuyv else None
+        ow, oh = self.out_width, self.out_height
+        out = np.empty((n, oh, ow, 3), np.uint8) if want_out else None
+        yuyv = np.empty((n, oh, ow, 2), np.uint8) if want_yuyv else None
         mask = np.empty((n, self.height, self.width), np.uint8) if want_mask else None
         ok = self._lib.bsb_composite(self._h, n, _ptr(frames), self.width * 3, fb,
-                                     _ptr(out) if want_out else None, self.width * 3, fb,
-                                     _ptr(yuyv) if want_yuyv else None, npx * 2,
+                                     _ptr(out) if want_out else None, ow * 3, ow * oh * 3,
+                                     _ptr(yuyv) if want_yuyv else None, ow * oh * 2,
                                      _ptr(mask) if want_mask else None, npx)
         if not ok:
             self._fail("bsb_composite")
@@ -110,9 +137,10 @@ class MaskGen:
         """bsb_composite into caller-provided (e.g. pinned) host arrays; frames [n, H, W, 3]."""
         n = frames.shape[0]
         fb, npx = self.height * self.width * 3, self.height * self.width
+        ow, opx = self.out_width, self.out_width * self.out_height
         ok = self._lib.bsb_composite(self._h, n, _ptr(frames), self.width * 3, fb,
-                                     _ptr(out) if out is not None else None, self.width * 3, fb,
-                                     _ptr(yuyv) if yuyv is not None else None, npx * 2,
+                                     _ptr(out) if out is not None else None, ow * 3, opx * 3,
+                                     _ptr(yuyv) if yuyv is not None else None, opx * 2,
                                      _ptr(mask) if mask is not None else None, npx)
         if not ok:
             self._fail("bsb_composite")
@@ -120,10 +148,10 @@ class MaskGen:
     def composite_yuyv_into(self, yuyv_frames: np.ndarray, out=None, yuyv=None, mask=None):
         """bsb_composite_yuyv: camera YUYV frames [n, H, W, 2] in, results into caller-provided host arrays."""
         n = yuyv_frames.shape[0]
-        fb, npx = self.height * self.width * 3, self.height * self.width
+        npx, opx = self.height * self.width, self.out_width * self.out_height
         ok = self._lib.bsb_composite_yuyv(self._h, n, _ptr(yuyv_frames), npx * 2,
-                                          _ptr(out) if out is not None else None, fb,
-                                          _ptr(yuyv) if yuyv is not None else None, npx * 2,
+                                          _ptr(out) if out is not None else None, opx * 3,
+                                          _ptr(yuyv) if yuyv is not None else None, opx * 2,
                                           _ptr(mask) if mask is not None else None, npx)
         if not ok:
             self._fail("bsb_composite_yuyv")
@@ -131,23 +159,23 @@ class MaskGen:
     def composite_yuyv(self, yuyv_frames: np.ndarray):
         yuyv_frames = np.ascontiguousarray(yuyv_frames, np.uint8)
         n = yuyv_frames.shape[0]
-        out = np.empty((n, self.height, self.width, 3), np.uint8)
-        yuyv = np.empty((n, self.height, self.width, 2), np.uint8)
+        out = np.empty((n, self.out_height, self.out_width, 3), np.uint8)
+        yuyv = np.empty((n, self.out_height, self.out_width, 2), np.uint8)
         mask = np.empty((n, self.height, self.width), np.uint8)
         self.composite_yuyv_into(yuyv_frames, out, yuyv, mask)
         return out, yuyv, mask
 
     def composite_device(self, n, d_frames, d_out=0, d_yuyv=0, d_mask=0, sync=False):
         """Fused path on DEVICE pointers (ints, e.g. torch.Tensor.data_ptr()); tightly packed frames."""
-        fb, npx = self.height * self.width * 3, self.height * self.width
-        if not self._lib.bsb_composite_device(self._h, n, d_frames, fb, d_out or None, fb, d_yuyv or None, npx * 2,
+        fb, npx, opx = self.height * self.width * 3, self.height * self.width, self.out_width * self.out_height
+        if not self._lib.bsb_composite_device(self._h, n, d_frames, fb, d_out or None, opx * 3, d_yuyv or None, opx * 2,
                                               d_mask or None, npx, int(sync)):
             self._fail("bsb_composite_device")
 
     def composite_yuyv_device(self, n, d_yuyv_in, d_out=0, d_yuyv=0, d_mask=0, sync=False):
         """Fused path from DEVICE-resident camera YUYV frames (tightly packed)."""
-        fb, npx = self.height * self.width * 3, self.height * self.width
-        if not self._lib.bsb_composite_yuyv_device(self._h, n, d_yuyv_in, d_out or None, fb, d_yuyv or None, npx * 2,
+        npx, opx = self.height * self.width, self.out_width * self.out_height
+        if not self._lib.bsb_composite_yuyv_device(self._h, n, d_yuyv_in, d_out or None, opx * 3, d_yuyv or None, opx * 2,
                                                    d_mask or None, npx, int(sync)):
             self._fail("bsb_composite_yuyv_device")
 
@@ -218,6 +246,31 @@ def convert_rgb_to_yuyv(lib, rgb, device=0):
     h, w, _ = rgb.shape
     out = np.empty((h, w, 2), np.uint8)
     if not lib.bsb_convert_rgb_to_yuyv(device, _ptr(rgb), _ptr(out), w, h):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return out
+
+
+def gaussian_blur(lib, src, ksize, device=0):
+    """cv::GaussianBlur(src, Size(k,k), 0) 8UC3 (app/deepseg.cc:657-658)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    out = np.empty_like(src)
+    if not lib.bsb_gaussian_blur(device, _ptr(src), _ptr(out), src.shape[1], src.shape[0], int(ksize)):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return out
+
+
+def gaussian_taps(lib, ksize):
+    q = (C.c_int * 255)()
+    if not lib.bsb_gaussian_taps(int(ksize), q):
+        raise BackscrubError(lib.bsb_last_error().decode())
+    return np.array(q[:ksize], np.int64)
+
+
+def flip(lib, src, flip_h, flip_v, device=0):
+    """cv::flip (app/deepseg.cc:667-673)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    out = np.empty_like(src)
+    if not lib.bsb_flip(device, _ptr(src), _ptr(out), src.shape[1], src.shape[0], int(bool(flip_h)), int(bool(flip_v))):
         raise BackscrubError(lib.bsb_last_error().decode())
     return out
 

@@ -105,12 +105,46 @@ int bsb_set_background(bsb_ctx* ctx, const uint8_t* bg_raw, int bg_w, int bg_h, 
   return 1;
 }
 
+int bsb_set_background_ring(bsb_ctx* ctx, const uint8_t* frames, int count, int bg_w, int bg_h, size_t bg_pitch, size_t frame_stride, int advance) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->set_background_ring(frames, count, bg_w, bg_h, bg_pitch, frame_stride, advance, &err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+int bsb_set_background_cursor(bsb_ctx* ctx, int index) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->set_background_cursor(index, &err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+int bsb_set_bgblur(bsb_ctx* ctx, int ksize) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->set_bgblur(ksize, &err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+int bsb_set_output(bsb_ctx* ctx, int flip_h, int flip_v, int out_w, int out_h) {
+  if (!check_ctx(ctx)) return 0;
+  std::string err;
+  if (!ctx->eng->set_output(flip_h != 0, flip_v != 0, out_w, out_h, &err)) { report(&ctx->cb, "error: " + err); return 0; }
+  return 1;
+}
+
+int bsb_output_size(bsb_ctx* ctx, int* out_w, int* out_h) {
+  if (!check_ctx(ctx)) return 0;
+  if (out_w) *out_w = ctx->eng->out_w();
+  if (out_h) *out_h = ctx->eng->out_h();
+  return 1;
+}
+
 int bsb_get_background(bsb_ctx* ctx, uint8_t* out, size_t out_pitch) {
   if (!check_ctx(ctx)) return 0;
   const bsb::Callbacks* cbp = &ctx->cb;
   Engine* e = ctx->eng;
   if (!out || out_pitch < (size_t)e->W() * 3) { report(cbp, "error: invalid output buffer"); return 0; }
-  if (!e->has_background()) { report(cbp, "error: no background set"); return 0; }
   API_CUDA(cudaSetDevice(e->device()));
   API_CUDA(cudaStreamSynchronize(e->stream()));
   const size_t row = (size_t)e->W() * 3;
@@ -125,11 +159,11 @@ int bsb_composite(bsb_ctx* ctx, int n_frames, const uint8_t* frames, size_t fram
   const bsb::Callbacks* cbp = &ctx->cb;
   Engine* e = ctx->eng;
   const size_t row = (size_t)e->W() * 3, fbytes = row * e->H(), npix = (size_t)e->W() * e->H();
+  const size_t orow = (size_t)e->out_w() * 3, obytes = orow * e->out_h(), opix = (size_t)e->out_w() * e->out_h();
   if (n_frames < 1 || n_frames > e->max_batch()) { report(cbp, "error: n_frames out of range (1..max_batch)"); return 0; }
   if (!frames || frame_pitch < row) { report(cbp, "error: invalid frame"); return 0; }
-  if (out && out_pitch < row) { report(cbp, "error: invalid output pitch"); return 0; }
-  if (!e->has_background() && (out || out_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
-  if (out_yuyv && (e->W() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
+  if (out && out_pitch < orow) { report(cbp, "error: invalid output pitch"); return 0; }
+  if (out_yuyv && (e->out_w() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
   API_CUDA(cudaSetDevice(e->device()));
   if (frame_pitch == row && frame_stride == fbytes) {
     API_CUDA(cudaMemcpyAsync(e->d_frames(), frames, fbytes * n_frames, cudaMemcpyHostToDevice, e->stream()));
@@ -139,17 +173,17 @@ int bsb_composite(bsb_ctx* ctx, int n_frames, const uint8_t* frames, size_t fram
                                  cudaMemcpyHostToDevice, e->stream()));
   }
   std::string err;
-  if (!e->run(n_frames, e->d_frames(), row, fbytes, out ? e->d_out() : nullptr, fbytes, out_yuyv ? e->d_yuyv() : nullptr, npix * 2,
+  if (!e->run(n_frames, e->d_frames(), row, fbytes, out ? e->d_out() : nullptr, obytes, out_yuyv ? e->d_yuyv() : nullptr, opix * 2,
               out_mask ? e->d_mask() : nullptr, npix, false, &err)) {
     report(cbp, "error: failed to process video frame: " + err); return 0;
   }
   if (out) {
-    if (out_pitch == row && out_stride == fbytes) API_CUDA(cudaMemcpyAsync(out, e->d_out(), fbytes * n_frames, cudaMemcpyDeviceToHost, e->stream()));
+    if (out_pitch == orow && out_stride == obytes) API_CUDA(cudaMemcpyAsync(out, e->d_out(), obytes * n_frames, cudaMemcpyDeviceToHost, e->stream()));
     else for (int b = 0; b < n_frames; ++b)
-      API_CUDA(cudaMemcpy2DAsync(out + (size_t)b * out_stride, out_pitch, e->d_out() + b * fbytes, row, row, (size_t)e->H(), cudaMemcpyDeviceToHost, e->stream()));
+      API_CUDA(cudaMemcpy2DAsync(out + (size_t)b * out_stride, out_pitch, e->d_out() + b * obytes, orow, orow, (size_t)e->out_h(), cudaMemcpyDeviceToHost, e->stream()));
   }
   if (out_yuyv) for (int b = 0; b < n_frames; ++b)
-    API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * npix * 2, npix * 2, cudaMemcpyDeviceToHost, e->stream()));
+    API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * opix * 2, opix * 2, cudaMemcpyDeviceToHost, e->stream()));
   if (out_mask) for (int b = 0; b < n_frames; ++b)
     API_CUDA(cudaMemcpyAsync(out_mask + (size_t)b * mask_stride, e->d_mask() + b * npix, npix, cudaMemcpyDeviceToHost, e->stream()));
   API_CUDA(cudaStreamSynchronize(e->stream()));
@@ -163,7 +197,7 @@ int bsb_composite_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_frames, si
   const bsb::Callbacks* cbp = &ctx->cb;
   Engine* e = ctx->eng;
   if (!d_frames) { report(cbp, "error: invalid frame"); return 0; }
-  if (!e->has_background() && (d_out || d_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  if (d_yuyv && (e->out_w() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
   std::string err;
   if (!e->run(n_frames, d_frames, (size_t)e->W() * 3, frame_stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, false, &err)) {
     report(cbp, "error: " + err); return 0;
@@ -177,25 +211,26 @@ int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_frames, s
   if (!check_ctx(ctx)) return 0;
   const bsb::Callbacks* cbp = &ctx->cb;
   Engine* e = ctx->eng;
-  const size_t npix = (size_t)e->W() * e->H(), fbytes = npix * 3;
+  const size_t npix = (size_t)e->W() * e->H();
+  const size_t opix = (size_t)e->out_w() * e->out_h(), obytes = opix * 3;
   if (n_frames < 1 || n_frames > e->max_batch()) { report(cbp, "error: n_frames out of range (1..max_batch)"); return 0; }
   if (!yuyv_frames || in_stride < npix * 2) { report(cbp, "error: invalid frame"); return 0; }
-  if (!e->has_background() && (out || out_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  if (out_yuyv && (e->out_w() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
   API_CUDA(cudaSetDevice(e->device()));
   if (in_stride == npix * 2) API_CUDA(cudaMemcpyAsync(e->d_yuyv_in(), yuyv_frames, npix * 2 * n_frames, cudaMemcpyHostToDevice, e->stream()));
   else for (int b = 0; b < n_frames; ++b)
     API_CUDA(cudaMemcpyAsync(e->d_yuyv_in() + b * npix * 2, yuyv_frames + (size_t)b * in_stride, npix * 2, cudaMemcpyHostToDevice, e->stream()));
   std::string err;
-  if (!e->run_yuyv(n_frames, e->d_yuyv_in(), out ? e->d_out() : nullptr, fbytes, out_yuyv ? e->d_yuyv() : nullptr, npix * 2,
+  if (!e->run_yuyv(n_frames, e->d_yuyv_in(), out ? e->d_out() : nullptr, obytes, out_yuyv ? e->d_yuyv() : nullptr, opix * 2,
                    out_mask ? e->d_mask() : nullptr, npix, &err)) {
     report(cbp, "error: failed to process video frame: " + err); return 0;
   }
   if (out) for (int b = 0; b < n_frames; ++b)
-    API_CUDA(cudaMemcpyAsync(out + (size_t)b * out_stride, e->d_out() + b * fbytes, fbytes, cudaMemcpyDeviceToHost, e->stream()));
+    API_CUDA(cudaMemcpyAsync(out + (size_t)b * out_stride, e->d_out() + b * obytes, obytes, cudaMemcpyDeviceToHost, e->stream()));
   if (out_yuyv) {
-    if (yuyv_stride == npix * 2) API_CUDA(cudaMemcpyAsync(out_yuyv, e->d_yuyv(), npix * 2 * n_frames, cudaMemcpyDeviceToHost, e->stream()));
+    if (yuyv_stride == opix * 2) API_CUDA(cudaMemcpyAsync(out_yuyv, e->d_yuyv(), opix * 2 * n_frames, cudaMemcpyDeviceToHost, e->stream()));
     else for (int b = 0; b < n_frames; ++b)
-      API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * npix * 2, npix * 2, cudaMemcpyDeviceToHost, e->stream()));
+      API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * opix * 2, opix * 2, cudaMemcpyDeviceToHost, e->stream()));
   }
   if (out_mask) for (int b = 0; b < n_frames; ++b)
     API_CUDA(cudaMemcpyAsync(out_mask + (size_t)b * mask_stride, e->d_mask() + b * npix, npix, cudaMemcpyDeviceToHost, e->stream()));
@@ -210,7 +245,7 @@ int bsb_composite_yuyv_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_yuyv_
   const bsb::Callbacks* cbp = &ctx->cb;
   Engine* e = ctx->eng;
   if (!d_yuyv_frames) { report(cbp, "error: invalid frame"); return 0; }
-  if (!e->has_background() && (d_out || d_yuyv)) { report(cbp, "error: no background set (bsb_set_background)"); return 0; }
+  if (d_yuyv && (e->out_w() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
   std::string err;
   if (!e->run_yuyv(n_frames, d_yuyv_frames, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, &err)) { report(cbp, "error: " + err); return 0; }
   if (sync) { API_CUDA(cudaStreamSynchronize(e->stream())); API_CUDA(cudaGetLastError()); }
@@ -286,6 +321,41 @@ int bsb_convert_yuyv_to_bgr(int device, const uint8_t* yuyv, uint8_t* bgr, int w
   if (npix) bsb::launch_yuyv_to_bgr(nullptr, a.u8(), o.u8(), npix);
   if (!stage_end()) return 0;
   cudaMemcpy(bgr, o.p, npix * 3, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+int bsb_gaussian_taps(int ksize, int* taps) {
+  bsb::GaussTaps t{};
+  if (!taps || !bsb::gauss_taps(ksize, &t)) { g_last_error = "strength value must be odd (1..255)"; return 0; }
+  for (int i = 0; i < ksize; ++i) taps[i] = t.q[i];
+  return 1;
+}
+
+int bsb_gaussian_blur(int device, const uint8_t* src, uint8_t* dst, int width, int height, int ksize) {
+  bsb::GaussTaps t{};
+  if (!src || !dst || width <= 0 || height <= 0) { g_last_error = "invalid argument"; return 0; }
+  if (!bsb::gauss_taps(ksize, &t)) { g_last_error = "strength value must be odd (1..255)"; return 0; }
+  if (!stage_begin(device)) return 0;
+  const size_t nb = (size_t)width * height * 3;
+  DevBuf a, o, tmp;
+  if (!a.alloc(nb) || !o.alloc(nb) || !tmp.alloc(nb * 2)) { g_last_error = "cudaMalloc failed"; return 0; }
+  cudaMemcpy(a.p, src, nb, cudaMemcpyHostToDevice);
+  bsb::launch_gauss_blur(nullptr, 1, a.u8(), (size_t)width * 3, nb, static_cast<uint16_t*>(tmp.p), o.u8(), (size_t)width * 3, nb, width, height, t);
+  if (!stage_end()) return 0;
+  cudaMemcpy(dst, o.p, nb, cudaMemcpyDeviceToHost);
+  return 1;
+}
+
+int bsb_flip(int device, const uint8_t* src, uint8_t* dst, int width, int height, int flip_h, int flip_v) {
+  if (!src || !dst || width <= 0 || height <= 0) { g_last_error = "invalid argument"; return 0; }
+  if (!stage_begin(device)) return 0;
+  const size_t nb = (size_t)width * height * 3;
+  DevBuf a, o;
+  if (!a.alloc(nb) || !o.alloc(nb)) { g_last_error = "cudaMalloc failed"; return 0; }
+  cudaMemcpy(a.p, src, nb, cudaMemcpyHostToDevice);
+  bsb::launch_flip_u8c3(nullptr, 1, a.u8(), nb, o.u8(), nb, width, height, flip_h != 0, flip_v != 0);
+  if (!stage_end()) return 0;
+  cudaMemcpy(dst, o.p, nb, cudaMemcpyDeviceToHost);
   return 1;
 }
 

@@ -573,8 +573,18 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMalloc((void**)&d_yuyv_, B * fpx * 2));
   CUDA_OK(cudaMalloc((void**)&d_mask_, B * fpx));
   CUDA_OK(cudaMalloc((void**)&d_yuyv_in_, B * fpx * 2));
-  CUDA_OK(cudaMalloc((void**)&d_bg_, fpx * 3));
-  CUDA_OK(cudaMemset(d_bg_, 0, fpx * 3));
+  {
+    // app/deepseg.cc:603: until a background is set the frame is blended over plain green
+    std::vector<uint8_t> green(fpx * 3);
+    for (size_t i = 0; i < fpx; ++i) { green[3 * i] = 0; green[3 * i + 1] = 255; green[3 * i + 2] = 0; }
+    CUDA_OK(cudaMalloc((void**)&d_bg_, fpx * 3));
+    CUDA_OK(cudaMemcpy(d_bg_, green.data(), fpx * 3, cudaMemcpyHostToDevice));
+    bg_cap_ = fpx * 3;
+    CUDA_OK(cudaMalloc((void**)&d_bg_cursor_, sizeof(int)));
+    CUDA_OK(cudaMemset(d_bg_cursor_, 0, sizeof(int)));
+  }
+  out_w_ = W_; out_h_ = H_;
+  out_cap_ = B * fpx * 3; yuyv_cap_ = B * fpx * 2;
   CUDA_OK(cudaMallocHost((void**)&h_mask_, fpx));
   if (!upload_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
   if (!upload_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
@@ -590,7 +600,8 @@ Engine::~Engine() {
   if (stream_) { cudaStreamSynchronize(stream_); }
   for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)rowsum_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
                   (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_, (void*)d_yuyv_in_,
-                  tab_in_.blob, tab_up_.blob, tab_bg_.blob})
+                  tab_in_.blob, tab_up_.blob, tab_bg_.blob, tab_out_.blob, (void*)d_bg_cursor_, (void*)d_bg_eff_, (void*)d_bg_frames_,
+                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_})
     if (p) cudaFree(p);
   if (h_mask_) cudaFreeHost(h_mask_);
   if (stream_) cudaStreamDestroy(stream_);
@@ -694,18 +705,54 @@ void Engine::enqueue_decision(int n) {
 
 void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
                           uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride) {
+  const size_t fbytes = (size_t)W_ * H_ * 3;
+  const bool flip = flip_h_ || flip_v_, resized = out_w_ != W_ || out_h_ != H_, tail = flip || resized;
+  const bool want_rgb = d_out || d_yuyv;
   PostArgs a{};
   a.B = n; a.W = W_; a.H = H_;
   a.frames = d_frames; a.frame_pitch = pitch; a.frame_stride = stride;
   a.bg = d_bg_; a.bg_pitch = (size_t)W_ * 3; a.bg_stride = 0;
+  bool ring = false;
+  if (has_bg_) {
+    if (bgblur_k_) a.bg = d_bg_eff_;                       // blurred once, when the background / strength was set
+    if (bg_count_ > 1) { ring = true; a.bg_stride = fbytes; a.bg_cursor = d_bg_cursor_; a.bg_count = bg_count_; a.bg_advance = bg_advance_; }
+  } else if (bgblur_k_ && want_rgb) {
+    // app/deepseg.cc:652-658: no background source => the background is the blurred camera frame itself
+    launch_gauss_blur(stream_, n, d_frames, pitch, stride, d_gauss_tmp_, d_bg_frames_, (size_t)W_ * 3, fbytes, W_, H_, taps_);
+    a.bg = d_bg_frames_; a.bg_stride = fbytes;
+  }
   a.ofinal = ofinal_; a.ow = ow_; a.oh = oh_;
   a.out_x = out_roidim_[0]; a.out_y = out_roidim_[1]; a.out_w = out_roidim_[2]; a.out_h = out_roidim_[3];
   a.roi_x = roidim_[0]; a.roi_y = roidim_[1]; a.roi_w = roidim_[2]; a.roi_h = roidim_[3];
   a.tab = tab_up_.tab; a.area2x2 = false;
-  a.out = d_out; a.out_pitch = (size_t)W_ * 3; a.out_stride = out_stride;
-  a.yuyv = d_yuyv; a.yuyv_stride = yuyv_stride;
+  a.out_pitch = (size_t)W_ * 3;
+  if (!tail) {
+    a.out = d_out; a.out_stride = out_stride;
+    a.yuyv = d_yuyv; a.yuyv_stride = yuyv_stride;
+  } else {
+    a.out = want_rgb ? d_stage_a_ : nullptr; a.out_stride = fbytes;
+    a.yuyv = nullptr; a.yuyv_stride = 0;
+  }
   a.mask = d_mask; a.mask_stride = mask_stride;
   launch_post(stream_, a);
+  if (ring && bg_advance_) launch_advance_cursor(stream_, d_bg_cursor_, (int)(((long)n * bg_advance_) % bg_count_), bg_count_);
+  if (!tail || !want_rgb) return;
+  // app/deepseg.cc:667-679: flip, then scale to the virtual-camera geometry, then YUYV (:681)
+  const size_t obytes = (size_t)out_w_ * out_h_ * 3;
+  const uint8_t* cur = d_stage_a_; size_t cur_stride = fbytes;
+  if (flip) {
+    uint8_t* dst = (!resized && d_out) ? d_out : d_stage_b_;
+    const size_t ds = (!resized && d_out) ? out_stride : fbytes;
+    launch_flip_u8c3(stream_, n, cur, cur_stride, dst, ds, W_, H_, flip_h_, flip_v_);
+    cur = dst; cur_stride = ds;
+  }
+  if (resized) {
+    uint8_t* dst = d_out ? d_out : d_stage_c_;
+    const size_t ds = d_out ? out_stride : obytes;
+    launch_resize_u8c3(stream_, cur, W_, H_, (size_t)W_ * 3, dst, out_w_, out_h_, (size_t)out_w_ * 3, tab_out_.tab, tab_out_.area2x2, n, cur_stride, ds);
+    cur = dst; cur_stride = ds;
+  }
+  if (d_yuyv) launch_rgb_to_yuyv(stream_, cur, d_yuyv, (size_t)out_w_ * out_h_, n, cur_stride, yuyv_stride);
 }
 
 bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
@@ -735,7 +782,7 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
   const GraphKey key{n, d_frames, pitch, stride, d_out, d_yuyv, d_mask, d_yuyv_in};
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
-    if (graphs_.size() >= 64) { for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second); graphs_.clear(); }
+    if (graphs_.size() >= 64) drop_graphs();
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
     if (d_yuyv_in) launch_yuyv_to_bgr(stream_, d_yuyv_in, const_cast<uint8_t*>(d_frames), (size_t)n * W_ * H_);
@@ -772,27 +819,107 @@ bool Engine::infer(int n, const float* h_in, float* h_out, std::string* err) {
   return true;
 }
 
-bool Engine::set_background(const uint8_t* bg_raw, int bw, int bh, size_t pitch, std::string* err) {
-  if (!bg_raw || bw <= 0 || bh <= 0 || pitch < (size_t)bw * 3) { *err = "invalid background"; return false; }
+void Engine::drop_graphs() {
+#ifndef BSB_EMU
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  graphs_.clear();
+#endif
+}
+
+bool Engine::ensure(void** p, size_t* cap, size_t need, std::string* err) {
+  if (need <= *cap && *p) return true;
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  drop_graphs();                                  // captured launches hold the old pointer
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  CUDA_OK(cudaMalloc(p, need));
+  *cap = need;
+  return true;
+}
+
+bool Engine::set_background_ring(const uint8_t* frames, int count, int bw, int bh, size_t pitch, size_t frame_stride, int advance,
+                                 std::string* err) {
+  if (!frames || count < 1 || bw <= 0 || bh <= 0 || pitch < (size_t)bw * 3 || advance < 0 ||
+      (count > 1 && frame_stride < pitch * (size_t)(bh - 1) + (size_t)bw * 3)) { *err = "invalid background"; return false; }
   CUDA_OK(cudaSetDevice(device_));
-  const size_t need = (size_t)bw * bh * 3;
-  if (need > bg_raw_cap_) {
-    if (d_bg_raw_) cudaFree(d_bg_raw_);
-    d_bg_raw_ = nullptr;
-    CUDA_OK(cudaMalloc((void**)&d_bg_raw_, need));
-    bg_raw_cap_ = need;
-  }
+  const size_t raw = (size_t)bw * bh * 3, fbytes = (size_t)W_ * H_ * 3;
+  if (!ensure((void**)&d_bg_raw_, &bg_raw_cap_, raw * count, err)) return false;
+  if (!ensure((void**)&d_bg_, &bg_cap_, fbytes * count, err)) return false;
   if (bw != bg_w_ || bh != bg_h_) {
     CUDA_OK(cudaStreamSynchronize(stream_));
     if (!upload_tab(build_resize_tab(bw, bh, W_, H_), &tab_bg_, err)) return false;
     bg_w_ = bw; bg_h_ = bh;
   }
-  CUDA_OK(cudaMemcpy2DAsync(d_bg_raw_, (size_t)bw * 3, bg_raw, pitch, (size_t)bw * 3, (size_t)bh, cudaMemcpyHostToDevice, stream_));
+  if (count != bg_count_ || advance != bg_advance_ || !has_bg_) { CUDA_OK(cudaStreamSynchronize(stream_)); drop_graphs(); }
+  for (int i = 0; i < count; ++i)
+    CUDA_OK(cudaMemcpy2DAsync(d_bg_raw_ + (size_t)i * raw, (size_t)bw * 3, frames + (size_t)i * frame_stride, pitch, (size_t)bw * 3, (size_t)bh,
+                              cudaMemcpyHostToDevice, stream_));
   // app/background.cc:178-194: cv::resize(raw, out, Size(width, height))
-  launch_resize_u8c3(stream_, d_bg_raw_, bw, bh, (size_t)bw * 3, d_bg_, W_, H_, (size_t)W_ * 3, tab_bg_.tab, tab_bg_.area2x2);
+  launch_resize_u8c3(stream_, d_bg_raw_, bw, bh, (size_t)bw * 3, d_bg_, W_, H_, (size_t)W_ * 3, tab_bg_.tab, tab_bg_.area2x2, count, raw, fbytes);
+  CUDA_OK(cudaMemsetAsync(d_bg_cursor_, 0, sizeof(int), stream_));
+  bg_count_ = count; bg_advance_ = advance;
+  has_bg_ = true;
+  if (!refresh_bg_blur(err)) return false;
   CUDA_OK(cudaStreamSynchronize(stream_));
   CUDA_OK(cudaGetLastError());
-  has_bg_ = true;
+  return true;
+}
+
+bool Engine::set_background_cursor(int index, std::string* err) {
+  if (index < 0 || index >= bg_count_) { *err = "background index out of range"; return false; }
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaMemcpyAsync(d_bg_cursor_, &index, sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  return true;
+}
+
+// (re)compute the blurred copy of the background ring; per-frame work only in camera-blur mode
+bool Engine::refresh_bg_blur(std::string* err) {
+  if (!bgblur_k_) return true;
+  const size_t fbytes = (size_t)W_ * H_ * 3;
+  if (!ensure((void**)&d_gauss_tmp_, &gauss_tmp_cap_, (size_t)max_batch_ * fbytes * sizeof(uint16_t), err)) return false;
+  if (!has_bg_) return ensure((void**)&d_bg_frames_, &bg_frames_cap_, (size_t)max_batch_ * fbytes, err);
+  if (!ensure((void**)&d_bg_eff_, &bg_eff_cap_, fbytes * bg_count_, err)) return false;
+  for (int i = 0; i < bg_count_; i += max_batch_) {
+    const int n = std::min(max_batch_, bg_count_ - i);
+    launch_gauss_blur(stream_, n, d_bg_ + (size_t)i * fbytes, (size_t)W_ * 3, fbytes, d_gauss_tmp_, d_bg_eff_ + (size_t)i * fbytes, (size_t)W_ * 3,
+                      fbytes, W_, H_, taps_);
+  }
+  CUDA_OK(cudaGetLastError());
+  return true;
+}
+
+bool Engine::set_bgblur(int k, std::string* err) {
+  GaussTaps t{};
+  if (k != 0 && !gauss_taps(k, &t)) { *err = "strength value must be odd (1..255)"; return false; }   // app/deepseg.cc:423-426
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  drop_graphs();
+  bgblur_k_ = k; taps_ = t;
+  if (!refresh_bg_blur(err)) return false;
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  return true;
+}
+
+bool Engine::set_output(bool flip_h, bool flip_v, int out_w, int out_h, std::string* err) {
+  if (out_w <= 0) out_w = W_;
+  if (out_h <= 0) out_h = H_;
+  if (out_w > 16384 || out_h > 16384) { *err = "output size out of range"; return false; }
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  drop_graphs();
+  const size_t B = (size_t)max_batch_, fbytes = (size_t)W_ * H_ * 3, obytes = (size_t)out_w * out_h * 3;
+  const bool flip = flip_h || flip_v, resized = out_w != W_ || out_h != H_;
+  if (flip || resized) { if (!ensure((void**)&d_stage_a_, &stage_a_cap_, B * fbytes, err)) return false; }
+  if (flip) { if (!ensure((void**)&d_stage_b_, &stage_b_cap_, B * fbytes, err)) return false; }
+  if (resized) {
+    if (!ensure((void**)&d_stage_c_, &stage_c_cap_, B * obytes, err)) return false;
+    if (!upload_tab(build_resize_tab(W_, H_, out_w, out_h), &tab_out_, err)) return false;
+    // host-buffer API staging must hold the larger of the two geometries
+    if (!ensure((void**)&d_out_, &out_cap_, B * std::max(fbytes, obytes), err)) return false;
+    if (!ensure((void**)&d_yuyv_, &yuyv_cap_, B * std::max(fbytes, obytes) / 3 * 2, err)) return false;
+  }
+  flip_h_ = flip_h; flip_v_ = flip_v; out_w_ = out_w; out_h_ = out_h;
   return true;
 }
 

@@ -81,7 +81,20 @@ class Engine {
   bool run_yuyv(int n, const uint8_t* d_yuyv_in, uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
                 uint8_t* d_mask, size_t mask_stride, std::string* err);
   bool infer(int n, const float* h_in, float* h_out, std::string* err);
-  bool set_background(const uint8_t* bg_raw, int bw, int bh, size_t pitch, std::string* err);
+  bool set_background(const uint8_t* bg_raw, int bw, int bh, size_t pitch, std::string* err) {
+    return set_background_ring(bg_raw, 1, bw, bh, pitch, 0, 0, err);
+  }
+  // animated background (app/background.cc:126-176 decodes, :178-194 resizes): `count` decoded images are
+  // resized into a device ring; batch frame b of a call blends ring image (cursor + b*advance) % count and the
+  // cursor then moves on by n*advance (advance 0: the caller moves it with set_background_cursor)
+  bool set_background_ring(const uint8_t* frames, int count, int bw, int bh, size_t pitch, size_t frame_stride, int advance,
+                           std::string* err);
+  bool set_background_cursor(int index, std::string* err);
+  // app/deepseg.cc:657-658 `-p bgblur:k`: Gaussian-blur the background (the grabbed one, else a copy of the
+  // camera frame); k = 0 switches it off
+  bool set_bgblur(int k, std::string* err);
+  // app/deepseg.cc:667-679: cv::flip and cv::resize to the virtual-camera size before the YUYV conversion
+  bool set_output(bool flip_h, bool flip_v, int out_w, int out_h, std::string* err);
   bool sync(std::string* err);
   bool reset_state(std::string* err);
   double time_stage(int stage, int n, int iters, std::string* err);
@@ -89,6 +102,10 @@ class Engine {
   // accessors
   int W() const { return W_; }
   int H() const { return H_; }
+  int out_w() const { return out_w_; }
+  int out_h() const { return out_h_; }
+  int bgblur() const { return bgblur_k_; }
+  int bg_count() const { return bg_count_; }
   int max_batch() const { return max_batch_; }
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
@@ -98,7 +115,15 @@ class Engine {
   void in_hwc(int* v) const { v[0] = mh_; v[1] = mw_; v[2] = 3; }
   void out_hwc(int* v) const { v[0] = oh_; v[1] = ow_; v[2] = oc_; }
   double flops() const { return flops_; }
-  int launches_per_call() const { int n = 4; for (const Step& s : steps_) n += s.launches(); return n; }
+  int launches_per_call() const {
+    int n = 4;
+    for (const Step& s : steps_) n += s.launches();
+    if (bgblur_k_ && !has_bg_) n += 2;
+    if (bg_count_ > 1 && bg_advance_) n += 1;
+    const bool resized = out_w_ != W_ || out_h_ != H_;
+    if (flip_h_ || flip_v_ || resized) n += (flip_h_ || flip_v_ ? 1 : 0) + (resized ? 1 : 0) + 1;   // + stand-alone YUYV
+    return n;
+  }
   long get_tensor(int t, float* out, long cap, std::string* err);
   long get_stage_u8(int which, int frame, uint8_t* out, long cap, std::string* err);
 
@@ -107,7 +132,7 @@ class Engine {
   uint8_t* d_out() const { return d_out_; }
   uint8_t* d_yuyv() const { return d_yuyv_; }
   uint8_t* d_mask() const { return d_mask_; }
-  uint8_t* d_bg() const { return d_bg_; }
+  uint8_t* d_bg() const { return d_bg_; }          // resized, unblurred (what grab_background returns)
   uint8_t* d_yuyv_in() const { return d_yuyv_in_; }
   uint8_t* h_mask() const { return h_mask_; }
   bool has_background() const { return has_bg_; }
@@ -159,8 +184,26 @@ class Engine {
   size_t bg_raw_cap_ = 0;
   uint8_t* h_mask_ = nullptr;        // pinned host W*H
   bool has_bg_ = false;
-  DevResizeTab tab_in_, tab_up_, tab_bg_;
+  DevResizeTab tab_in_, tab_up_, tab_bg_, tab_out_;
   int bg_w_ = 0, bg_h_ = 0;
+
+  // optional stages around the blend (app/deepseg.cc:649-679)
+  bool ensure(void** p, size_t* cap, size_t need, std::string* err);   // grow-only device buffer; drops the graphs
+  bool refresh_bg_blur(std::string* err);
+  void drop_graphs();
+  int bg_count_ = 1, bg_advance_ = 0;
+  size_t bg_cap_ = 0;
+  int* d_bg_cursor_ = nullptr;
+  int bgblur_k_ = 0;
+  GaussTaps taps_{};
+  uint8_t* d_bg_eff_ = nullptr;      // blurred copy of the background ring
+  uint8_t* d_bg_frames_ = nullptr;   // [B][H][W][3] blurred camera frames (bgblur without a background)
+  uint16_t* d_gauss_tmp_ = nullptr;  // [B][H][W*3] row sums
+  size_t bg_eff_cap_ = 0, bg_frames_cap_ = 0, gauss_tmp_cap_ = 0;
+  bool flip_h_ = false, flip_v_ = false;
+  int out_w_ = 0, out_h_ = 0;
+  uint8_t* d_stage_a_ = nullptr, *d_stage_b_ = nullptr, *d_stage_c_ = nullptr;
+  size_t stage_a_cap_ = 0, stage_b_cap_ = 0, stage_c_cap_ = 0, out_cap_ = 0, yuyv_cap_ = 0;
 
   struct GraphKey {
     int n; const void* f; size_t pitch, stride; const void* o; const void* y; const void* m; const void* yin = nullptr;

@@ -126,6 +126,7 @@ struct PostArgs {
   int B, W, H;
   const uint8_t* frames; size_t frame_pitch, frame_stride;   // row pitch / per-frame stride (bytes)
   const uint8_t* bg; size_t bg_pitch, bg_stride;             // bg_stride 0 => one static background
+  const int* bg_cursor; int bg_count, bg_advance;             // non-null: frame b blends ring image (*cursor + b*advance) % count
   const uint8_t* ofinal; int ow, oh;                          // [B][oh*ow]
   int out_x, out_y, out_w, out_h;                              // out_roidim inside ofinal
   int roi_x, roi_y, roi_w, roi_h;                              // roidim inside the frame
@@ -138,8 +139,19 @@ struct PostArgs {
 void launch_post(cudaStream_t s, const PostArgs& a);
 
 // app/background.cc:178-194: cv::resize(raw -> W x H), 3 channels
+// n images (frame strides in bytes; n = 1 for the background provider)
 void launch_resize_u8c3(cudaStream_t s, const uint8_t* src, int sw, int sh, size_t spitch,
-                        uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2);
+                        uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2,
+                        int n = 1, size_t sstride = 0, size_t dstride = 0);
+
+// app/deepseg.cc:657-658: cv::GaussianBlur(bg, bg, Size(k,k), 0), 8UC3 — OpenCV's 8.8 fixed-point taps (sum 256)
+struct GaussTaps { int k; uint16_t q[255]; };
+bool gauss_taps(int k, GaussTaps* out);           // false unless k is odd, 1..255
+// n frames; tmp holds n*H*W*3 16-bit row sums
+void launch_gauss_blur(cudaStream_t s, int n, const uint8_t* src, size_t spitch, size_t sstride, uint16_t* tmp,
+                       uint8_t* dst, size_t dpitch, size_t dstride, int W, int H, const GaussTaps& g);
+// app/deepseg.cc:667-673: cv::flip on n packed frames
+void launch_flip_u8c3(cudaStream_t s, int n, const uint8_t* src, size_t sstride, uint8_t* dst, size_t dstride, int W, int H, bool flip_h, bool flip_v);
 
 // cv::cvtColor(COLOR_YUV2BGR_YUYV): camera YUYV frames -> BGR (what cv::VideoCapture does for the
 // reference, app/deepseg.cc:553).  n frames of W x H, tightly packed.
@@ -147,7 +159,10 @@ void launch_yuyv_to_bgr(cudaStream_t s, const uint8_t* yuyv, uint8_t* bgr, size_
 
 // stand-alone stage kernels (exported through the C-ABI for stage-level parity tests)
 void launch_alpha_blend(cudaStream_t s, const uint8_t* a, const uint8_t* b, const uint8_t* mask, uint8_t* out, size_t npix);
-void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix);
+// npix pixels per frame (even), n frames
+void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix, int n = 1, size_t rgb_stride = 0, size_t yuyv_stride = 0);
+// *cursor = (*cursor + step) % count, after the frames of a call have been blended
+void launch_advance_cursor(cudaStream_t s, int* cursor, int step, int count);
 
 // number of kernel launches issued through the launchers above (bench gpu_launches)
 long launch_count();

@@ -21,6 +21,13 @@ BSB_D uint8_t lin_v(int h0, int h1, int b0, int b1) {
   return bsb_sat_u8((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
 }
 
+// background of batch frame b: one static image (bg_stride 0), one image per frame, or a ring of
+// bg_count images entered at the device-side cursor (animated backgrounds, app/background.cc:126-176)
+BSB_D size_t bg_frame_offset(const PostArgs& a, int b) {
+  if (a.bg_cursor) b = (int)(((unsigned)__ldg(a.bg_cursor) + (unsigned)b * (unsigned)a.bg_advance) % (unsigned)a.bg_count);
+  return (size_t)b * a.bg_stride;
+}
+
 // ---------------------------------------------------------------------------
 // ROI crop -> resize -> BGR2RGB into the zero-padded model-sized image.
 // One thread = one destination pixel (3 channels).
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
 
   // ---- D: blend (+ YUYV, + mask) ----
   const size_t fo = (size_t)b * a.frame_stride + (size_t)y * a.frame_pitch + (size_t)x0 * 3;
-  const size_t bo = (size_t)b * a.bg_stride + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
+  const size_t bo = bg_frame_offset(a, b) + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
   const bool full = npx == PT_PX;
   const bool fast_in = full && ((reinterpret_cast<uintptr_t>(a.frames + fo) | reinterpret_cast<uintptr_t>(a.bg + bo)) & 15) == 0;
   Px16 f, g, o;
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   unsigned f[12], g[12];
   if (OUT || YUYV) {
     const uint8_t* fp = a.frames + (size_t)b * a.frame_stride + (size_t)y * a.frame_pitch + (size_t)x0 * 3;
-    const uint8_t* gp = a.bg + (size_t)b * a.bg_stride + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
+    const uint8_t* gp = a.bg + bg_frame_offset(a, b) + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const uint4 t = ldg_stream(fp + 16 * k);
@@ -616,9 +623,11 @@ void launch_post(cudaStream_t s, const PostArgs& a) {
 // cv::resize(src -> dst) 8UC3 (background provider).  One thread = one dst pixel.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_resize_u8c3(const uint8_t* src, int sw, int sh, size_t spitch,
-                                                     uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab t, bool area2x2) {
+                                                     uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab t, bool area2x2,
+                                                     size_t sstride, size_t dstride) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)dw * dh) return;
+  src += (size_t)blockIdx.y * sstride; dst += (size_t)blockIdx.y * dstride;
   const int dx = (int)(idx % dw), dy = (int)(idx / dw);
   uint8_t* d = dst + (size_t)dy * dpitch + (size_t)dx * 3;
   if (area2x2) {
@@ -639,9 +648,11 @@ __global__ void __launch_bounds__(256) k_resize_u8c3(const uint8_t* src, int sw,
 }
 
 void launch_resize_u8c3(cudaStream_t s, const uint8_t* src, int sw, int sh, size_t spitch,
-                        uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2) {
+                        uint8_t* dst, int dw, int dh, size_t dpitch, ResizeTab tab, bool area2x2,
+                        int n, size_t sstride, size_t dstride) {
   const long total = (long)dw * dh;
-  BSB_LAUNCH(k_resize_u8c3, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, sw, sh, spitch, dst, dw, dh, dpitch, tab, area2x2);
+  BSB_LAUNCH(k_resize_u8c3, dim3((unsigned)((total + 255) / 256), (unsigned)n), dim3(256), 0, s, src, sw, sh, spitch, dst, dw, dh, dpitch, tab, area2x2,
+             sstride, dstride);
   count_launch();
 }
 
@@ -698,9 +709,10 @@ void launch_alpha_blend(cudaStream_t s, const uint8_t* a, const uint8_t* b, cons
   count_launch();
 }
 
-__global__ void __launch_bounds__(256) k_rgb_to_yuyv(const uint8_t* rgb, uint8_t* yuyv, size_t npairs) {
+__global__ void __launch_bounds__(256) k_rgb_to_yuyv(const uint8_t* rgb, uint8_t* yuyv, size_t npairs, size_t rgb_stride, size_t yuyv_stride) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
+  rgb += (size_t)blockIdx.y * rgb_stride; yuyv += (size_t)blockIdx.y * yuyv_stride;
   const uint8_t* s = rgb + 6 * p;
   int Y0, U0, V0, Y1, U1, V1;
   rgb2yuv(s[0], s[1], s[2], Y0, U0, V0);
@@ -709,9 +721,9 @@ __global__ void __launch_bounds__(256) k_rgb_to_yuyv(const uint8_t* rgb, uint8_t
   d[0] = (uint8_t)Y0; d[1] = (uint8_t)((V0 + V1) / 2); d[2] = (uint8_t)Y1; d[3] = (uint8_t)((U0 + U1) / 2);
 }
 
-void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix) {
+void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_t npix, int n, size_t rgb_stride, size_t yuyv_stride) {
   const size_t npairs = npix / 2;
-  BSB_LAUNCH(k_rgb_to_yuyv, dim3((unsigned)((npairs + 255) / 256)), dim3(256), 0, s, rgb, yuyv, npairs);
+  BSB_LAUNCH(k_rgb_to_yuyv, dim3((unsigned)((npairs + 255) / 256), (unsigned)n), dim3(256), 0, s, rgb, yuyv, npairs, rgb_stride, yuyv_stride);
   count_launch();
 }
 

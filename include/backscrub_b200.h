@@ -89,8 +89,27 @@ BSB_API int bsb_maskgen_process(bsb_ctx* ctx, const uint8_t* frame, size_t frame
  * the decoded raw frame and performs grab_background's cv::resize(raw -> W x H) on the
  * GPU.  Call again whenever the decoded frame changes (video backgrounds). */
 BSB_API int bsb_set_background(bsb_ctx* ctx, const uint8_t* bg_raw, int bg_w, int bg_h, size_t bg_pitch);
-/* the resized background (what grab_background hands back), copied to host */
+/* the resized background (what grab_background hands back), copied to host.  Until a background is set it is
+ * plain green, like `bg` in app/deepseg.cc:603. */
 BSB_API int bsb_get_background(bsb_ctx* ctx, uint8_t* out, size_t out_pitch);
+/* Animated background (the video branch of app/background.cc:126-176 decodes; :178-194 resizes): `count` decoded
+ * images, `frame_stride` bytes apart, are resized into a device-resident ring.  Batch frame b of a composite call
+ * blends ring image (cursor + b*advance) % count, and the cursor then moves on by n_frames*advance.  advance 0
+ * leaves pacing to the caller (bsb_set_background_cursor), as the reference paces by wall clock. */
+BSB_API int bsb_set_background_ring(bsb_ctx* ctx, const uint8_t* frames, int count, int bg_w, int bg_h, size_t bg_pitch,
+                                    size_t frame_stride, int advance);
+BSB_API int bsb_set_background_cursor(bsb_ctx* ctx, int index);
+
+/* ---- per-frame options of the reference's main loop around alpha_blend (app/deepseg.cc:649-679) ----
+ * `-p bgblur:k` (:415-434, :657-658): cv::GaussianBlur(bg, bg, Size(k,k), 0) on the background — the grabbed
+ * one, or, when no background was set, a copy of the camera frame (:652-654).  k odd in 1..255 ("strength value
+ * must be odd"), 0 = off.  OpenCV's bit-exact 8-bit path. */
+BSB_API int bsb_set_bgblur(bsb_ctx* ctx, int ksize);
+/* `-H`/`-V` cv::flip of the composited frame (:667-673) and cv::resize to the virtual-camera geometry when it
+ * differs from the capture geometry (:677-679); both before the YUYV conversion.  out_w/out_h <= 0 = frame size.
+ * After this call `out` buffers are out_w x out_h x 3 and `out_yuyv` out_w x out_h x 2; the mask stays W x H. */
+BSB_API int bsb_set_output(bsb_ctx* ctx, int flip_h, int flip_v, int out_w, int out_h);
+BSB_API int bsb_output_size(bsb_ctx* ctx, int* out_w, int* out_h);
 
 /* ---- fused per-frame path: one CUDA-graph launch per call ---------------------------
  * mask generation (bs_maskgen_process) + alpha_blend(bg, frame, mask)
@@ -128,6 +147,11 @@ BSB_API int bsb_alpha_blend(int device, const uint8_t* srca, const uint8_t* srcb
 BSB_API int bsb_convert_rgb_to_yuyv(int device, const uint8_t* rgb, uint8_t* yuyv, int width, int height);
 /* cv::cvtColor(COLOR_YUV2BGR_YUYV) (camera ingest, app/deepseg.cc:553,725) */
 BSB_API int bsb_convert_yuyv_to_bgr(int device, const uint8_t* yuyv, uint8_t* bgr, int width, int height);
+/* cv::GaussianBlur(src, dst, Size(k,k), 0) 8UC3 (app/deepseg.cc:657-658) and its 8.8 fixed-point taps (host only) */
+BSB_API int bsb_gaussian_blur(int device, const uint8_t* src, uint8_t* dst, int width, int height, int ksize);
+BSB_API int bsb_gaussian_taps(int ksize, int* taps);
+/* cv::flip(src, dst, code) 8UC3 (app/deepseg.cc:667-673) */
+BSB_API int bsb_flip(int device, const uint8_t* src, uint8_t* dst, int width, int height, int flip_h, int flip_v);
 /* cv::resize(src, dst, Size(dw, dh)) 8UC3 (app/background.cc:178-194) */
 BSB_API int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
 

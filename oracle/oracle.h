@@ -112,6 +112,13 @@ void or_alpha_blend(const uint8_t* srca, const uint8_t* srcb, const uint8_t* mas
 /* cv::cvtColor(COLOR_YUV2BGR_YUYV): the YUYV camera frame -> BGR conversion (app/deepseg.cc:553,725) */
 void or_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, int w, int h);
 
+/* cv::GaussianBlur(src, dst, Size(k,k), 0) 8UC3 BORDER_DEFAULT, OpenCV's bit-exact 8.8 fixed-point path
+ * (app/deepseg.cc:657-658).  q receives the k fixed-point taps (sum 256).  Both return 0 on success. */
+int or_gaussian_kernel_q8(int k, int* q);
+int or_gaussian_blur_u8c3(const uint8_t* src, int w, int h, size_t sstride, uint8_t* dst, size_t dstride, int k);
+/* cv::flip (app/deepseg.cc:667-673) */
+void or_flip_u8c3(const uint8_t* src, uint8_t* dst, int w, int h, int flip_h, int flip_v);
+
 /* ---- pipeline (lib/libbackscrub.cc:161-376 restated, deterministic) ---- */
 enum { OR_MODEL_UNKNOWN = 0, OR_MODEL_BODYPIX, OR_MODEL_DEEPLAB, OR_MODEL_MEET, OR_MODEL_MLKIT };
 typedef struct or_maskgen or_maskgen;
@@ -137,6 +144,16 @@ int or_maskgen_post_from_output(or_maskgen* g, const float* model_output, uint8_
 int or_composite(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
                  const uint8_t* bg_raw, int bw, int bh, size_t bstride,
                  uint8_t* out_rgb, uint8_t* out_yuyv, uint8_t* out_mask);
+
+/* the whole main-loop body of app/deepseg.cc:640-681 with its options:
+ *   bg_raw NULL  -> the background is a copy of the camera frame (only meaningful with bgblur_k, :652-654)
+ *   bgblur_k     -> cv::GaussianBlur(bg, k x k, 0) after grab_background (:657-658); 0 = off
+ *   flip_h/flip_v-> cv::flip (:667-673);  out_w x out_h -> cv::resize to the virtual-camera size (:677-679)
+ * out_rgb / out_yuyv are out_w x out_h; out_mask stays W x H. */
+typedef struct { int bgblur_k, flip_h, flip_v, out_w, out_h; } or_frame_opts;
+int or_composite_ex(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
+                    const uint8_t* bg_raw, int bw, int bh, size_t bstride, const or_frame_opts* o,
+                    uint8_t* out_rgb, uint8_t* out_yuyv, uint8_t* out_mask);
 
 #ifdef __cplusplus
 }

@@ -193,3 +193,86 @@ void or_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, int w, int h) {
     }
   }
 }
+
+
+/* ---------------------------------------------------------------------------
+ * cv::GaussianBlur(src, dst, Size(k,k), 0) for CV_8UC3, BORDER_DEFAULT (app/deepseg.cc:657-658, `-p bgblur:k`).
+ *
+ * OpenCV is a system dependency of the reference (not under /root/reference); this restates the
+ * published bit-exact 8-bit path of OpenCV 4.x (modules/imgproc/src/smooth.dispatch.cpp:
+ * getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED + GaussianBlurFixedPoint) and is pinned
+ * bit-exact against the in-container cv2 4.13 for k = 1..255 kernels and k in {3,5,7,9,11,25,51} images:
+ *   sigma = 0.15 k + 0.35;   g[i] = exp(-(i-(k-1)/2)^2 / (2 sigma^2)) / sum   (double)
+ *   q[i]  = round-half-even(g[i]*256 + carried rounding error) for the first half (mirrored),
+ *   q[centre] = 256 - 2*sum(first half)        => sum q == 256 exactly (8.8 fixed point)
+ *   rows:  h = sum_j q[j]*src[x+j]   (16 bit, exact)      cols: v = sum_j q[j]*h[y+j] (32 bit, exact)
+ *   dst = (v + 32768) >> 16
+ * k <= 9 with sigma 0 use OpenCV's tabulated small kernels (1; 1 2 1; 1 4 6 4 1; ...), which the formula
+ * above does not produce.
+ * --------------------------------------------------------------------------- */
+int or_gaussian_kernel_q8(int k, int* q) {
+  if (k < 1 || !(k & 1) || k > 255) return -1;
+  static const double small[5][9] = {
+      {1.0}, {0.25, 0.5, 0.25}, {0.0625, 0.25, 0.375, 0.25, 0.0625},
+      {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125},
+      {4.0 / 256, 13.0 / 256, 30.0 / 256, 51.0 / 256, 60.0 / 256, 51.0 / 256, 30.0 / 256, 13.0 / 256, 4.0 / 256}};
+  double g[255];
+  const int n2 = k / 2;
+  if (k <= 9) {
+    for (int i = 0; i < k; ++i) g[i] = small[n2][i];
+  } else {
+    const double sigma = fma((double)k, 0.15, 0.35);
+    const double scale2x = -0.125 / (sigma * sigma);
+    double sum = 0.0;
+    for (int i = 0, x = 1 - k; i < n2; ++i, x += 2) { g[i] = exp((double)(x * x) * scale2x); sum += g[i]; }
+    sum = sum * 2.0 + 1.0;
+    const double mul = 1.0 / sum;
+    for (int i = 0; i < n2; ++i) g[i] *= mul;
+    g[n2] = mul;
+  }
+  double err = 0.0;
+  int acc = 0;
+  for (int i = 0; i < n2; ++i) {
+    const double adj = g[i] * 256.0 + err;
+    const int v = (int)nearbyint(adj);
+    err = adj - (double)v;
+    q[i] = q[k - 1 - i] = v;
+    acc += v;
+  }
+  q[n2] = 256 - 2 * acc;
+  return 0;
+}
+
+int or_gaussian_blur_u8c3(const uint8_t* src, int w, int h, size_t sstride, uint8_t* dst, size_t dstride, int k) {
+  int q[255];
+  if (or_gaussian_kernel_q8(k, q)) return -1;
+  const int r = k / 2;
+  uint16_t* tmp = (uint16_t*)malloc((size_t)w * h * 3 * sizeof(uint16_t));
+  if (!tmp) return -1;
+  for (int y = 0; y < h; ++y) {
+    const uint8_t* s = src + (size_t)y * sstride;
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < 3; ++c) {
+        uint32_t a = 0;
+        for (int j = 0; j < k; ++j) a += (uint32_t)q[j] * s[(size_t)reflect101(x + j - r, w) * 3 + c];
+        tmp[((size_t)y * w + x) * 3 + c] = (uint16_t)a;
+      }
+  }
+  for (int y = 0; y < h; ++y)
+    for (size_t i = 0; i < (size_t)w * 3; ++i) {
+      uint32_t a = 0;
+      for (int j = 0; j < k; ++j) a += (uint32_t)q[j] * tmp[(size_t)reflect101(y + j - r, h) * w * 3 + i];
+      dst[(size_t)y * dstride + i] = (uint8_t)((a + 32768u) >> 16);
+    }
+  free(tmp);
+  return 0;
+}
+
+/* cv::flip(src, dst, code): code 1 = horizontal (around the y axis), 0 = vertical, -1 = both (app/deepseg.cc:667-673) */
+void or_flip_u8c3(const uint8_t* src, uint8_t* dst, int w, int h, int flip_h, int flip_v) {
+  for (int y = 0; y < h; ++y) {
+    const uint8_t* s = src + (size_t)(flip_v ? h - 1 - y : y) * w * 3;
+    uint8_t* d = dst + (size_t)y * w * 3;
+    for (int x = 0; x < w; ++x) memcpy(d + (size_t)x * 3, s + (size_t)(flip_h ? w - 1 - x : x) * 3, 3);
+  }
+}

@@ -213,3 +213,33 @@ int or_composite(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
   free(bg); free(fr);
   return 0;
 }
+
+
+int or_composite_ex(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
+                    const uint8_t* bg_raw, int bw, int bh, size_t bstride, const or_frame_opts* o,
+                    uint8_t* out_rgb, uint8_t* out_yuyv, uint8_t* out_mask) {
+  const int W = g->W, H = g->H;
+  const size_t npix = (size_t)W * H;
+  const int ow = o->out_w > 0 ? o->out_w : W, oh = o->out_h > 0 ? o->out_h : H;
+  int rc = or_maskgen_process(g, frame_bgr, stride, out_mask);
+  if (rc) return rc;
+  uint8_t* fr = (uint8_t*)malloc(npix * 3);
+  uint8_t* bg = (uint8_t*)malloc(npix * 3);
+  uint8_t* cur = (uint8_t*)malloc(npix * 3);
+  for (int y = 0; y < H; ++y) memcpy(fr + (size_t)y * W * 3, frame_bgr + (size_t)y * stride, (size_t)W * 3);
+  /* app/deepseg.cc:649-655: the grabbed background, else a copy of the camera frame */
+  if (bg_raw) or_resize_linear_u8(bg_raw, bw, bh, bstride, bg, W, H, (size_t)W * 3, 3);
+  else memcpy(bg, fr, npix * 3);
+  /* :657-658 (in place in the reference; GaussianBlur clones the source when src == dst) */
+  if (o->bgblur_k) {
+    memcpy(cur, bg, npix * 3);
+    if (or_gaussian_blur_u8c3(cur, W, H, (size_t)W * 3, bg, (size_t)W * 3, o->bgblur_k)) { free(fr); free(bg); free(cur); return -1; }
+  }
+  or_alpha_blend(bg, fr, g->mask, cur, npix);                                   /* :661 */
+  if (o->flip_h || o->flip_v) { or_flip_u8c3(cur, bg, W, H, o->flip_h, o->flip_v); memcpy(cur, bg, npix * 3); }   /* :667-673 */
+  if (ow != W || oh != H) or_resize_linear_u8(cur, W, H, (size_t)W * 3, out_rgb, ow, oh, (size_t)ow * 3, 3);     /* :677-679 */
+  else memcpy(out_rgb, cur, npix * 3);
+  if (out_yuyv) or_convert_rgb_to_yuyv(out_rgb, out_yuyv, ow, oh);              /* :681 */
+  free(fr); free(bg); free(cur);
+  return 0;
+}

@@ -71,6 +71,10 @@ def lib() -> C.CDLL:
         L.or_maskgen_model.restype = C.c_void_p
         L.or_maskgen_model.argtypes = [C.c_void_p]
         L.or_composite.argtypes = [C.c_void_p, u8p, C.c_size_t, u8p, C.c_int, C.c_int, C.c_size_t, u8p, u8p, u8p]
+        L.or_composite_ex.argtypes = [C.c_void_p, u8p, C.c_size_t, u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, u8p, u8p, u8p]
+        L.or_gaussian_kernel_q8.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.or_gaussian_blur_u8c3.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_size_t, C.c_int]
+        L.or_flip_u8c3.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.or_model_type_from_name.argtypes = [C.c_char_p]
         _LIB = L
     return _LIB
@@ -293,6 +297,34 @@ def yuyv_to_bgr(yuyv):
     return dst
 
 
+def gaussian_kernel_q8(k):
+    q = (C.c_int * 255)()
+    if lib().or_gaussian_kernel_q8(k, q):
+        raise ValueError(f"bad gaussian kernel size {k}")
+    return np.array(q[:k], np.int64)
+
+
+def gaussian_blur(src, k):
+    src = _cu(src)
+    h, w, _ = src.shape
+    dst = np.empty_like(src)
+    if lib().or_gaussian_blur_u8c3(_u(src), w, h, C.c_size_t(w * 3), _u(dst), C.c_size_t(w * 3), k):
+        raise ValueError(f"bad gaussian kernel size {k}")
+    return dst
+
+
+def flip(src, flip_h, flip_v):
+    src = _cu(src)
+    h, w, _ = src.shape
+    dst = np.empty_like(src)
+    lib().or_flip_u8c3(_u(src), _u(dst), w, h, int(flip_h), int(flip_v))
+    return dst
+
+
+class FrameOpts(C.Structure):
+    _fields_ = [("bgblur_k", C.c_int), ("flip_h", C.c_int), ("flip_v", C.c_int), ("out_w", C.c_int), ("out_h", C.c_int)]
+
+
 def alpha_blend(srca, srcb, mask):
     srca, srcb, mask = _cu(srca), _cu(srcb), _cu(mask)
     out = np.empty_like(srca)
@@ -406,6 +438,25 @@ class MaskGen:
                                 C.c_size_t(bw * 3), _u(out), _u(yuyv) if want_yuyv else None, _u(mask))
         if rc:
             raise RuntimeError(f"or_composite rc={rc}")
+        return out, yuyv, mask
+
+    def composite_ex(self, frame_bgr, bg_raw=None, bgblur=0, flip_h=False, flip_v=False, out_size=None, want_yuyv=True):
+        """app/deepseg.cc:640-681 with its options; bg_raw None = blur-the-camera-frame mode."""
+        frame_bgr = _cu(frame_bgr)
+        ow, oh = out_size if out_size else (self.W, self.H)
+        o = FrameOpts(int(bgblur), int(flip_h), int(flip_v), ow, oh)
+        if bg_raw is not None:
+            bg_raw = _cu(bg_raw)
+            bh, bw = bg_raw.shape[:2]
+        else:
+            bh = bw = 0
+        out = np.empty((oh, ow, 3), np.uint8)
+        yuyv = np.empty((oh, ow, 2), np.uint8) if want_yuyv else None
+        mask = np.empty((self.H, self.W), np.uint8)
+        rc = lib().or_composite_ex(self.h, _u(frame_bgr), C.c_size_t(self.W * 3), _u(bg_raw) if bg_raw is not None else None,
+                                   bw, bh, C.c_size_t(bw * 3), C.byref(o), _u(out), _u(yuyv) if want_yuyv else None, _u(mask))
+        if rc:
+            raise RuntimeError(f"or_composite_ex rc={rc}")
         return out, yuyv, mask
 
     def _arr_u8(self, fn, shape):

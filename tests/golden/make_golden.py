@@ -46,6 +46,15 @@ def image_ops():
     for name, (a, b) in {"unit": (float(np.float32(1 / 255.0)), 0.0), "deeplab": (float(np.float32(1 / 127.5)), -1.0)}.items():
         comp = cv2.GComputation(g_in, cv2.gapi.convertTo(g_in, cv2.CV_32F, a, b))
         d[f"convert_{name}"] = comp.apply(cv2.gin(np.arange(256, dtype=np.uint8).reshape(16, 16)))
+    # `-p bgblur:k` (app/deepseg.cc:657-658) and cv::flip (:667-673)
+    for k, (w, h) in {25: (56, 40), 7: (30, 20), 51: (40, 24)}.items():
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        d[f"gauss{k}_src"], d[f"gauss{k}_dst"] = src, cv2.GaussianBlur(src, (k, k), 0)
+    d["gauss_taps25"] = np.rint(cv2.getGaussianKernel(25, 0).ravel() * 256)   # informative only (no error diffusion)
+    src = rng.integers(0, 256, (9, 14, 3), dtype=np.uint8)
+    d["flip_src"] = src
+    for code in (1, 0, -1):
+        d[f"flip_{code}"] = cv2.flip(src, code)
     np.savez_compressed(os.path.join(OUT, "image_ops_golden.npz"), **d)
 
 

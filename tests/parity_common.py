@@ -146,8 +146,93 @@ def check_errors(lib, tmp_path):
     g = api.MaskGen(lib, model_path("mlkit"), 640, 480, max_batch=1)
     with pytest.raises(api.BackscrubError):
         g.composite(np.zeros((2, 480, 640, 3), np.uint8))          # n > max_batch
-    with pytest.raises(api.BackscrubError, match="background"):
-        g.composite(np.zeros((480, 640, 3), np.uint8))             # no background set
+    with pytest.raises(api.BackscrubError, match="must be odd"):
+        g.set_bgblur(24)                                           # app/deepseg.cc:423-426
+    with pytest.raises(api.BackscrubError, match="invalid background"):
+        g.set_background_ring(np.zeros((0, 4, 4, 3), np.uint8))
     with pytest.raises(api.BackscrubError):
         g.process(np.zeros((10, 10, 3), np.uint8))
+    g.close()
+
+
+def check_app_stage_functions(lib):
+    """Gaussian taps for every legal strength; blur / flip stage kernels vs the oracle (pinned on cv2)."""
+    for k in range(1, 256, 2):
+        assert np.array_equal(api.gaussian_taps(lib, k), po.gaussian_kernel_q8(k)), k
+    rng = np.random.default_rng(5)
+    for (w, h, k) in [(640, 480, 25), (300, 40, 3), (37, 21, 9), (70, 50, 51), (33, 9, 101), (16, 16, 1)]:
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(api.gaussian_blur(lib, a, k), po.gaussian_blur(a, k)), (w, h, k)
+    a = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    for fh, fv in [(1, 0), (0, 1), (1, 1), (0, 0)]:
+        assert np.array_equal(api.flip(lib, a, fh, fv), po.flip(a, fh, fv))
+
+
+def check_app_options(lib, key="meet_lite", W=640, H=480):
+    """The main loop's options around the blend (app/deepseg.cc:649-681): default green background, bgblur of the
+    grabbed background and of the camera frame, flip, virtual-camera resize, animated background ring."""
+    bg = synth.background()
+    frames = np.stack([synth.frame(W, H, t=t) for t in range(4)])
+
+    def run(setup, ref_kw, bg_raw=bg, n=2, batch=2):
+        g = api.MaskGen(lib, model_path(key), W, H, max_batch=batch)
+        o = po.MaskGen(model_path(key), W, H)
+        if bg_raw is not None:
+            g.set_background(bg_raw)
+        setup(g)
+        for s in range(0, n, batch):
+            out, yuyv, mask = g.composite(frames[s:s + batch])
+            for b in range(out.shape[0]):
+                ro, ry, rm = o.composite_ex(frames[s + b], bg_raw, **ref_kw)
+                assert np.array_equal(mask[b], rm), (ref_kw, s + b)
+                assert out[b].shape == ro.shape and np.array_equal(out[b], ro), (ref_kw, s + b)
+                assert np.array_equal(yuyv[b], ry), (ref_kw, s + b)
+        g.close()
+
+    # no background, no blur: plain green (app/deepseg.cc:603)
+    g = api.MaskGen(lib, model_path(key), W, H)
+    o = po.MaskGen(model_path(key), W, H)
+    green = np.zeros((H, W, 3), np.uint8); green[..., 1] = 255
+    assert np.array_equal(g.background(), green)
+    out, yuyv, mask = g.composite(frames[0])
+    ro, ry, rm = o.composite(frames[0], green)
+    assert np.array_equal(out, ro) and np.array_equal(yuyv, ry) and np.array_equal(mask, rm)
+    g.close()
+
+    run(lambda g: g.set_bgblur(25), dict(bgblur=25))                                   # blurred still background
+    run(lambda g: g.set_bgblur(25), dict(bgblur=25), bg_raw=None)                      # blurred camera frame
+    run(lambda g: g.set_bgblur(7), dict(bgblur=7), bg_raw=None, n=3, batch=1)
+    run(lambda g: g.set_output(flip_h=True), dict(flip_h=True))
+    run(lambda g: g.set_output(flip_v=True, out_size=(320, 240)), dict(flip_v=True, out_size=(320, 240)))   # 2x down: INTER_AREA path
+    run(lambda g: g.set_output(True, True, (854, 480)), dict(flip_h=True, flip_v=True, out_size=(854, 480)))
+    run(lambda g: (g.set_bgblur(11), g.set_output(out_size=(1280, 720))), dict(bgblur=11, out_size=(1280, 720)))
+
+    # options can be switched on a live context (graphs are re-captured) and switched off again
+    g = api.MaskGen(lib, model_path(key), W, H, max_batch=1)
+    o = po.MaskGen(model_path(key), W, H)
+    g.set_background(bg)
+    for t, (k, fh) in enumerate([(0, False), (5, True), (0, False), (25, False)]):
+        g.set_bgblur(k); g.set_output(flip_h=fh)
+        out, yuyv, mask = g.composite(frames[t])
+        ro, ry, rm = o.composite_ex(frames[t], bg, bgblur=k, flip_h=fh)
+        assert np.array_equal(out, ro) and np.array_equal(yuyv, ry) and np.array_equal(mask, rm), t
+    g.close()
+
+    # animated background: ring of 3 images, one step per camera frame, batches of 2 -> wraps inside a batch
+    ring = np.stack([bg, bg[::-1].copy(), np.roll(bg, 100, axis=1)])
+    g = api.MaskGen(lib, model_path(key), W, H, max_batch=2)
+    o = po.MaskGen(model_path(key), W, H)
+    g.set_background_ring(ring, advance=1)
+    g.set_bgblur(9)
+    t = 0
+    for s in (0, 2):
+        out, yuyv, mask = g.composite(frames[s:s + 2])
+        for b in range(2):
+            ro, ry, rm = o.composite_ex(frames[s + b], ring[t % 3], bgblur=9)
+            assert np.array_equal(out[b], ro) and np.array_equal(yuyv[b], ry) and np.array_equal(mask[b], rm), (s, b)
+            t += 1
+    g.set_background_cursor(2)                                   # caller-paced: pick an image explicitly
+    out, _, _ = g.composite(frames[:1])
+    ro, _, _ = o.composite_ex(frames[0], ring[2], bgblur=9)
+    assert np.array_equal(out[0], ro)
     g.close()

@@ -56,6 +56,14 @@ def test_stage_functions(lib):
     pc.check_stage_functions(lib)
 
 
+def test_app_stage_functions(lib):
+    pc.check_app_stage_functions(lib)
+
+
+def test_app_options(lib):
+    pc.check_app_options(lib)
+
+
 def test_yuyv_ingest(lib):
     pc.check_yuyv_ingest(lib)
 

@@ -102,3 +102,15 @@ def test_large_batch_stream_consistency(lib):
 
 def test_4k_bodypix(lib):                     # BASELINE config 5 geometry (documented out_roidim deviation)
     pc.check_pipeline(lib, "bodypix", 3840, 2160, n_frames=1)
+
+
+def test_app_stage_functions(lib):            # `-p bgblur:k` Gaussian taps + blur, cv::flip
+    pc.check_app_stage_functions(lib)
+
+
+def test_app_options(lib):                    # green default, bgblur (still / camera), flip, vcam resize, animated ring
+    pc.check_app_options(lib)
+
+
+def test_app_options_720p_meet(lib):          # the BASELINE config-4 geometry with the blur-my-background mode
+    pc.check_app_options(lib, "meet_full", 1280, 720)

@@ -133,3 +133,65 @@ def test_yuyv_to_bgr_bit_exact():
             row[0, 0::2, 1] = u
             row[0, 1::2, 1] = v
             assert np.array_equal(po.yuyv_to_bgr(row), cv2.cvtColor(row, cv2.COLOR_YUV2BGR_YUYV))
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 9, 11, 25, 51, 101])
+def test_gaussian_blur_bit_exact(k):  # app/deepseg.cc:657-658 `-p bgblur:k`
+    """cv::GaussianBlur(8UC3, k x k, sigma 0): OpenCV's bit-exact 8.8 fixed-point path, IPP on and off,
+    including kernels wider than the image (multiple border reflections)."""
+    for shape in [(48, 64, 3), (30, 17, 3), (120, 200, 3)]:
+        src = RNG.integers(0, 256, shape, dtype=np.uint8)
+        got = po.gaussian_blur(src, k)
+        for ipp in (True, False):
+            cv2.ipp.setUseIPP(ipp)
+            assert np.array_equal(got, cv2.GaussianBlur(src, (k, k), 0)), (k, shape, ipp)
+        cv2.ipp.setUseIPP(True)
+
+
+def test_gaussian_taps_all_strengths():
+    """taps for every odd k: the error-diffused 8.8 quantisation of cv2.getGaussianKernel(k, 0), summing to 256;
+    even / out-of-range strengths are rejected (app/deepseg.cc:423-426)."""
+    for k in range(1, 256, 2):
+        kd = cv2.getGaussianKernel(k, 0).ravel()
+        ref = np.zeros(k, np.int64)
+        err, acc = 0.0, 0
+        for i in range(k // 2):
+            adj = kd[i] * 256.0 + err
+            v = int(np.rint(adj))
+            err = adj - v
+            ref[i] = ref[k - 1 - i] = v
+            acc += v
+        ref[k // 2] = 256 - 2 * acc
+        q = po.gaussian_kernel_q8(k)
+        assert np.array_equal(q, ref) and q.sum() == 256, k
+    for bad in (0, 2, 24, 257, -3):
+        with pytest.raises(ValueError):
+            po.gaussian_kernel_q8(bad)
+
+
+def test_flip_bit_exact():  # app/deepseg.cc:667-673
+    src = RNG.integers(0, 256, (21, 34, 3), dtype=np.uint8)
+    for code, (fh, fv) in {1: (1, 0), 0: (0, 1), -1: (1, 1)}.items():
+        assert np.array_equal(po.flip(src, fh, fv), cv2.flip(src, code))
+
+
+def test_composite_ex_matches_cv2_composition():
+    """or_composite_ex (the main-loop body with its options) vs the same steps composed from cv2 calls."""
+    from tests import synth
+    from tests.conftest import model_path
+    W, H = 640, 480
+    bg_raw = synth.background()
+    fr = synth.frame(W, H, t=2)
+    for bg_src, k, fh, fv, osz in [(bg_raw, 25, True, False, (320, 240)), (None, 9, False, True, (854, 480)), (bg_raw, 0, True, True, None)]:
+        o = po.MaskGen(model_path("meet_lite"), W, H)
+        out, yuyv, mask = o.composite_ex(fr, bg_src, bgblur=k, flip_h=fh, flip_v=fv, out_size=osz)
+        bg = cv2.resize(bg_src, (W, H)) if bg_src is not None else fr.copy()
+        if k:
+            bg = cv2.GaussianBlur(bg, (k, k), 0)
+        ref = po.alpha_blend(bg, fr, mask)
+        if fh or fv:
+            ref = cv2.flip(ref, -1 if (fh and fv) else (1 if fh else 0))
+        if osz:
+            ref = cv2.resize(ref, osz)
+        assert np.array_equal(out, ref)
+        assert np.array_equal(yuyv, po.convert_rgb_to_yuyv(ref))
