@@ -68,10 +68,128 @@ __global__ void __launch_bounds__(256) k_gauss_cols(const uint16_t* tmp, uint8_t
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused tile kernel for 3 <= k <= 31 (the default strength is 25): one block = 64 x 32 output pixels.
+//   A  the reflected (32+2r) x (64+2r) source patch is staged de-interleaved (one byte plane per channel),
+//   B  row sums with DP4A: a thread owns 4 adjacent outputs of one plane row; it reads aligned 32-bit words
+//      and the taps come pre-shifted per output (hq[i][g], byte b = q[4g+b-i]) so no byte realignment is needed;
+//      the 16-bit sums are stored transposed (row index fastest) so that
+//   C  column sums run on DP2A: a thread owns two vertically adjacent outputs and reads (row, row+1) pairs as
+//      words; cw[g] packs the tap pairs of both outputs (low half: q[2g],q[2g+1]; high half: q[2g-1],q[2g]),
+//   D  the re-interleaved tile goes out in 16-byte stores.
+// All sums are exact integers (<= 255*256*256 < 2^24), so the regrouping is bit-neutral.
+// ---------------------------------------------------------------------------
+constexpr int GF_TW = 64, GF_TH = 32, GF_MAXR = 15, GF_RM = GF_TH + 2 * GF_MAXR, GF_PW = 100, GF_HR = 66;
+constexpr int GF_NW = 9, GF_NV = 16;
+
+struct GaussFast { int k, nw, nv; unsigned hq[4][GF_NW]; unsigned cw[GF_NV]; };
+
+__global__ void __launch_bounds__(256) k_gauss_fused(const uint8_t* src, size_t spitch, size_t sstride, uint8_t* dst, size_t dpitch,
+                                                     size_t dstride, int W, int H, GaussFast g, int vec_ok) {
+  __shared__ __align__(16) uint8_t P[3 * GF_RM * GF_PW];      // planes; reused as the interleaved output tile in C/D
+  __shared__ __align__(16) uint16_t Ht[3 * GF_TW * GF_HR];
+  const int r = g.k >> 1, tid = threadIdx.x;
+  const int x0 = blockIdx.x * GF_TW, y0 = blockIdx.y * GF_TH, b = blockIdx.z;
+  const int tw = min(GF_TW, W - x0), th = min(GF_TH, H - y0);
+  const int rows = GF_TH + 2 * r, cols = GF_TW + 2 * r;
+  const uint8_t* frame = src + (size_t)b * sstride;
+
+  // ---- A: stage + de-interleave ----
+  const bool interior = x0 - r >= 0 && x0 + GF_TW + r <= W && y0 - r >= 0 && y0 + GF_TH + r <= H;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int row = warp; row < rows; row += 8) {
+    int gy = y0 + row - r;
+    if (!interior) gy = bsb_reflect101(gy, H);
+    const uint8_t* srow = frame + (size_t)gy * spitch;
+    for (int col = lane; col < cols; col += 32) {
+      int gx = x0 + col - r;
+      if (!interior) gx = bsb_reflect101(gx, W);
+      const uint8_t* sp = srow + (size_t)gx * 3;
+      uint8_t* pp = P + row * GF_PW + col;
+      pp[0] = sp[0]; pp[GF_RM * GF_PW] = sp[1]; pp[2 * GF_RM * GF_PW] = sp[2];
+    }
+  }
+  __syncthreads();
+
+  // ---- B: row sums (DP4A), stored transposed ----
+  for (int cm = warp; cm < 3 * (GF_TW / 4); cm += 8) {          // one (plane, 4-pixel group) per warp, lanes walk the rows
+    const int c = cm / (GF_TW / 4), m = cm % (GF_TW / 4);
+    for (int row = lane; row < rows; row += 32) {
+      const unsigned* pw = reinterpret_cast<const unsigned*>(P + (c * GF_RM + row) * GF_PW + 4 * m);
+      unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+      for (int q = 0; q < GF_NW; ++q) {
+        if (q < g.nw) {
+          const unsigned w = pw[q];
+          a0 = __dp4a(w, g.hq[0][q], a0); a1 = __dp4a(w, g.hq[1][q], a1);
+          a2 = __dp4a(w, g.hq[2][q], a2); a3 = __dp4a(w, g.hq[3][q], a3);
+        }
+      }
+      uint16_t* hp = Ht + (c * GF_TW + 4 * m) * GF_HR + row;
+      hp[0] = (uint16_t)a0; hp[GF_HR] = (uint16_t)a1; hp[2 * GF_HR] = (uint16_t)a2; hp[3 * GF_HR] = (uint16_t)a3;
+    }
+  }
+  __syncthreads();
+
+  // ---- C: column sums (DP2A), re-interleaved into the output tile ----
+  uint8_t* O = P;                                               // [GF_TH][GF_TW * 3]
+  for (int it = tid; it < 3 * (GF_TH / 2) * GF_TW; it += 256) {
+    const int x = it % GF_TW, yp = (it / GF_TW) % (GF_TH / 2), c = it / (GF_TW * (GF_TH / 2));
+    const unsigned* hw = reinterpret_cast<const unsigned*>(Ht + (c * GF_TW + x) * GF_HR + 2 * yp);
+    unsigned a0 = 32768u, a1 = 32768u;
+#pragma unroll
+    for (int q = 0; q < GF_NV; ++q) {
+      if (q < g.nv) {
+        const unsigned w = hw[q];
+        a0 = __dp2a_lo(w, g.cw[q], a0); a1 = __dp2a_hi(w, g.cw[q], a1);
+      }
+    }
+    O[(2 * yp) * (GF_TW * 3) + x * 3 + c] = (uint8_t)(a0 >> 16);
+    O[(2 * yp + 1) * (GF_TW * 3) + x * 3 + c] = (uint8_t)(a1 >> 16);
+  }
+  __syncthreads();
+
+  // ---- D: write out ----
+  uint8_t* out = dst + (size_t)b * dstride + (size_t)y0 * dpitch + (size_t)x0 * 3;
+  if (vec_ok && tw == GF_TW) {
+    for (int i = tid; i < th * (GF_TW * 3 / 16); i += 256) {
+      const int row = i / (GF_TW * 3 / 16), v = i % (GF_TW * 3 / 16);
+      *reinterpret_cast<uint4*>(out + (size_t)row * dpitch + 16 * v) = *reinterpret_cast<const uint4*>(O + row * (GF_TW * 3) + 16 * v);
+    }
+  } else {
+    for (int i = tid; i < th * tw * 3; i += 256) {
+      const int row = i / (tw * 3), l = i - row * (tw * 3);
+      out[(size_t)row * dpitch + l] = O[row * (GF_TW * 3) + l];
+    }
+  }
+}
+
+static bool gauss_fast_params(const GaussTaps& t, GaussFast* f) {
+  if (t.k < 3 || t.k > 2 * GF_MAXR + 1) return false;
+  f->k = t.k; f->nw = (t.k + 3 + 3) / 4; f->nv = (t.k + 1 + 1) / 2;
+  auto q = [&](int j) -> unsigned { return (j >= 0 && j < t.k) ? (unsigned)t.q[j] : 0u; };
+  for (int i = 0; i < 4; ++i)
+    for (int w = 0; w < GF_NW; ++w) {
+      unsigned v = 0;
+      for (int b = 0; b < 4; ++b) v |= q(4 * w + b - i) << (8 * b);
+      f->hq[i][w] = v;
+    }
+  for (int w = 0; w < GF_NV; ++w) f->cw[w] = q(2 * w) | (q(2 * w + 1) << 8) | (q(2 * w - 1) << 16) | (q(2 * w) << 24);
+  return true;
+}
+
 size_t gauss_cols_smem(int k) { return (size_t)(GAUSS_CH + 2 * (k >> 1)) * GAUSS_CL * sizeof(uint16_t); }
 
 void launch_gauss_blur(cudaStream_t s, int n, const uint8_t* src, size_t spitch, size_t sstride, uint16_t* tmp,
                        uint8_t* dst, size_t dpitch, size_t dstride, int W, int H, const GaussTaps& g) {
+  GaussFast f;
+  if (gauss_fast_params(g, &f)) {
+    const int vec_ok = (reinterpret_cast<uintptr_t>(dst) % 16 == 0 && dpitch % 16 == 0 && dstride % 16 == 0) ? 1 : 0;
+    BSB_LAUNCH(k_gauss_fused, dim3((unsigned)ceil_div(W, GF_TW), (unsigned)ceil_div(H, GF_TH), (unsigned)n), dim3(256), 0, s,
+               src, spitch, sstride, dst, dpitch, dstride, W, H, f, vec_ok);
+    count_launch();
+    return;
+  }
   BSB_LAUNCH(k_gauss_rows, dim3((unsigned)ceil_div(W, GAUSS_TW), (unsigned)H, (unsigned)n), dim3(256), 0, s,
              src, spitch, sstride, tmp, W, H, g);
   count_launch();

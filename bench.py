@@ -32,6 +32,9 @@ WORKLOADS = {
     "mlkit480": dict(model="selfiesegmentation_mlkit-256x256-2021_01_19-v1215.f16.tflite", W=640, H=480, desc="MLKit-256, 640x480 stream"),
     # configs[2]
     "deeplab720": dict(model="deeplabv3_257_mv_gpu.tflite", W=1280, H=720, desc="deeplabv3_257_mv_gpu, 1280x720 stream"),
+    # configs[4]: 4k camera frames over an animated (video) background — one decoded background image per camera frame
+    "bodypix4k": dict(model="body-pix-float-050-8.tflite", W=3840, H=2160, animated="rotating_earth.webm", streams=4, batch=8,
+                      desc="body-pix-float-050-8, 3840x2160 stream, animated 960x540 webm background"),
     "mlkit720": dict(model="selfiesegmentation_mlkit-256x256-2021_01_19-v1215.f16.tflite", W=1280, H=720, desc="MLKit-256, 1280x720 stream"),
 }
 METRIC = "composited frames/sec"
@@ -45,8 +48,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="meet720", choices=list(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=8, help="independent streams (contexts) per GPU")
-    ap.add_argument("--batch", type=int, default=32, help="consecutive frames per stream per step")
+    ap.add_argument("--streams", type=int, default=None, help="independent streams (contexts) per GPU (default 8; 4 at 4k)")
+    ap.add_argument("--batch", type=int, default=None, help="consecutive frames per stream per step (default 32; 8 at 4k)")
+    ap.add_argument("--bgblur", type=int, default=0, help="`-p bgblur:k` of the reference: Gaussian-blur the background (odd k)")
+    ap.add_argument("--camera-blur", action="store_true", help="with --bgblur: no background source, blur the camera frame itself")
     ap.add_argument("--tensor-cores", action="store_true", help="tcgen05 3xTF32 pointwise convs (not bit-exact; IoU-validated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -60,6 +65,31 @@ def dist_env():
     return rank, world, local
 
 
+RING_FRAMES = 16
+
+
+def background_ring(wl):
+    """Decoded frames of the animated background (cv2/FFmpeg on the host, like app/background.cc:126-176);
+    a rolled still image if the container's cv2 cannot decode VP9."""
+    from tests import synth
+    path = os.path.join(ROOT, "backgrounds", wl["animated"])
+    frames = []
+    try:
+        import cv2
+        cap = cv2.VideoCapture(path)
+        while len(frames) < RING_FRAMES:
+            ok, f = cap.read()
+            if not ok:
+                break
+            frames.append(f)
+    except Exception:
+        frames = []
+    if len(frames) == RING_FRAMES:
+        return np.stack(frames), f"{wl['animated']} (first {RING_FRAMES} decoded frames, one per camera frame)"
+    still = synth.background()
+    return np.stack([np.roll(still, 16 * i, axis=1) for i in range(RING_FRAMES)]), "synthetic ring (video decode unavailable)"
+
+
 def synthetic_frames(W, H, n, stream):
     from tests import synth
     return np.stack([synth.frame(W, H, t=t, stream=stream) for t in range(n)])
@@ -69,12 +99,12 @@ def synthetic_frames(W, H, n, stream):
 # CPU path: the oracle port of the reference's TFLite+OpenCV pipeline, frame-parallel over
 # host threads (the reference itself cannot be built offline — SURVEY.md §8c).
 # ----------------------------------------------------------------------------------------
-def cpu_path_fps(wl, threads, frames_per_thread, warm=1):
+def cpu_path_fps(wl, threads, frames_per_thread, warm=1, bgblur=0, camera_blur=False):
     from oracle import pyoracle as po
     from tests import synth
     model = os.path.join(ROOT, "models", wl["model"])
     W, H = wl["W"], wl["H"]
-    bg = synth.background()
+    ring = background_ring(wl)[0] if wl.get("animated") else synth.background()[None]
     gens = [po.MaskGen(model, W, H) for _ in range(threads)]
     frames = [synthetic_frames(W, H, frames_per_thread + warm, s) for s in range(min(threads, 4))]
 
@@ -84,7 +114,7 @@ def cpu_path_fps(wl, threads, frames_per_thread, warm=1):
     def work(i, lo, hi):
         g, fr = gens[i], frames[i % len(frames)]
         for t in range(lo, hi):
-            g.composite(po.yuyv_to_bgr(fr[t]), bg, want_yuyv=True)
+            g.composite_ex(po.yuyv_to_bgr(fr[t]), None if camera_blur else ring[t % len(ring)], bgblur=bgblur, want_yuyv=True)
 
     def run(lo, hi):
         th = [threading.Thread(target=work, args=(i, lo, hi)) for i in range(threads)]
@@ -112,12 +142,13 @@ def run_reference(args, wl):
     cores = host_cores()
     threads = max(1, min(cores, 64))
     # calibrate one frame, then size each step to ~ (120 s / (steps + warmup)) of wall time at most
-    fps1, _ = cpu_path_fps(wl, 1, 1, warm=1)
+    kw = dict(bgblur=args.bgblur, camera_blur=args.camera_blur)
+    fps1, _ = cpu_path_fps(wl, 1, 1, warm=1, **kw)
     budget = 100.0 / max(1, args.steps + args.warmup)
     fpt = max(1, int(min(4, budget * fps1)))
     vals = []
     for s in range(args.warmup + args.steps):
-        fps, dt = cpu_path_fps(wl, threads, fpt, warm=0)
+        fps, dt = cpu_path_fps(wl, threads, fpt, warm=0, **kw)
         if s >= args.warmup:
             vals.append((fps, dt))
     total_frames = threads * fpt * len(vals)
@@ -127,7 +158,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_time / len(vals), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-        "config": {"workload": wl["desc"], "frames_per_step": threads * fpt},
+        "config": {"workload": wl["desc"], "frames_per_step": threads * fpt, "bgblur": args.bgblur or None,
+                   "background": "blurred camera frame" if args.camera_blur else ("animated" if wl.get("animated") else "still image")},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{threads} threads x {fpt} frame(s) per step, oracle port of TFLite-reference kernels + OpenCV ops"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,19 +240,33 @@ def run_b200(args, wl):
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
     full_affinity = bind_near_gpu(torch, dev)
+    bound_cpus = len(os.sched_getaffinity(0))
     if bs.device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: backscrub_b200 has no CPU path")
-    W, H, S, B = wl["W"], wl["H"], args.streams, args.batch
+    W, H = wl["W"], wl["H"]
+    S, B = args.streams or wl.get("streams", 8), args.batch or wl.get("batch", 32)
+    if args.camera_blur and not args.bgblur:
+        raise SystemExit("--camera-blur needs --bgblur K")
     model = os.path.join(ROOT, "models", wl["model"])
     fb, npx = W * H * 3, W * H
     R = 2                                     # ring slots per stream: S*R*B frames in + out exceed the 126 MB L2
     bg = synth.background()
+    bg_desc = "still 1280x720 PNG (resized once; read from L2)"
+    if wl.get("animated"):
+        ring_frames, bg_desc = background_ring(wl)
+    if args.camera_blur:
+        bg_desc = "none: the Gaussian-blurred camera frame (app/deepseg.cc:652-658)"
     from backscrub_b200 import sharding
     my_streams = sharding.streams_for_rank(world * S, rank, world)      # stream ids served by this GPU
     ctxs, rings = [], []
     for s in range(S):
         c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=4 if args.tensor_cores else 0)
-        c.set_background(bg)
+        if wl.get("animated") and not args.camera_blur:
+            c.set_background_ring(ring_frames, advance=1)
+        elif not args.camera_blur:
+            c.set_background(bg)
+        if args.bgblur:
+            c.set_bgblur(args.bgblur)
         ctxs.append(c)
         from oracle import pyoracle as _po        # only to synthesise camera-format (YUYV) input frames
         host = np.stack([_po.convert_rgb_to_yuyv(f) for f in synthetic_frames(W, H, B, stream=my_streams[s])])
@@ -338,9 +384,10 @@ def run_b200(args, wl):
         os.sched_setaffinity(0, full_affinity)          # the CPU baseline may use every host core
         cores = host_cores()
         threads = max(1, min(cores, 64))
-        fps1, _ = cpu_path_fps(wl, 1, 1, warm=1)
+        kw = dict(bgblur=args.bgblur, camera_blur=args.camera_blur)
+        fps1, _ = cpu_path_fps(wl, 1, 1, warm=1, **kw)
         fpt = max(1, int(min(8, 12.0 * fps1)))             # ~12 s of wall time
-        v, dt = cpu_path_fps(wl, threads, fpt, warm=0)
+        v, dt = cpu_path_fps(wl, threads, fpt, warm=0, **kw)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{threads} threads x {fpt} frames of the same workload ({dt:.1f} s), oracle port (TFLite-reference kernels + OpenCV ops restated)",
                "single_thread_value": fps1}
@@ -352,7 +399,7 @@ def run_b200(args, wl):
             "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "batch": B, "frames_per_step": world * S * B,
                        "input": "camera YUYV frames (YUYV->BGR ingest on the GPU)", "outputs": "RGB composite + YUYV + mask", "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
-                       "host_affinity_cpus": len(os.sched_getaffinity(0)) if cpu is None else None, "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
+                       "background": bg_desc, "bgblur": args.bgblur or None, "host_affinity_cpus": bound_cpus, "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
             "gpu_launches": args.steps * S * c0.launches_per_call,
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stages": stages,
             "cnn_mflop_per_frame": c0.flops / 1e6,

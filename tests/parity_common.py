@@ -160,7 +160,8 @@ def check_app_stage_functions(lib):
     for k in range(1, 256, 2):
         assert np.array_equal(api.gaussian_taps(lib, k), po.gaussian_kernel_q8(k)), k
     rng = np.random.default_rng(5)
-    for (w, h, k) in [(640, 480, 25), (300, 40, 3), (37, 21, 9), (70, 50, 51), (33, 9, 101), (16, 16, 1)]:
+    for (w, h, k) in [(640, 480, 25), (300, 40, 3), (37, 21, 9), (70, 50, 51), (33, 9, 101), (16, 16, 1),
+                      (100, 70, 31), (65, 33, 27), (10, 8, 25), (130, 64, 13), (64, 32, 5), (4, 3, 29)]:
         a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         assert np.array_equal(api.gaussian_blur(lib, a, k), po.gaussian_blur(a, k)), (w, h, k)
     a = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
