@@ -284,13 +284,13 @@ def resize_u8c3(lib, src, dw, dh, device=0):
     return out
 
 
-def pointwise(lib, A, W, bias=None, act=0, use_tc=False, device=0):
+def pointwise(lib, A, W, bias=None, act=0, use_tc=False, device=0, variant=None):
     """1x1 convolution stage: A [M, K] x W [N, K]^T (+ bias, activation) on the GPU."""
     A = np.ascontiguousarray(A, np.float32); W = np.ascontiguousarray(W, np.float32)
     M, K = A.shape; N = W.shape[0]
     b = np.ascontiguousarray(bias, np.float32) if bias is not None else None
     out = np.empty((M, N), np.float32)
-    if not lib.bsb_pointwise(device, int(use_tc), M, K, N, _ptr(A), _ptr(W), _ptr(b) if b is not None else None, act, _ptr(out)):
+    if not lib.bsb_pointwise(device, int(use_tc) if variant is None else int(variant), M, K, N, _ptr(A), _ptr(W), _ptr(b) if b is not None else None, act, _ptr(out)):
         raise BackscrubError(lib.bsb_last_error().decode())
     return out
 

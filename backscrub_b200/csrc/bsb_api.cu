@@ -381,7 +381,7 @@ int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst
   return 1;
 }
 
-int bsb_pointwise(int device, int use_tc, int M, int K, int N, const float* A, const float* W, const float* bias, int act, float* out) {
+int bsb_pointwise(int device, int variant, int M, int K, int N, const float* A, const float* W, const float* bias, int act, float* out) {
   if (!A || !W || !out || M <= 0 || K <= 0 || N <= 0) { g_last_error = "invalid argument"; return 0; }
   if (!stage_begin(device)) return 0;
   DevBuf dA, dW, dW2, dB, dO;
@@ -389,6 +389,7 @@ int bsb_pointwise(int device, int use_tc, int M, int K, int N, const float* A, c
   cudaMemcpy(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice);
   if (bias) cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
   bsb::Epilogue e; e.bias = bias ? (const float*)dB.p : nullptr; e.act1 = act;
+  const bool use_tc = variant == 1;
   if (use_tc) {
     const int bn = bsb::pointwise_tc_tile_n(N);
     if (bn <= 0 || K % 4) { g_last_error = "shape not supported by the tensor-core kernel"; return 0; }
@@ -412,11 +413,39 @@ int bsb_pointwise(int device, int use_tc, int M, int K, int N, const float* A, c
     for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) wt[(size_t)k * n4 + n] = W[(size_t)n * K + k];
     if (!dW.alloc(wt.size() * 4)) { g_last_error = "cudaMalloc failed"; return 0; }
     cudaMemcpy(dW.p, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice);
+    const int saved = bsb::pointwise_variant();
+    bsb::set_pointwise_variant(variant);
     bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+    bsb::set_pointwise_variant(saved);
   }
   if (!stage_end()) return 0;
   cudaMemcpy(out, dO.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
   return 1;
+}
+
+double bsb_time_pointwise(int device, int variant, int M, int K, int N, int iters) {
+  if (M <= 0 || K <= 0 || N <= 0 || iters < 1 || variant == 1) { g_last_error = "invalid argument"; return -1.0; }
+  if (!stage_begin(device)) return -1.0;
+  const int n4 = (N + 3) / 4 * 4;
+  DevBuf dA, dW, dB, dO;
+  if (!dA.alloc((size_t)M * K * 4) || !dO.alloc((size_t)M * N * 4) || !dW.alloc((size_t)K * n4 * 4) || !dB.alloc((size_t)N * 4)) { g_last_error = "cudaMalloc failed"; return -1.0; }
+  cudaMemset(dA.p, 0, (size_t)M * K * 4); cudaMemset(dW.p, 0, (size_t)K * n4 * 4); cudaMemset(dB.p, 0, (size_t)N * 4);
+  bsb::Epilogue e; e.bias = (const float*)dB.p; e.act1 = 3;
+  const int saved = bsb::pointwise_variant();
+  bsb::set_pointwise_variant(variant);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 2; ++i) bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+  cudaEventRecord(e0, nullptr);
+  for (int i = 0; i < iters; ++i) bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+  cudaEventRecord(e1, nullptr);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  bsb::set_pointwise_variant(saved);
+  if (!stage_end()) return -1.0;
+  return (double)ms / iters;
 }
 
 // ---- introspection ----------------------------------------------------------------

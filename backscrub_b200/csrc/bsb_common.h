@@ -19,6 +19,11 @@
 
 #define BSB_HD __host__ __device__ __forceinline__
 #define BSB_D __device__ __forceinline__
+#ifdef BSB_EMU
+#define BSB_D_NOINLINE __attribute__((noinline))
+#else
+#define BSB_D_NOINLINE __device__ __noinline__
+#endif
 
 namespace bsb {
 

@@ -38,6 +38,9 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
                       const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
                       const float* in_scale, int rows_per_frame, const float* in_add, int ld_add);
 
+void set_pointwise_variant(int v);   // 0 heuristics, 2 classic tiles, 3 register-tiled (A/B measurements; same bits)
+int pointwise_variant();
+
 // Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators) — kernels_tc.cu.
 // w_hi / w_lo: [npad][kpad] zero-padded copies of W[N][K] split as w = hi + lo with hi tf32-representable;
 // kpad % 32 == 0, npad % pointwise_tc_tile_n(N) == 0.  Returns false if the shape is not supported.

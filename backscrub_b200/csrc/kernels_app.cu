@@ -97,16 +97,31 @@ __global__ void __launch_bounds__(256) k_gauss_fused(const uint8_t* src, size_t 
   // ---- A: stage + de-interleave ----
   const bool interior = x0 - r >= 0 && x0 + GF_TW + r <= W && y0 - r >= 0 && y0 + GF_TH + r <= H;
   const int warp = tid >> 5, lane = tid & 31;
+  // (loads of three column groups and two rows are issued before any store: the patch comes from L2/HBM and the
+  //  loop is latency bound unless several requests per thread are in flight)
+#pragma unroll 2
   for (int row = warp; row < rows; row += 8) {
     int gy = y0 + row - r;
     if (!interior) gy = bsb_reflect101(gy, H);
     const uint8_t* srow = frame + (size_t)gy * spitch;
-    for (int col = lane; col < cols; col += 32) {
-      int gx = x0 + col - r;
-      if (!interior) gx = bsb_reflect101(gx, W);
-      const uint8_t* sp = srow + (size_t)gx * 3;
-      uint8_t* pp = P + row * GF_PW + col;
-      pp[0] = sp[0]; pp[GF_RM * GF_PW] = sp[1]; pp[2 * GF_RM * GF_PW] = sp[2];
+    uint8_t v[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int col = lane + 32 * j;
+      if (col < cols) {
+        int gx = x0 + col - r;
+        if (!interior) gx = bsb_reflect101(gx, W);
+        const uint8_t* sp = srow + (size_t)gx * 3;
+        v[j][0] = sp[0]; v[j][1] = sp[1]; v[j][2] = sp[2];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int col = lane + 32 * j;
+      if (col < cols) {
+        uint8_t* pp = P + row * GF_PW + col;
+        pp[0] = v[j][0]; pp[GF_RM * GF_PW] = v[j][1]; pp[2 * GF_RM * GF_PW] = v[j][2];
+      }
     }
   }
   __syncthreads();

@@ -30,6 +30,13 @@ BSB_D float epilogue(float total, int ch, size_t pix, const EpiDev& e) {
   return v;
 }
 
+// four adjacent channels of one row, as a real call: keeps the 32/64-output epilogue of the register-tiled
+// kernel from being unrolled into tens of thousands of instructions
+BSB_D_NOINLINE float4 epilogue4(float4 v, int ch, size_t pix, const EpiDev& e) {
+  return make_float4(epilogue(v.x, ch, pix, e), epilogue(v.y, ch + 1, pix, e), epilogue(v.z, ch + 2, pix, e), epilogue(v.w, ch + 3, pix, e));
+}
+BSB_D_NOINLINE float epilogue1(float v, int ch, size_t pix, const EpiDev& e) { return epilogue(v, ch, pix, e); }
+
 // ---------------------------------------------------------------------------
 // Dense KxK conv, small Cin (stem).  One thread = one output pixel x 4 output channels.
 // Weights [kh][kw][ic][oc4] staged in shared memory (broadcast reads).
@@ -251,6 +258,125 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
   }
 }
 
+// Register-tiled variant for the GEMM-heavy layers (DeepLab / BodyPix, K and N in the hundreds):
+// block tile 128 x (16*TN), thread tile 8 rows x TN columns (TN = 4 or 8), BK = 16, shared memory double
+// buffered with the next chunk prefetched into registers while the current one is consumed.  Per k step a
+// thread issues 2 + TN/4 LDS.128 for 8*TN FFMAs, so the kernel is FFMA-issue bound rather than LDS bound.
+// Every accumulator still sees its products in ascending k (bit-exact vs the oracle).
+template <int TN>
+__global__ void __launch_bounds__(256) k_pointwise_tile(PWArgs a) {
+  constexpr int BM = 128, BN = 16 * TN, BK = 16, LDA = BM + 4, WV = TN / 4;
+  __shared__ __align__(16) float As[2][BK * LDA];
+  __shared__ __align__(16) float Ws[2][BK * BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float4 ra[2], rw[WV];
+  const bool vec_a = (a.ld_a & 3) == 0;
+
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = tid + 256 * i, m = q >> 2, kq = (q & 3) * 4;
+      const int gm = m0 + m, gk = k0 + kq;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gm < a.M) {
+        const float* ap = a.A + (size_t)gm * a.ld_a + gk;
+        if (gk + 3 < a.K && vec_a) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(ap));
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (gk + j < a.K) v[j] = __ldg(ap + j);
+        }
+        if (a.in_scale) {
+          const float* sp = a.in_scale + (size_t)(gm / a.rows_per_frame) * a.K + gk;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (gk + j < a.K) v[j] = v[j] * __ldg(sp + j);
+        }
+        if (a.in_add) {
+          const float* dp = a.in_add + (size_t)gm * a.ld_add + gk;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (gk + j < a.K) v[j] = v[j] + __ldg(dp + j);
+        }
+      }
+      ra[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < WV; ++i) {
+      const int q = tid + 256 * i, k = q / (BN / 4), nq = (q % (BN / 4)) * 4;
+      rw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < a.K && n0 + nq < a.n4) rw[i] = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(k0 + k) * a.n4 + n0 + nq));
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = tid + 256 * i, m = q >> 2, kq = (q & 3) * 4;
+      float* d = &As[buf][kq * LDA + m];
+      d[0] = ra[i].x; d[LDA] = ra[i].y; d[2 * LDA] = ra[i].z; d[3 * LDA] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < WV; ++i) {
+      const int q = tid + 256 * i, k = q / (BN / 4), nq = (q % (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Ws[buf][k * BN + nq]) = rw[i];
+    }
+  };
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < a.K; k0 += BK) {
+    const bool more = k0 + BK < a.K;
+    if (more) gload(k0 + BK);
+    const float* as = &As[buf][ty * 8];
+    const float* ws = &Ws[buf][tx * 4];
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(as + k * LDA);
+      const float4 a1 = *reinterpret_cast<const float4*>(as + k * LDA + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int h = 0; h < WV; ++h) {
+        const float4 w4 = *reinterpret_cast<const float4*>(ws + k * BN + 64 * h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][4 * h] = fmaf(av[i], w4.x, acc[i][4 * h]);
+          acc[i][4 * h + 1] = fmaf(av[i], w4.y, acc[i][4 * h + 1]);
+          acc[i][4 * h + 2] = fmaf(av[i], w4.z, acc[i][4 * h + 2]);
+          acc[i][4 * h + 3] = fmaf(av[i], w4.w, acc[i][4 * h + 3]);
+        }
+      }
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // ---- epilogue ----
+  const bool vec_o = (a.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + ty * 8 + i;
+    if (gm >= a.M) continue;
+    float* op = a.out + (size_t)gm * a.ld_out;
+#pragma unroll
+    for (int h = 0; h < WV; ++h) {
+      const int ch = n0 + tx * 4 + 64 * h;
+      if (ch + 3 < a.N && vec_o) {
+        *reinterpret_cast<float4*>(op + ch) = epilogue4(make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]), ch, (size_t)gm, a.e);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ch + j < a.N) op[ch + j] = epilogue1(acc[i][4 * h + j], ch + j, (size_t)gm, a.e);
+      }
+    }
+  }
+}
+
 // Row-streaming variant for small K x N (the high-resolution MobileNet layers, K, N <= 64):
 // the whole weight matrix sits in shared memory; a thread owns 4 output channels of one
 // pixel and walks K in ascending order (float4 loads of the pixel row are shared by the
@@ -296,10 +422,33 @@ __global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
   }
 }
 
+// kernel selection override for A/B measurements: 0 = heuristics, 2 = never the register-tiled kernel, 3 = always
+// (set through bsb_pointwise's `variant` argument or the BSB_PW_VARIANT environment variable; results are
+// bit-identical whichever kernel runs)
+static int g_pw_variant = -1;
+void set_pointwise_variant(int v) { g_pw_variant = v; }
+int pointwise_variant() {
+  if (g_pw_variant < 0) { const char* e = getenv("BSB_PW_VARIANT"); g_pw_variant = e ? atoi(e) : 0; }
+  return g_pw_variant;
+}
+
 void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int ld_a,
                       const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
                       const float* in_scale, int rows_per_frame, const float* in_add, int ld_add) {
   PWArgs a{A, w_kn, out, in_scale, in_add, M, K, N, n4, ld_a, ld_out, rows_per_frame > 0 ? rows_per_frame : 1, ld_add, to_dev(e)};
+  const int variant = pointwise_variant();
+  // GEMM-heavy layers: register-tiled kernel (128-row tiles need enough rows to fill the 148 SMs)
+  // (measured per layer shape at batch 32, profiles/r1_pw_sweep_b32.txt: it wins for deep K with moderate N)
+  if (variant == 3 || (variant == 0 && (K >= 384 || (K >= 192 && N <= 160)) && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
+    const int pad64 = (N + 63) / 64 * 64, pad128 = (N + 127) / 128 * 128;
+    if (pad128 == pad64 && (long)ceil_div(M, 128) * (pad128 / 128) >= 2 * 148) {
+      auto k = k_pointwise_tile<8>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad128 / 128)), dim3(256), 0, s, a);
+    } else {
+      auto k = k_pointwise_tile<4>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad64 / 64)), dim3(256), 0, s, a);
+    }
+    count_launch();
+    return;
+  }
   if (K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 65536) {
     const int ct = n4 / 4, rows_per_block = 256 / ct;
     long blocks = ((long)M + rows_per_block - 1) / rows_per_block;

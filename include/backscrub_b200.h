@@ -155,11 +155,14 @@ BSB_API int bsb_flip(int device, const uint8_t* src, uint8_t* dst, int width, in
 /* cv::resize(src, dst, Size(dw, dh)) 8UC3 (app/background.cc:178-194) */
 BSB_API int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
 
-/* 1x1 convolution stage on HOST buffers: out[M][N] = act(A[M][K] * W[N][K]^T + bias).  use_tc = 0: exact FFMA
- * kernel (k-ascending fmaf, bit-identical to the oracle); 1: tcgen05 3xTF32 tensor-core kernel (needs K % 4 == 0).
+/* 1x1 convolution stage on HOST buffers: out[M][N] = act(A[M][K] * W[N][K]^T + bias).  variant 0: exact FFMA
+ * kernels, chosen by shape (k-ascending fmaf, bit-identical to the oracle); 1: tcgen05 3xTF32 tensor-core kernel
+ * (needs K % 4 == 0); 2 / 3: force the classic / the register-tiled exact FFMA kernel (same bits as 0).
  * act is a TFLite fused-activation code (0 none, 1 relu, 3 relu6). */
-BSB_API int bsb_pointwise(int device, int use_tc, int M, int K, int N, const float* A, const float* W,
+BSB_API int bsb_pointwise(int device, int variant, int M, int K, int N, const float* A, const float* W,
                           const float* bias, int act, float* out);
+/* ms per launch of the exact FFMA pointwise kernel `variant` (0, 2, 3) on an M x K x N problem (CUDA events) */
+BSB_API double bsb_time_pointwise(int device, int variant, int M, int K, int N, int iters);
 
 /* ---- introspection (tests, bench) -------------------------------------------------- */
 /* geometry: roidim / in_roidim / out_roidim as x,y,w,h (lib/libbackscrub.cc:234-246);

@@ -237,3 +237,18 @@ def check_app_options(lib, key="meet_lite", W=640, H=480):
     ro, _, _ = o.composite_ex(frames[0], ring[2], bgblur=9)
     assert np.array_equal(out[0], ro)
     g.close()
+
+
+def check_pointwise_variants(lib):
+    """Every exact FFMA pointwise kernel (shape heuristics, classic tiles, register-tiled) gives the oracle's bits,
+    including ragged M / K / N tails."""
+    rng = np.random.default_rng(11)
+    for (M, K, N, act) in [(33 * 33, 96, 32, 0), (300, 160, 64, 3), (129, 40, 21, 0), (257, 512, 256, 3), (1000, 24, 130, 1), (64, 16, 8, 0),
+                           (38000, 20, 128, 3)]:   # last one: enough 128-wide tiles for the 8x8 register tile
+        A = rng.standard_normal((M, K)).astype(np.float32)
+        W = rng.standard_normal((N, K)).astype(np.float32)
+        b = rng.standard_normal(N).astype(np.float32)
+        ref = po.conv2d(A.reshape(1, M, K), W.reshape(N, 1, 1, K), b, padding=po.PAD_VALID, act=act).reshape(M, N)
+        for variant in (0, 2, 3):
+            got = api.pointwise(lib, A, W, b, act=act, variant=variant)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (M, K, N, variant)

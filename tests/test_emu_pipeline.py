@@ -56,6 +56,10 @@ def test_stage_functions(lib):
     pc.check_stage_functions(lib)
 
 
+def test_pointwise_variants(lib):
+    pc.check_pointwise_variants(lib)
+
+
 def test_app_stage_functions(lib):
     pc.check_app_stage_functions(lib)
 

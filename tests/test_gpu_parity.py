@@ -114,3 +114,7 @@ def test_app_options(lib):                    # green default, bgblur (still / c
 
 def test_app_options_720p_meet(lib):          # the BASELINE config-4 geometry with the blur-my-background mode
     pc.check_app_options(lib, "meet_full", 1280, 720)
+
+
+def test_pointwise_variants(lib):             # classic / register-tiled exact FFMA kernels: same bits
+    pc.check_pointwise_variants(lib)

@@ -1,0 +1,31 @@
+"""Time the exact FFMA pointwise kernels per layer shape on the GPU (old heuristics = variant 2, register-tiled = 3).
+    python tools/pw_sweep.py [batch]
+"""
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import backscrub_b200 as bs  # noqa: E402
+from tests.conftest import MODELS, model_path  # noqa: E402
+from tools import tflite_graph as tg  # noqa: E402
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+lib = bs.lib()
+seen = collections.OrderedDict()
+for key in MODELS:
+    g = tg.load(model_path(key))
+    for op in g.ops:
+        if op.kind == "CONV_2D":
+            w = g.tensors[op.inputs[1]].shape
+            o = g.tensors[op.outputs[0]].shape
+            if w[1] == 1 and w[2] == 1 and o[1] * o[2] > 1:
+                seen.setdefault((o[1] * o[2], w[3], w[0]), []).append(key)
+print(f"batch {batch}: rows/frame K N | old ms | tile ms | speedup | TFLOP/s tile | models")
+for (rows, K, N), keys in sorted(seen.items(), key=lambda kv: -kv[0][0] * kv[0][1] * kv[0][2]):
+    M = rows * batch
+    t2 = lib.bsb_time_pointwise(0, 2, M, K, N, 20)
+    t3 = lib.bsb_time_pointwise(0, 3, M, K, N, 20)
+    fl = 2.0 * M * K * N
+    print(f"{rows:6d} {K:4d} {N:4d} | {t2:8.4f} | {t3:8.4f} | {t2 / t3:5.2f}x | {fl / t3 / 1e9:7.2f} | {','.join(sorted(set(keys)))}")
