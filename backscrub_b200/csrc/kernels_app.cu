@@ -84,6 +84,9 @@ constexpr int GF_NW = 9, GF_NV = 16;
 
 struct GaussFast { int k, nw, nv; unsigned hq[4][GF_NW]; unsigned cw[GF_NV]; };
 
+// NWC / NVC > 0: tap-word counts fixed at compile time (the default strength 25 -> 7 / 13), so the dot-product
+// chains are straight-line code; 0: run-time loops for the other strengths.
+template <int NWC, int NVC>
 __global__ void __launch_bounds__(256) k_gauss_fused(const uint8_t* src, size_t spitch, size_t sstride, uint8_t* dst, size_t dpitch,
                                                      size_t dstride, int W, int H, GaussFast g, int vec_ok) {
   __shared__ __align__(16) uint8_t P[3 * GF_RM * GF_PW];      // planes; reused as the interleaved output tile in C/D
@@ -93,48 +96,57 @@ __global__ void __launch_bounds__(256) k_gauss_fused(const uint8_t* src, size_t 
   const int tw = min(GF_TW, W - x0), th = min(GF_TH, H - y0);
   const int rows = GF_TH + 2 * r, cols = GF_TW + 2 * r;
   const uint8_t* frame = src + (size_t)b * sstride;
-
-  // ---- A: stage + de-interleave ----
-  const bool interior = x0 - r >= 0 && x0 + GF_TW + r <= W && y0 - r >= 0 && y0 + GF_TH + r <= H;
   const int warp = tid >> 5, lane = tid & 31;
-  // (loads of three column groups and two rows are issued before any store: the patch comes from L2/HBM and the
-  //  loop is latency bound unless several requests per thread are in flight)
+
+  // ---- A: stage + de-interleave (loads of three column groups and two rows are issued before any store: the
+  //      patch comes from L2/HBM and the loop is latency bound unless several requests per thread are in flight)
+  const bool interior = x0 - r >= 0 && x0 + GF_TW + r <= W && y0 - r >= 0 && y0 + GF_TH + r <= H;
+  if (interior) {
+    const uint8_t* base = frame + (size_t)(y0 - r) * spitch + (size_t)(x0 - r) * 3;
 #pragma unroll 2
-  for (int row = warp; row < rows; row += 8) {
-    int gy = y0 + row - r;
-    if (!interior) gy = bsb_reflect101(gy, H);
-    const uint8_t* srow = frame + (size_t)gy * spitch;
-    uint8_t v[3][3];
+    for (int row = warp; row < rows; row += 8) {
+      const uint8_t* srow = base + (size_t)row * spitch;
+      uint8_t v[3][3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int col = lane + 32 * j;
-      if (col < cols) {
-        int gx = x0 + col - r;
-        if (!interior) gx = bsb_reflect101(gx, W);
-        const uint8_t* sp = srow + (size_t)gx * 3;
-        v[j][0] = sp[0]; v[j][1] = sp[1]; v[j][2] = sp[2];
+      for (int j = 0; j < 3; ++j) {
+        const int col = lane + 32 * j;
+        if (col < cols) { const uint8_t* sp = srow + col * 3; v[j][0] = sp[0]; v[j][1] = sp[1]; v[j][2] = sp[2]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int col = lane + 32 * j;
+        if (col < cols) { uint8_t* pp = P + row * GF_PW + col; pp[0] = v[j][0]; pp[GF_RM * GF_PW] = v[j][1]; pp[2 * GF_RM * GF_PW] = v[j][2]; }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int col = lane + 32 * j;
-      if (col < cols) {
+  } else {
+    for (int row = warp; row < rows; row += 8) {
+      const uint8_t* srow = frame + (size_t)bsb_reflect101(y0 + row - r, H) * spitch;
+      for (int col = lane; col < cols; col += 32) {
+        const uint8_t* sp = srow + (size_t)bsb_reflect101(x0 + col - r, W) * 3;
         uint8_t* pp = P + row * GF_PW + col;
-        pp[0] = v[j][0]; pp[GF_RM * GF_PW] = v[j][1]; pp[2 * GF_RM * GF_PW] = v[j][2];
+        pp[0] = sp[0]; pp[GF_RM * GF_PW] = sp[1]; pp[2 * GF_RM * GF_PW] = sp[2];
       }
     }
   }
   __syncthreads();
 
   // ---- B: row sums (DP4A), stored transposed ----
+  const int nw = NWC > 0 ? NWC : g.nw, nv = NVC > 0 ? NVC : g.nv;
   for (int cm = warp; cm < 3 * (GF_TW / 4); cm += 8) {          // one (plane, 4-pixel group) per warp, lanes walk the rows
     const int c = cm / (GF_TW / 4), m = cm % (GF_TW / 4);
     for (int row = lane; row < rows; row += 32) {
       const unsigned* pw = reinterpret_cast<const unsigned*>(P + (c * GF_RM + row) * GF_PW + 4 * m);
       unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      if constexpr (NWC > 0) {
 #pragma unroll
-      for (int q = 0; q < GF_NW; ++q) {
-        if (q < g.nw) {
+        for (int q = 0; q < NWC; ++q) {
+          const unsigned w = pw[q];
+          a0 = __dp4a(w, g.hq[0][q], a0); a1 = __dp4a(w, g.hq[1][q], a1);
+          a2 = __dp4a(w, g.hq[2][q], a2); a3 = __dp4a(w, g.hq[3][q], a3);
+        }
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < nw; ++q) {
           const unsigned w = pw[q];
           a0 = __dp4a(w, g.hq[0][q], a0); a1 = __dp4a(w, g.hq[1][q], a1);
           a2 = __dp4a(w, g.hq[2][q], a2); a3 = __dp4a(w, g.hq[3][q], a3);
@@ -152,9 +164,15 @@ __global__ void __launch_bounds__(256) k_gauss_fused(const uint8_t* src, size_t 
     const int x = it % GF_TW, yp = (it / GF_TW) % (GF_TH / 2), c = it / (GF_TW * (GF_TH / 2));
     const unsigned* hw = reinterpret_cast<const unsigned*>(Ht + (c * GF_TW + x) * GF_HR + 2 * yp);
     unsigned a0 = 32768u, a1 = 32768u;
+    if constexpr (NVC > 0) {
 #pragma unroll
-    for (int q = 0; q < GF_NV; ++q) {
-      if (q < g.nv) {
+      for (int q = 0; q < NVC; ++q) {
+        const unsigned w = hw[q];
+        a0 = __dp2a_lo(w, g.cw[q], a0); a1 = __dp2a_hi(w, g.cw[q], a1);
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < nv; ++q) {
         const unsigned w = hw[q];
         a0 = __dp2a_lo(w, g.cw[q], a0); a1 = __dp2a_hi(w, g.cw[q], a1);
       }
@@ -200,8 +218,9 @@ void launch_gauss_blur(cudaStream_t s, int n, const uint8_t* src, size_t spitch,
   GaussFast f;
   if (gauss_fast_params(g, &f)) {
     const int vec_ok = (reinterpret_cast<uintptr_t>(dst) % 16 == 0 && dpitch % 16 == 0 && dstride % 16 == 0) ? 1 : 0;
-    BSB_LAUNCH(k_gauss_fused, dim3((unsigned)ceil_div(W, GF_TW), (unsigned)ceil_div(H, GF_TH), (unsigned)n), dim3(256), 0, s,
-               src, spitch, sstride, dst, dpitch, dstride, W, H, f, vec_ok);
+    const dim3 grid((unsigned)ceil_div(W, GF_TW), (unsigned)ceil_div(H, GF_TH), (unsigned)n);
+    if (f.nw == 7 && f.nv == 13) { auto kern = k_gauss_fused<7, 13>; BSB_LAUNCH(kern, grid, dim3(256), 0, s, src, spitch, sstride, dst, dpitch, dstride, W, H, f, vec_ok); }
+    else { auto kern = k_gauss_fused<0, 0>; BSB_LAUNCH(kern, grid, dim3(256), 0, s, src, spitch, sstride, dst, dpitch, dstride, W, H, f, vec_ok); }
     count_launch();
     return;
   }

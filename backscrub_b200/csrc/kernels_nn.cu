@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
 // thread issues 2 + TN/4 LDS.128 for 8*TN FFMAs, so the kernel is FFMA-issue bound rather than LDS bound.
 // Every accumulator still sees its products in ascending k (bit-exact vs the oracle).
 template <int TN>
-__global__ void __launch_bounds__(256) k_pointwise_tile(PWArgs a) {
+__global__ void __launch_bounds__(256, TN == 8 ? 2 : 3) k_pointwise_tile(PWArgs a) {
   constexpr int BM = 128, BN = 16 * TN, BK = 16, LDA = BM + 4, WV = TN / 4;
   __shared__ __align__(16) float As[2][BK * LDA];
   __shared__ __align__(16) float Ws[2][BK * BN];
