@@ -438,8 +438,8 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
   PWArgs a{A, w_kn, out, in_scale, in_add, M, K, N, n4, ld_a, ld_out, rows_per_frame > 0 ? rows_per_frame : 1, ld_add, to_dev(e)};
   const int variant = pointwise_variant();
   // GEMM-heavy layers: register-tiled kernel (128-row tiles need enough rows to fill the 148 SMs)
-  // (measured per layer shape at batch 32, profiles/r1_pw_sweep_b32.txt: it wins for deep K with moderate N)
-  if (variant == 3 || (variant == 0 && (K >= 384 || (K >= 192 && N <= 160)) && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
+  // (measured per layer shape at batch 32, profiles/r1_pw_sweep_b32.txt + run 19: it wins or ties from K = 160 up)
+  if (variant == 3 || (variant == 0 && K >= 160 && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
     const int pad64 = (N + 63) / 64 * 64, pad128 = (N + 127) / 128 * 128;
     if (pad128 == pad64 && (long)ceil_div(M, 128) * (pad128 / 128) >= 2 * 148) {
       auto k = k_pointwise_tile<8>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad128 / 128)), dim3(256), 0, s, a);
