@@ -373,8 +373,20 @@ def run_b200(args, wl):
     bytes_per_frame = 9 * npx + ow * oh + npx + 2 * npx        # 9WH + ow*oh, + WH mask, + 2WH YUYV (both written)
     t_post = c0.time_stage(3, B, 10) * 1e-3                    # seconds per launch (B frames)
     achieved = bytes_per_frame * B / t_post / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "post_traffic.json"))).get(args.workload, {}).get(str(B))
+    except Exception:
+        pass
+    if args.bgblur or wl.get("animated"):
+        traffic = None                                          # captured for the plain still-background configuration only
+    # whole-pipeline algorithmic HBM bytes per frame: YUYV ingest (2WH in, 3WH out) + ROI read (3 roi) + post stage
+    roi = c0.roidim
+    pipeline_bytes = 5 * npx + 3 * roi[2] * roi[3] + bytes_per_frame
     roofline = {"bound": "hbm", "kernel": "k_post (mask upsample + 5x5 blur + alpha blend + YUYV)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/post_traffic.json (ncu --set full, dram read+write per launch)" if traffic else None,
+                "pipeline_bytes_per_frame": pipeline_bytes, "pipeline_hbm_frac": value * pipeline_bytes / 1e9 / (peak * world),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": bytes_per_frame * B, "ms_per_launch": t_post * 1e3}
 
