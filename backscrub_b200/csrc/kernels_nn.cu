@@ -529,9 +529,9 @@ BSB_D void fma4(float4& acc, const float4& v, const float4& w) {
   acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
 }
 
-template <int KS, int S>
+template <int KS, int S, int D = 1>   // D = dilation (DeepLab / BodyPix atrous layers): taps sit D pixels apart
 __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
-  constexpr int CNT = 3 * S + KS;
+  constexpr int CNT = 3 * S + (KS - 1) * D + 1;
   const int groups = a.c / 4, strips = (a.ow + 3) / 4;
   const long total = (long)a.B * a.oh * strips * groups;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
   const int ix0 = ox0 * S - a.pl;
 #pragma unroll
   for (int fy = 0; fy < KS; ++fy) {
-    const int iy = oy * S - a.pt + fy;
+    const int iy = oy * S - a.pt + fy * D;
     if (iy < 0 || iy >= a.ih) continue;
     const float* rowp = inb + (size_t)iy * a.iw * a.ld_in;
     float4 v[CNT];
@@ -564,8 +564,8 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int fx = 0; fx < KS; ++fx) {
-        const int ix = ix0 + j * S + fx;
-        if (ix >= 0 && ix < a.iw) fma4(acc[j], v[j * S + fx], wr[fx]);
+        const int ix = ix0 + j * S + fx * D;
+        if (ix >= 0 && ix < a.iw) fma4(acc[j], v[j * S + fx * D], wr[fx]);
       }
   }
 #pragma unroll
@@ -584,11 +584,14 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
                       int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e) {
   DWArgs a{in, w, out, B, ih, iw, c, ld_in, kh, kw, stride_h, stride_w, dil_h, dil_w, pad_t, pad_l, oh, ow, ld_out, to_dev(e)};
   const bool vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0);
-  if (vec && dil_h == 1 && dil_w == 1 && kh == kw && stride_h == stride_w && (kh == 3 || kh == 5) && (stride_h == 1 || stride_h == 2)) {
+  const bool atrous = dil_h == dil_w && (dil_h == 2 || dil_h == 4) && kh == 3 && kw == 3 && stride_h == 1 && stride_w == 1;
+  if (vec && ((dil_h == 1 && dil_w == 1) || atrous) && kh == kw && stride_h == stride_w && (kh == 3 || kh == 5) && (stride_h == 1 || stride_h == 2)) {
     const long nthreads = (long)B * oh * ((ow + 3) / 4) * (c / 4);
     if (nthreads >= 148L * 1024) {   // enough strips to fill the GPU; small layers keep one pixel per thread
     const dim3 grid((unsigned)((nthreads + 127) / 128)), block(128);
-    if (kh == 3 && stride_h == 1) { auto k = k_depthwise_strip<3, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    if (atrous && dil_h == 2) { auto k = k_depthwise_strip<3, 1, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    else if (atrous) { auto k = k_depthwise_strip<3, 1, 4>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    else if (kh == 3 && stride_h == 1) { auto k = k_depthwise_strip<3, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
     else if (kh == 3) { auto k = k_depthwise_strip<3, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
     else if (stride_h == 1) { auto k = k_depthwise_strip<5, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
     else { auto k = k_depthwise_strip<5, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }

@@ -52,6 +52,13 @@ def test_infer_batch(lib):
     pc.check_infer_batch(lib, "meet_lite", n=3)
 
 
+@pytest.mark.slow
+@pytest.mark.parametrize("key,n", [("bodypix", 8), ("deeplab", 5)])
+def test_infer_batch_atrous_strips(lib, key, n):
+    """batches large enough that the dilated depthwise layers take the strip kernel (dilation 2 / 4)."""
+    pc.check_infer_batch(lib, key, n=n)
+
+
 def test_stage_functions(lib):
     pc.check_stage_functions(lib)
 

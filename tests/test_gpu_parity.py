@@ -118,3 +118,8 @@ def test_app_options_720p_meet(lib):          # the BASELINE config-4 geometry w
 
 def test_pointwise_variants(lib):             # classic / register-tiled exact FFMA kernels: same bits
     pc.check_pointwise_variants(lib)
+
+
+@pytest.mark.parametrize("key,n", [("bodypix", 8), ("deeplab", 16)])
+def test_infer_batch_atrous_strips(lib, key, n):   # dilated depthwise strips + register-tiled pointwise at real batch sizes
+    pc.check_infer_batch(lib, key, n=n)
