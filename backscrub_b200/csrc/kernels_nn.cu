@@ -439,9 +439,9 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
   const int variant = pointwise_variant();
   // GEMM-heavy layers: register-tiled kernel (128-row tiles need enough rows to fill the 148 SMs)
   // (measured per layer shape at batch 32, profiles/r1_pw_sweep_b32.txt + run 19: it wins or ties from K = 160 up)
-  if (variant == 3 || (variant == 0 && K >= 160 && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
+  if (variant == 3 || variant == 4 || variant == 8 || (variant == 0 && K >= 160 && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
     const int pad64 = (N + 63) / 64 * 64, pad128 = (N + 127) / 128 * 128;
-    if (pad128 == pad64 && (long)ceil_div(M, 128) * (pad128 / 128) >= 2 * 148) {
+    if (variant == 8 || (variant != 4 && pad128 == pad64 && (long)ceil_div(M, 128) * (pad128 / 128) >= 2 * 148)) {
       auto k = k_pointwise_tile<8>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad128 / 128)), dim3(256), 0, s, a);
     } else {
       auto k = k_pointwise_tile<4>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad64 / 64)), dim3(256), 0, s, a);
@@ -449,7 +449,7 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
     count_launch();
     return;
   }
-  if (K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 65536) {
+  if (variant < 16 && K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 65536) {
     const int ct = n4 / 4, rows_per_block = 256 / ct;
     long blocks = ((long)M + rows_per_block - 1) / rows_per_block;
     if (blocks > 148L * 16) blocks = 148L * 16;             // grid-stride: a few waves of 148 SMs
@@ -462,6 +462,7 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
   int bn = 64;
   if (pad32 < pad64) bn = 32;
   if (pad16 < (bn == 64 ? pad64 : pad32)) bn = 16;
+  if (variant >= 16) bn = variant;                           // A/B measurements: force the classic kernel's N tile (16 / 32 / 64)
   // small problems: one row per thread (TM = 1) gives 4x more blocks to spread over the 148 SMs
   const int rt = 256 / (bn / 4);
   const bool small = (long)ceil_div(M, rt * 4) * ceil_div(N, bn) < 2 * 148;

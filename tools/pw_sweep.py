@@ -22,10 +22,12 @@ for key in MODELS:
             o = g.tensors[op.outputs[0]].shape
             if w[1] == 1 and w[2] == 1 and o[1] * o[2] > 1:
                 seen.setdefault((o[1] * o[2], w[3], w[0]), []).append(key)
-print(f"batch {batch}: rows/frame K N | old ms | tile ms | speedup | TFLOP/s tile | models")
+# variants: 2 = rows/classic heuristics, 16/32/64 = classic kernel with that N tile, 4 / 8 = register-tiled 8x4 / 8x8
+print(f"batch {batch}: rows/frame K N | heur ms | bn16 | bn32 | bn64 | tile4 | tile8 | best TFLOP/s | models")
 for (rows, K, N), keys in sorted(seen.items(), key=lambda kv: -kv[0][0] * kv[0][1] * kv[0][2]):
     M = rows * batch
-    t2 = lib.bsb_time_pointwise(0, 2, M, K, N, 20)
-    t3 = lib.bsb_time_pointwise(0, 3, M, K, N, 20)
+    if M * K * N < 2e8:
+        continue
+    ts = [lib.bsb_time_pointwise(0, v, M, K, N, 20) for v in (2, 16, 32, 64, 4, 8)]
     fl = 2.0 * M * K * N
-    print(f"{rows:6d} {K:4d} {N:4d} | {t2:8.4f} | {t3:8.4f} | {t2 / t3:5.2f}x | {fl / t3 / 1e9:7.2f} | {','.join(sorted(set(keys)))}")
+    print(f"{rows:6d} {K:4d} {N:4d} | " + " | ".join(f"{t:7.4f}" for t in ts) + f" | {fl / min(ts) / 1e9:7.2f} | {','.join(sorted(set(keys)))}")
