@@ -439,9 +439,11 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
   const int variant = pointwise_variant();
   // GEMM-heavy layers: register-tiled kernel (128-row tiles need enough rows to fill the 148 SMs)
   // (measured per layer shape at batch 32, profiles/r1_pw_sweep_b32.txt + run 19: it wins or ties from K = 160 up)
-  if (variant == 3 || variant == 4 || variant == 8 || (variant == 0 && K >= 160 && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
+  if (variant == 3 || variant == 4 || variant == 8 || (variant == 0 && ((K >= 128 && N >= 32) || (K >= 192 && N >= 16)) && (long)ceil_div(M, 128) * ceil_div(N, 64) >= 148)) {
+    // 8x8 register tiles (128 columns) unless padding N to 128 wastes a whole 64-column tile
     const int pad64 = (N + 63) / 64 * 64, pad128 = (N + 127) / 128 * 128;
-    if (variant == 8 || (variant != 4 && pad128 == pad64 && (long)ceil_div(M, 128) * (pad128 / 128) >= 2 * 148)) {
+    const bool wide = variant == 8 || (variant != 4 && pad128 - N < 64 && (long)ceil_div(M, 128) * (pad128 / 128) >= 148);
+    if (wide) {
       auto k = k_pointwise_tile<8>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad128 / 128)), dim3(256), 0, s, a);
     } else {
       auto k = k_pointwise_tile<4>; BSB_LAUNCH(k, dim3((unsigned)ceil_div(M, 128), (unsigned)(pad64 / 64)), dim3(256), 0, s, a);
@@ -449,7 +451,11 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
     count_launch();
     return;
   }
-  if (variant < 16 && K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096 && M >= 65536) {
+  const bool rows_ok = K % 4 == 0 && ld_a % 4 == 0 && (!in_add || ld_add % 4 == 0) && n4 <= 64 && K * n4 <= 4096;
+  // measured (profiles/r1_pw_sweep3_b32.txt): the row-streaming kernel wins for very narrow outputs (<= 8 channels),
+  // 20..28 output channels, and K <= 8; the classic tiles win elsewhere (e.g. 16 -> 16, 64 -> 64)
+  const bool rows_wins = n4 <= 8 || (n4 >= 20 && n4 <= 28) || K <= 8;
+  if (rows_ok && (variant == 5 || (variant < 16 && M >= 4096 && rows_wins))) {
     const int ct = n4 / 4, rows_per_block = 256 / ct;
     long blocks = ((long)M + rows_per_block - 1) / rows_per_block;
     if (blocks > 148L * 16) blocks = 148L * 16;             // grid-stride: a few waves of 148 SMs

@@ -249,6 +249,6 @@ def check_pointwise_variants(lib):
         W = rng.standard_normal((N, K)).astype(np.float32)
         b = rng.standard_normal(N).astype(np.float32)
         ref = po.conv2d(A.reshape(1, M, K), W.reshape(N, 1, 1, K), b, padding=po.PAD_VALID, act=act).reshape(M, N)
-        for variant in (0, 2, 3, 4, 8, 16, 32, 64):
+        for variant in (0, 2, 3, 4, 5, 8, 16, 32, 64):
             got = api.pointwise(lib, A, W, b, act=act, variant=variant)
             assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (M, K, N, variant)

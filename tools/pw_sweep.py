@@ -23,11 +23,11 @@ for key in MODELS:
             if w[1] == 1 and w[2] == 1 and o[1] * o[2] > 1:
                 seen.setdefault((o[1] * o[2], w[3], w[0]), []).append(key)
 # variants: 2 = rows/classic heuristics, 16/32/64 = classic kernel with that N tile, 4 / 8 = register-tiled 8x4 / 8x8
-print(f"batch {batch}: rows/frame K N | heur ms | bn16 | bn32 | bn64 | tile4 | tile8 | best TFLOP/s | models")
+print(f"batch {batch}: rows/frame K N | heur ms | rows | bn16 | bn32 | bn64 | tile4 | tile8 | best TFLOP/s | models")
 for (rows, K, N), keys in sorted(seen.items(), key=lambda kv: -kv[0][0] * kv[0][1] * kv[0][2]):
     M = rows * batch
-    if M * K * N < 2e8:
+    if M < 4096:
         continue
-    ts = [lib.bsb_time_pointwise(0, v, M, K, N, 20) for v in (2, 16, 32, 64, 4, 8)]
+    ts = [lib.bsb_time_pointwise(0, v, M, K, N, 20) for v in (0, 5, 16, 32, 64, 4, 8)]
     fl = 2.0 * M * K * N
     print(f"{rows:6d} {K:4d} {N:4d} | " + " | ".join(f"{t:7.4f}" for t in ts) + f" | {fl / min(ts) / 1e9:7.2f} | {','.join(sorted(set(keys)))}")
