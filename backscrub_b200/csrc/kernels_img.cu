@@ -665,31 +665,62 @@ BSB_D void yuv2bgr_px(int y, int ruv, int guv, int buv, uint8_t* o) {
   o[0] = bsb_sat_u8((yy + buv) >> 20); o[1] = bsb_sat_u8((yy + guv) >> 20); o[2] = bsb_sat_u8((yy + ruv) >> 20);
 }
 
-__global__ void __launch_bounds__(256) k_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, size_t ngroups, size_t npix) {
+__global__ void __launch_bounds__(256) k_yuyv_to_bgr(const uint8_t* yuyv, uint8_t* bgr, size_t ngroups, size_t npix, int vec_ok) {
   const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gidx >= ngroups) return;
+  if (gidx >= ngroups) return;          // (only in the last, partial block: full blocks reach the barrier below together)
   const size_t p0 = gidx * 8;
-  __align__(16) uint8_t in[16];
-  __align__(8) uint8_t out[24];
   const int n = (npix - p0) < 8 ? (int)(npix - p0) : 8;
-  if (n == 8) *reinterpret_cast<uint4*>(in) = __ldg(reinterpret_cast<const uint4*>(yuyv + 2 * p0));
-  else for (int i = 0; i < 2 * n; ++i) in[i] = yuyv[2 * p0 + i];
+  unsigned w[4] = {0u, 0u, 0u, 0u};     // 8 pixels = 4 words of Y0 U Y1 V
+  if (n == 8) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(yuyv + 2 * p0));
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  } else {
+    for (int i = 0; i < 2 * n; ++i) w[i >> 2] |= (unsigned)yuyv[2 * p0 + i] << (8 * (i & 3));
+  }
+  unsigned o[6] = {0u, 0u, 0u, 0u, 0u, 0u};   // 24 output bytes, assembled in registers
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (2 * k >= n) break;
-    const int u = (int)in[4 * k + 1] - 128, v = (int)in[4 * k + 3] - 128;
+    const int u = (int)((w[k] >> 8) & 255u) - 128, v = (int)(w[k] >> 24) - 128;
     const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
-    yuv2bgr_px(in[4 * k], ruv, guv, buv, out + 6 * k);
-    yuv2bgr_px(in[4 * k + 2], ruv, guv, buv, out + 6 * k + 3);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int yy = max((int)((w[k] >> (16 * h)) & 255u) - 16, 0) * 1220542;
+      const unsigned px[3] = {bsb_sat_u8((yy + buv) >> 20), bsb_sat_u8((yy + guv) >> 20), bsb_sat_u8((yy + ruv) >> 20)};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int byte = 6 * k + 3 * h + c;
+        o[byte >> 2] |= px[c] << (8 * (byte & 3));
+      }
+    }
+  }
+  // full blocks: stage the 24-byte groups in shared memory and write 16-byte vectors (a warp then writes 768
+  // contiguous bytes in 1.5 passes instead of three 8-byte-strided passes that each touch every sector)
+  __shared__ __align__(16) uint2 stage[256 * 3];
+  const size_t blk_p0 = (size_t)blockIdx.x * blockDim.x * 8;
+  const bool full_block = blk_p0 + (size_t)blockDim.x * 8 <= npix && blockDim.x == 256 && vec_ok;
+  if (full_block) {
+    uint2* q = stage + threadIdx.x * 3;
+    q[0] = make_uint2(o[0], o[1]); q[1] = make_uint2(o[2], o[3]); q[2] = make_uint2(o[4], o[5]);
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(bgr + 3 * blk_p0);
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+    dst[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x < 128) dst[256 + threadIdx.x] = src[256 + threadIdx.x];
+    return;
   }
   uint8_t* d = bgr + 3 * p0;
-  if (n == 8) { uint2* q = reinterpret_cast<uint2*>(d); const uint2* sv = reinterpret_cast<const uint2*>(out); q[0] = sv[0]; q[1] = sv[1]; q[2] = sv[2]; }
-  else for (int i = 0; i < 3 * n; ++i) d[i] = out[i];
+  if (n == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+    uint2* q = reinterpret_cast<uint2*>(d);
+    q[0] = make_uint2(o[0], o[1]); q[1] = make_uint2(o[2], o[3]); q[2] = make_uint2(o[4], o[5]);
+  } else {
+    for (int i = 0; i < 3 * n; ++i) d[i] = (uint8_t)(o[i >> 2] >> (8 * (i & 3)));
+  }
 }
 
 void launch_yuyv_to_bgr(cudaStream_t s, const uint8_t* yuyv, uint8_t* bgr, size_t npix_total) {
   const size_t ngroups = (npix_total + 7) / 8;
-  BSB_LAUNCH(k_yuyv_to_bgr, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, s, yuyv, bgr, ngroups, npix_total);
+  const int vec_ok = (reinterpret_cast<uintptr_t>(bgr) & 15) == 0 ? 1 : 0;
+  BSB_LAUNCH(k_yuyv_to_bgr, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, s, yuyv, bgr, ngroups, npix_total, vec_ok);
   count_launch();
 }
 

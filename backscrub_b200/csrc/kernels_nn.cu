@@ -122,38 +122,61 @@ __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
   __syncthreads();
   const long total = (long)a.B * a.oh * a.ow;
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int ox = (int)(pix % a.ow), oy = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
-  const uint8_t* inb = a.in + (size_t)b * a.ih * a.iw * 3;
+  const bool valid = pix < total;
   float acc[16];
 #pragma unroll
   for (int o = 0; o < 16; ++o) acc[o] = 0.f;
-  const int iy0 = oy * a.sh - a.pt, ix0 = ox * a.sw - a.pl;
-  for (int fy = 0; fy < a.kh; ++fy) {
-    const int iy = iy0 + fy;
-    if (iy < 0 || iy >= a.ih) continue;
-    for (int fx = 0; fx < a.kw; ++fx) {
-      const int ix = ix0 + fx;
-      if (ix < 0 || ix >= a.iw) continue;
-      const uint8_t* ip = inb + ((size_t)iy * a.iw + ix) * 3;
-      const float* wp = ws + (fy * a.kw + fx) * 48;
+  if (valid) {
+    const int ox = (int)(pix % a.ow), oy = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
+    const uint8_t* inb = a.in + (size_t)b * a.ih * a.iw * 3;
+    const int iy0 = oy * a.sh - a.pt, ix0 = ox * a.sw - a.pl;
+    for (int fy = 0; fy < a.kh; ++fy) {
+      const int iy = iy0 + fy;
+      if (iy < 0 || iy >= a.ih) continue;
+      for (int fx = 0; fx < a.kw; ++fx) {
+        const int ix = ix0 + fx;
+        if (ix < 0 || ix >= a.iw) continue;
+        const uint8_t* ip = inb + ((size_t)iy * a.iw + ix) * 3;
+        const float* wp = ws + (fy * a.kw + fx) * 48;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = fmaf((float)ip[c], a.scale, a.offset);
+        for (int c = 0; c < 3; ++c) {
+          const float v = fmaf((float)ip[c], a.scale, a.offset);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wp + c * 16 + q * 4);
-          acc[4 * q] = fmaf(v, w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + c * 16 + q * 4);
+            acc[4 * q] = fmaf(v, w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+          }
         }
       }
     }
   }
-  float* op = a.out + (size_t)pix * a.ld_out;
+  float4 r[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<float4*>(op + 4 * q) = make_float4(epilogue(acc[4 * q], 4 * q, (size_t)pix, a.e), epilogue(acc[4 * q + 1], 4 * q + 1, (size_t)pix, a.e),
-                                                         epilogue(acc[4 * q + 2], 4 * q + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], 4 * q + 3, (size_t)pix, a.e));
+    r[q] = valid ? make_float4(epilogue(acc[4 * q], 4 * q, (size_t)pix, a.e), epilogue(acc[4 * q + 1], 4 * q + 1, (size_t)pix, a.e),
+                               epilogue(acc[4 * q + 2], 4 * q + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], 4 * q + 3, (size_t)pix, a.e))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.ld_out == 16) {
+    // packed output: a thread's 16 channels are 64 contiguous bytes, so four strided float4 stores per thread would
+    // touch every sector four times; transpose through shared memory and let the block write 8 KB contiguously
+    __shared__ float4 stage[4 * 129];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) stage[q * 129 + threadIdx.x] = r[q];
+    __syncthreads();
+    const long blk0 = (long)blockIdx.x * blockDim.x;
+    float4* dst = reinterpret_cast<float4*>(a.out + (size_t)blk0 * 16);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int j = it * 128 + threadIdx.x;                   // float4 index inside the block's output: pixel j / 4, quad j % 4
+      if (blk0 + (j >> 2) < total) dst[j] = stage[(j & 3) * 129 + (j >> 2)];
+    }
+    return;
+  }
+  if (!valid) return;
+  float* op = a.out + (size_t)pix * a.ld_out;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(op + 4 * q) = r[q];
 }
 
 void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw, float scale, float offset,
@@ -934,6 +957,35 @@ __global__ void __launch_bounds__(128) k_tconv2x2(const float* in, int B, int ih
   const int ix = (int)(pix % iw), iy = (int)((pix / iw) % ih), b = (int)(pix / ((long)iw * ih));
   const float* ip = in + (size_t)pix * ld_in;
   const bool vec = (ic % 4 == 0) && (ld_in % 4 == 0);
+  if (vec && ic == 16 && oc <= 2 && ld_out == oc && (ow & 1) == 0) {
+    // the MLKit / Meet heads: 16 inputs held in registers, each output row (2 pixels x oc) leaves as one vector store
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ip + c));
+      v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+    }
+#pragma unroll
+    for (int fy = 0; fy < 2; ++fy) {
+      float r[2][2];                      // [fx][o]
+#pragma unroll
+      for (int fx = 0; fx < 2; ++fx)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          r[fx][o] = 0.f;
+          if (o >= oc) continue;
+          const float* wp = ws + ((o * 2 + fy) * 2 + fx) * 16;
+          float acc = __ldg(bias + o);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc = fmaf(v[c], wp[c], acc);
+          r[fx][o] = bsb_act(acc, act2);
+        }
+      float* op = out + (((size_t)b * oh + 2 * iy + fy) * ow + 2 * ix) * oc;
+      if (oc == 2) *reinterpret_cast<float4*>(op) = make_float4(r[0][0], r[0][1], r[1][0], r[1][1]);
+      else *reinterpret_cast<float2*>(op) = make_float2(r[0][0], r[1][0]);
+    }
+    return;
+  }
   for (int fy = 0; fy < 2; ++fy)
     for (int fx = 0; fx < 2; ++fx) {
       float* op = out + (((size_t)b * oh + 2 * iy + fy) * ow + 2 * ix + fx) * ld_out;
