@@ -236,6 +236,8 @@ def run_b200(args, wl):
     rank, world, local = dist_env()
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
