@@ -236,9 +236,19 @@ def run_b200(args, wl):
     rank, world, local = dist_env()
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner / debug lines to stdout while the communicator comes up; rank 0's stdout must
+        # carry exactly one JSON line, so point fd 1 at stderr for the duration of the initialisation
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
     full_affinity = bind_near_gpu(torch, dev)
