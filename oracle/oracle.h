@@ -17,8 +17,14 @@
  * Parity status: every op is pinned by the TFLite single-op KATs transcribed
  * in tests/ and by oracle/_ref (the reference's own transpose_conv_bias.cc
  * compiled in place); the integer image ops are pinned bit-exact against
- * cv2 4.13.  WHOLE-MODEL outputs are parity-UNPINNED (the reference has no
- * image->mask golden and TFLite/XNNPACK cannot be built offline).
+ * cv2 4.13.  WHOLE-MODEL outputs are parity-UNPINNED against the reference's
+ * own TFLite+XNNPACK binary (it has no image->mask golden and cannot be built
+ * offline).  What stands in: OpenCV 4.13's dnn module (a third-party TFLite
+ * importer + kernels; OpenCV is the reference's system dependency) agrees with
+ * this interpreter on the whole MLKit graph to 1e-5 and on every DeepLab /
+ * BodyPix layer it imports correctly (tests/test_oracle_model.py, committed as
+ * tests/golden/model_cv2dnn_golden.npz), and a torch-fp64 evaluation agrees on
+ * every tensor of all five graphs.
  *
  * Numeric contract shared with the CUDA path (documented deviations from
  * the reference kernels; each is below the 1e-5/3e-6 tolerances the

@@ -106,7 +106,21 @@ def pipeline():
     np.savez_compressed(os.path.join(OUT, "pipeline_golden.npz"), **d)
 
 
+def model_cv2dnn():
+    """Whole-model output of the MLKit graph computed by OpenCV's own dnn module (cv2.dnn.readNetFromTFLite): a
+    third-party implementation of the same .tflite file.  Stored as float16-rounded probabilities plus the decision
+    bitmap (the comparison tolerance is 1e-3 on the rounded values, exact on the decisions away from the threshold)."""
+    g = po.MaskGen(model_path("mlkit"), 640, 480)
+    g.process(synth.frame(640, 480, t=3))
+    x = g.input_f32
+    net = cv2.dnn.readNetFromTFLite(model_path("mlkit"))
+    net.setInput(np.ascontiguousarray(x.transpose(2, 0, 1)[None]))
+    out = net.forward()[0, 0]
+    np.savez_compressed(os.path.join(OUT, "model_cv2dnn_golden.npz"), mlkit_prob_f16=out.astype(np.float16),
+                        mlkit_decision=np.packbits(out > 0.65), mlkit_margin_ok=np.packbits(np.abs(out - 0.65) > 1e-3))
+
+
 if __name__ == "__main__":
-    image_ops(); tconv_ref(); model_torch(); pipeline()
+    image_ops(); tconv_ref(); model_torch(); pipeline(); model_cv2dnn()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

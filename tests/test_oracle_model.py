@@ -81,3 +81,59 @@ def test_rejects_bad_file(tmp_path):
         po.Model(str(p))
     with pytest.raises(RuntimeError):
         po.Model(str(tmp_path / "missing.tflite"))
+
+
+# ---- third-party cross-check: OpenCV's dnn module imports .tflite files (cv2.dnn.readNetFromTFLite) and runs them
+# with its own CPU kernels.  OpenCV is the reference's system dependency, and this is an implementation of the same
+# graphs that shares no code with the oracle or with tests/torch_graph.py. ----
+def _cv2dnn_forward(path, x, layer=None):
+    import cv2
+    net = cv2.dnn.readNetFromTFLite(path)
+    net.setInput(np.ascontiguousarray(x.transpose(2, 0, 1)[None]))
+    out = net.forward(layer) if layer else net.forward()
+    return (out[0].transpose(1, 2, 0) if out.ndim == 4 else out), net
+
+
+def test_mlkit_whole_model_matches_opencv_dnn():
+    """BASELINE configs 1-2 model: the oracle's output agrees with OpenCV dnn's on the whole graph (136 ops: fp16
+    DEQUANTIZE, convs, depthwise, SE blocks, hard-swish, bilinear resize, Convolution2DTransposeBias, logistic)."""
+    g = po.MaskGen(model_path("mlkit"), 640, 480)
+    g.process(synth.frame(640, 480, t=3))
+    x = g.input_f32
+    ref = po.Model(model_path("mlkit")).invoke(x)[0]
+    got, _ = _cv2dnn_forward(model_path("mlkit"), x)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 5e-5                      # probabilities in [0, 1]
+    assert np.array_equal(got > 0.65, ref > 0.65) or ((got > 0.65) != (ref > 0.65)).sum() <= 2
+
+
+@pytest.mark.parametrize("key,n_ops", [("bodypix", 13), ("deeplab", 25)])
+def test_mobilenet_prefix_matches_opencv_dnn(key, n_ops):
+    """DeepLab / BodyPix: every layer up to the first atrous depthwise conv agrees with OpenCV dnn (its TFLite importer
+    drops dilation_*_factor, so from that layer on OpenCV computes a different network and cannot serve as a pin)."""
+    import cv2
+    from tools import tflite_graph as tg
+    g = po.MaskGen(model_path(key), 640, 480)
+    g.process(synth.frame(640, 480, t=3))
+    x = g.input_f32
+    m = po.Model(model_path(key))
+    m.invoke(x)
+    gr = tg.load(model_path(key))
+    net = cv2.dnn.readNetFromTFLite(model_path(key))
+    names = set(net.getLayerNames())
+    net.setInput(np.ascontiguousarray(x.transpose(2, 0, 1)[None]))
+    checked = 0
+    for op in gr.ops[:n_ops]:
+        t = op.outputs[0]
+        nm = gr.tensors[t].name
+        layer = nm + "/activ" if nm + "/activ" in names else (nm if nm in names else None)
+        if layer is None:
+            continue
+        assert op.opts.get("dil_h", 1) == 1
+        out = net.forward(layer)
+        ref = m.tensor(t)
+        got = out[0].transpose(1, 2, 0).reshape(ref.shape)
+        assert np.abs(got - ref).max() < 5e-4 * max(1.0, float(np.abs(ref).max())), (op.idx, op.kind)
+        checked += 1
+    assert checked >= n_ops - 1
+    assert gr.ops[n_ops].kind == "DEPTHWISE_CONV_2D" and gr.ops[n_ops].opts["dil_h"] == 2
