@@ -128,6 +128,51 @@ def cpu_path_fps(wl, threads, frames_per_thread, warm=1, bgblur=0, camera_blur=F
     return threads * frames_per_thread / dt, dt
 
 
+def cnn_calibration(wl):
+    """How far the scalar oracle port is from optimised CPU inference kernels, on the CNN alone and on one thread:
+    the port, a torch fp32 (oneDNN) evaluation of the same .tflite graph, and — where its importer accepts the
+    graph — OpenCV dnn.  Informative only: the reference's own TFLite-XNNPACK build is not available offline."""
+    out = {}
+    try:
+        import torch
+        from oracle import pyoracle as po
+        from tests import torch_graph
+        model = os.path.join(ROOT, "models", wl["model"])
+        m = po.Model(model)
+        h, w, c = m.shape(m.input)[1:]
+        x = np.random.default_rng(0).random((h, w, c), dtype=np.float32)
+
+        def best(fn, n=3):
+            fn()
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+            return min(ts) * 1e3
+        out["port_cnn_ms"] = best(lambda: m.invoke(x))
+        nt = torch.get_num_threads()
+        torch.set_num_threads(1)
+        out["torch_fp32_cnn_ms"] = best(lambda: torch_graph.run(model, x, dtype=torch.float32))
+        torch.set_num_threads(nt)
+        try:
+            if "selfie" not in wl["model"]:
+                raise RuntimeError("OpenCV's TFLite importer rejects the Meet graphs and drops the dilation of DeepLab / BodyPix")
+            import cv2
+            net = cv2.dnn.readNetFromTFLite(model)
+            cv2.setNumThreads(1)
+            blob = np.ascontiguousarray(x.transpose(2, 0, 1)[None])
+
+            def f():
+                net.setInput(blob); net.forward()
+            out["opencv_dnn_cnn_ms"] = best(f)
+            cv2.setNumThreads(-1)
+        except Exception:
+            out["opencv_dnn_cnn_ms"] = None            # importer rejects this graph (Meet) or ignores dilation (DeepLab / BodyPix)
+        out["note"] = "single thread, CNN only; the model card quotes ~120 frames/s (8 ms) for Meet on TFLite-XNNPACK"
+    except Exception as e:  # calibration is optional
+        out["error"] = str(e)[:120]
+    return out
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -414,7 +459,7 @@ def run_b200(args, wl):
         v, dt = cpu_path_fps(wl, threads, fpt, warm=0, **kw)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{threads} threads x {fpt} frames of the same workload ({dt:.1f} s), oracle port (TFLite-reference kernels + OpenCV ops restated)",
-               "single_thread_value": fps1}
+               "single_thread_value": fps1, "calibration": cnn_calibration(wl)}
 
     if rank == 0:
         line = {
