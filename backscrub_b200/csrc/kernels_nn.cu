@@ -268,14 +268,21 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
     __syncthreads();
   }
   // ---- epilogue ----
+  const bool vec_o = (a.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int gm = m0 + ty + RT * i;
     if (gm >= a.M) continue;
     float* op = a.out + (size_t)gm * a.ld_out;
+    const int ch0 = n0 + tx * 4;
+    if (vec_o && ch0 + 3 < a.N) {      // one 16-byte store per row segment instead of four strided scalar stores
+      *reinterpret_cast<float4*>(op + ch0) = make_float4(epilogue(acc[i][0], ch0, (size_t)gm, a.e), epilogue(acc[i][1], ch0 + 1, (size_t)gm, a.e),
+                                                         epilogue(acc[i][2], ch0 + 2, (size_t)gm, a.e), epilogue(acc[i][3], ch0 + 3, (size_t)gm, a.e));
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int ch = n0 + tx * 4 + j;
+      const int ch = ch0 + j;
       if (ch < a.N) op[ch] = epilogue(acc[i][j], ch, (size_t)gm, a.e);
     }
   }
@@ -547,6 +554,11 @@ __global__ void __launch_bounds__(256) k_depthwise(DWArgs a) {
     }
   }
   float* op = a.out + (size_t)pix * a.ld_out + c0;
+  if (VEC == 4) {   // (the launcher picks VEC = 4 only when c, ld_in and ld_out are multiples of 4)
+    *reinterpret_cast<float4*>(op) = make_float4(epilogue(acc[0], c0, (size_t)pix, a.e), epilogue(acc[1 % VEC], c0 + 1, (size_t)pix, a.e),
+                                                 epilogue(acc[2 % VEC], c0 + 2, (size_t)pix, a.e), epilogue(acc[3 % VEC], c0 + 3, (size_t)pix, a.e));
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) op[j] = epilogue(acc[j], c0 + j, (size_t)pix, a.e);
 }
@@ -914,6 +926,18 @@ __global__ void __launch_bounds__(256) k_resize_bilinear(const float* in, int B,
   const float* p01 = inb + ((size_t)y0 * iw + x1) * ld_in;
   const float* p11 = inb + ((size_t)y1 * iw + x1) * ld_in;
   float* op = out + (size_t)pix * ld_out + c0;
+  if (VEC == 4 && ((c | ld_in | ld_out) & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    // channel counts that are multiples of 4 (all but DeepLab's 21-class head): 16-byte loads and one 16-byte store
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(p00)), v10 = __ldg(reinterpret_cast<const float4*>(p10));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(p01)), v11 = __ldg(reinterpret_cast<const float4*>(p11));
+    float4 r;
+    r.x = ((v00.x * wy0 * wx0 + v10.x * dy * wx0) + v01.x * wy0 * dx) + v11.x * dy * dx;
+    r.y = ((v00.y * wy0 * wx0 + v10.y * dy * wx0) + v01.y * wy0 * dx) + v11.y * dy * dx;
+    r.z = ((v00.z * wy0 * wx0 + v10.z * dy * wx0) + v01.z * wy0 * dx) + v11.z * dy * dx;
+    r.w = ((v00.w * wy0 * wx0 + v10.w * dy * wx0) + v01.w * wy0 * dx) + v11.w * dy * dx;
+    *reinterpret_cast<float4*>(op) = r;
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     if (c0 + j >= c) break;
