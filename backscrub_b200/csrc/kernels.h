@@ -138,6 +138,8 @@ struct PostArgs {
   uint8_t* out; size_t out_pitch, out_stride;                  // may be null
   uint8_t* yuyv; size_t yuyv_stride;                           // may be null (W*2 bytes per row)
   uint8_t* mask; size_t mask_stride;                           // may be null (W bytes per row)
+  int frame_l1;                                                // frame loads allocate in L1 (measurement switch)
+  int wide;                                                    // 32-byte aligned everywhere: 256-bit loads / stores
 };
 void launch_post(cudaStream_t s, const PostArgs& a);
 

@@ -335,6 +335,36 @@ BSB_D uint4 ldg_stream(const uint8_t* p) {
   return r;
 #endif
 }
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  A thread owns 48 bytes (16 BGR pixels); split as 32 + 16 with
+// the 32-byte part on a sector boundary (even chunk: [0,32) + [32,48); odd chunk: [16,48) + [0,16)), every 32-byte
+// sector is then touched by exactly one instruction of the warp instead of two.
+struct U8x8 { unsigned v[8]; };
+BSB_D U8x8 ldg256(const uint8_t* p, bool l1) {
+  U8x8 r;
+#if defined(BSB_EMU)
+  (void)l1;
+  for (int i = 0; i < 8; ++i) r.v[i] = reinterpret_cast<const unsigned*>(p)[i];
+#else
+  if (l1) asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+#endif
+  return r;
+}
+BSB_D void stg256(uint8_t* p, const unsigned* v) {
+#if defined(BSB_EMU)
+  for (int i = 0; i < 8; ++i) reinterpret_cast<unsigned*>(p)[i] = v[i];
+#else
+  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+#endif
+}
+// 48 bytes at p (chunk parity `odd`) -> w[12]
+BSB_D void load48_wide(const uint8_t* p, bool odd, bool l1, unsigned* w) {
+  const U8x8 a = ldg256(p + (odd ? 16 : 0), l1);
+  const uint4 c = l1 ? __ldg(reinterpret_cast<const uint4*>(p + (odd ? 0 : 32))) : ldg_stream(p + (odd ? 0 : 32));
+  w[0] = odd ? c.x : a.v[0]; w[1] = odd ? c.y : a.v[1]; w[2] = odd ? c.z : a.v[2]; w[3] = odd ? c.w : a.v[3];
+  w[4] = odd ? a.v[0] : a.v[4]; w[5] = odd ? a.v[1] : a.v[5]; w[6] = odd ? a.v[2] : a.v[6]; w[7] = odd ? a.v[3] : a.v[7];
+  w[8] = odd ? a.v[4] : c.x; w[9] = odd ? a.v[5] : c.y; w[10] = odd ? a.v[6] : c.z; w[11] = odd ? a.v[7] : c.w;
+}
 BSB_D void prefetch_l2(const uint8_t* p) {
 #if !defined(BSB_EMU)
   asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
@@ -351,6 +381,14 @@ BSB_D void stg_stream(uint8_t* p, uint4 v) {
 #endif
 }
 
+
+BSB_D void store48_wide(uint8_t* p, bool odd, const unsigned* w) {
+  unsigned a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = odd ? w[4 + i] : w[i];
+  stg256(p + (odd ? 16 : 0), a);
+  stg_stream(p + (odd ? 0 : 32), make_uint4(odd ? w[0] : w[8], odd ? w[1] : w[9], odd ? w[2] : w[10], odd ? w[3] : w[11]));
+}
 
 // one pixel: pair channels (two 16-bit lanes) + single channel; returns T = (c0, c1, c2, x) bytes
 template <int PAIR_SEL, int SINGLE_SEL, int T_SEL>
@@ -481,12 +519,17 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   if (OUT || YUYV) {
     const uint8_t* fp = a.frames + (size_t)b * a.frame_stride + (size_t)y * a.frame_pitch + (size_t)x0 * 3;
     const uint8_t* gp = a.bg + bg_frame_offset(a, b) + (size_t)y * a.bg_pitch + (size_t)x0 * 3;
+    if (a.wide) {
+      load48_wide(fp, (tid & 1) != 0, a.frame_l1 != 0, f);
+      load48_wide(gp, (tid & 1) != 0, true, g);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const uint4 t = ldg_stream(fp + 16 * k);
-      f[4 * k] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
-      const uint4 s = __ldg(reinterpret_cast<const uint4*>(gp + 16 * k));
-      g[4 * k] = s.x; g[4 * k + 1] = s.y; g[4 * k + 2] = s.z; g[4 * k + 3] = s.w;
+      for (int k = 0; k < 3; ++k) {
+        const uint4 t = a.frame_l1 ? __ldg(reinterpret_cast<const uint4*>(fp + 16 * k)) : ldg_stream(fp + 16 * k);
+        f[4 * k] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
+        const uint4 s = __ldg(reinterpret_cast<const uint4*>(gp + 16 * k));
+        g[4 * k] = s.x; g[4 * k + 1] = s.y; g[4 * k + 2] = s.z; g[4 * k + 3] = s.w;
+      }
     }
   }
 
@@ -578,13 +621,19 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   }
   if (OUT) {
     uint8_t* op = a.out + (size_t)b * a.out_stride + (size_t)y * a.out_pitch + (size_t)x0 * 3;
+    if (a.wide) store48_wide(op, (tid & 1) != 0, o);
+    else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) stg_stream(op + 16 * k, make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+      for (int k = 0; k < 3; ++k) stg_stream(op + 16 * k, make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+    }
   }
   if (YUYV) {
     uint8_t* yp = a.yuyv + (size_t)b * a.yuyv_stride + ((size_t)y * a.W + x0) * 2;
-    stg_stream(yp, make_uint4(yy[0], yy[1], yy[2], yy[3]));
-    stg_stream(yp + 16, make_uint4(yy[4], yy[5], yy[6], yy[7]));
+    if (a.wide) stg256(yp, yy);
+    else {
+      stg_stream(yp, make_uint4(yy[0], yy[1], yy[2], yy[3]));
+      stg_stream(yp + 16, make_uint4(yy[4], yy[5], yy[6], yy[7]));
+    }
   }
 }
 
@@ -604,7 +653,15 @@ static bool post_fast_ok(const PostArgs& a) {
   return true;
 }
 
-void launch_post(cudaStream_t s, const PostArgs& a) {
+void launch_post(cudaStream_t s, const PostArgs& a_in) {
+  PostArgs a = a_in;
+  static const int frame_l1 = [] { const char* e = getenv("BSB_POST_L1"); return e ? atoi(e) : 0; }();
+  static const int wide_en = [] { const char* e = getenv("BSB_POST_WIDE"); return e ? atoi(e) : 1; }();
+  a.frame_l1 = frame_l1;
+  auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+  a.wide = wide_en && a.W % 32 == 0 && al32(a.frames) && al32(a.bg) && a.frame_pitch % 32 == 0 && a.frame_stride % 32 == 0 &&
+           a.bg_pitch % 32 == 0 && a.bg_stride % 32 == 0 && (!a.out || (al32(a.out) && a.out_pitch % 32 == 0 && a.out_stride % 32 == 0)) &&
+           (!a.yuyv || (al32(a.yuyv) && a.yuyv_stride % 32 == 0));
   if (post_fast_ok(a)) {
     dim3 grid((unsigned)ceil_div(a.W, PF_W), (unsigned)ceil_div(a.H, PF_H), (unsigned)a.B);
     if (a.yuyv && a.out) { auto k = k_post_fast<true, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
