@@ -655,7 +655,8 @@ static bool post_fast_ok(const PostArgs& a) {
 
 void launch_post(cudaStream_t s, const PostArgs& a_in) {
   PostArgs a = a_in;
-  static const int frame_l1 = [] { const char* e = getenv("BSB_POST_L1"); return e ? atoi(e) : 0; }();
+  // measurement switches (profiles/r1_post_ab_run29.txt): both on is the fastest at 720p and at 4k
+  static const int frame_l1 = [] { const char* e = getenv("BSB_POST_L1"); return e ? atoi(e) : 1; }();
   static const int wide_en = [] { const char* e = getenv("BSB_POST_WIDE"); return e ? atoi(e) : 1; }();
   a.frame_l1 = frame_l1;
   auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
