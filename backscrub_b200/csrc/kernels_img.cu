@@ -84,11 +84,13 @@ __global__ void __launch_bounds__(256) k_bilateral_norm(int B, const uint8_t* in
                                                         float scale, float offset, float* out_f32, uint8_t* out_u8) {
   __shared__ float cw[768];
   __shared__ unsigned tile[BF_SH * BF_SW];
+  __shared__ float sw[16];
   (void)B;
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * BF_TW, y0 = blockIdx.y * BF_TH, b = blockIdx.z;
   const uint8_t* img = in_u8 + (size_t)b * mh * mw * 3;
   for (int i = tid; i < 768; i += 256) cw[i] = __ldg(color_w + i);
+  if (tid < 13) sw[tid] = __ldg(space_w + tid);
   for (int i = tid; i < BF_SH * BF_SW; i += 256) {
     const int ty = i / BF_SW, tx = i - ty * BF_SW;
     const uint8_t* p = img + ((size_t)bsb_reflect101(y0 + ty - 2, mh) * mw + bsb_reflect101(x0 + tx - 2, mw)) * 3;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) k_bilateral_norm(int B, const uint8_t* in
       if (i * i + j * j > 4) continue;
       const unsigned v = t0[i * BF_SW + j];
       const int v0 = (int)(v & 255u), v1 = (int)((v >> 8) & 255u), v2 = (int)(v >> 16);
-      const float w = __ldg(space_w + k) * cw[abs(v0 - c0) + abs(v1 - c1) + abs(v2 - c2)];
+      const float w = sw[k] * cw[abs(v0 - c0) + abs(v1 - c1) + abs(v2 - c2)];
       ++k;
       wsum = wsum + w;
       s0 = fmaf((float)v0, w, s0);
