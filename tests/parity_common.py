@@ -164,6 +164,10 @@ def check_app_stage_functions(lib):
                       (100, 70, 31), (65, 33, 27), (10, 8, 25), (130, 64, 13), (64, 32, 5), (4, 3, 29)]:
         a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         assert np.array_equal(api.gaussian_blur(lib, a, k), po.gaussian_blur(a, k)), (w, h, k)
+    for k in range(3, 42, 2):                                    # every fused-kernel strength (3..31) and the first generic ones
+        w, h = int(rng.integers(3, 150)), int(rng.integers(3, 80))
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(api.gaussian_blur(lib, a, k), po.gaussian_blur(a, k)), (w, h, k)
     a = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
     for fh, fv in [(1, 0), (0, 1), (1, 1), (0, 0)]:
         assert np.array_equal(api.flip(lib, a, fh, fv), po.flip(a, fh, fv))
