@@ -621,11 +621,65 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
   }
 }
 
+// Whole-plane variant for the 33x33 atrous layers of DeepLab / BodyPix (stride 1, 3x3, any dilation): one block owns
+// 16 channels of one frame, stages that 33x33x16 slice in shared memory once (every input byte is read from L2/HBM
+// exactly once, where the strip kernel re-reads each pixel up to nine times through L2) and produces all its outputs
+// from there.  Tap order and the skipping of out-of-image taps are those of the oracle.
+// NOT YET MEASURED on hardware: opt-in through BSB_DW_PLANE=1 until a B200 run decides.
+constexpr int DWP_CS = 16;
+__global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
+  BSB_DYN_SMEM(smem_raw);
+  float* plane = reinterpret_cast<float*>(smem_raw);           // [ih*iw][16]
+  float* ws = plane + (size_t)a.ih * a.iw * DWP_CS;             // [9][16]
+  const int c0 = blockIdx.x * DWP_CS, b = blockIdx.y;
+  const int hw = a.ih * a.iw;
+  const float* inb = a.in + (size_t)b * hw * a.ld_in + c0;
+  for (int i = threadIdx.x; i < hw * (DWP_CS / 4); i += blockDim.x) {
+    const int p = i >> 2, q = i & 3;
+    *reinterpret_cast<float4*>(plane + p * DWP_CS + 4 * q) = __ldg(reinterpret_cast<const float4*>(inb + (size_t)p * a.ld_in + 4 * q));
+  }
+  for (int i = threadIdx.x; i < 9 * DWP_CS; i += blockDim.x) ws[i] = __ldg(a.w + (size_t)(i / DWP_CS) * a.c + c0 + (i % DWP_CS));
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.oh * a.ow * (DWP_CS / 4); i += blockDim.x) {
+    const int p = i >> 2, q = i & 3;
+    const int oy = p / a.ow, ox = p - oy * a.ow;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy) {
+      const int iy = oy - a.pt + a.dh * fy;
+      if (iy < 0 || iy >= a.ih) continue;
+#pragma unroll
+      for (int fx = 0; fx < 3; ++fx) {
+        const int ix = ox - a.pl + a.dw * fx;
+        if (ix < 0 || ix >= a.iw) continue;
+        fma4(acc, *reinterpret_cast<const float4*>(plane + (iy * a.iw + ix) * DWP_CS + 4 * q),
+             *reinterpret_cast<const float4*>(ws + (fy * 3 + fx) * DWP_CS + 4 * q));
+      }
+    }
+    const size_t pix = (size_t)b * a.oh * a.ow + p;
+    const int ch = c0 + 4 * q;
+    *reinterpret_cast<float4*>(a.out + pix * a.ld_out + ch) = make_float4(epilogue(acc.x, ch, pix, a.e), epilogue(acc.y, ch + 1, pix, a.e),
+                                                                        epilogue(acc.z, ch + 2, pix, a.e), epilogue(acc.w, ch + 3, pix, a.e));
+  }
+}
+
 void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                       const float* w, int kh, int kw, int stride_h, int stride_w, int dil_h, int dil_w,
                       int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e) {
   DWArgs a{in, w, out, B, ih, iw, c, ld_in, kh, kw, stride_h, stride_w, dil_h, dil_w, pad_t, pad_l, oh, ow, ld_out, to_dev(e)};
   const bool vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0);
+  static const int plane_en = [] { const char* e = getenv("BSB_DW_PLANE"); return e ? atoi(e) : 0; }();
+  const size_t plane_smem = ((size_t)ih * iw + 9) * DWP_CS * sizeof(float);
+  if (plane_en && (c % DWP_CS == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && kh == 3 && kw == 3 && stride_h == 1 && stride_w == 1 &&
+      oh == ih && ow == iw && plane_smem <= 100 * 1024) {
+#ifndef BSB_EMU
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(k_depthwise_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); configured = true; }
+#endif
+    BSB_LAUNCH(k_depthwise_plane, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
+    count_launch();
+    return;
+  }
   const bool atrous = dil_h == dil_w && (dil_h == 2 || dil_h == 4) && kh == 3 && kw == 3 && stride_h == 1 && stride_w == 1;
   if (vec && ((dil_h == 1 && dil_w == 1) || atrous) && kh == kw && stride_h == stride_w && (kh == 3 || kh == 5) && (stride_h == 1 || stride_h == 2)) {
     const long nthreads = (long)B * oh * ((ow + 3) / 4) * (c / 4);

@@ -232,6 +232,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
   bool needs;
   {
     std::lock_guard<std::mutex> lk(g_mu);
+    static const bool trace = getenv("CUEMU_TRACE") != nullptr;     // name every kernel once, the first time it is launched
+    if (trace && g_needs_fibers.find(key) == g_needs_fibers.end()) fprintf(stderr, "cuemu: launch %s\n", (const char*)key);
     needs = g_needs_fibers[key];
     ++g_launches;
   }

@@ -95,3 +95,24 @@ def test_planner_fuses(lib):
         g = api.MaskGen(lib, model_path(key), 640, 480)
         assert g.launches_per_call <= max_launches, (key, g.launches_per_call)
         g.close()
+
+
+@pytest.mark.slow
+def test_depthwise_plane_opt_in():
+    """BSB_DW_PLANE=1 (whole-plane depthwise for the 33x33 atrous layers; opt-in until measured on a B200) must give
+    the oracle's bits.  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    from tests.conftest import ROOT
+    code = ("from tests import parity_common as pc\n"
+            "from tests.emu.emu_lib import emu\n"
+            "lib = emu()\n"
+            "pc.check_infer_batch(lib, 'bodypix', n=2)\n"
+            "pc.check_infer_batch(lib, 'deeplab', n=1)\n"
+            "assert pc.check_tensors(lib, 'bodypix') > 20\n"
+            "print('plane ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, BSB_DW_PLANE="1", CUEMU_TRACE="1", PYTHONPATH=ROOT),
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "plane ok" in out.stdout, out.stderr[-2000:]
+    assert "k_depthwise_plane" in out.stderr                     # the opt-in kernel really ran
