@@ -256,3 +256,46 @@ def check_pointwise_variants(lib):
         for variant in (0, 2, 3, 4, 5, 8, 16, 32, 64):
             got = api.pointwise(lib, A, W, b, act=act, variant=variant)
             assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (M, K, N, variant)
+
+
+def check_app_option_edges(lib, key="meet_lite", W=640, H=480):
+    """Less common combinations of the per-frame options: YUYV-only output behind flip + resize, mask-only calls in
+    camera-blur mode, a caller-paced background ring, and the even-width rule for YUYV at the output size."""
+    import pytest
+    bg = synth.background()
+    fr = np.stack([synth.frame(W, H, t=t) for t in range(2)])
+    g = api.MaskGen(lib, model_path(key), W, H, max_batch=2)
+    o = po.MaskGen(model_path(key), W, H)
+    g.set_background(bg)
+    g.set_output(flip_h=True, out_size=(320, 240))
+    out, yuyv, mask = g.composite(fr, want_out=False, want_yuyv=True, want_mask=False)
+    assert out is None and mask is None
+    for b in range(2):
+        assert np.array_equal(yuyv[b], o.composite_ex(fr[b], bg, flip_h=True, out_size=(320, 240))[1])
+    g.close()
+
+    g = api.MaskGen(lib, model_path(key), W, H)
+    o = po.MaskGen(model_path(key), W, H)
+    g.set_bgblur(25)
+    assert np.array_equal(g.composite(fr[0], want_out=False, want_yuyv=False)[2], o.process(fr[0]))
+    g.close()
+
+    ring = np.stack([bg, bg[::-1].copy()])
+    g = api.MaskGen(lib, model_path(key), W, H, max_batch=2)
+    o = po.MaskGen(model_path(key), W, H)
+    g.set_background_ring(ring, advance=0)
+    g.set_background_cursor(1)
+    out, _, _ = g.composite(fr)
+    for b in range(2):
+        assert np.array_equal(out[b], o.composite_ex(fr[b], ring[1])[0])
+    with pytest.raises(api.BackscrubError, match="out of range"):
+        g.set_background_cursor(2)
+    g.close()
+
+    g = api.MaskGen(lib, model_path(key), W, H)
+    g.set_output(out_size=(321, 240))
+    with pytest.raises(api.BackscrubError, match="even width"):
+        g.composite(fr[0])
+    assert g.composite(fr[0], want_yuyv=False)[0].shape == (240, 321, 3)
+    assert g.process(fr[1]).shape == (H, W)
+    g.close()

@@ -75,6 +75,10 @@ def test_app_options(lib):
     pc.check_app_options(lib)
 
 
+def test_app_option_edges(lib):
+    pc.check_app_option_edges(lib)
+
+
 def test_yuyv_ingest(lib):
     pc.check_yuyv_ingest(lib)
 
