@@ -76,3 +76,9 @@ def grab_background(raw, width, height, device=0):
 FLAG_KEEP_TENSORS = _binding.FLAG_KEEP_TENSORS
 FLAG_NO_GRAPH = _binding.FLAG_NO_GRAPH
 FLAG_TENSOR_CORES = _binding.FLAG_TENSOR_CORES
+
+
+def set_tuning(name: str, value: int) -> None:
+    """Process-wide launcher switch (include/backscrub_b200.h: bsb_set_tuning); selects between bit-identical kernels."""
+    if not lib().bsb_set_tuning(name.encode(), int(value)):
+        raise BackscrubError(lib().bsb_last_error().decode())

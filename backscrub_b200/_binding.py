@@ -13,6 +13,8 @@ f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int)
 DEBUG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 STAGE_CB = C.CFUNCTYPE(None, C.c_void_p)
+BG_READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), i32p, i32p, C.POINTER(C.c_size_t))
+BG_REWIND_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 FLAG_KEEP_TENSORS, FLAG_NO_GRAPH, FLAG_TENSOR_CORES = 1, 2, 4
 
@@ -24,7 +26,11 @@ SYMBOLS = [
     "bsb_gaussian_blur", "bsb_gaussian_taps", "bsb_flip",
     "bsb_composite", "bsb_composite_device", "bsb_composite_yuyv", "bsb_composite_yuyv_device", "bsb_convert_yuyv_to_bgr", "bsb_synchronize", "bsb_stream", "bsb_alpha_blend",
     "bsb_convert_rgb_to_yuyv", "bsb_resize_u8c3", "bsb_pointwise", "bsb_time_pointwise", "bsb_geometry", "bsb_infer", "bsb_get_tensor",
-    "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops",
+    "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops", "bsb_set_tuning", "bsb_frame_size",
+    "bsb_calcmask_new", "bsb_calcmask_delete", "bsb_calcmask_set_input_frame", "bsb_calcmask_get_output_mask", "bsb_calcmask_timings",
+    "bsb_calcmask_frames_done", "bsb_calcmask_mask_serial",
+    "bsb_background_new_still", "bsb_background_new_video", "bsb_background_delete", "bsb_background_grab", "bsb_background_grab_into",
+    "bsb_background_thumbnail", "bsb_background_frame", "bsb_background_running",
 ]
 
 
@@ -83,4 +89,29 @@ def bind(path: str) -> C.CDLL:
     L.bsb_time_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.bsb_model_flops.restype = C.c_double
     L.bsb_model_flops.argtypes = [C.c_void_p]
+    L.bsb_set_tuning.argtypes = [C.c_char_p, C.c_int]
+    L.bsb_frame_size.argtypes = [C.c_void_p, i32p, i32p]
+    L.bsb_calcmask_new.restype = C.c_void_p
+    L.bsb_calcmask_new.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+    L.bsb_calcmask_delete.restype = None
+    L.bsb_calcmask_delete.argtypes = [C.c_void_p]
+    L.bsb_calcmask_set_input_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.bsb_calcmask_get_output_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.bsb_calcmask_timings.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+    L.bsb_calcmask_frames_done.restype = C.c_long
+    L.bsb_calcmask_frames_done.argtypes = [C.c_void_p]
+    L.bsb_calcmask_mask_serial.restype = C.c_long
+    L.bsb_calcmask_mask_serial.argtypes = [C.c_void_p]
+    L.bsb_background_new_still.restype = C.c_void_p
+    L.bsb_background_new_still.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int]
+    L.bsb_background_new_video.restype = C.c_void_p
+    L.bsb_background_new_video.argtypes = [C.c_int, C.c_double, C.c_int, BG_READ_CB, BG_REWIND_CB, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_size_t, C.c_int]
+    L.bsb_background_delete.restype = None
+    L.bsb_background_delete.argtypes = [C.c_void_p]
+    L.bsb_background_grab.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.bsb_background_grab_into.argtypes = [C.c_void_p, C.c_void_p]
+    L.bsb_background_thumbnail.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, i32p, i32p]
+    L.bsb_background_frame.argtypes = [C.c_void_p]
+    L.bsb_background_running.argtypes = [C.c_void_p]
     return L

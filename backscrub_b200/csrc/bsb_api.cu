@@ -449,6 +449,13 @@ double bsb_time_pointwise(int device, int variant, int M, int K, int N, int iter
 }
 
 // ---- introspection ----------------------------------------------------------------
+int bsb_frame_size(bsb_ctx* ctx, int* width, int* height) {
+  if (!check_ctx(ctx)) return 0;
+  if (width) *width = ctx->eng->W();
+  if (height) *height = ctx->eng->H();
+  return 1;
+}
+
 int bsb_geometry(bsb_ctx* ctx, int roidim[4], int in_roidim[4], int out_roidim[4], int in_hwc[3], int out_hwc[3]) {
   if (!check_ctx(ctx)) return 0;
   Engine* e = ctx->eng;
@@ -507,5 +514,18 @@ double bsb_time_stage(bsb_ctx* ctx, int stage, int n_frames, int iters) {
 long bsb_total_launches(void) { return bsb::launch_count(); }
 
 double bsb_model_flops(bsb_ctx* ctx) { return check_ctx(ctx) ? ctx->eng->flops() : 0.0; }
+
+int bsb_set_tuning(const char* name, int value) {
+  if (!name) { g_last_error = "null tuning name"; return 0; }
+  bsb::Tuning& t = bsb::tuning();
+  const std::string n(name);
+  if (n == "pw_variant") t.pw_variant = value;
+  else if (n == "dw_plane") t.dw_plane = value;
+  else if (n == "post_tma") t.post_tma = value;
+  else if (n == "post_wide") t.post_wide = value;
+  else if (n == "post_l1") t.post_l1 = value;
+  else { g_last_error = "unknown tuning switch '" + n + "'"; return 0; }
+  return 1;
+}
 
 }  // extern "C"

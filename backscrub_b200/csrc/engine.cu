@@ -49,7 +49,7 @@ HostResizeTab build_resize_tab(int sw, int sh, int dw, int dh) {
   return t;
 }
 
-static bool upload_tab(const HostResizeTab& h, DevResizeTab* d, std::string* err) {
+bool upload_resize_tab(const HostResizeTab& h, DevResizeTab* d, std::string* err) {
   const size_t nx = h.xofs.size(), ny = h.yofs0.size();
   auto al = [](size_t n) { return (n + 15) / 16 * 16; };
   const size_t o_xofs = 0, o_y0 = o_xofs + al(nx * 4), o_y1 = o_y0 + al(ny * 4), o_xw = o_y1 + al(ny * 4), o_yw = o_xw + al(nx * 4);
@@ -126,7 +126,7 @@ bool Engine::plan(std::string* err) {
     I.frame_elems = (size_t)I.h * I.w * I.ld;
   }
   auto is_pw = [&](const GOp& O) {
-    if (O.kind != OP_CONV_2D) return false;
+    if (O.kind != OP_CONV_2D || O.in.size() < 2 || O.in[1] < 0) return false;
     const GTensor& w = g_.tensors[O.in[1]];
     return w.shape.size() == 4 && w.shape[1] == 1 && w.shape[2] == 1 && O.stride_w == 1 && O.stride_h == 1;
   };
@@ -193,8 +193,11 @@ bool Engine::plan(std::string* err) {
     auto need = [&](bool c, const char* what) { if (!c) { *err = std::string("unsupported model construct: ") + what; } return c; };
     switch (O.kind) {
       case OP_CONV_2D: {
-        if (!need(O.in.size() >= 2 && g_.tensors[O.in[1]].is_const, "CONV_2D with non-constant weights")) return false;
+        if (!need(O.in.size() >= 2 && O.in[1] >= 0 && g_.tensors[O.in[1]].is_const, "CONV_2D with non-constant weights")) return false;
         const GTensor& w = g_.tensors[O.in[1]];
+        if (!need(w.shape.size() == 4 && w.f32.size() == w.count(), "CONV_2D weights that are not a rank-4 float tensor")) return false;
+        if (!need(O.in.size() < 3 || O.in[2] < 0 || (int)g_.tensors[O.in[2]].f32.size() == w.shape[0], "CONV_2D bias size")) return false;
+        if (!need(w.shape[3] == tinfo_[O.in[0]].c, "CONV_2D input depth")) return false;
         const int oc = w.shape[0], kh = w.shape[1], kw = w.shape[2], ic = w.shape[3];
         st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
         if (O.in.size() > 2 && O.in[2] >= 0) { st.has_bias = true; st.b_off = add_blob(g_.tensors[O.in[2]].f32); }
@@ -225,8 +228,9 @@ bool Engine::plan(std::string* err) {
         break;
       }
       case OP_FULLY_CONNECTED: {
-        if (!need(O.in.size() >= 2 && g_.tensors[O.in[1]].is_const, "FULLY_CONNECTED with non-constant weights")) return false;
+        if (!need(O.in.size() >= 2 && O.in[1] >= 0 && g_.tensors[O.in[1]].is_const, "FULLY_CONNECTED with non-constant weights")) return false;
         const GTensor& w = g_.tensors[O.in[1]];
+        if (!need(w.shape.size() >= 2 && w.f32.size() == w.count(), "FULLY_CONNECTED weights that are not a float matrix")) return false;
         st.kind = Step::PW; st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
         const int out_depth = w.shape[w.shape.size() - 2], in_depth = w.shape[w.shape.size() - 1];
         if (!need(tinfo_[st.in].c == in_depth, "FULLY_CONNECTED over flattened spatial dims")) return false;
@@ -237,7 +241,9 @@ bool Engine::plan(std::string* err) {
       }
       case OP_DEPTHWISE_CONV_2D: {
         if (!need(O.depth_mult == 1, "depthwise multiplier != 1")) return false;
+        if (!need(O.in.size() >= 2 && O.in[1] >= 0 && g_.tensors[O.in[1]].is_const, "DEPTHWISE_CONV_2D with non-constant weights")) return false;
         const GTensor& w = g_.tensors[O.in[1]];
+        if (!need(w.shape.size() == 4 && w.f32.size() == w.count() && w.shape[3] == tinfo_[O.in[0]].c, "DEPTHWISE_CONV_2D weight shape")) return false;
         st.kind = Step::DW; st.in = O.in[0]; st.out = O.out; st.act1 = O.act;
         st.kh = w.shape[1]; st.kw = w.shape[2]; st.sh = O.stride_h; st.sw = O.stride_w; st.dh = O.dil_h; st.dw = O.dil_w;
         int o_h, o_w;
@@ -269,7 +275,9 @@ bool Engine::plan(std::string* err) {
           if (is_pw(F)) { N = w.shape[0]; K = w.shape[3]; }
           else if (F.kind == OP_FULLY_CONNECTED) { N = w.shape[w.shape.size() - 2]; K = w.shape[w.shape.size() - 1]; }
           else break;
-          if (K != tinfo_[cur].c || K > 512 || N > 512 || tinfo_[F.out].h != 1 || tinfo_[F.out].w != 1) break;
+          // the FC weights are staged in shared memory by k_pool_fc: keep K x N4 inside the opt-in limit
+          if (K != tinfo_[cur].c || K > 512 || N > 512 || (size_t)K * ((N + 3) / 4 * 4) * 4 > 192 * 1024 ||
+              tinfo_[F.out].h != 1 || tinfo_[F.out].w != 1) break;
           Step tmp;
           pack_pw_weights(w, N, K, tmp);
           Step::Fc& fc = st.fc[st.n_fc++];
@@ -287,13 +295,18 @@ bool Engine::plan(std::string* err) {
       }
       case OP_RESIZE_BILINEAR: {
         st.kind = Step::RESIZE; st.in = O.in[0]; st.out = O.out; st.align_corners = O.align_corners; st.half_pixel = O.half_pixel;
+        if (!need(O.in.size() >= 2 && O.in[1] >= 0, "RESIZE_BILINEAR without a size tensor")) return false;
         const GTensor& sz = g_.tensors[O.in[1]];
         if (!need(sz.is_const && sz.i32.size() == 2 && sz.i32[0] == tinfo_[O.out].h && sz.i32[1] == tinfo_[O.out].w, "RESIZE_BILINEAR size")) return false;
         break;
       }
       case OP_CUSTOM: {
         if (!need(O.custom == "Convolution2DTransposeBias", "unknown custom op")) return false;
+        if (!need(O.in.size() >= 3 && O.in[1] >= 0 && O.in[2] >= 0 && g_.tensors[O.in[1]].is_const && g_.tensors[O.in[2]].is_const,
+                  "Convolution2DTransposeBias with non-constant weights / bias")) return false;
         const GTensor& w = g_.tensors[O.in[1]];
+        if (!need(w.shape.size() == 4 && w.f32.size() == w.count() && w.shape[3] == tinfo_[O.in[0]].c &&
+                  (int)g_.tensors[O.in[2]].f32.size() == w.shape[0], "Convolution2DTransposeBias weight shape")) return false;
         if (!need(w.shape[1] == 2 && w.shape[2] == 2 && O.stride_w == 2 && O.stride_h == 2 && O.tconv_same &&
                   tinfo_[O.out].h == 2 * tinfo_[O.in[0]].h && tinfo_[O.out].w == 2 * tinfo_[O.in[0]].w,
                   "Convolution2DTransposeBias other than k2 s2 SAME on even sizes")) return false;
@@ -586,8 +599,8 @@ bool Engine::upload(std::string* err) {
   out_w_ = W_; out_h_ = H_;
   out_cap_ = B * fpx * 3; yuyv_cap_ = B * fpx * 2;
   CUDA_OK(cudaMallocHost((void**)&h_mask_, fpx));
-  if (!upload_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
-  if (!upload_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
+  if (!upload_resize_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
+  if (!upload_resize_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
   if (tab_up_.area2x2) { *err = "mask upsample degenerated to a 2x down-scale"; return false; }
   CUDA_OK(cudaDeviceSynchronize());
   return true;
@@ -779,7 +792,8 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
     return true;
   }
 #ifndef BSB_EMU
-  const GraphKey key{n, d_frames, pitch, stride, d_out, d_yuyv, d_mask, d_yuyv_in};
+  const GraphKey key{n, d_frames, pitch, stride, d_out, d_yuyv, d_mask, d_yuyv_in, d_out ? out_stride : 0, d_yuyv ? yuyv_stride : 0,
+                     d_mask ? mask_stride : 0};
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
     if (graphs_.size() >= 64) drop_graphs();
@@ -790,10 +804,19 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
     enqueue_cnn(n, true);
     enqueue_decision(n);
     enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride);
-    CUDA_OK(cudaStreamEndCapture(stream_, &graph));
+    // the capture is always closed, also when a launch inside it failed: a stream left in capture mode would
+    // poison every later call on this context
+    const cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
+    if (ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      *err = std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce);
+      return false;
+    }
     cudaGraphExec_t exec = nullptr;
-    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); *err = std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie); return false; }
     it = graphs_.emplace(key, exec).first;
   }
   CUDA_OK(cudaGraphLaunch(it->second, stream_));
@@ -847,7 +870,7 @@ bool Engine::set_background_ring(const uint8_t* frames, int count, int bw, int b
   if (!ensure((void**)&d_bg_, &bg_cap_, fbytes * count, err)) return false;
   if (bw != bg_w_ || bh != bg_h_) {
     CUDA_OK(cudaStreamSynchronize(stream_));
-    if (!upload_tab(build_resize_tab(bw, bh, W_, H_), &tab_bg_, err)) return false;
+    if (!upload_resize_tab(build_resize_tab(bw, bh, W_, H_), &tab_bg_, err)) return false;
     bg_w_ = bw; bg_h_ = bh;
   }
   if (count != bg_count_ || advance != bg_advance_ || !has_bg_) { CUDA_OK(cudaStreamSynchronize(stream_)); drop_graphs(); }
@@ -914,7 +937,7 @@ bool Engine::set_output(bool flip_h, bool flip_v, int out_w, int out_h, std::str
   if (flip) { if (!ensure((void**)&d_stage_b_, &stage_b_cap_, B * fbytes, err)) return false; }
   if (resized) {
     if (!ensure((void**)&d_stage_c_, &stage_c_cap_, B * obytes, err)) return false;
-    if (!upload_tab(build_resize_tab(W_, H_, out_w, out_h), &tab_out_, err)) return false;
+    if (!upload_resize_tab(build_resize_tab(W_, H_, out_w, out_h), &tab_out_, err)) return false;
     // host-buffer API staging must hold the larger of the two geometries
     if (!ensure((void**)&d_out_, &out_cap_, B * std::max(fbytes, obytes), err)) return false;
     if (!ensure((void**)&d_yuyv_, &yuyv_cap_, B * std::max(fbytes, obytes) / 3 * 2, err)) return false;

@@ -11,6 +11,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "kernels.h"
@@ -58,6 +59,8 @@ struct HostResizeTab {
 HostResizeTab build_resize_tab(int sw, int sh, int dw, int dh);
 
 struct DevResizeTab { void* blob = nullptr; ResizeTab tab{}; bool area2x2 = false; };
+// tables -> device memory of the current device (frees a previous blob)
+bool upload_resize_tab(const HostResizeTab& h, DevResizeTab* d, std::string* err);
 
 struct Callbacks {
   void (*ondebug)(void*, const char*) = nullptr;
@@ -205,11 +208,13 @@ class Engine {
   uint8_t* d_stage_a_ = nullptr, *d_stage_b_ = nullptr, *d_stage_c_ = nullptr;
   size_t stage_a_cap_ = 0, stage_b_cap_ = 0, stage_c_cap_ = 0, out_cap_ = 0, yuyv_cap_ = 0;
 
+  // everything a captured launch sequence bakes into its kernel arguments
   struct GraphKey {
-    int n; const void* f; size_t pitch, stride; const void* o; const void* y; const void* m; const void* yin = nullptr;
+    int n; const void* f; size_t pitch, stride; const void* o; const void* y; const void* m; const void* yin;
+    size_t ostride, ystride, mstride;
     bool operator<(const GraphKey& r) const {
-      if (n != r.n) return n < r.n; if (f != r.f) return f < r.f; if (pitch != r.pitch) return pitch < r.pitch;
-      if (stride != r.stride) return stride < r.stride; if (o != r.o) return o < r.o; if (y != r.y) return y < r.y; if (m != r.m) return m < r.m; return yin < r.yin;
+      return std::tie(n, f, pitch, stride, o, y, m, yin, ostride, ystride, mstride) <
+             std::tie(r.n, r.f, r.pitch, r.stride, r.o, r.y, r.m, r.yin, r.ostride, r.ystride, r.mstride);
     }
   };
 #ifndef BSB_EMU

@@ -172,4 +172,20 @@ void launch_advance_cursor(cudaStream_t s, int* cursor, int step, int count);
 // number of kernel launches issued through the launchers above (bench gpu_launches)
 long launch_count();
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (cudaFuncSetAttribute is per device and
+// per function; the largest request so far is remembered per (device, function) under a mutex, so contexts on several
+// devices and the host threads of one process can share the launchers).  Returns false if the driver refuses.
+bool ensure_dyn_smem(const void* func, size_t bytes);
+
+// Measurement switches of the launchers (bsb_set_tuning in the C ABI; tools/ and bench.py A/B runs).  They never change
+// results, only which bit-identical kernel variant runs.  Defaults are the measured-best choices.
+struct Tuning {
+  int pw_variant = 0;      // launch_pointwise: 0 heuristics, 2 classic tiles, 3/4/8 register-tiled, 5 row-streaming, 16/32/64 classic N tile
+  int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
+  int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
+  int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses
+  int post_l1 = 1;         // k_post_fast: frame loads allocate in L1
+};
+Tuning& tuning();
+
 }  // namespace bsb

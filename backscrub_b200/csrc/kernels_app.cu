@@ -228,13 +228,7 @@ void launch_gauss_blur(cudaStream_t s, int n, const uint8_t* src, size_t spitch,
              src, spitch, sstride, tmp, W, H, g);
   count_launch();
   const size_t smem = gauss_cols_smem(g.k);
-#ifndef BSB_EMU
-  static size_t configured = 0;   // largest opt-in so far (per process; every context uses the same kernel)
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_gauss_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-#endif
+  ensure_dyn_smem(reinterpret_cast<const void*>(k_gauss_cols), smem);
   BSB_LAUNCH(k_gauss_cols, dim3((unsigned)ceil_div(W * 3, GAUSS_CL), (unsigned)ceil_div(H, GAUSS_CH), (unsigned)n), dim3(256), smem, s,
              tmp, dst, dpitch, dstride, W, H, g);
   count_launch();

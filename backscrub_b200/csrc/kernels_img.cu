@@ -671,9 +671,8 @@ static bool post_fast_ok(const PostArgs& a) {
 void launch_post(cudaStream_t s, const PostArgs& a_in) {
   PostArgs a = a_in;
   // measurement switches (profiles/r1_post_ab_run29.txt): both on is the fastest at 720p and at 4k
-  static const int frame_l1 = [] { const char* e = getenv("BSB_POST_L1"); return e ? atoi(e) : 1; }();
-  static const int wide_en = [] { const char* e = getenv("BSB_POST_WIDE"); return e ? atoi(e) : 1; }();
-  a.frame_l1 = frame_l1;
+  const int wide_en = tuning().post_wide;
+  a.frame_l1 = tuning().post_l1;
   auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
   a.wide = wide_en && a.W % 32 == 0 && al32(a.frames) && al32(a.bg) && a.frame_pitch % 32 == 0 && a.frame_stride % 32 == 0 &&
            a.bg_pitch % 32 == 0 && a.bg_stride % 32 == 0 && (!a.out || (al32(a.out) && a.out_pitch % 32 == 0 && a.out_stride % 32 == 0)) &&

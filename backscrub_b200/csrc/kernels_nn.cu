@@ -8,6 +8,8 @@
 // bit-identical to the CPU oracle; parallelism comes from pixels x channels x frames.
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 
 #include "kernels.h"
 
@@ -16,6 +18,27 @@ namespace bsb {
 static std::atomic<long> g_launches{0};
 long launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1); }
+
+Tuning& tuning() { static Tuning t; return t; }
+
+bool ensure_dyn_smem(const void* func, size_t bytes) {
+#ifdef BSB_EMU
+  (void)func; (void)bytes;
+  return true;
+#else
+  if (bytes <= 48 * 1024) return true;
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> configured;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = configured[std::make_pair(dev, func)];
+  if (bytes <= have) return true;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+  have = bytes;
+  return true;
+#endif
+}
 
 struct EpiDev {
   const float* bias; const float* residual; int ld_res; int act1, act2, act3;
@@ -453,14 +476,10 @@ __global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
 }
 
 // kernel selection override for A/B measurements: 0 = heuristics, 2 = never the register-tiled kernel, 3 = always
-// (set through bsb_pointwise's `variant` argument or the BSB_PW_VARIANT environment variable; results are
-// bit-identical whichever kernel runs)
-static int g_pw_variant = -1;
-void set_pointwise_variant(int v) { g_pw_variant = v; }
-int pointwise_variant() {
-  if (g_pw_variant < 0) { const char* e = getenv("BSB_PW_VARIANT"); g_pw_variant = e ? atoi(e) : 0; }
-  return g_pw_variant;
-}
+// (set through bsb_pointwise's `variant` argument or bsb_set_tuning("pw_variant", v); results are bit-identical
+// whichever kernel runs)
+void set_pointwise_variant(int v) { tuning().pw_variant = v; }
+int pointwise_variant() { return tuning().pw_variant; }
 
 void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int ld_a,
                       const float* w_kn, int n4, float* out, int ld_out, const Epilogue& e,
@@ -668,14 +687,10 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
                       int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e) {
   DWArgs a{in, w, out, B, ih, iw, c, ld_in, kh, kw, stride_h, stride_w, dil_h, dil_w, pad_t, pad_l, oh, ow, ld_out, to_dev(e)};
   const bool vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0);
-  static const int plane_en = [] { const char* e = getenv("BSB_DW_PLANE"); return e ? atoi(e) : 0; }();
   const size_t plane_smem = ((size_t)ih * iw + 9) * DWP_CS * sizeof(float);
-  if (plane_en && (c % DWP_CS == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && kh == 3 && kw == 3 && stride_h == 1 && stride_w == 1 &&
-      oh == ih && ow == iw && plane_smem <= 100 * 1024) {
-#ifndef BSB_EMU
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(k_depthwise_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); configured = true; }
-#endif
+  if (tuning().dw_plane && (dil_h > 1 || dil_w > 1) && (c % DWP_CS == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && kh == 3 && kw == 3 &&
+      stride_h == 1 && stride_w == 1 && oh == ih && ow == iw && plane_smem <= 100 * 1024 &&
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane), plane_smem)) {
     BSB_LAUNCH(k_depthwise_plane, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
     count_launch();
     return;
@@ -794,10 +809,7 @@ void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, co
   for (int i = 0; i < n_fc && i < 2; ++i) f[i] = FcDev{fc[i].w, fc[i].bias, fc[i].K, fc[i].N, fc[i].n4, fc[i].act1, fc[i].act2};
   size_t wbytes = 16;
   for (int i = 0; i < n_fc && i < 2; ++i) wbytes = std::max(wbytes, sizeof(float) * (size_t)f[i].K * f[i].n4);
-#ifndef BSB_EMU
-  static size_t configured = 48 * 1024;
-  if (wbytes > configured) { cudaFuncSetAttribute(k_pool_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes); configured = wbytes; }
-#endif
+  ensure_dyn_smem(reinterpret_cast<const void*>(k_pool_fc), wbytes);
   BSB_LAUNCH(k_pool_fc, dim3((unsigned)B), dim3(256), wbytes, s, rowsum_scratch, h, C, (float)(h * w), pool_act, pooled_out, n_fc, f[0], f[1], out, ld_out);
   count_launch();
 }
@@ -939,10 +951,7 @@ void launch_mb_block(cudaStream_t s, int B, const MbBlockArgs& a) {
   const int fc_max = std::max(std::max(a.f0.K * a.f0.n4, a.f1.K * a.f1.n4), a.cexp * a.n4_2);
   size_t total;
   mb_layout(a.h, a.w, a.cin, a.cexp, fc_max, &m.off_es, &m.off_ds, &m.off_rs, &m.off_fw, &total);
-#ifndef BSB_EMU
-  static size_t configured = 48 * 1024;
-  if (total > configured) { cudaFuncSetAttribute(k_mb_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total); configured = total; }
-#endif
+  ensure_dyn_smem(reinterpret_cast<const void*>(k_mb_block), total);
   BSB_LAUNCH(k_mb_block, dim3((unsigned)B), dim3(512), total, s, m);
   count_launch();
 }

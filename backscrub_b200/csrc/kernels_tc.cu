@@ -249,12 +249,12 @@ __global__ void __launch_bounds__(256, 1) k_pointwise_tc(TcArgs a) {
 }
 
 template <int BN>
-static void launch_tc_bn(cudaStream_t s, const TcArgs& a, int npad) {
+static bool launch_tc_bn(cudaStream_t s, const TcArgs& a, int npad) {
   const size_t smem = 3 * (2 * 128 * 128 + 2 * BN * 128);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(k_pointwise_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_pointwise_tc<BN>), smem)) return false;
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)(npad / BN));
   k_pointwise_tc<BN><<<grid, 256, smem, s>>>(a);
+  return true;
 }
 
 int pointwise_tc_tile_n(int N) {       // tile width the launcher will use for this N (weights are padded to a multiple of it)
@@ -272,15 +272,17 @@ bool launch_pointwise_tc(cudaStream_t s, int M, int K, int N, const float* A, in
   TcArgs a{A, w_hi, w_lo, out, M, K, N, ld_a, ld_out, kpad, EpiDevTc{e.bias, e.residual, e.ld_res, e.act1, e.act2, e.act3}};
   const int bn = pointwise_tc_tile_n(N);
   if (npad % bn != 0) return false;
+  bool ok = false;
   switch (bn) {
-    case 16: launch_tc_bn<16>(s, a, npad); break;
-    case 32: launch_tc_bn<32>(s, a, npad); break;
-    case 64: launch_tc_bn<64>(s, a, npad); break;
-    case 80: launch_tc_bn<80>(s, a, npad); break;
-    case 96: launch_tc_bn<96>(s, a, npad); break;
-    case 128: launch_tc_bn<128>(s, a, npad); break;
+    case 16: ok = launch_tc_bn<16>(s, a, npad); break;
+    case 32: ok = launch_tc_bn<32>(s, a, npad); break;
+    case 64: ok = launch_tc_bn<64>(s, a, npad); break;
+    case 80: ok = launch_tc_bn<80>(s, a, npad); break;
+    case 96: ok = launch_tc_bn<96>(s, a, npad); break;
+    case 128: ok = launch_tc_bn<128>(s, a, npad); break;
     default: return false;
   }
+  if (!ok) return false;          // the caller falls back to the exact FFMA kernel
   count_launch();
   return true;
 }

@@ -159,6 +159,7 @@ bool load_tflite(const std::string& path, Graph* g, std::string* err) {
     g->input = ins[0]; g->output = outs[0];
     auto check_t = [&](int t) { if (t < -1 || t >= (int)n_t) throw Malformed("tensor index out of range"); };
     check_t(g->input); check_t(g->output);
+    if (g->input < 0 || g->output < 0) throw Malformed("graph input/output is an optional (-1) tensor");
 
     uint32_t n_ops; size_t ops = sg.vec(3, &n_ops);
     g->ops.assign(n_ops, GOp());
@@ -173,6 +174,8 @@ bool load_tflite(const std::string& path, Graph* g, std::string* err) {
       O.out = o.empty() ? -1 : o[0];
       for (int t : O.in) check_t(t);
       check_t(O.out);
+      if (O.out < 0) throw Malformed("operator without an output tensor");
+      if (!O.in.empty() && O.in[0] < 0) throw Malformed("operator whose first input is optional (-1)");
       Table bo = ot.sub(4);
       const bool has = bo.pos != 0;
       switch (O.kind) {

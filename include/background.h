@@ -1,28 +1,29 @@
-/* include/background.h — the reference's app/background.h:14-23 API with grab_background()'s
- * per-frame cv::resize moved to the GPU.
+/* include/background.h — the reference's app/background.h:14-23 interface, provided by the B200 library.
  *
- * Decoding (cv::VideoCapture / cv::imread, the reader thread and its pacing,
- * app/background.cc:13-176) is I/O and stays in the application: keep the reference's
- * app/background.cc for load_background()/grab_thumbnail() and replace only the body of
- * grab_background() with the adapter below, or call bsb_set_background() directly whenever a
- * new decoded frame is available and let bsb_composite() blend against the resident copy.
+ * Same three C++-linkage functions with the same signatures and return values; they are defined by
+ * backscrub_b200/shim/background_shim.cc (compiled by the integrator in place of app/background.cc).  Decoding
+ * stays on the host (cv::VideoCapture / cv::imread); the reader thread's pacing / looping / frame counting live in
+ * the library's provider object (bsb_background_*, include/backscrub_b200.h) and grab_background()'s per-frame
+ * cv::resize runs on the GPU.
  */
-#ifndef _BACKGROUND_B200_H_
-#define _BACKGROUND_B200_H_
+#ifndef _BACKGROUND_H_
+#define _BACKGROUND_H_
 
 #include <opencv2/core/mat.hpp>
 
-#include "backscrub_b200.h"
+#include <memory>
+#include <string>
 
-// app/background.cc:178-194: cv::resize(raw, out, cv::Size(width, height)) — on the GPU.
-// `raw` is the decoded background frame (CV_8UC3); returns 0 on success, -1 on error.
-static inline int bsb_grab_background(bsb_ctx *ctx, const cv::Mat &raw, int width, int height, cv::Mat &out) {
-	if (!ctx || raw.empty() || raw.type() != CV_8UC3)
-		return -1;
-	if (!bsb_set_background(ctx, raw.data, raw.cols, raw.rows, raw.step))
-		return -1;
-	out.create(height, width, CV_8UC3);
-	return bsb_get_background(ctx, out.data, out.step) ? 0 : -1;
-}
+struct background_t;
+
+// Load a background (image or video file, stream URL).  nullptr on error; the handle cleans up after itself.
+std::shared_ptr<background_t> load_background(const std::string& path, int debug);
+
+// Latest background frame resized to width x height.  Returns the frame number (1 for a still image; a looping
+// video wraps to 0) or -1 on error.
+int grab_background(std::shared_ptr<background_t> handle, int width, int height, cv::Mat &out);
+
+// Copy of the current thumbnail (empty until one exists).  <0 on error, 0 on success.
+int grab_thumbnail(std::shared_ptr<background_t> handle, cv::Mat &out);
 
 #endif

@@ -135,6 +135,47 @@ BSB_API int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_f
 BSB_API int bsb_composite_yuyv_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_yuyv_frames,
                                       uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,
                                       uint8_t* d_mask, size_t mask_stride, int sync);
+/* ---- asynchronous mask front-end: the reference's CalcMask (app/deepseg.cc:159-286) ----
+ * A worker thread owns the mask-generation context.  set_input_frame clones the frame and wakes the worker (a
+ * frame that arrives while the worker is busy replaces the pending one: latest frame wins); get_output_mask copies
+ * the newest finished mask ONCE (returns 1) and otherwise leaves `out` untouched and returns 0, so the caller keeps
+ * blending with its previous mask exactly like `ai.get_output_mask(mask)` in app/deepseg.cc:641; -1 after a
+ * processing error (the reference exits the process there).  timings: waitns, prepns, tfltns, maskns, loopns
+ * (app/deepseg.cc:233-237, printed by `-d`). */
+typedef struct bsb_calcmask bsb_calcmask;
+BSB_API bsb_calcmask* bsb_calcmask_new(const char* modelname, size_t threads, size_t width, size_t height, int device);
+BSB_API void bsb_calcmask_delete(bsb_calcmask* cm);
+BSB_API int bsb_calcmask_set_input_frame(bsb_calcmask* cm, const uint8_t* frame, size_t frame_pitch);
+BSB_API int bsb_calcmask_get_output_mask(bsb_calcmask* cm, uint8_t* out, size_t out_pitch);
+BSB_API int bsb_calcmask_timings(bsb_calcmask* cm, long ns[5]);
+/* frames the worker has finished; the 1-based index (count of set_input_frame calls) of the frame behind the newest mask */
+BSB_API long bsb_calcmask_frames_done(bsb_calcmask* cm);
+BSB_API long bsb_calcmask_mask_serial(bsb_calcmask* cm);
+
+/* ---- background provider object: the reference's background_t (app/background.cc:13-202) ----
+ * still image: the decoded image is kept; grab returns it resized and frame number 1.
+ * video: a reader thread pulls decoded frames through `read` (1 = a frame, 0 = end of stream; the pixels must stay
+ * valid until the next call), publishes the latest one under a mutex, counts frames, paces itself to `fps`
+ * (all sources play in real time, app/background.cc:84-92) and at end of stream calls `rewind` (1 = repositioned
+ * at frame 0) and starts over with frame number 0, or stops when the source cannot rewind (:93-102).
+ * `first`: the frame load_background() decoded while probing (may be NULL); start_frame: 0 after a successful
+ * rewind of the probe reads, else 2 (:146-149).  grab: cv::resize(latest -> width x height) on the GPU, returns the
+ * frame number (1 for stills, may wrap to 0), -1 on error (app/background.cc:178-194).  grab_into: the same resize
+ * straight into a context's device-resident background (no host round trip).  thumbnail: 160-pixel-wide copy of the
+ * latest frame, refreshed by the reader when debug > 1 (:65-78); returns 0 and the size (0 x 0 if none yet). */
+typedef struct bsb_background bsb_background;
+typedef int (*bsb_bg_read_cb)(void* user, const uint8_t** data, int* width, int* height, size_t* pitch);
+typedef int (*bsb_bg_rewind_cb)(void* user);
+BSB_API bsb_background* bsb_background_new_still(int device, const uint8_t* raw, int width, int height, size_t pitch, int debug);
+BSB_API bsb_background* bsb_background_new_video(int device, double fps, int start_frame, bsb_bg_read_cb read, bsb_bg_rewind_cb rewind,
+                                                 void* user, const uint8_t* first, int width, int height, size_t pitch, int debug);
+BSB_API void bsb_background_delete(bsb_background* bg);
+BSB_API int bsb_background_grab(bsb_background* bg, int width, int height, uint8_t* out, size_t out_pitch);
+BSB_API int bsb_background_grab_into(bsb_background* bg, bsb_ctx* ctx);
+BSB_API int bsb_background_thumbnail(bsb_background* bg, uint8_t* out, size_t capacity, int* width, int* height);
+BSB_API int bsb_background_frame(bsb_background* bg);
+BSB_API int bsb_background_running(bsb_background* bg);
+
 BSB_API int bsb_synchronize(bsb_ctx* ctx);
 /* the context's cudaStream_t (for event timing on the launching stream) */
 BSB_API void* bsb_stream(bsb_ctx* ctx);
@@ -167,6 +208,8 @@ BSB_API double bsb_time_pointwise(int device, int variant, int M, int K, int N, 
 /* ---- introspection (tests, bench) -------------------------------------------------- */
 /* geometry: roidim / in_roidim / out_roidim as x,y,w,h (lib/libbackscrub.cc:234-246);
  * model input / output dims as h,w,c */
+/* frame size the context was created for */
+BSB_API int bsb_frame_size(bsb_ctx* ctx, int* width, int* height);
 BSB_API int bsb_geometry(bsb_ctx* ctx, int roidim[4], int in_roidim[4], int out_roidim[4], int in_hwc[3], int out_hwc[3]);
 /* run only the CNN on a caller-provided fp32 NHWC input batch (host), output to host */
 BSB_API int bsb_infer(bsb_ctx* ctx, int n_frames, const float* input, float* output);
@@ -189,6 +232,11 @@ BSB_API long bsb_total_launches(void);
 BSB_API double bsb_time_stage(bsb_ctx* ctx, int stage, int n_frames, int iters);
 /* algorithmic FLOPs of one CNN frame (2*MAC) */
 BSB_API double bsb_model_flops(bsb_ctx* ctx);
+/* Process-wide measurement switches of the kernel launchers (A/B runs in bench.py / tools/): they select between
+ * bit-identical kernel variants and never change results.  Names: "pw_variant", "dw_plane", "post_tma", "post_wide",
+ * "post_l1".  Set them before creating contexts (captured CUDA graphs keep the variant they were captured with).
+ * Returns 1, or 0 for an unknown name. */
+BSB_API int bsb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus
 }

@@ -1,42 +1,3 @@
-// tests/cpp/stub/opencv2/core/core.hpp — MINIMAL stand-in for OpenCV's cv::Mat, test-only.
-// This image has no OpenCV C++ headers, so the header-only adapters in include/ (which take cv::Mat&
-// exactly like the reference's lib/libbackscrub.h) are compiled against this stub to prove they build
-// and behave; with a real OpenCV the genuine <opencv2/core/core.hpp> is found first instead.
+// tests/cpp/stub/opencv2/core/core.hpp — test-only stand-in (see mat.hpp)
 #pragma once
-#include <cstddef>
-#include <cstdint>
-#include <cstdlib>
-#include <memory>
-
-#define CV_8U 0
-#define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
-#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
-#define CV_8UC2 CV_MAKETYPE(CV_8U, 2)
-#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
-
-namespace cv {
-class Mat {
- public:
-  int rows = 0, cols = 0;
-  uint8_t* data = nullptr;
-  size_t step = 0;
-  Mat() = default;
-  Mat(int r, int c, int type, void* ext, size_t st = 0) : rows(r), cols(c), data(static_cast<uint8_t*>(ext)), type_(type) {
-    step = st ? st : (size_t)c * channels();
-  }
-  Mat(int r, int c, int type) { create(r, c, type); }
-  void create(int r, int c, int type) {
-    rows = r; cols = c; type_ = type; step = (size_t)c * channels();
-    own_.reset(static_cast<uint8_t*>(std::malloc(step * (size_t)r)), std::free);
-    data = own_.get();
-  }
-  int type() const { return type_; }
-  int channels() const { return (type_ >> 3) + 1; }
-  bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-  size_t total() const { return (size_t)rows * cols; }
-  size_t elemSize() const { return (size_t)channels(); }
- private:
-  int type_ = 0;
-  std::shared_ptr<uint8_t> own_;
-};
-}  // namespace cv
+#include "mat.hpp"

@@ -1,12 +1,14 @@
-// tests/cpp/stub/opencv2/core/core.hpp — MINIMAL stand-in for OpenCV's cv::Mat, test-only.
-// This image has no OpenCV C++ headers, so the header-only adapters in include/ (which take cv::Mat&
-// exactly like the reference's lib/libbackscrub.h) are compiled against this stub to prove they build
-// and behave; with a real OpenCV the genuine <opencv2/core/core.hpp> is found first instead.
+// tests/cpp/stub/opencv2/core/mat.hpp — MINIMAL stand-in for OpenCV's cv::Mat, test-only.
+// This image has no OpenCV C++ headers, so the reference-compatible C++ layer (include/lib/libbackscrub.h,
+// include/background.h and the shims that define them) is compiled against this stub to prove it builds, links and
+// behaves; with a real OpenCV the genuine <opencv2/core/mat.hpp> is found instead.
 #pragma once
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
+#include <string>
 
 #define CV_8U 0
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
@@ -26,10 +28,20 @@ class Mat {
   }
   Mat(int r, int c, int type) { create(r, c, type); }
   void create(int r, int c, int type) {
+    if (own_ && r == rows && c == cols && type == type_) return;
     rows = r; cols = c; type_ = type; step = (size_t)c * channels();
-    own_.reset(static_cast<uint8_t*>(std::malloc(step * (size_t)r)), std::free);
+    own_.reset(static_cast<uint8_t*>(std::malloc(step * (size_t)r + 1)), std::free);
     data = own_.get();
   }
+  Mat clone() const {
+    Mat m;
+    if (empty()) return m;
+    m.create(rows, cols, type_);
+    for (int y = 0; y < rows; ++y) std::memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols * channels());
+    return m;
+  }
+  void copyTo(Mat& dst) const { dst = clone(); }
+  void release() { own_.reset(); data = nullptr; rows = cols = 0; step = 0; }
   int type() const { return type_; }
   int channels() const { return (type_ >> 3) + 1; }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }

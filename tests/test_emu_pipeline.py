@@ -102,21 +102,26 @@ def test_planner_fuses(lib):
 
 
 @pytest.mark.slow
-def test_depthwise_plane_opt_in():
-    """BSB_DW_PLANE=1 (whole-plane depthwise for the 33x33 atrous layers; opt-in until measured on a B200) must give
-    the oracle's bits.  The switch is read once per process, hence the subprocess."""
+def test_depthwise_plane_and_strips():
+    """The whole-plane depthwise kernel (default for the 33x33 atrous layers) and the strip kernel it replaced
+    (bsb_set_tuning("dw_plane", 0)) must both give the oracle's bits.  Run in a subprocess so the emulator's launch
+    trace (CUEMU_TRACE) can prove which kernel ran."""
     import os
     import subprocess
     import sys
     from tests.conftest import ROOT
-    code = ("from tests import parity_common as pc\n"
+    code = ("import sys\n"
+            "from tests import parity_common as pc\n"
             "from tests.emu.emu_lib import emu\n"
             "lib = emu()\n"
+            "assert lib.bsb_set_tuning(b'dw_plane', int(sys.argv[1]))\n"
+            "assert not lib.bsb_set_tuning(b'no_such_switch', 1)\n"
             "pc.check_infer_batch(lib, 'bodypix', n=2)\n"
             "pc.check_infer_batch(lib, 'deeplab', n=1)\n"
             "assert pc.check_tensors(lib, 'bodypix') > 20\n"
             "print('plane ok')\n")
-    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, BSB_DW_PLANE="1", CUEMU_TRACE="1", PYTHONPATH=ROOT),
-                         capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0 and "plane ok" in out.stdout, out.stderr[-2000:]
-    assert "k_depthwise_plane" in out.stderr                     # the opt-in kernel really ran
+    for v in ("1", "0"):
+        out = subprocess.run([sys.executable, "-c", code, v], cwd=ROOT, env=dict(os.environ, CUEMU_TRACE="1", PYTHONPATH=ROOT),
+                             capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "plane ok" in out.stdout, out.stderr[-2000:]
+        assert ("k_depthwise_plane" in out.stderr) == (v == "1")
