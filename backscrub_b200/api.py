@@ -223,6 +223,11 @@ class MaskGen:
         return ms
 
     @property
+    def yuyv_native(self) -> bool:
+        """the last composite_yuyv call read the camera YUYV frames in place (no BGR frame was materialised)"""
+        return bool(self._lib.bsb_yuyv_native(self._h))
+
+    @property
     def launches_per_call(self) -> int:
         return self._lib.bsb_launches_per_call(self._h, 1)
 

@@ -579,8 +579,9 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMalloc((void**)&filt_u8_, B * in_px * 3));
   CUDA_OK(cudaMalloc((void**)&state_, out_px));
   CUDA_OK(cudaMemset(state_, 0, out_px));
-  CUDA_OK(cudaMalloc((void**)&ofinal_, B * out_px));
-  CUDA_OK(cudaMemset(ofinal_, 0, B * out_px));
+  opitch_ = (ow_ + 15) / 16 * 16;
+  CUDA_OK(cudaMalloc((void**)&ofinal_, B * (size_t)oh_ * opitch_));
+  CUDA_OK(cudaMemset(ofinal_, 0, B * (size_t)oh_ * opitch_));
   CUDA_OK(cudaMalloc((void**)&d_frames_, B * fpx * 3));
   CUDA_OK(cudaMalloc((void**)&d_out_, B * fpx * 3));
   CUDA_OK(cudaMalloc((void**)&d_yuyv_, B * fpx * 2));
@@ -602,6 +603,7 @@ bool Engine::upload(std::string* err) {
   if (!upload_resize_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
   if (!upload_resize_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
   if (tab_up_.area2x2) { *err = "mask upsample degenerated to a 2x down-scale"; return false; }
+  if (!refresh_bg_yuyv(err)) return false;
   CUDA_OK(cudaDeviceSynchronize());
   return true;
 }
@@ -614,7 +616,7 @@ Engine::~Engine() {
   for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)rowsum_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
                   (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_, (void*)d_yuyv_in_,
                   tab_in_.blob, tab_up_.blob, tab_bg_.blob, tab_out_.blob, (void*)d_bg_cursor_, (void*)d_bg_eff_, (void*)d_bg_frames_,
-                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_})
+                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_, (void*)d_bg_yuyv_})
     if (p) cudaFree(p);
   if (h_mask_) cudaFreeHost(h_mask_);
   if (stream_) cudaStreamDestroy(stream_);
@@ -623,9 +625,14 @@ Engine::~Engine() {
 // ---------------------------------------------------------------------------
 // enqueue: the per-call kernel sequence (captured into a CUDA graph by run())
 // ---------------------------------------------------------------------------
-void Engine::enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride) {
-  launch_resize_roi_swap(stream_, n, d_frames, stride, pitch, roidim_[0], roidim_[1], roidim_[2], roidim_[3], tab_in_.tab,
-                         in_u8_, mw_, mh_, in_roidim_[0], in_roidim_[1], in_roidim_[2], in_roidim_[3], tab_in_.area2x2);
+void Engine::enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride, const uint8_t* d_yuyv_in) {
+  // camera YUYV frames are read in place (each bilinear tap converted like cv::COLOR_YUV2BGR_YUYV would have)
+  if (d_yuyv_in)
+    launch_resize_roi_swap(stream_, n, d_yuyv_in, (size_t)W_ * H_ * 2, (size_t)W_ * 2, roidim_[0], roidim_[1], roidim_[2], roidim_[3], tab_in_.tab,
+                           in_u8_, mw_, mh_, in_roidim_[0], in_roidim_[1], in_roidim_[2], in_roidim_[3], tab_in_.area2x2, true);
+  else
+    launch_resize_roi_swap(stream_, n, d_frames, stride, pitch, roidim_[0], roidim_[1], roidim_[2], roidim_[3], tab_in_.tab,
+                           in_u8_, mw_, mh_, in_roidim_[0], in_roidim_[1], in_roidim_[2], in_roidim_[3], tab_in_.area2x2);
   // with the fused stem the fp32 input tensor is only materialised for introspection (KEEP_TENSORS)
   float* f32 = (stem_u8_ok_ && !(flags_ & 1u)) ? nullptr : tptr(g_.input);
   launch_bilateral_norm(stream_, n, in_u8_, mw_, mh_, lut_, lut_ + 768, scaling_, offset_, f32, filt_u8_);
@@ -713,28 +720,28 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
 }
 
 void Engine::enqueue_decision(int n) {
-  launch_decision_iir(stream_, model_type_, n, tptr(g_.output), oh_, ow_, oc_, state_, ofinal_);
+  launch_decision_iir(stream_, model_type_, n, tptr(g_.output), oh_, ow_, oc_, state_, ofinal_, opitch_);
 }
 
-void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
-                          uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride) {
+// PostArgs of one call.  `yuyv_native` (optional out): the frames can stay in camera YUYV format for the post kernel.
+PostArgs Engine::post_args(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                           uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in) const {
   const size_t fbytes = (size_t)W_ * H_ * 3;
   const bool flip = flip_h_ || flip_v_, resized = out_w_ != W_ || out_h_ != H_, tail = flip || resized;
   const bool want_rgb = d_out || d_yuyv;
   PostArgs a{};
   a.B = n; a.W = W_; a.H = H_;
   a.frames = d_frames; a.frame_pitch = pitch; a.frame_stride = stride;
+  a.yuyv_in = d_yuyv_in; a.yuyv_in_stride = (size_t)W_ * H_ * 2;
   a.bg = d_bg_; a.bg_pitch = (size_t)W_ * 3; a.bg_stride = 0;
-  bool ring = false;
   if (has_bg_) {
     if (bgblur_k_) a.bg = d_bg_eff_;                       // blurred once, when the background / strength was set
-    if (bg_count_ > 1) { ring = true; a.bg_stride = fbytes; a.bg_cursor = d_bg_cursor_; a.bg_count = bg_count_; a.bg_advance = bg_advance_; }
+    if (bg_count_ > 1) { a.bg_stride = fbytes; a.bg_cursor = d_bg_cursor_; a.bg_count = bg_count_; a.bg_advance = bg_advance_; }
   } else if (bgblur_k_ && want_rgb) {
-    // app/deepseg.cc:652-658: no background source => the background is the blurred camera frame itself
-    launch_gauss_blur(stream_, n, d_frames, pitch, stride, d_gauss_tmp_, d_bg_frames_, (size_t)W_ * 3, fbytes, W_, H_, taps_);
-    a.bg = d_bg_frames_; a.bg_stride = fbytes;
+    a.bg = d_bg_frames_; a.bg_stride = fbytes;            // the blurred camera frame itself (filled by enqueue_post)
   }
-  a.ofinal = ofinal_; a.ow = ow_; a.oh = oh_;
+  if (bg_yuyv_valid_ && !(bgblur_k_ && !has_bg_)) a.bg_yuyv = d_bg_yuyv_;
+  a.ofinal = ofinal_; a.ow = ow_; a.oh = oh_; a.opitch = opitch_;
   a.out_x = out_roidim_[0]; a.out_y = out_roidim_[1]; a.out_w = out_roidim_[2]; a.out_h = out_roidim_[3];
   a.roi_x = roidim_[0]; a.roi_y = roidim_[1]; a.roi_w = roidim_[2]; a.roi_h = roidim_[3];
   a.tab = tab_up_.tab; a.area2x2 = false;
@@ -747,6 +754,19 @@ void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t s
     a.yuyv = nullptr; a.yuyv_stride = 0;
   }
   a.mask = d_mask; a.mask_stride = mask_stride;
+  return a;
+}
+
+void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                          uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in) {
+  const size_t fbytes = (size_t)W_ * H_ * 3;
+  const bool flip = flip_h_ || flip_v_, resized = out_w_ != W_ || out_h_ != H_, tail = flip || resized;
+  const bool want_rgb = d_out || d_yuyv;
+  const bool ring = has_bg_ && bg_count_ > 1;
+  // app/deepseg.cc:652-658: no background source => the background is the blurred camera frame itself
+  if (!has_bg_ && bgblur_k_ && want_rgb)
+    launch_gauss_blur(stream_, n, d_frames, pitch, stride, d_gauss_tmp_, d_bg_frames_, (size_t)W_ * 3, fbytes, W_, H_, taps_);
+  const PostArgs a = post_args(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, d_yuyv_in);
   launch_post(stream_, a);
   if (ring && bg_advance_) launch_advance_cursor(stream_, d_bg_cursor_, (int)(((long)n * bg_advance_) % bg_count_), bg_count_);
   if (!tail || !want_rgb) return;
@@ -768,6 +788,30 @@ void Engine::enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t s
   if (d_yuyv) launch_rgb_to_yuyv(stream_, cur, d_yuyv, (size_t)out_w_ * out_h_, n, cur_stride, yuyv_stride);
 }
 
+// Camera YUYV input: the pre-processing kernel always reads the YUYV frames in place; the BGR frame is materialised
+// (k_yuyv_to_bgr into `d_frames`) only when the post stage cannot read YUYV itself — no TMA path for this geometry, or
+// the blur-my-background mode, whose Gaussian runs on the BGR frame.
+bool Engine::yuyv_native(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                         uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in) const {
+  if (!d_yuyv_in || (bgblur_k_ && !has_bg_)) return false;
+  return post_tma_eligible(post_args(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, d_yuyv_in));
+}
+
+void Engine::enqueue_all(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                         uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in,
+                         bool native, bool sync_cbs) {
+  const long l0 = thread_launch_count();
+  if (d_yuyv_in && !native) launch_yuyv_to_bgr(stream_, d_yuyv_in, const_cast<uint8_t*>(d_frames), (size_t)n * W_ * H_);
+  enqueue_pre(n, d_frames, pitch, stride, d_yuyv_in);
+  if (sync_cbs && cb_.onprep) { cudaStreamSynchronize(stream_); cb_.onprep(cb_.caller_ctx); }
+  enqueue_cnn(n, true);
+  if (sync_cbs && cb_.oninfer) { cudaStreamSynchronize(stream_); cb_.oninfer(cb_.caller_ctx); }
+  enqueue_decision(n);
+  if (sync_cbs && cb_.onmask) { cudaStreamSynchronize(stream_); cb_.onmask(cb_.caller_ctx); }
+  enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, native ? d_yuyv_in : nullptr);
+  last_call_launches_ = (int)(thread_launch_count() - l0);
+}
+
 bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
                  uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, bool use_callbacks, std::string* err,
                  const uint8_t* d_yuyv_in) {
@@ -780,14 +824,9 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
   eager = true;
 #endif
   if (eager) {
-    if (d_yuyv_in) launch_yuyv_to_bgr(stream_, d_yuyv_in, const_cast<uint8_t*>(d_frames), (size_t)n * W_ * H_);
-    enqueue_pre(n, d_frames, pitch, stride);
-    if (cbs && cb_.onprep) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onprep(cb_.caller_ctx); }
-    enqueue_cnn(n, true);
-    if (cbs && cb_.oninfer) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.oninfer(cb_.caller_ctx); }
-    enqueue_decision(n);
-    if (cbs && cb_.onmask) { CUDA_OK(cudaStreamSynchronize(stream_)); cb_.onmask(cb_.caller_ctx); }
-    enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride);
+    const bool native = yuyv_native(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, d_yuyv_in);
+    last_native_ = native;
+    enqueue_all(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, d_yuyv_in, native, cbs);
     CUDA_OK(cudaGetLastError());
     return true;
   }
@@ -797,13 +836,11 @@ bool Engine::run(int n, const uint8_t* d_frames, size_t pitch, size_t stride, ui
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
     if (graphs_.size() >= 64) drop_graphs();
+    const bool native = yuyv_native(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, d_yuyv_in);
+    last_native_ = native;
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-    if (d_yuyv_in) launch_yuyv_to_bgr(stream_, d_yuyv_in, const_cast<uint8_t*>(d_frames), (size_t)n * W_ * H_);
-    enqueue_pre(n, d_frames, pitch, stride);
-    enqueue_cnn(n, true);
-    enqueue_decision(n);
-    enqueue_post(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride);
+    enqueue_all(n, d_frames, pitch, stride, d_out, out_stride, d_yuyv, yuyv_stride, d_mask, mask_stride, d_yuyv_in, native, false);
     // the capture is always closed, also when a launch inside it failed: a stream left in capture mode would
     // poison every later call on this context
     const cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
@@ -883,6 +920,7 @@ bool Engine::set_background_ring(const uint8_t* frames, int count, int bw, int b
   bg_count_ = count; bg_advance_ = advance;
   has_bg_ = true;
   if (!refresh_bg_blur(err)) return false;
+  if (!refresh_bg_yuyv(err)) return false;
   CUDA_OK(cudaStreamSynchronize(stream_));
   CUDA_OK(cudaGetLastError());
   return true;
@@ -912,6 +950,20 @@ bool Engine::refresh_bg_blur(std::string* err) {
   return true;
 }
 
+// YUYV of the effective background (ring): what convert_rgb_to_yuyv (app/deepseg.cc:87-106) yields wherever the composite
+// equals the background, so all-background tiles of the post stage are copies.  Recomputed when the background changes.
+bool Engine::refresh_bg_yuyv(std::string* err) {
+  bg_yuyv_valid_ = false;
+  if (W_ & 1) return true;
+  const size_t npix = (size_t)W_ * H_;
+  if (!ensure((void**)&d_bg_yuyv_, &bg_yuyv_cap_, npix * 2 * (size_t)bg_count_, err)) return false;
+  const uint8_t* src = (has_bg_ && bgblur_k_) ? d_bg_eff_ : d_bg_;
+  launch_rgb_to_yuyv(stream_, src, d_bg_yuyv_, npix, bg_count_, npix * 3, npix * 2);
+  CUDA_OK(cudaGetLastError());
+  bg_yuyv_valid_ = true;
+  return true;
+}
+
 bool Engine::set_bgblur(int k, std::string* err) {
   GaussTaps t{};
   if (k != 0 && !gauss_taps(k, &t)) { *err = "strength value must be odd (1..255)"; return false; }   // app/deepseg.cc:423-426
@@ -920,6 +972,7 @@ bool Engine::set_bgblur(int k, std::string* err) {
   drop_graphs();
   bgblur_k_ = k; taps_ = t;
   if (!refresh_bg_blur(err)) return false;
+  if (!refresh_bg_yuyv(err)) return false;
   CUDA_OK(cudaStreamSynchronize(stream_));
   return true;
 }
@@ -966,11 +1019,13 @@ double Engine::time_stage(int stage, int n, int iters, std::string* err) {
   const size_t row = (size_t)W_ * 3, fbytes = row * H_, npix = (size_t)W_ * H_;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
+  // the last call's input format decides which kernels are timed (camera YUYV read in place, or BGR frames)
+  const uint8_t* yin = last_native_ ? d_yuyv_in_ : nullptr;
   auto once = [&]() {
-    if (stage == 0 || stage == 4) enqueue_pre(n, d_frames_, row, fbytes);
+    if (stage == 0 || stage == 4) enqueue_pre(n, d_frames_, row, fbytes, yin);
     if (stage == 1 || stage == 4) enqueue_cnn(n, true);
     if (stage == 2 || stage == 4) enqueue_decision(n);
-    if (stage == 3 || stage == 4) enqueue_post(n, d_frames_, row, fbytes, d_out_, fbytes, d_yuyv_, npix * 2, d_mask_, npix);
+    if (stage == 3 || stage == 4) enqueue_post(n, d_frames_, row, fbytes, d_out_, fbytes, d_yuyv_, npix * 2, d_mask_, npix, yin);
   };
   once();                                   // warm-up (instruction cache, tables)
   cudaStreamSynchronize(stream_);
@@ -1007,11 +1062,13 @@ long Engine::get_stage_u8(int which, int frame, uint8_t* out, long cap, std::str
   const uint8_t* src = nullptr; long n = 0;
   if (which == 0) { n = (long)mh_ * mw_ * 3; src = in_u8_ + (size_t)frame * n; }
   else if (which == 1) { n = (long)mh_ * mw_ * 3; src = filt_u8_ ? filt_u8_ + (size_t)frame * n : nullptr; }
-  else if (which == 2) { n = (long)oh_ * ow_; src = ofinal_ + (size_t)frame * n; }
+  else if (which == 2) { n = (long)oh_ * ow_; src = ofinal_ + (size_t)frame * oh_ * opitch_; }
   if (!src) { *err = which == 1 ? "stage buffer needs BSB_FLAG_KEEP_TENSORS" : "unknown stage"; return -1; }
   if (cap < n) { *err = "output buffer too small"; return -1; }
-  if (cudaSetDevice(device_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess ||
-      cudaMemcpy(out, src, (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "CUDA error in get_stage_u8"; return -1; }
+  if (cudaSetDevice(device_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) { *err = "CUDA error in get_stage_u8"; return -1; }
+  const cudaError_t ce = which == 2 ? cudaMemcpy2D(out, (size_t)ow_, src, (size_t)opitch_, (size_t)ow_, (size_t)oh_, cudaMemcpyDeviceToHost)
+                                    : cudaMemcpy(out, src, (size_t)n, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) { *err = "CUDA error in get_stage_u8"; return -1; }
   return n;
 }
 

@@ -119,6 +119,7 @@ class Engine {
   void out_hwc(int* v) const { v[0] = oh_; v[1] = ow_; v[2] = oc_; }
   double flops() const { return flops_; }
   int launches_per_call() const {
+    if (last_call_launches_ > 0) return last_call_launches_;      // counted while the last call was enqueued / captured
     int n = 4;
     for (const Step& s : steps_) n += s.launches();
     if (bgblur_k_ && !has_bg_) n += 2;
@@ -139,16 +140,25 @@ class Engine {
   uint8_t* d_yuyv_in() const { return d_yuyv_in_; }
   uint8_t* h_mask() const { return h_mask_; }
   bool has_background() const { return has_bg_; }
+  bool last_native() const { return last_native_; }
 
  private:
   Engine() = default;
   bool plan(std::string* err);
   bool upload(std::string* err);
-  void enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride);
+  void enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t stride, const uint8_t* d_yuyv_in = nullptr);
+  PostArgs post_args(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                     uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in) const;
+  bool yuyv_native(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                   uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in) const;
+  void enqueue_all(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
+                   uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in,
+                   bool native, bool sync_cbs);
+  bool refresh_bg_yuyv(std::string* err);
   void enqueue_cnn(int n, bool from_u8);
   void enqueue_decision(int n);
   void enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
-                    uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride);
+                    uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in = nullptr);
   float* tptr(int t) const {
     const TensorInfo& I = tinfo_[t];
     return I.alias_parent >= 0 ? arena_ + tinfo_[I.alias_parent].offset + I.alias_off : arena_ + I.offset;
@@ -182,7 +192,8 @@ class Engine {
   uint8_t* in_u8_ = nullptr;         // [B][mh][mw][3] zero outside in_roidim
   uint8_t* filt_u8_ = nullptr;       // [B][mh][mw][3] (KEEP_TENSORS only)
   uint8_t* state_ = nullptr;         // [oh*ow] IIR state
-  uint8_t* ofinal_ = nullptr;        // [B][oh*ow]
+  uint8_t* ofinal_ = nullptr;        // [B][oh][opitch_]
+  int opitch_ = 0;                   // ofinal row pitch (ow rounded up to 16 bytes: TMA-addressable)
   uint8_t* d_frames_ = nullptr, *d_out_ = nullptr, *d_yuyv_ = nullptr, *d_mask_ = nullptr, *d_bg_ = nullptr, *d_bg_raw_ = nullptr, *d_yuyv_in_ = nullptr;
   size_t bg_raw_cap_ = 0;
   uint8_t* h_mask_ = nullptr;        // pinned host W*H
@@ -206,6 +217,11 @@ class Engine {
   bool flip_h_ = false, flip_v_ = false;
   int out_w_ = 0, out_h_ = 0;
   uint8_t* d_stage_a_ = nullptr, *d_stage_b_ = nullptr, *d_stage_c_ = nullptr;
+  uint8_t* d_bg_yuyv_ = nullptr;     // YUYV of the effective background (ring): all-background tiles are copies
+  size_t bg_yuyv_cap_ = 0;
+  bool bg_yuyv_valid_ = false;
+  bool last_native_ = false;         // the last call read camera YUYV in place (no BGR frame was materialised)
+  int last_call_launches_ = 0;
   size_t stage_a_cap_ = 0, stage_b_cap_ = 0, stage_c_cap_ = 0, out_cap_ = 0, yuyv_cap_ = 0;
 
   // everything a captured launch sequence bakes into its kernel arguments

@@ -110,7 +110,8 @@ struct ResizeTab {        // OpenCV INTER_LINEAR 8-bit tables (device pointers)
 // zero-padded model-sized u8 image.  frames: B x (H x W x 3, stride bytes).
 void launch_resize_roi_swap(cudaStream_t s, int B, const uint8_t* frames, size_t frame_stride, size_t frame_pitch,
                             int roi_x, int roi_y, int roi_w, int roi_h, ResizeTab tab,
-                            uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h, bool area2x2);
+                            uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h, bool area2x2,
+                            bool in_yuyv = false);   // in_yuyv: `frames` are camera YUYV frames (pitch W*2), converted per tap
 
 // lib/libbackscrub.cc:295-302: bilateralFilter(5,100,100) + convertTo(CV_32F, scale, offset)
 void launch_bilateral_norm(cudaStream_t s, int B, const uint8_t* in_u8, int mw, int mh,
@@ -118,9 +119,10 @@ void launch_bilateral_norm(cudaStream_t s, int B, const uint8_t* in_u8, int mw, 
                            float* out_f32, uint8_t* out_u8_dbg);
 
 // lib/libbackscrub.cc:314-361: decision + 3-tap bit-shift IIR over B consecutive frames.
-// state: [oh*ow] persistent; ofinal: [B][oh*ow] state after each frame.
+// state: [oh*ow] persistent; ofinal: [B][oh][opitch] state after each frame (opitch >= ow: rows are padded to a
+// multiple of 16 bytes so the post kernel can fetch patches of it with TMA).
 void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
-                         uint8_t* state, uint8_t* ofinal);
+                         uint8_t* state, uint8_t* ofinal, int opitch);
 
 // lib/libbackscrub.cc:366-371 + app/deepseg.cc:108-134,87-106 fused:
 // mask = blur5x5(resize(ofinal(out_roi) -> roi)) inside roidim, 255 outside;
@@ -130,7 +132,7 @@ struct PostArgs {
   const uint8_t* frames; size_t frame_pitch, frame_stride;   // row pitch / per-frame stride (bytes)
   const uint8_t* bg; size_t bg_pitch, bg_stride;             // bg_stride 0 => one static background
   const int* bg_cursor; int bg_count, bg_advance;             // non-null: frame b blends ring image (*cursor + b*advance) % count
-  const uint8_t* ofinal; int ow, oh;                          // [B][oh*ow]
+  const uint8_t* ofinal; int ow, oh, opitch;                  // [B][oh][opitch]
   int out_x, out_y, out_w, out_h;                              // out_roidim inside ofinal
   int roi_x, roi_y, roi_w, roi_h;                              // roidim inside the frame
   ResizeTab tab;                                               // out_roi -> roi upsample tables
@@ -140,8 +142,15 @@ struct PostArgs {
   uint8_t* mask; size_t mask_stride;                           // may be null (W bytes per row)
   int frame_l1;                                                // frame loads allocate in L1 (measurement switch)
   int wide;                                                    // 32-byte aligned everywhere: 256-bit loads / stores
+  // TMA path only (k_post_tma): the camera frames may stay in their wire format (YUYV, W*2 bytes per row, tightly
+  // packed, `yuyv_in_stride` bytes per frame) and are converted per tile; `bg_yuyv` is the background (ring) already
+  // converted to YUYV, same indexing as `bg` with W*2-byte rows, so all-background tiles are pure copies.
+  const uint8_t* yuyv_in; size_t yuyv_in_stride;
+  const uint8_t* bg_yuyv;
 };
 void launch_post(cudaStream_t s, const PostArgs& a);
+// true if launch_post will take the TMA kernel for these arguments (the only one that can read a.yuyv_in)
+bool post_tma_eligible(const PostArgs& a);
 
 // app/background.cc:178-194: cv::resize(raw -> W x H), 3 channels
 // n images (frame strides in bytes; n = 1 for the background provider)
@@ -169,8 +178,9 @@ void launch_rgb_to_yuyv(cudaStream_t s, const uint8_t* rgb, uint8_t* yuyv, size_
 // *cursor = (*cursor + step) % count, after the frames of a call have been blended
 void launch_advance_cursor(cudaStream_t s, int* cursor, int step, int count);
 
-// number of kernel launches issued through the launchers above (bench gpu_launches)
+// number of kernel launches issued through the launchers above (bench gpu_launches); per calling thread
 long launch_count();
+long thread_launch_count();
 
 // Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (cudaFuncSetAttribute is per device and
 // per function; the largest request so far is remembered per (device, function) under a mutex, so contexts on several

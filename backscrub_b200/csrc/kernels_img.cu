@@ -7,6 +7,7 @@
 // fixed-point arithmetic restated (see oracle/oracle_img.c for the formulas and their
 // cv2 pins); results are bit-exact against the oracle.
 #include "kernels.h"
+#include "post_math.h"
 
 namespace bsb {
 
@@ -32,6 +33,10 @@ BSB_D size_t bg_frame_offset(const PostArgs& a, int b) {
 // ROI crop -> resize -> BGR2RGB into the zero-padded model-sized image.
 // One thread = one destination pixel (3 channels).
 // ---------------------------------------------------------------------------
+// IN_YUYV: `frames` are camera YUYV frames (W*2-byte rows); every tap is first converted the way
+// cv::cvtColor(COLOR_YUV2BGR_YUYV) would have (cv::VideoCapture's conversion, app/deepseg.cc:553), so the result
+// equals converting the whole frame first — without materialising the BGR frame.
+template <bool IN_YUYV>
 __global__ void __launch_bounds__(256) k_resize_roi_swap(int B, const uint8_t* frames, size_t frame_stride, size_t pitch,
                                                          int roi_x, int roi_y, int roi_w, int roi_h, ResizeTab t,
                                                          uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h,
@@ -40,21 +45,45 @@ __global__ void __launch_bounds__(256) k_resize_roi_swap(int B, const uint8_t* f
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int dx = (int)(idx % in_w), dy = (int)((idx / in_w) % in_h), b = (int)(idx / ((long)in_w * in_h));
-  const uint8_t* roi = frames + (size_t)b * frame_stride + (size_t)roi_y * pitch + (size_t)roi_x * 3;
   uint8_t px[3];
-  if (area2x2) {
-    const uint8_t* s0 = roi + (size_t)(2 * dy) * pitch + (size_t)(2 * dx) * 3;
-    const uint8_t* s1 = s0 + pitch;
+  if (IN_YUYV) {
+    const uint8_t* img = frames + (size_t)b * frame_stride;
+    if (area2x2) {
+      int p00[3], p01[3], p10[3], p11[3];
+      const uint8_t* s0 = img + (size_t)(roi_y + 2 * dy) * pitch;
+      const uint8_t* s1 = s0 + pitch;
+      yuyv_px_to_bgr(s0, roi_x + 2 * dx, p00); yuyv_px_to_bgr(s0, roi_x + 2 * dx + 1, p01);
+      yuyv_px_to_bgr(s1, roi_x + 2 * dx, p10); yuyv_px_to_bgr(s1, roi_x + 2 * dx + 1, p11);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) px[c] = (uint8_t)((s0[c] + s0[3 + c] + s1[c] + s1[3 + c] + 2) >> 2);
+      for (int c = 0; c < 3; ++c) px[c] = (uint8_t)((p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2);
+    } else {
+      const int sx = __ldg(t.xofs + dx), sx1 = min(sx + 1, roi_w - 1);
+      const int a0 = __ldg(t.xw + 2 * dx), a1 = __ldg(t.xw + 2 * dx + 1);
+      const int b0 = __ldg(t.yw + 2 * dy), b1 = __ldg(t.yw + 2 * dy + 1);
+      const uint8_t* r0 = img + (size_t)(roi_y + __ldg(t.yofs0 + dy)) * pitch;
+      const uint8_t* r1 = img + (size_t)(roi_y + __ldg(t.yofs1 + dy)) * pitch;
+      int p00[3], p01[3], p10[3], p11[3];
+      yuyv_px_to_bgr(r0, roi_x + sx, p00); yuyv_px_to_bgr(r0, roi_x + sx1, p01);
+      yuyv_px_to_bgr(r1, roi_x + sx, p10); yuyv_px_to_bgr(r1, roi_x + sx1, p11);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[c] = lin_v(p00[c] * a0 + p01[c] * a1, p10[c] * a0 + p11[c] * a1, b0, b1);
+    }
   } else {
-    const int sx = __ldg(t.xofs + dx), sx1 = min(sx + 1, roi_w - 1);
-    const int a0 = __ldg(t.xw + 2 * dx), a1 = __ldg(t.xw + 2 * dx + 1);
-    const int b0 = __ldg(t.yw + 2 * dy), b1 = __ldg(t.yw + 2 * dy + 1);
-    const uint8_t* r0 = roi + (size_t)__ldg(t.yofs0 + dy) * pitch;
-    const uint8_t* r1 = roi + (size_t)__ldg(t.yofs1 + dy) * pitch;
+    const uint8_t* roi = frames + (size_t)b * frame_stride + (size_t)roi_y * pitch + (size_t)roi_x * 3;
+    if (area2x2) {
+      const uint8_t* s0 = roi + (size_t)(2 * dy) * pitch + (size_t)(2 * dx) * 3;
+      const uint8_t* s1 = s0 + pitch;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) px[c] = lin_v(lin_h(r0, sx, sx1, 3, c, a0, a1), lin_h(r1, sx, sx1, 3, c, a0, a1), b0, b1);
+      for (int c = 0; c < 3; ++c) px[c] = (uint8_t)((s0[c] + s0[3 + c] + s1[c] + s1[3 + c] + 2) >> 2);
+    } else {
+      const int sx = __ldg(t.xofs + dx), sx1 = min(sx + 1, roi_w - 1);
+      const int a0 = __ldg(t.xw + 2 * dx), a1 = __ldg(t.xw + 2 * dx + 1);
+      const int b0 = __ldg(t.yw + 2 * dy), b1 = __ldg(t.yw + 2 * dy + 1);
+      const uint8_t* r0 = roi + (size_t)__ldg(t.yofs0 + dy) * pitch;
+      const uint8_t* r1 = roi + (size_t)__ldg(t.yofs1 + dy) * pitch;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[c] = lin_v(lin_h(r0, sx, sx1, 3, c, a0, a1), lin_h(r1, sx, sx1, 3, c, a0, a1), b0, b1);
+    }
   }
   uint8_t* d = in_u8 + ((size_t)b * mh * mw + (size_t)(in_y + dy) * mw + (in_x + dx)) * 3;
   d[0] = px[2]; d[1] = px[1]; d[2] = px[0];   // BGR -> RGB
@@ -62,10 +91,12 @@ __global__ void __launch_bounds__(256) k_resize_roi_swap(int B, const uint8_t* f
 
 void launch_resize_roi_swap(cudaStream_t s, int B, const uint8_t* frames, size_t frame_stride, size_t frame_pitch,
                             int roi_x, int roi_y, int roi_w, int roi_h, ResizeTab tab,
-                            uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h, bool area2x2) {
+                            uint8_t* in_u8, int mw, int mh, int in_x, int in_y, int in_w, int in_h, bool area2x2, bool in_yuyv) {
   const long total = (long)B * in_w * in_h;
-  BSB_LAUNCH(k_resize_roi_swap, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, frames, frame_stride, frame_pitch,
-             roi_x, roi_y, roi_w, roi_h, tab, in_u8, mw, mh, in_x, in_y, in_w, in_h, area2x2);
+  if (in_yuyv) BSB_LAUNCH(k_resize_roi_swap<true>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, frames, frame_stride, frame_pitch,
+                          roi_x, roi_y, roi_w, roi_h, tab, in_u8, mw, mh, in_x, in_y, in_w, in_h, area2x2);
+  else BSB_LAUNCH(k_resize_roi_swap<false>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, frames, frame_stride, frame_pitch,
+                  roi_x, roi_y, roi_w, roi_h, tab, in_u8, mw, mh, in_x, in_y, in_w, in_h, area2x2);
   count_launch();
 }
 
@@ -164,9 +195,10 @@ BSB_D unsigned decide(int model_type, const float* t) {
 // The per-frame decisions of a pixel are independent (computed 8 at a time so their loads
 // overlap); only the 3-tap state update is sequential, and it is pure ALU on a bit mask.
 __global__ void __launch_bounds__(128) k_decision_iir(int model_type, int B, const float* out_f, int npix, int oc,
-                                                      uint8_t* state, uint8_t* ofinal) {
+                                                      uint8_t* state, uint8_t* ofinal, int ow, int opitch, int oframe) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= npix) return;
+  const int opos = (n / ow) * opitch + (n % ow);      // row-padded position inside one frame of ofinal
   unsigned st = state[n];
   for (int b0 = 0; b0 < B; b0 += 8) {
     unsigned bits = 0;
@@ -178,16 +210,17 @@ __global__ void __launch_bounds__(128) k_decision_iir(int model_type, int B, con
       if (b0 + j < B) {
         const unsigned val = ((bits >> j) & 1u) ? 255u : 0u;
         st = (val & 0xE0u) | (st >> 3);
-        ofinal[(size_t)(b0 + j) * npix + n] = (uint8_t)st;
+        ofinal[(size_t)(b0 + j) * oframe + opos] = (uint8_t)st;
       }
   }
   state[n] = (uint8_t)st;
 }
 
 void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
-                         uint8_t* state, uint8_t* ofinal) {
+                         uint8_t* state, uint8_t* ofinal, int opitch) {
   const int npix = oh * ow;
-  BSB_LAUNCH(k_decision_iir, dim3((unsigned)ceil_div(npix, 128)), dim3(128), 0, s, model_type, B, model_out, npix, oc, state, ofinal);
+  BSB_LAUNCH(k_decision_iir, dim3((unsigned)ceil_div(npix, 128)), dim3(128), 0, s, model_type, B, model_out, npix, oc, state, ofinal,
+             ow, opitch, oh * opitch);
   count_launch();
 }
 
@@ -235,7 +268,7 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
 
   if (hits_roi) {
     // ---- A: upsampled mask tile with halo, reflect-101 at the ROI border ----
-    const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)a.out_y * a.ow + a.out_x;
+    const uint8_t* src = a.ofinal + (size_t)b * a.opitch * a.oh + (size_t)a.out_y * a.opitch + a.out_x;
     for (int i = tid; i < PT_UH * PT_UW; i += 256) {
       const int uy = i / PT_UW, ux = i % PT_UW;
       const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
@@ -243,8 +276,8 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
       const int sx = __ldg(a.tab.xofs + gx), sx1 = min(sx + 1, a.out_w - 1);
       const int a0 = __ldg(a.tab.xw + 2 * gx), a1 = __ldg(a.tab.xw + 2 * gx + 1);
       const int b0 = __ldg(a.tab.yw + 2 * gy), b1 = __ldg(a.tab.yw + 2 * gy + 1);
-      const uint8_t* r0 = src + (size_t)__ldg(a.tab.yofs0 + gy) * a.ow;
-      const uint8_t* r1 = src + (size_t)__ldg(a.tab.yofs1 + gy) * a.ow;
+      const uint8_t* r0 = src + (size_t)__ldg(a.tab.yofs0 + gy) * a.opitch;
+      const uint8_t* r1 = src + (size_t)__ldg(a.tab.yofs1 + gy) * a.opitch;
       Us[uy * PT_US + ux] = lin_v(lin_h(r0, sx, sx1, 1, 0, a0, a1), lin_h(r1, sx, sx1, 1, 0, a0, a1), b0, b1);
     }
     __syncthreads();
@@ -338,85 +371,6 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
 //       mask) and one via DP4A, division by 255 on packed lanes, RGB->YUV with DP2A,
 //       16-byte streaming loads / stores.
 // ---------------------------------------------------------------------------
-constexpr int PF_W = 128, PF_H = 32, PF_PX = 16;
-constexpr int PF_UW = PF_W + 4, PF_UH = PF_H + 4, PF_US = 136, PF_RMAX = 40, PF_PS = 144;
-
-BSB_D uint4 ldg_stream(const uint8_t* p) {
-#if defined(BSB_EMU)
-  return *reinterpret_cast<const uint4*>(p);
-#else
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-#endif
-}
-// 256-bit global accesses (sm_100: LDG.256 / STG.256).  A thread owns 48 bytes (16 BGR pixels); split as 32 + 16 with
-// the 32-byte part on a sector boundary (even chunk: [0,32) + [32,48); odd chunk: [16,48) + [0,16)), every 32-byte
-// sector is then touched by exactly one instruction of the warp instead of two.
-struct U8x8 { unsigned v[8]; };
-BSB_D U8x8 ldg256(const uint8_t* p, bool l1) {
-  U8x8 r;
-#if defined(BSB_EMU)
-  (void)l1;
-  for (int i = 0; i < 8; ++i) r.v[i] = reinterpret_cast<const unsigned*>(p)[i];
-#else
-  if (l1) asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
-  else asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
-#endif
-  return r;
-}
-BSB_D void stg256(uint8_t* p, const unsigned* v) {
-#if defined(BSB_EMU)
-  for (int i = 0; i < 8; ++i) reinterpret_cast<unsigned*>(p)[i] = v[i];
-#else
-  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-#endif
-}
-// 48 bytes at p (chunk parity `odd`) -> w[12]
-BSB_D void load48_wide(const uint8_t* p, bool odd, bool l1, unsigned* w) {
-  const U8x8 a = ldg256(p + (odd ? 16 : 0), l1);
-  const uint4 c = l1 ? __ldg(reinterpret_cast<const uint4*>(p + (odd ? 0 : 32))) : ldg_stream(p + (odd ? 0 : 32));
-  w[0] = odd ? c.x : a.v[0]; w[1] = odd ? c.y : a.v[1]; w[2] = odd ? c.z : a.v[2]; w[3] = odd ? c.w : a.v[3];
-  w[4] = odd ? a.v[0] : a.v[4]; w[5] = odd ? a.v[1] : a.v[5]; w[6] = odd ? a.v[2] : a.v[6]; w[7] = odd ? a.v[3] : a.v[7];
-  w[8] = odd ? a.v[4] : c.x; w[9] = odd ? a.v[5] : c.y; w[10] = odd ? a.v[6] : c.z; w[11] = odd ? a.v[7] : c.w;
-}
-BSB_D void prefetch_l2(const uint8_t* p) {
-#if !defined(BSB_EMU)
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 32));
-#else
-  (void)p;
-#endif
-}
-BSB_D void stg_stream(uint8_t* p, uint4 v) {
-#if defined(BSB_EMU)
-  *reinterpret_cast<uint4*>(p) = v;
-#else
-  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#endif
-}
-
-
-BSB_D void store48_wide(uint8_t* p, bool odd, const unsigned* w) {
-  unsigned a[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = odd ? w[4 + i] : w[i];
-  stg256(p + (odd ? 16 : 0), a);
-  stg_stream(p + (odd ? 0 : 32), make_uint4(odd ? w[0] : w[8], odd ? w[1] : w[9], odd ? w[2] : w[10], odd ? w[3] : w[11]));
-}
-
-// one pixel: pair channels (two 16-bit lanes) + single channel; returns T = (c0, c1, c2, x) bytes
-template <int PAIR_SEL, int SINGLE_SEL, int T_SEL>
-BSB_D unsigned blend_px(unsigned g_pair_w, unsigned f_pair_w, unsigned g_single_w, unsigned f_single_w, unsigned m) {
-  const unsigned nm = 255u - m;
-  const unsigned gp = __byte_perm(g_pair_w, 0u, PAIR_SEL), fp = __byte_perm(f_pair_w, 0u, PAIR_SEL);
-  const unsigned x = gp * m + fp * nm;                                   // two lanes, each <= 65025
-  const unsigned y = x + __byte_perm(x, 0u, 0x4341) + 0x00010001u;       // (x + 1 + (x >> 8)) per lane; result in bytes 1, 3
-  const unsigned sw = __byte_perm(g_single_w, f_single_w, SINGLE_SEL);   // (g, f, g, f)
-  const unsigned xs = __dp4a(sw, m | (nm << 8), 0u);                     // g*m + f*(255-m)
-  const unsigned ys = xs + 1u + (xs >> 8);                               // result in byte 1
-  return __byte_perm(y, ys, T_SEL);
-}
 
 template <bool OUT, bool YUYV>
 __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
@@ -454,10 +408,10 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
     //      whatever the interpolation weights are (their sums are 2048 +- 1), so A1/A2/B are skipped. ----
     unsigned p_and = 255u, p_or = 0u;
     {
-      const uint8_t* src = a.ofinal + (size_t)b * a.ow * a.oh + (size_t)(a.out_y + rmin) * a.ow + a.out_x + cmin;
+      const uint8_t* src = a.ofinal + (size_t)b * a.opitch * a.oh + (size_t)(a.out_y + rmin) * a.opitch + a.out_x + cmin;
       for (int r = warp; r < nrows; r += 8)
         for (int c = lane; c < ncols; c += 32) {
-          const unsigned v = src[(size_t)r * a.ow + c];
+          const unsigned v = src[(size_t)r * a.opitch + c];
           Ps[r * PF_PS + c] = (uint8_t)v;
           p_and &= v; p_or |= v;
         }
@@ -551,35 +505,7 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   // ---- C: horizontal 5-sums on packed lanes -> 16 mask values ----
   unsigned m[PF_PX];
   const bool row_in = hits_roi && y >= a.roi_y && y < a.roi_y + a.roi_h;
-  if (row_in && tile_const >= 0) {
-#pragma unroll
-    for (int i = 0; i < PF_PX; ++i) m[i] = (unsigned)tile_const;
-    if (x0 < a.roi_x || x0 + PF_PX > a.roi_x + a.roi_w) {
-#pragma unroll
-      for (int i = 0; i < PF_PX; ++i) if (x0 + i < a.roi_x || x0 + i >= a.roi_x + a.roi_w) m[i] = 255u;
-    }
-  } else if (row_in) {
-    const uint4* vq = reinterpret_cast<const uint4*>(Vs + ly * PF_US + lx);
-    const uint4 q0 = vq[0], q1 = vq[1];
-    const uint2 q2 = *reinterpret_cast<const uint2*>(vq + 2);
-    const unsigned w[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-    unsigned c[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) c[k] = __byte_perm(w[k], w[k + 1], 0x5432);
-#pragma unroll
-    for (int k = 1; k <= 8; ++k) {
-      const unsigned s = w[k - 1] + w[k] + w[k + 1] + c[k - 1] + c[k];
-      m[2 * (k - 1)] = ((s & 0xffffu) * 5243u + 62916u) >> 17;          // (S + 12) / 25
-      m[2 * (k - 1) + 1] = ((s >> 16) * 5243u + 62916u) >> 17;
-    }
-    if (x0 < a.roi_x || x0 + PF_PX > a.roi_x + a.roi_w) {
-#pragma unroll
-      for (int i = 0; i < PF_PX; ++i) if (x0 + i < a.roi_x || x0 + i >= a.roi_x + a.roi_w) m[i] = 255u;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < PF_PX; ++i) m[i] = 255u;
-  }
+  post_mask16(a, row_in, tile_const, x0, Vs + ly * PF_US + lx, m);
 
   if (a.mask) {
     uint4 mv;
@@ -591,49 +517,9 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
   }
   if (!(OUT || YUYV)) return;
 
-  // ---- D: blend, 4 pixels = 3 words at a time.  Most 16-pixel runs are entirely background
-  //      (mask 255 -> out = bg) or entirely person (mask 0 -> out = frame): those skip the arithmetic. ----
+  // ---- D: blend (+ RGB->YUV) ----
   unsigned o[12], yy[8];
-  unsigned m_and = m[0], m_or = m[0];
-#pragma unroll
-  for (int i = 1; i < PF_PX; ++i) { m_and &= m[i]; m_or |= m[i]; }
-  const bool all_bg = m_and == 255u, all_fg = m_or == 0u;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const unsigned fA = f[3 * q], fB = f[3 * q + 1], fC = f[3 * q + 2];
-    const unsigned gA = g[3 * q], gB = g[3 * q + 1], gC = g[3 * q + 2];
-    // T = (c0, c1, c2, -) per pixel
-    unsigned T0, T1, T2, T3;
-    if (all_bg || all_fg) {
-      const unsigned sA = all_bg ? gA : fA, sB = all_bg ? gB : fB, sC = all_bg ? gC : fC;
-      T0 = sA; T1 = __byte_perm(sA, sB, 0x0543); T2 = __byte_perm(sB, sC, 0x0432); T3 = sC >> 8;
-      if (OUT) { o[3 * q] = sA; o[3 * q + 1] = sB; o[3 * q + 2] = sC; }
-    } else {
-      T0 = blend_px<0x4140, 0x6262, 0x0531>(gA, fA, gA, fA, m[4 * q]);          // A.b0 A.b1 | A.b2
-      T1 = blend_px<0x4140, 0x7373, 0x0315>(gB, fB, gA, fA, m[4 * q + 1]);      // B.b0 B.b1 | A.b3 (c0)
-      T2 = blend_px<0x4342, 0x4040, 0x0531>(gB, fB, gC, fC, m[4 * q + 2]);      // B.b2 B.b3 | C.b0
-      T3 = blend_px<0x4241, 0x7373, 0x0531>(gC, fC, gC, fC, m[4 * q + 3]);      // C.b1 C.b2 | C.b3
-      if (OUT) {
-        o[3 * q] = __byte_perm(T0, T1, 0x4210);
-        o[3 * q + 1] = __byte_perm(T1, T2, 0x5421);
-        o[3 * q + 2] = __byte_perm(T2, T3, 0x6542);
-      }
-    }
-    if (YUYV) {
-      const unsigned T[4] = {T0, T1, T2, T3};
-      unsigned Y[4], U[4]; int V[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned y14 = __dp2a_hi(1868u, T[j], __dp2a_lo(4899u | (9617u << 16), T[j], 8192u));
-        Y[j] = y14 >> 14;
-        U[j] = __dp2a_hi(8061u, T[j], 2105344u - 8061u * Y[j]) >> 14;
-        V[j] = (int)__dp2a_lo(14369u, T[j], 2105344u - 14369u * Y[j]) >> 14;
-        V[j] = min(max(V[j], 0), 255);
-      }
-      yy[2 * q] = Y[0] | ((unsigned)((V[0] + V[1]) >> 1) << 8) | (Y[1] << 16) | (((U[0] + U[1]) >> 1) << 24);
-      yy[2 * q + 1] = Y[2] | ((unsigned)((V[2] + V[3]) >> 1) << 8) | (Y[3] << 16) | (((U[2] + U[3]) >> 1) << 24);
-    }
-  }
+  post_blend16<OUT, YUYV>(f, g, m, o, yy);
   if (OUT) {
     uint8_t* op = a.out + (size_t)b * a.out_stride + (size_t)y * a.out_pitch + (size_t)x0 * 3;
     if (a.wide) store48_wide(op, (tid & 1) != 0, o);
@@ -668,7 +554,10 @@ static bool post_fast_ok(const PostArgs& a) {
   return true;
 }
 
+bool launch_post_tma(cudaStream_t s, const PostArgs& a);   // kernels_post.cu
+
 void launch_post(cudaStream_t s, const PostArgs& a_in) {
+  if (launch_post_tma(s, a_in)) return;
   PostArgs a = a_in;
   // measurement switches (profiles/r1_post_ab_run29.txt): both on is the fastest at 720p and at 4k
   const int wide_en = tuning().post_wide;
@@ -749,22 +638,8 @@ __global__ void __launch_bounds__(256) k_yuyv_to_bgr(const uint8_t* yuyv, uint8_
   } else {
     for (int i = 0; i < 2 * n; ++i) w[i >> 2] |= (unsigned)yuyv[2 * p0 + i] << (8 * (i & 3));
   }
-  unsigned o[6] = {0u, 0u, 0u, 0u, 0u, 0u};   // 24 output bytes, assembled in registers
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int u = (int)((w[k] >> 8) & 255u) - 128, v = (int)(w[k] >> 24) - 128;
-    const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int yy = max((int)((w[k] >> (16 * h)) & 255u) - 16, 0) * 1220542;
-      const unsigned px[3] = {bsb_sat_u8((yy + buv) >> 20), bsb_sat_u8((yy + guv) >> 20), bsb_sat_u8((yy + ruv) >> 20)};
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int byte = 6 * k + 3 * h + c;
-        o[byte >> 2] |= px[c] << (8 * (byte & 3));
-      }
-    }
-  }
+  unsigned o[6];                              // 24 output bytes, assembled in registers
+  yuyv8_to_bgr24(w, o);
   // full blocks: stage the 24-byte groups in shared memory and write 16-byte vectors (a warp then writes 768
   // contiguous bytes in 1.5 passes instead of three 8-byte-strided passes that each touch every sector)
   __shared__ __align__(16) uint2 stage[256 * 3];

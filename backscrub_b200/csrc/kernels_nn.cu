@@ -17,7 +17,9 @@ namespace bsb {
 
 static std::atomic<long> g_launches{0};
 long launch_count() { return g_launches.load(); }
-void count_launch() { g_launches.fetch_add(1); }
+static thread_local long t_launches = 0;
+long thread_launch_count() { return t_launches; }
+void count_launch() { g_launches.fetch_add(1); ++t_launches; }
 
 Tuning& tuning() { static Tuning t; return t; }
 

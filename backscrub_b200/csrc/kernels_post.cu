@@ -1,0 +1,363 @@
+// backscrub_b200/csrc/kernels_post.cu — TMA-staged variant of the fused post stage (sm_100a).
+//
+// Same stage as k_post_fast (kernels_img.cu): mask upsample (cv::resize 8UC1) + cv::blur 5x5 inside the ROI
+// (lib/libbackscrub.cc:366-371), alpha_blend (app/deepseg.cc:108-134), convert_rgb_to_yuyv (:87-106), mask store —
+// reorganised around the copy engine:
+//   * every global access of the tile is a TMA bulk tensor copy (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG)
+//     between global memory and shared memory, issued by one thread: no per-thread address arithmetic, no
+//     sector bookkeeping, image edges clipped by the tensor map;
+//   * the source patch of the small mask arrives first; if it is uniformly 255 (background) or 0 (person) — exact
+//     for any interpolation weights, see k_post_fast — the tile needs NO per-pixel arithmetic on the copy path:
+//       background tile:  out <- background tile, YUYV <- cached YUYV of the background, mask <- 255
+//                         (the camera frame is not even read),
+//       person tile:      out <- frame tile (camera YUYV converted per thread when the frames are in wire format),
+//       mixed tile:       the k_post_fast arithmetic on shared-memory operands;
+//   * results are staged in shared memory and leave with TMA stores.
+// Arithmetic is shared with k_post_fast through post_math.h, so both kernels produce the oracle's bits.
+#include "kernels.h"
+#include "post_math.h"
+
+#ifndef BSB_EMU
+#include <cuda.h>   // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time (no libcuda link)
+#endif
+
+namespace bsb {
+
+void count_launch();
+
+#ifndef BSB_EMU
+
+namespace tma {
+BSB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BSB_D void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+BSB_D void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+BSB_D void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+BSB_D bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+BSB_D void mbar_wait(uint64_t* bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
+BSB_D void load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+BSB_D void store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+BSB_D void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+BSB_D void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+BSB_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+BSB_D void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory"); }
+}  // namespace tma
+
+struct PostMaps { CUtensorMap frame, bg, bgy, out, yuyv, mask, ofinal; };
+struct PostTmaCfg { int has_out, has_yuyv, has_mask, has_bgy; };
+
+// patch of the small mask a 36 x 132 halo tile can touch: rows <= PT_RMAX, columns <= PT_PW (up-scales >= ~1.75x)
+constexpr int PT_RMAX = 24, PT_PW = 80;
+constexpr int PT_OFF_F = 0, PT_OFF_B = 12288, PT_OFF_Y = 24576, PT_OFF_M = 32768, PT_OFF_P = 36864;
+constexpr int PT_OFF_HS = PT_OFF_P + 2048;                       // [PT_RMAX][PF_US] u16
+constexpr int PT_OFF_US = PT_OFF_HS + PT_RMAX * PF_US * 2;       // [PF_UH][PF_US] u16
+constexpr int PT_OFF_VS = PT_OFF_US + PF_UH * PF_US * 2;         // [PF_H][PF_US] u16
+constexpr int PT_OFF_ROWS = PT_OFF_VS + PF_H * PF_US * 2;        // [PF_UH] uint4
+constexpr int PT_OFF_BAR = PT_OFF_ROWS + PF_UH * 16;
+constexpr int PT_SMEM = PT_OFF_BAR + 64;
+static_assert(PT_RMAX * PT_PW <= 2048 && PT_OFF_HS % 16 == 0 && PT_OFF_US % 16 == 0 && PT_OFF_VS % 16 == 0 && PT_OFF_ROWS % 16 == 0 && PT_OFF_BAR % 8 == 0, "smem layout");
+
+template <bool IN_YUYV>
+__global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint8_t* sF = smem + PT_OFF_F;            // frame tile [32][384] (BGR) or [32][256] (YUYV); later the blended tile
+  uint8_t* sB = smem + PT_OFF_B;            // background tile [32][384]
+  uint8_t* sY = smem + PT_OFF_Y;            // YUYV tile [32][256]: cached background YUYV in, result out
+  uint8_t* sM = smem + PT_OFF_M;            // mask tile [32][128]
+  uint8_t* sP = smem + PT_OFF_P;            // source patch of the small mask [PT_RMAX][PT_PW]
+  unsigned short* Hs = reinterpret_cast<unsigned short*>(smem + PT_OFF_HS);
+  unsigned short* Us = reinterpret_cast<unsigned short*>(smem + PT_OFF_US);
+  unsigned short* Vs = reinterpret_cast<unsigned short*>(smem + PT_OFF_VS);
+  uint4* rows = reinterpret_cast<uint4*>(smem + PT_OFF_ROWS);
+  uint64_t* barP = reinterpret_cast<uint64_t*>(smem + PT_OFF_BAR);
+  uint64_t* barB = barP + 1;
+  uint64_t* barF = barP + 2;
+
+  const int b = blockIdx.z;
+  const int tx0 = blockIdx.x * PF_W, ty0 = blockIdx.y * PF_H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + PF_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+
+  if (tid == 0) {
+    tma::mbar_init(barP, 1); tma::mbar_init(barB, 1); tma::mbar_init(barF, 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
+  int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0;
+  if (hits_roi) {
+    gy_lo = ty0 - a.roi_y - 2; gx_lo = tx0 - a.roi_x - 2;
+    const int gy_hi = gy_lo + PF_UH - 1, gx_hi = gx_lo + PF_UW - 1;
+    const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
+    const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
+    const int gx_min = gx_lo < 0 ? 0 : min(gx_lo, a.roi_w - 1);
+    const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
+    rmin = __ldg(a.tab.yofs0 + gy_min);
+    nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
+    cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
+    ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
+  }
+  if (tid == 0) {
+    if (hits_roi) {
+      tma::mbar_expect_tx(barP, PT_RMAX * PT_PW);
+      tma::load_3d(sP, &tm.ofinal, a.out_x + cmin, a.out_y + rmin, b, barP);
+    }
+    // the background tile (L2-resident for a still image) and its cached YUYV are fetched speculatively: a
+    // background tile then needs nothing else, and a mixed tile has its second operand early
+    int bgi = 0;
+    if (a.bg_cursor) bgi = (int)(((unsigned)__ldg(a.bg_cursor) + (unsigned)b * (unsigned)a.bg_advance) % (unsigned)a.bg_count);
+    else if (a.bg_stride) bgi = b;
+    tma::mbar_expect_tx(barB, 12288u + (cfg.has_bgy ? 8192u : 0u));
+    tma::load_3d(sB, &tm.bg, blockIdx.x * 96, ty0, bgi, barB);
+    if (cfg.has_bgy) tma::load_3d(sY, &tm.bgy, blockIdx.x * 64, ty0, bgi, barB);
+  }
+
+  int tile_const = -1;
+  if (hits_roi) {
+    if (tid >= 192 && tid < 192 + PF_UH) {          // row parameters of the vertical resize pass (used by mixed tiles)
+      const int uy = tid - 192;
+      int gy = gy_lo + uy;
+      gy = gy < 0 ? -gy : gy; gy = gy >= a.roi_h ? 2 * a.roi_h - 2 - gy : gy;     // reflect-101 (single fold)
+      gy = min(max(gy, 0), a.roi_h - 1);
+      rows[uy] = make_uint4((unsigned)__ldg(a.tab.yofs0 + gy), (unsigned)__ldg(a.tab.yofs1 + gy),
+                            (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
+    }
+    tma::mbar_wait(barP, 0);
+    unsigned p_and = 255u, p_or = 0u;
+    for (int r = warp; r < nrows; r += 8)
+      for (int c = lane; c < ncols; c += 32) { const unsigned v = sP[r * PT_PW + c]; p_and &= v; p_or |= v; }
+    const int all_hi = __syncthreads_and(p_and == 255u);
+    const int all_lo = all_hi ? 0 : __syncthreads_and(p_or == 0u);
+    tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
+  }
+  const bool inside = tx0 >= a.roi_x && min(tx0 + PF_W, a.W) <= a.roi_x + a.roi_w && ty0 >= a.roi_y && min(ty0 + PF_H, a.H) <= a.roi_y + a.roi_h;
+  const int kind = (!hits_roi || tile_const == 255) ? 0 : ((tile_const == 0 && inside) ? 1 : 2);   // background / person / mixed
+  if (kind != 0 && tid == 0) {
+    tma::mbar_expect_tx(barF, IN_YUYV ? 8192u : 12288u);
+    tma::load_3d(sF, &tm.frame, blockIdx.x * (IN_YUYV ? 64 : 96), ty0, b, barF);
+  }
+
+  if (kind == 2 && tile_const < 0) {
+    // ---- A1: horizontal pass of cv::resize on the patch rows (see k_post_fast) ----
+    {
+      const int phase = tid >> 7;
+      for (int ux = tid & 127; ux < PF_UW; ux += 128) {
+        int gx = gx_lo + ux;
+        gx = gx < 0 ? -gx : gx; gx = gx >= a.roi_w ? 2 * a.roi_w - 2 - gx : gx;
+        gx = min(max(gx, 0), a.roi_w - 1);
+        const uint2 xc = __ldg(a.tab.xcol + gx);
+        const int sx = (int)(xc.x & 0xffffu) - cmin, sx1 = (int)(xc.x >> 16) - cmin;
+        const int a0 = (int)(short)(xc.y & 0xffffu), a1 = (int)(short)(xc.y >> 16);
+        const uint8_t* pr = sP + phase * PT_PW;
+        unsigned short* hp = Hs + phase * PF_US + ux;
+        for (int r = phase; r < nrows; r += 2) {
+          *hp = (unsigned short)(((int)pr[sx] * a0 + (int)pr[sx1] * a1) >> 4);
+          pr += 2 * PT_PW; hp += 2 * PF_US;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- A2: vertical pass -> upsampled tile ----
+    for (int uy = warp; uy < PF_UH; uy += 8) {
+      const uint4 rp = rows[uy];
+      const unsigned short* h0 = Hs + ((int)rp.x - rmin) * PF_US + lane;
+      const unsigned short* h1 = Hs + ((int)rp.y - rmin) * PF_US + lane;
+      unsigned short* up = Us + uy * PF_US + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        up[32 * k] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[32 * k]) + __umulhi(rp.w, (unsigned)h1[32 * k]) + 2u) >> 2);
+      if (lane < PF_UW - 128)
+        up[128] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[128]) + __umulhi(rp.w, (unsigned)h1[128]) + 2u) >> 2);
+    }
+    __syncthreads();
+    // ---- B: vertical 5-sums, two columns per word, sliding window over 8 rows ----
+    for (int it = tid; it < (PF_UW / 2) * 4; it += 256) {
+      const int pair = it % (PF_UW / 2), seg = it / (PF_UW / 2);
+      const unsigned* up = reinterpret_cast<const unsigned*>(Us + (seg * 8) * PF_US) + pair;
+      unsigned* vp = reinterpret_cast<unsigned*>(Vs + (seg * 8) * PF_US) + pair;
+      unsigned u[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) u[k] = up[k * (PF_US / 2)];
+      unsigned v = u[0] + u[1] + u[2] + u[3] + u[4];
+      vp[0] = v;
+#pragma unroll
+      for (int k = 1; k < 8; ++k) { v = v + u[k + 4] - u[k - 1]; vp[k * (PF_US / 2)] = v; }
+    }
+    __syncthreads();
+  }
+
+  const int lx = (tid & 7) * PF_PX, ly = tid >> 3;
+  const int x0 = tx0 + lx, y = ty0 + ly;
+  uint4* mdst = reinterpret_cast<uint4*>(sM + ly * PF_W + lx);
+  uint4* ydst = reinterpret_cast<uint4*>(sY + ly * (PF_W * 2) + lx * 2);
+  const uint8_t* out_src = sB;
+
+  tma::mbar_wait(barB, 0);          // every tile waits for its speculative loads: shared memory must be quiet at exit
+  if (kind == 0) {
+    // ---- background tile: out = background tile, YUYV = cached YUYV tile, mask = 255.  No per-pixel arithmetic ----
+    if (cfg.has_mask) *mdst = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (cfg.has_yuyv && !cfg.has_bgy) {
+      const uint4* gq = reinterpret_cast<const uint4*>(sB + ly * (PF_W * 3) + lx * 3);
+      const uint4 g0 = gq[0], g1 = gq[1], g2 = gq[2];
+      const unsigned g[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
+      unsigned m[PF_PX], o[12], yy[8];
+#pragma unroll
+      for (int i = 0; i < PF_PX; ++i) m[i] = 255u;
+      post_blend16<false, true>(g, g, m, o, yy);
+      ydst[0] = make_uint4(yy[0], yy[1], yy[2], yy[3]); ydst[1] = make_uint4(yy[4], yy[5], yy[6], yy[7]);
+    }
+  } else {
+    unsigned m[PF_PX];
+    if (kind == 1) {
+#pragma unroll
+      for (int i = 0; i < PF_PX; ++i) m[i] = 0u;
+    } else {
+      const bool row_in = y >= a.roi_y && y < a.roi_y + a.roi_h;
+      post_mask16(a, row_in, tile_const, x0, Vs + ly * PF_US + lx, m);
+    }
+    tma::mbar_wait(barF, 0);
+    unsigned f[12], g[12];
+    if (IN_YUYV) {
+      const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (PF_W * 2) + lx * 2);
+      const uint4 w0 = fq[0], w1 = fq[1];
+      const unsigned wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
+      yuyv8_to_bgr24(wa, f); yuyv8_to_bgr24(wb, f + 6);
+    } else {
+      const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (PF_W * 3) + lx * 3);
+      const uint4 f0 = fq[0], f1 = fq[1], f2 = fq[2];
+      f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
+      f[8] = f2.x; f[9] = f2.y; f[10] = f2.z; f[11] = f2.w;
+    }
+    if (kind == 2) {
+      const uint4* gq = reinterpret_cast<const uint4*>(sB + ly * (PF_W * 3) + lx * 3);
+      const uint4 g0 = gq[0], g1 = gq[1], g2 = gq[2];
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+      g[8] = g2.x; g[9] = g2.y; g[10] = g2.z; g[11] = g2.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) g[i] = f[i];
+    }
+    unsigned o[12], yy[8];
+    post_blend16<true, true>(f, g, m, o, yy);
+    if (IN_YUYV) __syncthreads();                     // the YUYV tile is fully consumed before the (wider) BGR tile overwrites it
+    uint4* odst = reinterpret_cast<uint4*>(sF + ly * (PF_W * 3) + lx * 3);
+    odst[0] = make_uint4(o[0], o[1], o[2], o[3]); odst[1] = make_uint4(o[4], o[5], o[6], o[7]); odst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    ydst[0] = make_uint4(yy[0], yy[1], yy[2], yy[3]); ydst[1] = make_uint4(yy[4], yy[5], yy[6], yy[7]);
+    *mdst = make_uint4(m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24), m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24),
+                       m[8] | (m[9] << 8) | (m[10] << 16) | (m[11] << 24), m[12] | (m[13] << 8) | (m[14] << 16) | (m[15] << 24));
+    out_src = sF;
+  }
+  tma::fence_proxy_async();          // generic-proxy writes of the staging tiles -> visible to the TMA engine
+  __syncthreads();
+  if (tid == 0) {
+    if (cfg.has_out) tma::store_3d(&tm.out, out_src, blockIdx.x * 96, ty0, b);
+    if (cfg.has_yuyv) tma::store_3d(&tm.yuyv, sY, blockIdx.x * 64, ty0, b);
+    if (cfg.has_mask) tma::store_3d(&tm.mask, sM, tx0, ty0, b);
+    tma::store_commit();
+    tma::store_wait_read();          // shared memory may be handed to the next CTA only after the engine has read it
+  }
+}
+
+// ---- host side: tensor maps --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// [n2][n1][row_bytes] bytes, row pitch / plane stride in bytes; box = box_bytes x box_rows x 1.  Elements are 32-bit
+// words when `words` (row_bytes % 4 == 0), else bytes.
+static bool make_map(CUtensorMap* m, const void* base, bool words, size_t row_bytes, size_t n1, size_t n2, size_t pitch, size_t stride,
+                     unsigned box_bytes, unsigned box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  const unsigned es = words ? 4u : 1u;
+  const cuuint64_t gdim[3] = {row_bytes / es, n1, n2 ? n2 : 1};
+  const cuuint64_t gstr[2] = {pitch, stride ? stride : pitch * n1};
+  const cuuint32_t box[3] = {box_bytes / es, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, words ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool build_post_maps(const PostArgs& a, PostMaps* tm) {
+  const size_t W = (size_t)a.W, H = (size_t)a.H, B = (size_t)a.B;
+  const size_t nbg = a.bg_cursor ? (size_t)a.bg_count : (a.bg_stride ? B : 1);
+  bool ok = true;
+  if (a.yuyv_in) ok = ok && make_map(&tm->frame, a.yuyv_in, true, W * 2, H, B, W * 2, a.yuyv_in_stride, 256, PF_H);
+  else ok = ok && make_map(&tm->frame, a.frames, true, W * 3, H, B, a.frame_pitch, a.frame_stride, 384, PF_H);
+  ok = ok && make_map(&tm->bg, a.bg, true, W * 3, H, nbg, a.bg_pitch, a.bg_stride ? a.bg_stride : a.bg_pitch * H, 384, PF_H);
+  // unused maps still have to be valid descriptors: alias them to a live one
+  if (a.bg_yuyv) ok = ok && make_map(&tm->bgy, a.bg_yuyv, true, W * 2, H, nbg, W * 2, W * 2 * H, 256, PF_H); else tm->bgy = tm->bg;
+  if (a.out) ok = ok && make_map(&tm->out, a.out, true, W * 3, H, B, a.out_pitch, a.out_stride, 384, PF_H); else tm->out = tm->bg;
+  if (a.yuyv) ok = ok && make_map(&tm->yuyv, a.yuyv, true, W * 2, H, B, W * 2, a.yuyv_stride, 256, PF_H); else tm->yuyv = tm->bg;
+  if (a.mask) ok = ok && make_map(&tm->mask, a.mask, false, W, H, B, W, a.mask_stride, PF_W, PF_H); else tm->mask = tm->bg;
+  ok = ok && make_map(&tm->ofinal, a.ofinal, false, (size_t)a.ow, (size_t)a.oh, B, (size_t)a.opitch, (size_t)a.opitch * a.oh, PT_PW, PT_RMAX);
+  return ok;
+}
+
+static bool post_tma_shape_ok(const PostArgs& a) {
+  if (!tuning().post_tma || !encode_fn()) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.B < 1 || a.W % 16 != 0 || a.area2x2 || a.tab.xcol == nullptr) return false;
+  if (a.yuyv_in) { if (!al16(a.yuyv_in) || a.yuyv_in_stride % 16) return false; }
+  else if (!al16(a.frames) || a.frame_pitch % 16 || a.frame_stride % 16) return false;
+  if (!al16(a.bg) || a.bg_pitch % 16 || a.bg_stride % 16 || (a.bg_yuyv && !al16(a.bg_yuyv))) return false;
+  if (a.out && (!al16(a.out) || a.out_pitch % 16 || a.out_stride % 16)) return false;
+  if (a.yuyv && (!al16(a.yuyv) || a.yuyv_stride % 16)) return false;
+  if (a.mask && (!al16(a.mask) || a.mask_stride % 16)) return false;
+  if (!(a.out || a.yuyv || a.mask) || !al16(a.ofinal) || a.opitch % 16) return false;
+  if (a.ow > 32000 || a.oh > 32000 || a.roi_w < 8 || a.roi_h < 8) return false;
+  const double scale_y = (double)a.out_h / (double)a.roi_h, scale_x = (double)a.out_w / (double)a.roi_w;
+  if ((int)(PF_UH * scale_y) + 3 > PT_RMAX || (int)(PF_UW * scale_x) + 4 > PT_PW) return false;
+  return true;
+}
+
+bool post_tma_eligible(const PostArgs& a) {
+  PostMaps tm;
+  return post_tma_shape_ok(a) && build_post_maps(a, &tm);
+}
+
+bool launch_post_tma(cudaStream_t s, const PostArgs& a) {
+  PostMaps tm;
+  if (!post_tma_shape_ok(a) || !build_post_maps(a, &tm)) return false;
+  PostTmaCfg cfg{a.out ? 1 : 0, a.yuyv ? 1 : 0, a.mask ? 1 : 0, a.bg_yuyv ? 1 : 0};
+  const dim3 grid((unsigned)ceil_div(a.W, PF_W), (unsigned)ceil_div(a.H, PF_H), (unsigned)a.B);
+  if (a.yuyv_in) {
+    if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_post_tma<true>), PT_SMEM)) return false;
+    k_post_tma<true><<<grid, 256, PT_SMEM, s>>>(tm, a, cfg);
+  } else {
+    if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_post_tma<false>), PT_SMEM)) return false;
+    k_post_tma<false><<<grid, 256, PT_SMEM, s>>>(tm, a, cfg);
+  }
+  count_launch();
+  return true;
+}
+
+#else   // BSB_EMU: TMA cannot be emulated; the emulator build always takes k_post_fast / k_post
+
+bool post_tma_eligible(const PostArgs&) { return false; }
+bool launch_post_tma(cudaStream_t, const PostArgs&) { return false; }
+
+#endif
+
+}  // namespace bsb

@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--tensor-cores", action="store_true", help="tcgen05 3xTF32 pointwise convs (not bit-exact; IoU-validated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs (parsed.configs)")
+    ap.add_argument("--frames", default="person", choices=["person", "noise", "const"], help="synthetic stream kind (SURVEY 8d)")
+    ap.add_argument("--launches-per-step", type=int, default=4, help="graph launches per stream per timed step (lengthens the timed window)")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="bsb_set_tuning switch (A/B runs): pw_variant, dw_plane, post_tma, ...")
     return ap.parse_args()
 
 
@@ -90,9 +94,14 @@ def background_ring(wl):
     return np.stack([np.roll(still, 16 * i, axis=1) for i in range(RING_FRAMES)]), "synthetic ring (video decode unavailable)"
 
 
-def synthetic_frames(W, H, n, stream):
+def synthetic_frames(W, H, n, stream, kind="person"):
     from tests import synth
-    return np.stack([synth.frame(W, H, t=t, stream=stream) for t in range(n)])
+    return np.stack([synth.frame(W, H, t=t, stream=stream, kind=kind) for t in range(n)])
+
+
+def synthetic_yuyv(W, H, n, stream, kind="person"):
+    from tests import synth
+    return np.stack([synth.yuyv_frame(W, H, t=t, stream=stream, kind=kind) for t in range(n)])
 
 
 # ----------------------------------------------------------------------------------------
@@ -173,6 +182,19 @@ def cnn_calibration(wl):
     return out
 
 
+def tflite_probe():
+    """is a real TFLite runtime importable on this box?  (It is not in this image; when one
+    is, cpu_path_fps should be pointed at it — recorded so the reader knows which CPU arm ran.)"""
+    found = []
+    for mod in ("tflite_runtime.interpreter", "ai_edge_litert.interpreter", "tensorflow.lite"):
+        try:
+            __import__(mod)
+            found.append(mod)
+        except Exception:
+            pass
+    return {"importable": found, "used": "oracle port" if not found else "oracle port (runtime found but the XNNPACK arm is not wired up)"}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -203,10 +225,10 @@ def run_reference(args, wl):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_time / len(vals), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-        "config": {"workload": wl["desc"], "frames_per_step": threads * fpt, "bgblur": args.bgblur or None,
-                   "background": "blurred camera frame" if args.camera_blur else ("animated" if wl.get("animated") else "still image")},
+        "config": workload_config(wl, args, 0, 0, 0, 1, {"frames_per_step": threads * fpt}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{threads} threads x {fpt} frame(s) per step, oracle port of TFLite-reference kernels + OpenCV ops"},
+                         "sample": f"{threads} threads x {fpt} frame(s) per step, oracle port of TFLite-reference kernels + OpenCV ops",
+                         "tflite_probe": tflite_probe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -272,11 +294,213 @@ def bind_near_gpu(torch, dev):
     return old
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def post_bytes(W, H, ow, oh, B, yuyv_in, bg_per_frame, bg_cache):
+    """Algorithmic HBM bytes of ONE launch of the fused blur+composite kernel over B frames:
+    per frame: camera frame in (3WH as BGR, 2WH when the kernel reads the camera YUYV itself) + RGB composite out (3WH) +
+    YUYV out (2WH) + full-resolution mask out (WH) + the small mask (ow*oh);
+    background: 3WH per frame for an animated / per-frame background, but ONCE per launch for a still image (every frame
+    of the launch blends the same L2-resident image; round 1 counted it per frame, which overstated the fraction)."""
+    npx = W * H
+    per_frame = (2 if yuyv_in else 3) * npx + 3 * npx + 2 * npx + npx + ow * oh
+    bg = 3 * npx + (2 * npx if bg_cache else 0)
+    return B * per_frame + (B * bg if bg_per_frame else bg)
+
+
+def measure(args, wl, key, dev, rank, world, S, B, steps, warmup, lps, with_e2e, with_clocks, kind="person"):
+    """One workload on this rank's GPU: device-resident throughput, optional end-to-end, per-stage times, rooflines."""
+    import torch
+
+    import backscrub_b200 as bs
+    from backscrub_b200 import sharding
+    from tests import synth
+
+    W, H = wl["W"], wl["H"]
+    model = os.path.join(ROOT, "models", wl["model"])
+    fb, npx = W * H * 3, W * H
+    R = 2                                     # ring slots per stream: S*R*B frames in + out exceed the 126 MB L2
+    bg = synth.background()
+    bg_desc = "still 1280x720 PNG (resized once; read from L2)"
+    ring_frames = None
+    if wl.get("animated"):
+        ring_frames, bg_desc = background_ring(wl)
+    if args.camera_blur:
+        bg_desc = "none: the Gaussian-blurred camera frame (app/deepseg.cc:652-658)"
+    my_streams = sharding.streams_for_rank(world * S, rank, world)      # stream ids served by this GPU
+    ctxs, rings = [], []
+    for s in range(S):
+        c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=4 if args.tensor_cores else 0)
+        if ring_frames is not None and not args.camera_blur:
+            c.set_background_ring(ring_frames, advance=1)
+        elif not args.camera_blur:
+            c.set_background(bg)
+        if args.bgblur:
+            c.set_bgblur(args.bgblur)
+        ctxs.append(c)
+        host = synthetic_yuyv(W, H, B, stream=my_streams[s], kind=kind)     # camera-format input frames (plain numpy)
+        slots = []
+        for r in range(R):
+            d_in = torch.from_numpy(host).to(f"cuda:{dev}")
+            slots.append(dict(d_in=d_in, d_out=torch.empty((B, H, W, 3), dtype=torch.uint8, device=f"cuda:{dev}"),
+                              d_yuyv=torch.empty((B, H, W, 2), dtype=torch.uint8, device=f"cuda:{dev}"),
+                              d_mask=torch.empty((B, H, W), dtype=torch.uint8, device=f"cuda:{dev}")))
+        rings.append(dict(host=host, slots=slots))
+    ext = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+
+    def step(i):
+        for l in range(lps):
+            r = (i * lps + l) % R
+            for s, c in enumerate(ctxs):
+                sl = rings[s]["slots"][r]
+                c.composite_yuyv_device(B, sl["d_in"].data_ptr(), sl["d_out"].data_ptr(), sl["d_yuyv"].data_ptr(), sl["d_mask"].data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    sampler = ClockSampler(dev) if (with_clocks and rank == 0) else None      # samples through the value + e2e regions
+    for i in range(warmup):
+        step(i)
+    barrier()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    ev0.record(ext[0])
+    for e in ext[1:]:
+        e.wait_event(ev0)
+    for i in range(steps):
+        step(warmup + i)
+    for e, s in zip(ev1, ext):
+        e.record(s)
+    barrier()
+    ms = max(ev0.elapsed_time(e) for e in ev1)
+    frames_total, secs, value = sharding.reduce_throughput(S * B * lps * steps, ms * 1e-3,
+                                                            torch.distributed if world > 1 else None, f"cuda:{dev}")
+    ms = secs * 1e3
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + graph + D2H every step) ----
+    e2e = None
+    if with_e2e:
+        pin = lambda shape: torch.empty(shape, dtype=torch.uint8).pin_memory()
+        hb = []
+        for s in range(S):
+            h_in = pin((B, H, W, 2)); h_in.numpy()[:] = rings[s]["host"]
+            hb.append(dict(inp=h_in.numpy(), yuyv=pin((B, H, W, 2)).numpy(), keep=h_in))
+        e_steps = max(3, steps * lps // 2)
+
+        def worker(s, n):
+            for _ in range(n):
+                # the frame deepseg.cc hands to the loopback device is the YUYV one (app/deepseg.cc:681-690)
+                ctxs[s].composite_yuyv_into(hb[s]["inp"], yuyv=hb[s]["yuyv"])
+
+        def run_threads(n):
+            th = [threading.Thread(target=worker, args=(s, n)) for s in range(S)]
+            for t in th: t.start()
+            for t in th: t.join()
+
+        run_threads(2)
+        barrier()
+        t0 = time.perf_counter()
+        run_threads(e_steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=f"cuda:{dev}")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * npx * 2,
+               "d2h_bytes_per_step": S * B * npx * 2, "steps": e_steps, "frames_per_step": world * S * B,
+               "pcie_gbs_each_direction": world * S * B * e_steps * npx * 2 / dt / 1e9 / world,
+               "input": "camera YUYV frame in pinned host memory (read in place by the GPU kernels; app/deepseg.cc:553 converts it on the CPU)",
+               "result": "YUYV frame (what app/deepseg.cc:681-690 writes to the v4l2 loopback device)"}
+
+    if sampler:
+        # keep the GPU under the same load until nvidia-smi has delivered a few samples (it needs ~0.3 s to start)
+        t_end = time.perf_counter() + 1.0
+        i = 0
+        while time.perf_counter() < t_end:
+            step(warmup + steps + i); i += 1
+            if i % 4 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- per-stage device times + rooflines ----
+    stages = {}
+    c0 = ctxs[0]
+    for name, st in [("pre", 0), ("cnn", 1), ("decision", 2), ("post", 3), ("all", 4)]:
+        stages[name + "_ms_per_frame"] = c0.time_stage(st, B, 5) / B
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    oh, ow = c0.out_hwc[0], c0.out_hwc[1]
+    yuyv_native = bool(c0.yuyv_native)
+    bg_per_frame = bool(wl.get("animated")) or args.camera_blur
+    bytes_launch = post_bytes(W, H, ow, oh, B, yuyv_native, bg_per_frame, bg_cache=yuyv_native and not args.camera_blur)
+    t_post = c0.time_stage(3, B, 10) * 1e-3                    # seconds per launch (B frames), CUDA events on the context's stream
+    achieved = bytes_launch / t_post / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "post_traffic.json")))
+        traffic = tr.get(key, {}).get(f"{B}:{kind}")
+    except Exception:
+        pass
+    if args.bgblur:
+        traffic = None                                          # captured for the un-blurred configurations only
+    roi = c0.roidim
+    # whole-pipeline algorithmic HBM bytes per frame: camera frame read by the pre-processing stage (ROI, in its wire format)
+    # + the post stage; a BGR materialisation (2WH in + 3WH out) is added when the frames cannot stay in YUYV
+    pipeline_bytes = (2 if yuyv_native else 3) * roi[2] * roi[3] + bytes_launch / B + (0 if yuyv_native else 5 * npx)
+    flops = c0.flops
+    t_cnn = stages["cnn_ms_per_frame"] * 1e-3
+    roofline = {"bound": "hbm", "kernel": "k_post_tma" if yuyv_native else "k_post_fast",
+                "what": "mask upsample + 5x5 blur + alpha blend + RGB->YUYV + mask (one launch = %d frames)" % B,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/post_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
+                "traffic_frac_of_peak": (traffic / t_post / 1e9 / peak) if traffic else None,
+                "bytes_per_launch": bytes_launch, "ms_per_launch": t_post * 1e3,
+                "bytes_formula": "B*(%s frame + 3WH out + 2WH yuyv + WH mask + ow*oh) + background %s" %
+                                 ("2WH" if yuyv_native else "3WH", "per frame" if bg_per_frame else "ONCE per launch (still image)"),
+                "frames": kind,
+                "pipeline_bytes_per_frame": pipeline_bytes, "pipeline_hbm_frac": value * pipeline_bytes / 1e9 / (peak * world),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                # the CNN is not HBM-bound: report it against the FFMA pipe (148 SMs x 128 lanes x 2 x SM clock)
+                "cnn": {"mflop_per_frame": flops / 1e6, "us_per_frame_one_stream": t_cnn * 1e6,
+                        "achieved_tflops_one_stream": flops / t_cnn / 1e12,
+                        "achieved_tflops_pipeline": flops * value / world / 1e12,
+                        "ffma_peak_tflops": 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
+                        "launches_per_call": c0.launches_per_call}}
+
+    res = dict(value=value, ms=ms, e2e=e2e, clocks=clocks, stages=stages, roofline=roofline, S=S, B=B, lps=lps,
+               launches=c0.launches_per_call, bg_desc=bg_desc, flops=flops, yuyv_native=yuyv_native, steps=steps)
+    for c in ctxs:
+        bs.bs_maskgen_delete(c)
+    del rings, ctxs
+    torch.cuda.empty_cache()
+    return res
+
+
+def workload_config(wl, args, S, B, lps, world, extra=None):
+    """config keys shared by both arms (the driver compares them)"""
+    cfg = {"workload": wl["desc"], "frames": args.frames, "input": "camera YUYV frames", "outputs": "RGB composite + YUYV + mask",
+           "background": "blurred camera frame" if args.camera_blur else ("animated (one decoded image per frame)" if wl.get("animated") else "still image"),
+           "bgblur": args.bgblur or None}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 def run_b200(args, wl):
     import torch
 
     import backscrub_b200 as bs
-    from tests import synth
 
     rank, world, local = dist_env()
     if world > 1:
@@ -300,152 +524,29 @@ def run_b200(args, wl):
     bound_cpus = len(os.sched_getaffinity(0))
     if bs.device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: backscrub_b200 has no CPU path")
-    W, H = wl["W"], wl["H"]
-    S, B = args.streams or wl.get("streams", 8), args.batch or wl.get("batch", 32)
     if args.camera_blur and not args.bgblur:
         raise SystemExit("--camera-blur needs --bgblur K")
-    model = os.path.join(ROOT, "models", wl["model"])
-    fb, npx = W * H * 3, W * H
-    R = 2                                     # ring slots per stream: S*R*B frames in + out exceed the 126 MB L2
-    bg = synth.background()
-    bg_desc = "still 1280x720 PNG (resized once; read from L2)"
-    if wl.get("animated"):
-        ring_frames, bg_desc = background_ring(wl)
-    if args.camera_blur:
-        bg_desc = "none: the Gaussian-blurred camera frame (app/deepseg.cc:652-658)"
-    from backscrub_b200 import sharding
-    my_streams = sharding.streams_for_rank(world * S, rank, world)      # stream ids served by this GPU
-    ctxs, rings = [], []
-    for s in range(S):
-        c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=4 if args.tensor_cores else 0)
-        if wl.get("animated") and not args.camera_blur:
-            c.set_background_ring(ring_frames, advance=1)
-        elif not args.camera_blur:
-            c.set_background(bg)
-        if args.bgblur:
-            c.set_bgblur(args.bgblur)
-        ctxs.append(c)
-        from oracle import pyoracle as _po        # only to synthesise camera-format (YUYV) input frames
-        host = np.stack([_po.convert_rgb_to_yuyv(f) for f in synthetic_frames(W, H, B, stream=my_streams[s])])
-        slots = []
-        for r in range(R):
-            d_in = torch.from_numpy(host).to(f"cuda:{dev}")
-            slots.append(dict(d_in=d_in, d_out=torch.empty((B, H, W, 3), dtype=torch.uint8, device=f"cuda:{dev}"),
-                              d_yuyv=torch.empty((B, H, W, 2), dtype=torch.uint8, device=f"cuda:{dev}"),
-                              d_mask=torch.empty((B, H, W), dtype=torch.uint8, device=f"cuda:{dev}")))
-        rings.append(dict(host=host, slots=slots))
-    ext = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+    for t in args.tune:
+        name, _, val = t.partition("=")
+        bs.set_tuning(name, int(val))
+    S, B = args.streams or wl.get("streams", 8), args.batch or wl.get("batch", 32)
+    lps = max(1, args.launches_per_step)
+    m = measure(args, wl, args.workload, dev, rank, world, S, B, args.steps, args.warmup, lps, not args.no_e2e, True, kind=args.frames)
 
-    def step(i):
-        r = i % R
-        for s, c in enumerate(ctxs):
-            sl = rings[s]["slots"][r]
-            c.composite_yuyv_device(B, sl["d_in"].data_ptr(), sl["d_out"].data_ptr(), sl["d_yuyv"].data_ptr(), sl["d_mask"].data_ptr())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-resident throughput (`value`) ----
-    sampler = ClockSampler(dev) if rank == 0 else None      # samples through the value + e2e regions
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
-    ev0.record(ext[0])
-    for e in ext[1:]:
-        e.wait_event(ev0)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    for e, s in zip(ev1, ext):
-        e.record(s)
-    barrier()
-    ms = max(ev0.elapsed_time(e) for e in ev1)
-    frames_total, secs, value = sharding.reduce_throughput(S * B * args.steps, ms * 1e-3,
-                                                            torch.distributed if world > 1 else None, f"cuda:{dev}")
-    ms = secs * 1e3
-
-    # ---- end to end through the host-buffer C-ABI call (H2D + graph + D2H every step) ----
-    e2e = None
-    if not args.no_e2e:
-        pin = lambda shape: torch.empty(shape, dtype=torch.uint8).pin_memory()
-        hb = []
-        for s in range(S):
-            h_in = pin((B, H, W, 2)); h_in.numpy()[:] = rings[s]["host"]
-            hb.append(dict(inp=h_in.numpy(), yuyv=pin((B, H, W, 2)).numpy(), keep=h_in))
-        e_steps = max(3, args.steps // 2)
-
-        def worker(s, n):
-            for _ in range(n):
-                # the frame deepseg.cc hands to the loopback device is the YUYV one (app/deepseg.cc:681-690)
-                ctxs[s].composite_yuyv_into(hb[s]["inp"], yuyv=hb[s]["yuyv"])
-
-        def run_threads(n):
-            th = [threading.Thread(target=worker, args=(s, n)) for s in range(S)]
-            for t in th: t.start()
-            for t in th: t.join()
-
-        run_threads(2)
-        barrier()
-        t0 = time.perf_counter()
-        run_threads(e_steps)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=f"cuda:{dev}")
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * npx * 2,
-               "d2h_bytes_per_step": S * B * npx * 2, "steps": e_steps,
-               "pcie_gbs_each_direction": world * S * B * e_steps * npx * 2 / dt / 1e9 / world,
-               "input": "camera YUYV frame in pinned host memory (GPU does the YUYV->BGR ingest of app/deepseg.cc:553)",
-               "result": "YUYV frame (what app/deepseg.cc:681-690 writes to the v4l2 loopback device)"}
-
-    if sampler:
-        # keep the GPU under the same load until nvidia-smi has delivered a few samples (it needs ~0.3 s to start)
-        t_end = time.perf_counter() + 1.0
-        i = 0
-        while time.perf_counter() < t_end:
-            step(args.warmup + args.steps + i); i += 1
-            if i % 8 == 0:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-
-    # ---- per-stage device times + roofline of the HBM-bound blur+composite kernel ----
-    stages = {}
-    c0 = ctxs[0]
-    for name, st in [("pre", 0), ("cnn", 1), ("decision", 2), ("post", 3), ("all", 4)]:
-        stages[name + "_ms_per_frame"] = c0.time_stage(st, B, 5) / B
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    oh, ow = c0.out_hwc[0], c0.out_hwc[1]
-    bytes_per_frame = 9 * npx + ow * oh + npx + 2 * npx        # 9WH + ow*oh, + WH mask, + 2WH YUYV (both written)
-    t_post = c0.time_stage(3, B, 10) * 1e-3                    # seconds per launch (B frames)
-    achieved = bytes_per_frame * B / t_post / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "post_traffic.json"))).get(args.workload, {}).get(str(B))
-    except Exception:
-        pass
-    if args.bgblur or wl.get("animated"):
-        traffic = None                                          # captured for the plain still-background configuration only
-    # whole-pipeline algorithmic HBM bytes per frame: YUYV ingest (2WH in, 3WH out) + ROI read (3 roi) + post stage
-    roi = c0.roidim
-    pipeline_bytes = 5 * npx + 3 * roi[2] * roi[3] + bytes_per_frame
-    roofline = {"bound": "hbm", "kernel": "k_post (mask upsample + 5x5 blur + alpha blend + YUYV)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/post_traffic.json (ncu --set full, dram read+write per launch)" if traffic else None,
-                "pipeline_bytes_per_frame": pipeline_bytes, "pipeline_hbm_frac": value * pipeline_bytes / 1e9 / (peak * world),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "bytes_per_launch": bytes_per_frame * B, "ms_per_launch": t_post * 1e3}
+    # ---- the other BASELINE configs, short runs on one GPU (N = 1 only): parsed.configs ----
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and args.workload == "meet720" and not args.bgblur:
+        configs = {}
+        for key in ("mlkit480", "deeplab720", "bodypix4k"):
+            w2 = WORKLOADS[key]
+            S2, B2 = w2.get("streams", 8), w2.get("batch", 32)
+            try:
+                r = measure(args, w2, key, dev, 0, 1, S2, B2, max(2, args.steps // 5), 2, 1, not args.no_e2e, False)
+                configs[key] = {"workload": w2["desc"], "value": r["value"], "unit": UNIT, "streams_per_gpu": S2, "batch": B2,
+                                "ms_per_step": r["ms"] / r["steps"], "e2e": r["e2e"], "roofline": r["roofline"], "stages": r["stages"],
+                                "gpu_launches_per_call": r["launches"]}
+            except Exception as e:                   # a side config must never cost the headline line
+                configs[key] = {"workload": w2["desc"], "error": str(e)[:200]}
 
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) ----
     cpu = None
@@ -459,23 +560,27 @@ def run_b200(args, wl):
         v, dt = cpu_path_fps(wl, threads, fpt, warm=0, **kw)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{threads} threads x {fpt} frames of the same workload ({dt:.1f} s), oracle port (TFLite-reference kernels + OpenCV ops restated)",
-               "single_thread_value": fps1, "calibration": cnn_calibration(wl)}
+               "single_thread_value": fps1, "calibration": cnn_calibration(wl), "tflite_probe": tflite_probe()}
 
     if rank == 0:
+        fb, npx = wl["W"] * wl["H"] * 3, wl["W"] * wl["H"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+u8", "data": "synthetic",
-            "config": {"workload": wl["desc"], "streams_per_gpu": S, "batch": B, "frames_per_step": world * S * B,
-                       "input": "camera YUYV frames (YUYV->BGR ingest on the GPU)", "outputs": "RGB composite + YUYV + mask", "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)", "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
-                       "background": bg_desc, "bgblur": args.bgblur or None, "host_affinity_cpus": bound_cpus, "l2_policy": f"inputs+outputs of one step ({S * R * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB/step) exceed the 126 MB L2"},
-            "gpu_launches": args.steps * S * c0.launches_per_call,
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stages": stages,
-            "cnn_mflop_per_frame": c0.flops / 1e6,
+            "config": workload_config(wl, args, S, B, lps, world, {
+                "streams_per_gpu": S, "batch": B, "graph_launches_per_stream_per_step": lps, "frames_per_step": world * S * B * lps,
+                "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)",
+                "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                "background_detail": m["bg_desc"], "host_affinity_cpus": bound_cpus,
+                "camera_frames": "read in place as YUYV by the GPU kernels" if m["yuyv_native"] else "YUYV -> BGR on the GPU, then BGR pipeline",
+                "tuning": args.tune or None,
+                "l2_policy": f"inputs+outputs of one launch round ({S * 2 * B} frames ring, {S * B * (fb + 5 * npx) / 1e6:.0f} MB per round) exceed the 126 MB L2"}),
+            "gpu_launches": args.steps * lps * S * m["launches"],
+            "e2e": m["e2e"], "roofline": m["roofline"], "cpu_baseline": cpu, "clocks": m["clocks"], "stages": m["stages"],
+            "cnn_mflop_per_frame": m["flops"] / 1e6, "configs": configs,
         }
         print(json.dumps(line), flush=True)
-    for c in ctxs:
-        bs.bs_maskgen_delete(c)
     if world > 1:
         torch.distributed.destroy_process_group()
 

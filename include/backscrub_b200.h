@@ -230,6 +230,9 @@ BSB_API long bsb_total_launches(void);
  * 3 = post (mask upsample + blur + blend + YUYV), 4 = whole call.  Returns < 0 on error.
  * Measurement aid for bench.py's roofline block; it advances the IIR state. */
 BSB_API double bsb_time_stage(bsb_ctx* ctx, int stage, int n_frames, int iters);
+/* 1 if the last fused call read camera YUYV frames in place (pre-processing and post kernels convert per tap / per tile),
+ * 0 if a BGR frame was materialised first (k_yuyv_to_bgr) or the input was BGR */
+BSB_API int bsb_yuyv_native(bsb_ctx* ctx);
 /* algorithmic FLOPs of one CNN frame (2*MAC) */
 BSB_API double bsb_model_flops(bsb_ctx* ctx);
 /* Process-wide measurement switches of the kernel launchers (A/B runs in bench.py / tools/): they select between

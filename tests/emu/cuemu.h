@@ -144,6 +144,8 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
   for (size_t y = 0; y < h; ++y) { memmove((char*)d + y * dp, (const char*)s + y * sp, w); }
   return 0; }
+static inline cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind k) {
+  return cudaMemcpy2DAsync(d, dp, s, sp, w, h, k, nullptr); }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }

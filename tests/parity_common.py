@@ -299,3 +299,59 @@ def check_app_option_edges(lib, key="meet_lite", W=640, H=480):
     assert g.composite(fr[0], want_yuyv=False)[0].shape == (240, 321, 3)
     assert g.process(fr[1]).shape == (H, W)
     g.close()
+
+
+def check_post_variants(lib, key="meet_full", W=1280, H=720, n=3):
+    """The fused post stage under every kernel variant and tile class: TMA-staged kernel vs the k_post_fast fallback
+    (bsb_set_tuning("post_tma", 0/1)), BGR frames vs camera YUYV read in place, person-like / pure-noise / constant
+    frames (mixed / person / background tiles), every output subset, still and animated backgrounds.  All bit-exact
+    against the oracle."""
+    bg = synth.background()
+    ring = np.stack([bg, bg[::-1].copy(), np.roll(bg, 100, axis=1)])
+    try:
+        for tma in (1, 0):
+            assert lib.bsb_set_tuning(b"post_tma", tma)
+            for kind in ("person", "noise", "const"):
+                g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+                o = po.MaskGen(model_path(key), W, H)
+                g.set_background(bg)
+                bgr = np.stack([synth.frame(W, H, t=t, kind=kind) for t in range(n)])
+                yin = np.stack([po.convert_rgb_to_yuyv(f) for f in bgr])
+                ref = [o.composite(po.yuyv_to_bgr(yin[b]), bg) for b in range(n)]
+                out, yuyv, mask = g.composite_yuyv(yin)                              # camera YUYV in, all outputs
+                for b in range(n):
+                    assert np.array_equal(mask[b], ref[b][2]) and np.array_equal(out[b], ref[b][0]) and np.array_equal(yuyv[b], ref[b][1]), (tma, kind, b)
+                g.close()
+            # output subsets from YUYV input (a fresh context each time: the IIR starts at zero like the oracle's)
+            bgr = np.stack([synth.frame(W, H, t=t) for t in range(n)])
+            yin = np.stack([po.convert_rgb_to_yuyv(f) for f in bgr])
+            for want in ((True, False, False), (False, True, False), (False, False, True), (True, True, False)):
+                g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+                o = po.MaskGen(model_path(key), W, H)
+                g.set_background(bg)
+                bufs = [np.zeros((n, H, W, 3), np.uint8) if want[0] else None, np.zeros((n, H, W, 2), np.uint8) if want[1] else None,
+                        np.zeros((n, H, W), np.uint8) if want[2] else None]
+                g.composite_yuyv_into(yin, *bufs)
+                for b in range(n):
+                    r = o.composite(po.yuyv_to_bgr(yin[b]), bg)
+                    for got, exp in zip(bufs, r):
+                        if got is not None:
+                            assert np.array_equal(got[b], exp), (tma, want, b)
+                g.close()
+            # BGR input + animated background ring (one image per frame, wraps inside the batch)
+            g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+            o = po.MaskGen(model_path(key), W, H)
+            g.set_background_ring(ring, advance=1)
+            for rep in range(2):
+                out, yuyv, mask = g.composite(bgr)
+                for b in range(n):
+                    ro, ry, rm = o.composite(bgr[b], ring[(rep * n + b) % 3])
+                    assert np.array_equal(mask[b], rm) and np.array_equal(out[b], ro) and np.array_equal(yuyv[b], ry), (tma, "ring", rep, b)
+            # the same ring from camera YUYV
+            out, yuyv, mask = g.composite_yuyv(yin)
+            for b in range(n):
+                ro, ry, rm = o.composite(po.yuyv_to_bgr(yin[b]), ring[(2 * n + b) % 3])
+                assert np.array_equal(mask[b], rm) and np.array_equal(out[b], ro) and np.array_equal(yuyv[b], ry), (tma, "ring-yuyv", b)
+            g.close()
+    finally:
+        lib.bsb_set_tuning(b"post_tma", 1)

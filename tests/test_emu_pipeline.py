@@ -48,6 +48,11 @@ def test_every_tensor_bit_exact(lib, key):
     assert pc.check_tensors(lib, key) > 20
 
 
+def test_post_variants_on_the_emulator(lib):
+    """camera YUYV read in place by the pre-processing kernel, output subsets, rings (the TMA kernel itself needs a GPU)"""
+    pc.check_post_variants(lib, "meet_lite", 320, 240, n=2)
+
+
 def test_infer_batch(lib):
     pc.check_infer_batch(lib, "meet_lite", n=3)
 

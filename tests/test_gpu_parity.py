@@ -67,6 +67,11 @@ def test_yuyv_ingest(lib):
     pc.check_yuyv_ingest(lib, "mlkit", 640, 480, n=2)
 
 
+@pytest.mark.parametrize("key,W,H", [("meet_full", 1280, 720), ("mlkit", 640, 480), ("bodypix", 1920, 1080), ("meet_lite", 336, 250)])
+def test_post_kernel_variants(lib, key, W, H):
+    pc.check_post_variants(lib, key, W, H, n=3 if W < 1920 else 2)
+
+
 def test_mask_only_and_callbacks(lib):
     pc.check_mask_only_and_callbacks(lib, "mlkit")
 
