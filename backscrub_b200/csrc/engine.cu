@@ -420,6 +420,9 @@ bool Engine::plan(std::string* err) {
     steps_.swap(fused);
   }
 
+  // ---- the low-resolution middle of MobileNetV3-style graphs as one kernel ----
+  if (tuning().cnn_chain && !(flags_ & (1u | 8u))) detect_chain();
+
   // ---- liveness + arena (floats; every tensor is max_batch frames) ----
   const int ns = (int)steps_.size();
   auto root = [&](int t) { return tinfo_[t].alias_parent >= 0 ? tinfo_[t].alias_parent : t; };
@@ -495,6 +498,82 @@ bool Engine::plan(std::string* err) {
   return true;
 }
 
+// Find   DW(strided, from a larger tensor) -> SE -> PW(scaled)  { -> PW(expand) -> DW -> SE -> PW(scaled [+ residual]) }*
+//        -> PW -> SE(1 FC, of the narrow tensor) -> MUL(channel scale)
+// on tensors of <= 256 pixels and <= 128 channels, with every intermediate read only inside the run, and replace it
+// by one CHAIN step (kernels_chain.cu).  Same arithmetic per output element, so results do not change.
+bool Engine::detect_chain() {
+  const int ns = (int)steps_.size();
+  auto px = [&](int t) { return tinfo_[t].h * tinfo_[t].w; };
+  auto plain_pw = [&](const Step& s) {
+    return s.kind == Step::PW && !s.use_tc && s.in_add < 0 && s.K % 4 == 0 && (size_t)s.K * s.n4 <= 4096 && s.K <= 128 && s.N <= 128;
+  };
+  auto se_ok = [&](const Step& s, int in, int n_fc, int C) {
+    if (s.kind != Step::POOL || s.in != in || s.in2 >= 0 || s.n_fc != n_fc || C > 128) return false;
+    for (int k = 0; k < n_fc; ++k) if (s.fc[k].K > 128 || s.fc[k].N > 128) return false;
+    return s.fc[0].K == C;
+  };
+  for (int i = 0; i + 6 < ns; ++i) {
+    const Step& d0 = steps_[i];
+    if (d0.kind != Step::DW || d0.residual >= 0 || d0.dh != 1 || d0.dw != 1 || d0.kh != d0.kw || (d0.kh != 3 && d0.kh != 5) || d0.sh != d0.sw) continue;
+    const TensorInfo& T0 = tinfo_[d0.out];
+    const int h = T0.h, w = T0.w, P = h * w;
+    if (P > 256 || px(d0.in) <= P || T0.c > 128 || T0.c % 4 || tinfo_[d0.in].ld % 4 || chain_smem_bytes(h, w) == 0) continue;
+    std::vector<int> types;
+    int j = i + 1, curD = d0.out, curX = -1;
+    types.push_back(CH_DWG);
+    // entry: SE of D, scaled project into X
+    if (!(j + 1 < ns && se_ok(steps_[j], curD, 2, T0.c) && plain_pw(steps_[j + 1]) && steps_[j + 1].in == curD && steps_[j + 1].scale == steps_[j].out &&
+          steps_[j + 1].residual < 0 && steps_[j + 1].N <= 32)) continue;
+    types.push_back(CH_SE); types.push_back(CH_PW);
+    curX = steps_[j + 1].out; j += 2;
+    // inverted-residual blocks
+    while (j + 3 < ns) {
+      const Step& e = steps_[j]; const Step& dd = steps_[j + 1]; const Step& p = steps_[j + 2]; const Step& q = steps_[j + 3];
+      const bool ok = plain_pw(e) && e.in == curX && e.scale < 0 && e.residual < 0 && e.K <= 32 &&
+                      dd.kind == Step::DW && dd.in == e.out && dd.sh == 1 && dd.sw == 1 && dd.dh == 1 && dd.dw == 1 && dd.residual < 0 &&
+                      dd.kh == dd.kw && (dd.kh == 3 || dd.kh == 5) && px(dd.out) == P &&
+                      se_ok(p, dd.out, 2, e.N) && plain_pw(q) && q.in == dd.out && q.scale == p.out && q.N <= 32 &&
+                      (q.residual < 0 || q.residual == curX);
+      if (!ok) break;
+      types.push_back(CH_EXPAND_DW); types.push_back(-1); types.push_back(CH_SE); types.push_back(CH_PW);
+      curX = q.out; curD = dd.out; j += 4;
+    }
+    // exit: PW of X into D and SE (one FC) of X, in either graph order, then D * sv -> global
+    if (!(j + 2 < ns)) continue;
+    const bool pw_first = steps_[j].kind == Step::PW;
+    const Step& t0 = steps_[pw_first ? j : j + 1]; const Step& t1 = steps_[pw_first ? j + 1 : j]; const Step& t2 = steps_[j + 2];
+    if (!(plain_pw(t0) && t0.in == curX && t0.scale < 0 && t0.residual < 0 && t0.N % 4 == 0 &&
+          se_ok(t1, curX, 1, tinfo_[curX].c) && t1.fc[0].N == t0.N &&
+          t2.kind == Step::ELT && t2.elt_mode == 3 && t2.in == t0.out && t2.scale == t1.out && tinfo_[t2.out].ld % 4 == 0)) continue;
+    if (pw_first) { types.push_back(CH_PW | 256); types.push_back(CH_SE | 256); } else { types.push_back(CH_SE | 256); types.push_back(CH_PW | 256); }
+    types.push_back(CH_SCALE_STORE);
+    const int jend = j + 2;
+    // every tensor produced inside the run (except the last) must be read only inside it
+    bool contained = true;
+    for (int a = i; a < jend && contained; ++a) {
+      const int t = steps_[a].out;
+      for (int b = 0; b < ns && contained; ++b) {
+        if (b >= i && b <= jend) continue;
+        const Step& r = steps_[b];
+        for (int u : {r.in, r.in2, r.scale, r.in_add, r.residual}) if (u == t) contained = false;
+      }
+      if (t == g_.output) contained = false;
+    }
+    if (!contained) continue;
+    ChainPlan cp; cp.h = h; cp.w = w;
+    cp.seq.assign(steps_.begin() + i, steps_.begin() + jend + 1);
+    cp.types = types;
+    for (int a = i; a < jend; ++a) tinfo_[steps_[a].out].materialized = false;
+    Step c; c.kind = Step::CHAIN; c.op_index = d0.op_index; c.in = d0.in; c.out = steps_[jend].out; c.block = (int)chains_.size();
+    chains_.push_back(cp);
+    steps_.erase(steps_.begin() + i, steps_.begin() + jend + 1);
+    steps_.insert(steps_.begin() + i, c);
+    return true;                                   // one chain per graph
+  }
+  return false;
+}
+
 // ---------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------
@@ -559,6 +638,53 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMalloc((void**)&arena_, std::max<size_t>(arena_elems_, 64) * 4));
   CUDA_OK(cudaMemset(arena_, 0, std::max<size_t>(arena_elems_, 64) * 4));
   CUDA_OK(cudaMalloc((void**)&rowsum_, std::max<size_t>(rowsum_elems_ * B, 64) * 4));
+  // chain op lists (device pointers into the weight blob / arena are final from here on)
+  for (ChainPlan& cp : chains_) {
+    std::vector<ChainOp> ops;
+    const int ne = (int)cp.seq.size();
+    auto fc_of = [&](const Step::Fc& f) {
+      FcLayer l; l.w = wblob_ + f.w_off; l.bias = f.has_bias ? wblob_ + f.b_off : nullptr; l.K = f.K; l.N = f.N; l.n4 = f.n4; l.act1 = f.act1; l.act2 = f.act2;
+      return l;
+    };
+    for (int k = 0; k < ne; ++k) {
+      if (cp.types[k] < 0) continue;
+      const int ty = cp.types[k] & 255;
+      const bool tail = (cp.types[k] & 256) != 0;           // the exit pair works on the narrow tensor X
+      const Step& st = cp.seq[k];
+      ChainOp o{};
+      o.type = ty;
+      switch (ty) {
+        case CH_DWG:
+          o.cin = tinfo_[st.out].c; o.wd = wblob_ + st.w_off; o.bd = st.has_bias ? wblob_ + st.b_off : nullptr;
+          o.k = st.kh; o.s = st.sh; o.pt = st.pt; o.pl = st.pl; o.dact1 = st.act1; o.dact2 = st.act2;
+          o.gin = tptr(st.in); o.gin_ld = tinfo_[st.in].ld; o.ih = tinfo_[st.in].h; o.iw = tinfo_[st.in].w; o.gin_frame = tinfo_[st.in].frame_elems;
+          break;
+        case CH_SE:
+          o.src = tail ? 0 : 1; o.cin = st.fc[0].K; o.pool_act = st.act1; o.n_fc = st.n_fc;
+          o.f0 = fc_of(st.fc[0]); if (st.n_fc > 1) o.f1 = fc_of(st.fc[1]);
+          break;
+        case CH_PW: {
+          o.src = tail ? 0 : 1; o.dst = tail ? 1 : 0; o.cin = st.K; o.cout = st.N; o.w = wblob_ + st.w_off; o.b = st.has_bias ? wblob_ + st.b_off : nullptr;
+          o.n4 = st.n4; o.act1 = st.act1; o.act2 = st.act2; o.use_scale = st.scale >= 0 ? 1 : 0; o.residual = st.residual >= 0 ? 1 : 0; o.act3 = st.act3;
+          break;
+        }
+        case CH_EXPAND_DW: {
+          const Step& dd = cp.seq[k + 1];
+          o.cin = st.K; o.cout = st.N; o.w = wblob_ + st.w_off; o.b = st.has_bias ? wblob_ + st.b_off : nullptr; o.n4 = st.n4; o.act1 = st.act1; o.act2 = st.act2;
+          o.wd = wblob_ + dd.w_off; o.bd = dd.has_bias ? wblob_ + dd.b_off : nullptr; o.k = dd.kh; o.s = 1; o.pt = dd.pt; o.pl = dd.pl;
+          o.dact1 = dd.act1; o.dact2 = dd.act2;
+          break;
+        }
+        case CH_SCALE_STORE:
+          o.cin = tinfo_[st.in].c; o.act1 = st.act1; o.gout = tptr(st.out); o.gout_ld = tinfo_[st.out].ld; o.gout_frame = tinfo_[st.out].frame_elems;
+          break;
+      }
+      ops.push_back(o);
+    }
+    cp.n_ops = (int)ops.size();
+    CUDA_OK(cudaMalloc((void**)&cp.d_ops, ops.size() * sizeof(ChainOp)));
+    CUDA_OK(cudaMemcpy(cp.d_ops, ops.data(), ops.size() * sizeof(ChainOp), cudaMemcpyHostToDevice));
+  }
   // bilateral LUTs (cv::bilateralFilter d=5, sigma 100/100; oracle_img.c:or_bilateral_d5_u8c3)
   {
     std::vector<float> lut(768 + 16, 0.f);
@@ -618,6 +744,7 @@ Engine::~Engine() {
                   tab_in_.blob, tab_up_.blob, tab_bg_.blob, tab_out_.blob, (void*)d_bg_cursor_, (void*)d_bg_eff_, (void*)d_bg_frames_,
                   (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_, (void*)d_bg_yuyv_})
     if (p) cudaFree(p);
+  for (ChainPlan& cp : chains_) if (cp.d_ops) cudaFree(cp.d_ops);
   if (h_mask_) cudaFreeHost(h_mask_);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -710,6 +837,11 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
         a.w2 = wblob_ + fb.project.w_off; a.b2 = fb.project.has_bias ? wblob_ + fb.project.b_off : nullptr; a.n4_2 = fb.project.n4;
         a.a2a = fb.project.act1; a.a2b = fb.project.act2; a.residual = fb.project.residual >= 0 ? 1 : 0; a.a3 = fb.project.act3;
         launch_mb_block(stream_, n, a);
+        break;
+      }
+      case Step::CHAIN: {
+        const ChainPlan& cp = chains_[st.block];
+        launch_chain(stream_, n, cp.h, cp.w, cp.d_ops, cp.n_ops);
         break;
       }
       case Step::COPY:

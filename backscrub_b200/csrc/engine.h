@@ -30,8 +30,8 @@ struct TensorInfo {
 };
 
 struct Step {
-  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY, BLOCK } kind = ELT;
-  int block = -1;             // BLOCK: index into Engine::blocks_ (the four fused sub-steps)
+  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY, BLOCK, CHAIN } kind = ELT;
+  int block = -1;             // BLOCK: index into Engine::blocks_ (the four fused sub-steps); CHAIN: index into Engine::chains_
   int op_index = -1;
   int in = -1, in2 = -1, out = -1, scale = -1, in_add = -1, residual = -1;
   size_t w_off = 0, b_off = 0; bool has_bias = false;
@@ -178,6 +178,11 @@ class Engine {
   std::vector<Step> steps_;
   struct FusedBlock { Step expand, dw, pool, project; };
   std::vector<FusedBlock> blocks_;
+  // the low-resolution middle of the graph run by one kernel (kernels_chain.cu): the original steps in order, each
+  // tagged with the chain op it became
+  struct ChainPlan { int h = 0, w = 0; std::vector<Step> seq; std::vector<int> types; ChainOp* d_ops = nullptr; int n_ops = 0; };
+  std::vector<ChainPlan> chains_;
+  bool detect_chain();
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
   bool stem_u8_ok_ = false;          // step 0 is a 3->16 dense conv that is the only reader of the graph input

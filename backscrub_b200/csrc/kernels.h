@@ -80,6 +80,38 @@ struct MbBlockArgs {
 size_t mb_block_smem_bytes(int h, int w, int cin, int cexp, int cout, int fc_max_floats);   // 0 if it does not fit
 void launch_mb_block(cudaStream_t s, int B, const MbBlockArgs& a);
 
+// Low-resolution chain (the MobileNetV3 "middle" of the Meet / MLKit graphs: every tensor has P = h*w <= 256 pixels and
+// <= 128 channels): ONE kernel, one CTA per frame, walks a list of ops with every activation resident in shared
+// memory —  X [P][32] (the narrow block input / output), D [P][128] (the expanded tensor after its depthwise conv),
+// E [P][32] (one 32-channel slice of the expanded tensor).  Each op accumulates in the order of the stand-alone kernel it
+// replaces (k ascending fmaf, taps in (fy, fx) order, pool rows-then-columns), so results are bit-identical.
+enum ChainOpType : int {
+  CH_DWG = 0,         // depthwise k x k (stride s) from a GLOBAL tensor [ih*iw][ld] into D            (block entry)
+  CH_SE = 1,          // global average pool of D or X -> FC (-> FC) -> channel scale vector sv
+  CH_PW = 2,          // 1x1 conv: src (D or X, optionally * sv) -> dst (X or D), optional in-place residual
+  CH_EXPAND_DW = 3,   // X -> 1x1 expand (+act) -> depthwise k x k stride 1 (+act) -> D, 32 channels at a time
+  CH_SCALE_STORE = 4  // global out[p][c] = D[p][c] * sv[c]                                             (chain exit)
+};
+struct ChainOp {
+  int type;
+  int src, dst;                        // 0 = X, 1 = D
+  int cin, cout;                       // channels of src / dst (PW: K / N; EXPAND_DW: cin -> cout; DWG / SE: C)
+  // 1x1 conv / expand weights [K][n4]
+  const float* w; const float* b; int n4, act1, act2;
+  int use_scale, residual, act3;
+  // depthwise [k][k][C]
+  const float* wd; const float* bd; int k, s, pt, pl, dact1, dact2;
+  // DWG input / SCALE_STORE output (per-frame stride in floats)
+  const float* gin; int gin_ld, ih, iw; size_t gin_frame;
+  float* gout; int gout_ld; size_t gout_frame;
+  // SE
+  int pool_act, n_fc; FcLayer f0, f1;
+};
+// shared memory needed for a chain over h x w pixels (0 if it cannot run)
+size_t chain_smem_bytes(int h, int w);
+// ops: DEVICE array of n_ops ChainOp
+void launch_chain(cudaStream_t s, int B, int h, int w, const ChainOp* d_ops, int n_ops);
+
 // RESIZE_BILINEAR (reference resize_bilinear.h:29-117 float path)
 void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                             float* out, int oh, int ow, int ld_out, bool align_corners, bool half_pixel);
@@ -193,6 +225,7 @@ struct Tuning {
   int pw_variant = 0;      // launch_pointwise: 0 heuristics, 2 classic tiles, 3/4/8 register-tiled, 5 row-streaming, 16/32/64 classic N tile
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
+  int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses
   int post_l1 = 1;         // k_post_fast: frame loads allocate in L1
 };

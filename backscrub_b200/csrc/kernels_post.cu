@@ -58,16 +58,18 @@ BSB_D void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensorm
 struct PostMaps { CUtensorMap frame, bg, bgy, out, yuyv, mask, ofinal; };
 struct PostTmaCfg { int has_out, has_yuyv, has_mask, has_bgy; };
 
-// patch of the small mask a 36 x 132 halo tile can touch: rows <= PT_RMAX, columns <= PT_PW (up-scales >= ~1.75x)
-constexpr int PT_RMAX = 24, PT_PW = 80;
+// patch of the small mask a 36 x 132 halo tile can touch: rows <= PT_RMAX, columns <= PT_PCOLS (up-scales >= ~1.75x).
+// A TMA box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate raises "illegal
+// instruction"), so the box begins at the patch's first column rounded down to 16 and is 16 columns wider.
+constexpr int PT_RMAX = 24, PT_PCOLS = 80, PT_PW = PT_PCOLS + 16;
 constexpr int PT_OFF_F = 0, PT_OFF_B = 12288, PT_OFF_Y = 24576, PT_OFF_M = 32768, PT_OFF_P = 36864;
-constexpr int PT_OFF_HS = PT_OFF_P + 2048;                       // [PT_RMAX][PF_US] u16
+constexpr int PT_OFF_HS = PT_OFF_P + PT_RMAX * PT_PW;            // [PT_RMAX][PF_US] u16
 constexpr int PT_OFF_US = PT_OFF_HS + PT_RMAX * PF_US * 2;       // [PF_UH][PF_US] u16
 constexpr int PT_OFF_VS = PT_OFF_US + PF_UH * PF_US * 2;         // [PF_H][PF_US] u16
 constexpr int PT_OFF_ROWS = PT_OFF_VS + PF_H * PF_US * 2;        // [PF_UH] uint4
 constexpr int PT_OFF_BAR = PT_OFF_ROWS + PF_UH * 16;
 constexpr int PT_SMEM = PT_OFF_BAR + 64;
-static_assert(PT_RMAX * PT_PW <= 2048 && PT_OFF_HS % 16 == 0 && PT_OFF_US % 16 == 0 && PT_OFF_VS % 16 == 0 && PT_OFF_ROWS % 16 == 0 && PT_OFF_BAR % 8 == 0, "smem layout");
+static_assert(PT_PW % 16 == 0 && PT_OFF_HS % 16 == 0 && PT_OFF_US % 16 == 0 && PT_OFF_VS % 16 == 0 && PT_OFF_ROWS % 16 == 0 && PT_OFF_BAR % 8 == 0, "smem layout");
 
 template <bool IN_YUYV>
 __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
   __syncthreads();
 
   // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
-  int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0;
+  int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0, coff = 0;
   if (hits_roi) {
     gy_lo = ty0 - a.roi_y - 2; gx_lo = tx0 - a.roi_x - 2;
     const int gy_hi = gy_lo + PF_UH - 1, gx_hi = gx_lo + PF_UW - 1;
@@ -109,11 +111,12 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
     nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
     cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
     ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
+    coff = (a.out_x + cmin) & 15;                     // the patch's first column inside the 16-byte aligned box
   }
   if (tid == 0) {
     if (hits_roi) {
       tma::mbar_expect_tx(barP, PT_RMAX * PT_PW);
-      tma::load_3d(sP, &tm.ofinal, a.out_x + cmin, a.out_y + rmin, b, barP);
+      tma::load_3d(sP, &tm.ofinal, a.out_x + cmin - coff, a.out_y + rmin, b, barP);
     }
     // the background tile (L2-resident for a still image) and its cached YUYV are fetched speculatively: a
     // background tile then needs nothing else, and a mixed tile has its second operand early
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
     tma::mbar_wait(barP, 0);
     unsigned p_and = 255u, p_or = 0u;
     for (int r = warp; r < nrows; r += 8)
-      for (int c = lane; c < ncols; c += 32) { const unsigned v = sP[r * PT_PW + c]; p_and &= v; p_or |= v; }
+      for (int c = lane; c < ncols; c += 32) { const unsigned v = sP[r * PT_PW + coff + c]; p_and &= v; p_or |= v; }
     const int all_hi = __syncthreads_and(p_and == 255u);
     const int all_lo = all_hi ? 0 : __syncthreads_and(p_or == 0u);
     tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
         gx = gx < 0 ? -gx : gx; gx = gx >= a.roi_w ? 2 * a.roi_w - 2 - gx : gx;
         gx = min(max(gx, 0), a.roi_w - 1);
         const uint2 xc = __ldg(a.tab.xcol + gx);
-        const int sx = (int)(xc.x & 0xffffu) - cmin, sx1 = (int)(xc.x >> 16) - cmin;
+        const int sx = (int)(xc.x & 0xffffu) - cmin + coff, sx1 = (int)(xc.x >> 16) - cmin + coff;
         const int a0 = (int)(short)(xc.y & 0xffffu), a1 = (int)(short)(xc.y >> 16);
         const uint8_t* pr = sP + phase * PT_PW;
         unsigned short* hp = Hs + phase * PF_US + ux;
@@ -328,7 +331,7 @@ static bool post_tma_shape_ok(const PostArgs& a) {
   if (!(a.out || a.yuyv || a.mask) || !al16(a.ofinal) || a.opitch % 16) return false;
   if (a.ow > 32000 || a.oh > 32000 || a.roi_w < 8 || a.roi_h < 8) return false;
   const double scale_y = (double)a.out_h / (double)a.roi_h, scale_x = (double)a.out_w / (double)a.roi_w;
-  if ((int)(PF_UH * scale_y) + 3 > PT_RMAX || (int)(PF_UW * scale_x) + 4 > PT_PW) return false;
+  if ((int)(PF_UH * scale_y) + 3 > PT_RMAX || (int)(PF_UW * scale_x) + 4 > PT_PCOLS) return false;
   return true;
 }
 

@@ -236,8 +236,8 @@ BSB_API int bsb_yuyv_native(bsb_ctx* ctx);
 /* algorithmic FLOPs of one CNN frame (2*MAC) */
 BSB_API double bsb_model_flops(bsb_ctx* ctx);
 /* Process-wide measurement switches of the kernel launchers (A/B runs in bench.py / tools/): they select between
- * bit-identical kernel variants and never change results.  Names: "pw_variant", "dw_plane", "post_tma", "post_wide",
- * "post_l1".  Set them before creating contexts (captured CUDA graphs keep the variant they were captured with).
+ * bit-identical kernel variants and never change results.  Names: "pw_variant", "dw_plane", "post_tma", "cnn_chain",
+ * "post_wide", "post_l1".  Set them before creating contexts (captured CUDA graphs keep the variant they were captured with).
  * Returns 1, or 0 for an unknown name. */
 BSB_API int bsb_set_tuning(const char* name, int value);
 

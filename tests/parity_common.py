@@ -355,3 +355,27 @@ def check_post_variants(lib, key="meet_full", W=1280, H=720, n=3):
             g.close()
     finally:
         lib.bsb_set_tuning(b"post_tma", 1)
+
+
+def check_chain(lib, key, n=3, max_launches=45):
+    """The one-kernel low-resolution chain (kernels_chain.cu) vs the oracle and vs the stand-alone kernels it replaces
+    (bsb_set_tuning("cnn_chain", 0)): same bits, far fewer launches."""
+    m = po.Model(model_path(key))
+    rng = np.random.default_rng(23)
+    outs = {}
+    try:
+        for chain in (1, 0):
+            assert lib.bsb_set_tuning(b"cnn_chain", chain)
+            g = api.MaskGen(lib, model_path(key), 640, 480, max_batch=n)
+            x = rng.uniform(0, 1, (n, *g.in_hwc)).astype(np.float32) if chain else x
+            outs[chain] = g.infer(x)
+            g.set_background(synth.background())
+            g.composite(np.stack([synth.frame(640, 480, t=t) for t in range(n)]))
+            launches = g.launches_per_call
+            assert (launches <= max_launches) if chain else (launches > max_launches), (key, chain, launches)
+            g.close()
+    finally:
+        lib.bsb_set_tuning(b"cnn_chain", 1)
+    assert np.array_equal(outs[1].view(np.uint32), outs[0].view(np.uint32)), f"{key}: chain and stand-alone kernels differ"
+    for b in range(n):
+        assert np.array_equal(outs[1][b].view(np.uint32), m.invoke(x[b])[0].view(np.uint32)), f"{key}: frame {b} differs from the oracle"

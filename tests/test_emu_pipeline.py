@@ -53,6 +53,11 @@ def test_post_variants_on_the_emulator(lib):
     pc.check_post_variants(lib, "meet_lite", 320, 240, n=2)
 
 
+@pytest.mark.parametrize("key", ["meet_lite", "mlkit"])
+def test_chain_kernel(lib, key):
+    pc.check_chain(lib, key, n=2)
+
+
 def test_infer_batch(lib):
     pc.check_infer_batch(lib, "meet_lite", n=3)
 

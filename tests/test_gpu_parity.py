@@ -72,6 +72,11 @@ def test_post_kernel_variants(lib, key, W, H):
     pc.check_post_variants(lib, key, W, H, n=3 if W < 1920 else 2)
 
 
+@pytest.mark.parametrize("key,n", [("meet_full", 32), ("meet_lite", 5), ("mlkit", 16)])
+def test_chain_kernel(lib, key, n):
+    pc.check_chain(lib, key, n=n)
+
+
 def test_mask_only_and_callbacks(lib):
     pc.check_mask_only_and_callbacks(lib, "mlkit")
 
