@@ -525,6 +525,7 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "dw_plane") t.dw_plane = value;
   else if (n == "post_tma") t.post_tma = value;
   else if (n == "cnn_chain") t.cnn_chain = value;
+  else if (n == "pool_merge") t.pool_merge = value;
   else if (n == "post_wide") t.post_wide = value;
   else if (n == "post_l1") t.post_l1 = value;
   else { g_last_error = "unknown tuning switch '" + n + "'"; return 0; }

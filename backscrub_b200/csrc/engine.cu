@@ -638,6 +638,8 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMalloc((void**)&arena_, std::max<size_t>(arena_elems_, 64) * 4));
   CUDA_OK(cudaMemset(arena_, 0, std::max<size_t>(arena_elems_, 64) * 4));
   CUDA_OK(cudaMalloc((void**)&rowsum_, std::max<size_t>(rowsum_elems_ * B, 64) * 4));
+  CUDA_OK(cudaMalloc((void**)&pool_counters_, B * sizeof(unsigned)));
+  CUDA_OK(cudaMemset(pool_counters_, 0, B * sizeof(unsigned)));
   // chain op lists (device pointers into the weight blob / arena are final from here on)
   for (ChainPlan& cp : chains_) {
     std::vector<ChainOp> ops;
@@ -742,7 +744,7 @@ Engine::~Engine() {
   for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)rowsum_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
                   (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_, (void*)d_yuyv_in_,
                   tab_in_.blob, tab_up_.blob, tab_bg_.blob, tab_out_.blob, (void*)d_bg_cursor_, (void*)d_bg_eff_, (void*)d_bg_frames_,
-                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_, (void*)d_bg_yuyv_})
+                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_, (void*)d_bg_yuyv_, (void*)pool_counters_})
     if (p) cudaFree(p);
   for (ChainPlan& cp : chains_) if (cp.d_ops) cudaFree(cp.d_ops);
   if (h_mask_) cudaFreeHost(h_mask_);
@@ -806,7 +808,7 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
         }
         const bool two = st.in2 >= 0;
         launch_pool_fc(stream_, n, tptr(st.in), I.c, I.ld, two ? tptr(st.in2) : nullptr, two ? tinfo_[st.in2].c : 0,
-                       two ? tinfo_[st.in2].ld : 0, I.h, I.w, rowsum_, st.act1, nullptr, st.n_fc, fc, tptr(st.out), O.ld);
+                       two ? tinfo_[st.in2].ld : 0, I.h, I.w, rowsum_, st.act1, nullptr, st.n_fc, fc, tptr(st.out), O.ld, pool_counters_);
         break;
       }
       case Step::RESIZE:

@@ -46,7 +46,7 @@ struct Step {
   struct Fc { size_t w_off = 0, b_off = 0; bool has_bias = false; int K = 0, N = 0, n4 = 0, act1 = 0, act2 = 0; };
   int n_fc = 0;
   Fc fc[2];
-  int launches() const { return kind == POOL ? 2 : 1; }
+  int launches() const { return 1; }
 };
 
 struct HostResizeTab {
@@ -194,6 +194,7 @@ class Engine {
   float* lut_ = nullptr;             // color_w[768] + space_w[16]
   float* rowsum_ = nullptr;          // scratch of the global-average-pool row sums
   size_t rowsum_elems_ = 0;
+  unsigned* pool_counters_ = nullptr; // [B] arrival counters of the one-launch pool + SE kernel (zero between launches)
   uint8_t* in_u8_ = nullptr;         // [B][mh][mw][3] zero outside in_roidim
   uint8_t* filt_u8_ = nullptr;       // [B][mh][mw][3] (KEEP_TENSORS only)
   uint8_t* state_ = nullptr;         // [oh*ow] IIR state

@@ -62,7 +62,8 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
 struct FcLayer { const float* w = nullptr; const float* bias = nullptr; int K = 0, N = 0, n4 = 0, act1 = 0, act2 = 0; };
 void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, const float* inB, int cB, int ldB,
                     int h, int w, float* rowsum_scratch, int pool_act, float* pooled_out /*may be null*/,
-                    int n_fc, const FcLayer* fc, float* out, int ld_out);
+                    int n_fc, const FcLayer* fc, float* out, int ld_out,
+                    unsigned* counters = nullptr /* [B] zeroed arrival counters: enables the one-launch variant */);
 
 // Fused MobileNetV3 inverted-residual block at low resolution (<= 256 pixels per frame): 1x1 expand (+act) ->
 // depthwise k x k stride 1 (+act) -> global pool -> FC -> FC (squeeze-excite) -> channel scale -> 1x1 project
@@ -225,6 +226,7 @@ struct Tuning {
   int pw_variant = 0;      // launch_pointwise: 0 heuristics, 2 classic tiles, 3/4/8 register-tiled, 5 row-streaming, 16/32/64 classic N tile
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
+  int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses
   int post_l1 = 1;         // k_post_fast: frame loads allocate in L1

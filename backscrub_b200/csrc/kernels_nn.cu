@@ -756,13 +756,9 @@ BSB_D void stage_weights(float* ws, const float* w, int count) {
     *reinterpret_cast<float4*>(ws + i) = __ldg(reinterpret_cast<const float4*>(w + i));
 }
 
-__global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int C, float count, int pool_act, float* pooled_out,
-                                                 int n_fc, FcDev f0, FcDev f1, float* out, int ld_out) {
-  BSB_DYN_SMEM(smem_raw);
-  float* ws = reinterpret_cast<float*>(smem_raw);
-  __shared__ float v0[512];
-  __shared__ float v1[512];
-  const int b = blockIdx.x;
+// frame b: column sums of the row sums (y ascending), / count, activation, then the FC chain — one 256-thread block
+BSB_D void pool_fc_frame(const float* rowsum, int b, int h, int C, float count, int pool_act, float* pooled_out,
+                         int n_fc, const FcDev& f0, const FcDev& f1, float* out, int ld_out, float* ws, float* v0, float* v1, bool coherent) {
   if (n_fc > 0) stage_weights(ws, f0.w, f0.K * f0.n4);          // overlaps with the pooling reads below
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const float* p = rowsum + (size_t)b * h * C + ch;
@@ -771,11 +767,11 @@ __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int
     for (; y + 8 <= h; y += 8) {
       float r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = __ldg(p + (size_t)(y + j) * C);
+      for (int j = 0; j < 8; ++j) r[j] = coherent ? __ldcg(p + (size_t)(y + j) * C) : __ldg(p + (size_t)(y + j) * C);
 #pragma unroll
       for (int j = 0; j < 8; ++j) t = t + r[j];
     }
-    for (; y < h; ++y) t = t + __ldg(p + (size_t)y * C);
+    for (; y < h; ++y) t = t + (coherent ? __ldcg(p + (size_t)y * C) : __ldg(p + (size_t)y * C));
     const float a = bsb_act(bsb_div(t, count), pool_act);
     v0[ch] = a;
     if (pooled_out) pooled_out[(size_t)b * C + ch] = a;
@@ -800,17 +796,80 @@ __global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int
   }
 }
 
+__global__ void __launch_bounds__(256) k_pool_fc(const float* rowsum, int h, int C, float count, int pool_act, float* pooled_out,
+                                                 int n_fc, FcDev f0, FcDev f1, float* out, int ld_out) {
+  BSB_DYN_SMEM(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw);
+  __shared__ float v0[512];
+  __shared__ float v1[512];
+  pool_fc_frame(rowsum, blockIdx.x, h, C, count, pool_act, pooled_out, n_fc, f0, f1, out, ld_out, ws, v0, v1, false);
+}
+
+// Row sums and the per-frame tail in ONE launch: grid (blocks per frame, B).  Every block writes its share of
+// rowsum[b][y][c]; the block that finishes last for a frame (a per-frame arrival counter, reset for the next launch)
+// runs the column sums + FC chain for that frame.  Which block is last only decides WHO does the tail — the sums are
+// taken in the fixed (row, then column) order from the complete rowsum array, so results do not depend on timing.
+__global__ void __launch_bounds__(256) k_rowsum_fc(const float* inA, int cA, int ldA, const float* inB, int cB, int ldB, int h, int w,
+                                                   float* rowsum, unsigned* counters, float count, int pool_act,
+                                                   int n_fc, FcDev f0, FcDev f1, float* out, int ld_out) {
+  BSB_DYN_SMEM(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw);
+  __shared__ float v0[512];
+  __shared__ float v1[512];
+  __shared__ int is_last;
+  const int C = cA + cB, b = blockIdx.y;
+  const int per_frame = h * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += gridDim.x * blockDim.x) {
+    const int ch = i % C, y = i / C;
+    const size_t row = (size_t)b * h + y;
+    const float* p; int ld;
+    if (ch < cA) { p = inA + row * w * ldA + ch; ld = ldA; }
+    else { p = inB + row * w * ldB + (ch - cA); ld = ldB; }
+    float r = 0.f;
+    int x = 0;
+    for (; x + 8 <= w; x += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (size_t)(x + j) * ld);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r = r + v[j];
+    }
+    for (; x < w; ++x) r = r + __ldg(p + (size_t)x * ld);
+    rowsum[(size_t)b * per_frame + i] = r;
+  }
+  __threadfence();                                   // this block's row sums are visible device-wide ...
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counters + b, 1u);   // ... before its arrival is
+    is_last = prev == gridDim.x - 1;
+    if (is_last) counters[b] = 0u;                   // ready for the next launch (stream order)
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  pool_fc_frame(rowsum, b, h, C, count, pool_act, nullptr, n_fc, f0, f1, out, ld_out, ws, v0, v1, true);
+}
+
 void launch_pool_fc(cudaStream_t s, int B, const float* inA, int cA, int ldA, const float* inB, int cB, int ldB,
                     int h, int w, float* rowsum_scratch, int pool_act, float* pooled_out,
-                    int n_fc, const FcLayer* fc, float* out, int ld_out) {
+                    int n_fc, const FcLayer* fc, float* out, int ld_out, unsigned* counters) {
   const int C = cA + cB;
-  const long total = (long)B * h * C;
-  BSB_LAUNCH(k_rowsum, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, inA, cA, ldA, inB, cB, ldB, h, w, rowsum_scratch);
-  count_launch();
   FcDev f[2] = {{nullptr, nullptr, 0, 0, 0, 0, 0}, {nullptr, nullptr, 0, 0, 0, 0, 0}};
   for (int i = 0; i < n_fc && i < 2; ++i) f[i] = FcDev{fc[i].w, fc[i].bias, fc[i].K, fc[i].N, fc[i].n4, fc[i].act1, fc[i].act2};
   size_t wbytes = 16;
   for (int i = 0; i < n_fc && i < 2; ++i) wbytes = std::max(wbytes, sizeof(float) * (size_t)f[i].K * f[i].n4);
+  if (counters && !pooled_out && wbytes <= 48 * 1024 && tuning().pool_merge) {
+    // one launch: enough blocks per frame to spread the row sums, the last one per frame does the tail
+    const int per_frame = h * C;
+    int bpf = std::min(ceil_div(per_frame, 256), std::max(1, (148 * 8) / std::max(B, 1)));
+    BSB_LAUNCH(k_rowsum_fc, dim3((unsigned)bpf, (unsigned)B), dim3(256), wbytes, s, inA, cA, ldA, inB, cB, ldB, h, w, rowsum_scratch, counters,
+               (float)(h * w), pool_act, n_fc, f[0], f[1], out, ld_out);
+    count_launch();
+    return;
+  }
+  const long total = (long)B * h * C;
+  BSB_LAUNCH(k_rowsum, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, B, inA, cA, ldA, inB, cB, ldB, h, w, rowsum_scratch);
+  count_launch();
   ensure_dyn_smem(reinterpret_cast<const void*>(k_pool_fc), wbytes);
   BSB_LAUNCH(k_pool_fc, dim3((unsigned)B), dim3(256), wbytes, s, rowsum_scratch, h, C, (float)(h * w), pool_act, pooled_out, n_fc, f[0], f[1], out, ld_out);
   count_launch();

@@ -62,17 +62,23 @@ struct PostTmaCfg { int has_out, has_yuyv, has_mask, has_bgy; };
 // A TMA box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate raises "illegal
 // instruction"), so the box begins at the patch's first column rounded down to 16 and is 16 columns wider.
 constexpr int PT_RMAX = 24, PT_PCOLS = 80, PT_PW = PT_PCOLS + 16;
-constexpr int PT_OFF_F = 0, PT_OFF_B = 12288, PT_OFF_Y = 24576, PT_OFF_M = 32768, PT_OFF_P = 36864;
-constexpr int PT_OFF_HS = PT_OFF_P + PT_RMAX * PT_PW;            // [PT_RMAX][PF_US] u16
-constexpr int PT_OFF_US = PT_OFF_HS + PT_RMAX * PF_US * 2;       // [PF_UH][PF_US] u16
-constexpr int PT_OFF_VS = PT_OFF_US + PF_UH * PF_US * 2;         // [PF_H][PF_US] u16
-constexpr int PT_OFF_ROWS = PT_OFF_VS + PF_H * PF_US * 2;        // [PF_UH] uint4
+// shared memory: the four TMA tiles, then the mask-building scratch of mixed tiles.  Vs reuses Hs (dead after the
+// vertical resize pass) and the mask staging tile reuses Us (dead after the 5-sum pass), which keeps a CTA under 56 KB:
+// four CTAs per SM.
+constexpr int PT_OFF_F = 0, PT_OFF_B = 12288, PT_OFF_Y = 24576, PT_OFF_P = 32768;
+constexpr int PT_OFF_HS = PT_OFF_P + PT_RMAX * PT_PW;            // [PT_RMAX][PF_US] u16, later Vs [PF_H][PF_US] u16
+constexpr int PT_HV_BYTES = (PT_RMAX > PF_H ? PT_RMAX : PF_H) * PF_US * 2;
+constexpr int PT_OFF_VS = PT_OFF_HS;
+constexpr int PT_OFF_US = PT_OFF_HS + PT_HV_BYTES;               // [PF_UH][PF_US] u16, later the mask tile [32][128]
+constexpr int PT_OFF_M = PT_OFF_US;
+constexpr int PT_OFF_ROWS = PT_OFF_US + PF_UH * PF_US * 2;       // [PF_UH] uint4
 constexpr int PT_OFF_BAR = PT_OFF_ROWS + PF_UH * 16;
 constexpr int PT_SMEM = PT_OFF_BAR + 64;
-static_assert(PT_PW % 16 == 0 && PT_OFF_HS % 16 == 0 && PT_OFF_US % 16 == 0 && PT_OFF_VS % 16 == 0 && PT_OFF_ROWS % 16 == 0 && PT_OFF_BAR % 8 == 0, "smem layout");
+static_assert(PT_PW % 16 == 0 && PT_OFF_HS % 128 == 0 && PT_OFF_US % 128 == 0 && PT_OFF_ROWS % 16 == 0 && PT_OFF_BAR % 8 == 0 &&
+              PF_UH * PF_US * 2 >= 4096 && PT_SMEM <= 56 * 1024, "smem layout");
 
 template <bool IN_YUYV>
-__global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
+__global__ void __launch_bounds__(256, 4) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint8_t* sF = smem + PT_OFF_F;            // frame tile [32][384] (BGR) or [32][256] (YUYV); later the blended tile
   uint8_t* sB = smem + PT_OFF_B;            // background tile [32][384]
@@ -126,6 +132,12 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
     tma::mbar_expect_tx(barB, 12288u + (cfg.has_bgy ? 8192u : 0u));
     tma::load_3d(sB, &tm.bg, blockIdx.x * 96, ty0, bgi, barB);
     if (cfg.has_bgy) tma::load_3d(sY, &tm.bgy, blockIdx.x * 64, ty0, bgi, barB);
+    // ... and so is the camera tile when the tile can contain a person at all: waiting for the classification first
+    // would put a second memory round trip on the critical path of every person / mixed tile
+    if (hits_roi) {
+      tma::mbar_expect_tx(barF, IN_YUYV ? 8192u : 12288u);
+      tma::load_3d(sF, &tm.frame, blockIdx.x * (IN_YUYV ? 64 : 96), ty0, b, barF);
+    }
   }
 
   int tile_const = -1;
@@ -139,19 +151,26 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
                             (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
     }
     tma::mbar_wait(barP, 0);
-    unsigned p_and = 255u, p_or = 0u;
-    for (int r = warp; r < nrows; r += 8)
-      for (int c = lane; c < ncols; c += 32) { const unsigned v = sP[r * PT_PW + coff + c]; p_and &= v; p_or |= v; }
-    const int all_hi = __syncthreads_and(p_and == 255u);
-    const int all_lo = all_hi ? 0 : __syncthreads_and(p_or == 0u);
+    // all-255 / all-0 test of the patch, one 32-bit word per thread (24 words per box row): bytes outside
+    // [coff, coff + ncols) are forced to the neutral value of each test
+    bool hi = true, lo = true;
+    for (int i = tid; i < nrows * (PT_PW / 4); i += 256) {
+      const int r = i / (PT_PW / 4), wc = i - r * (PT_PW / 4);
+      const int c0 = wc * 4 - coff;                                   // patch column of the word's first byte
+      if (c0 + 3 < 0 || c0 >= ncols) continue;
+      unsigned keep = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (c0 + k >= 0 && c0 + k < ncols) keep |= 0xffu << (8 * k);
+      const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PT_PW + wc * 4);
+      hi = hi && ((v | ~keep) == 0xffffffffu);
+      lo = lo && ((v & keep) == 0u);
+    }
+    const int all_hi = __syncthreads_and(hi);
+    const int all_lo = all_hi ? 0 : __syncthreads_and(lo);
     tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
   }
   const bool inside = tx0 >= a.roi_x && min(tx0 + PF_W, a.W) <= a.roi_x + a.roi_w && ty0 >= a.roi_y && min(ty0 + PF_H, a.H) <= a.roi_y + a.roi_h;
   const int kind = (!hits_roi || tile_const == 255) ? 0 : ((tile_const == 0 && inside) ? 1 : 2);   // background / person / mixed
-  if (kind != 0 && tid == 0) {
-    tma::mbar_expect_tx(barF, IN_YUYV ? 8192u : 12288u);
-    tma::load_3d(sF, &tm.frame, blockIdx.x * (IN_YUYV ? 64 : 96), ty0, b, barF);
-  }
 
   if (kind == 2 && tile_const < 0) {
     // ---- A1: horizontal pass of cv::resize on the patch rows (see k_post_fast) ----
@@ -209,6 +228,7 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
   const uint8_t* out_src = sB;
 
   tma::mbar_wait(barB, 0);          // every tile waits for its speculative loads: shared memory must be quiet at exit
+  if (hits_roi) tma::mbar_wait(barF, 0);
   if (kind == 0) {
     // ---- background tile: out = background tile, YUYV = cached YUYV tile, mask = 255.  No per-pixel arithmetic ----
     if (cfg.has_mask) *mdst = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -231,7 +251,6 @@ __global__ void __launch_bounds__(256, 3) k_post_tma(const __grid_constant__ Pos
       const bool row_in = y >= a.roi_y && y < a.roi_y + a.roi_h;
       post_mask16(a, row_in, tile_const, x0, Vs + ly * PF_US + lx, m);
     }
-    tma::mbar_wait(barF, 0);
     unsigned f[12], g[12];
     if (IN_YUYV) {
       const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (PF_W * 2) + lx * 2);

@@ -436,6 +436,9 @@ def measure(args, wl, key, dev, rank, world, S, B, steps, warmup, lps, with_e2e,
     # ---- per-stage device times + rooflines ----
     stages = {}
     c0 = ctxs[0]
+    # bsb_time_stage replays the kernels on the context-owned buffers: fill them with a real batch first (the
+    # device-pointer steps above never touch them), so the stage times are those of real frames and real masks
+    c0.composite_yuyv_into(rings[0]["host"], yuyv=np.empty((B, H, W, 2), np.uint8))
     for name, st in [("pre", 0), ("cnn", 1), ("decision", 2), ("post", 3), ("all", 4)]:
         stages[name + "_ms_per_frame"] = c0.time_stage(st, B, 5) / B
     peaks = load_peaks()
