@@ -424,26 +424,37 @@ int bsb_pointwise(int device, int variant, int M, int K, int N, const float* A, 
 }
 
 double bsb_time_pointwise(int device, int variant, int M, int K, int N, int iters) {
-  if (M <= 0 || K <= 0 || N <= 0 || iters < 1 || variant == 1) { g_last_error = "invalid argument"; return -1.0; }
+  if (M <= 0 || K <= 0 || N <= 0 || iters < 1) { g_last_error = "invalid argument"; return -1.0; }
   if (!stage_begin(device)) return -1.0;
   const int n4 = (N + 3) / 4 * 4;
-  DevBuf dA, dW, dB, dO;
-  if (!dA.alloc((size_t)M * K * 4) || !dO.alloc((size_t)M * N * 4) || !dW.alloc((size_t)K * n4 * 4) || !dB.alloc((size_t)N * 4)) { g_last_error = "cudaMalloc failed"; return -1.0; }
-  cudaMemset(dA.p, 0, (size_t)M * K * 4); cudaMemset(dW.p, 0, (size_t)K * n4 * 4); cudaMemset(dB.p, 0, (size_t)N * 4);
+  const bool use_tc = variant == 1;
+  const int bn = use_tc ? bsb::pointwise_tc_tile_n(N) : 0;
+  if (use_tc && (bn <= 0 || K % 4)) { g_last_error = "shape not supported by the tensor-core kernel"; return -1.0; }
+  const int kpad = (K + 31) / 32 * 32, npad = use_tc ? (N + bn - 1) / bn * bn : 0;
+  DevBuf dA, dW, dW2, dB, dO;
+  const size_t wbytes = use_tc ? (size_t)npad * kpad * 4 : (size_t)K * n4 * 4;
+  if (!dA.alloc((size_t)M * K * 4) || !dO.alloc((size_t)M * N * 4) || !dW.alloc(wbytes) || !dW2.alloc(wbytes) || !dB.alloc((size_t)N * 4)) { g_last_error = "cudaMalloc failed"; return -1.0; }
+  cudaMemset(dA.p, 0, (size_t)M * K * 4); cudaMemset(dW.p, 0, wbytes); cudaMemset(dW2.p, 0, wbytes); cudaMemset(dB.p, 0, (size_t)N * 4);
   bsb::Epilogue e; e.bias = (const float*)dB.p; e.act1 = 3;
   const int saved = bsb::pointwise_variant();
-  bsb::set_pointwise_variant(variant);
+  if (!use_tc) bsb::set_pointwise_variant(variant);
+  bool ok = true;
+  auto once = [&]() {
+    if (use_tc) ok = ok && bsb::launch_pointwise_tc(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, (const float*)dW2.p, kpad, npad, (float*)dO.p, N, e);
+    else bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+  };
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 2; ++i) bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+  for (int i = 0; i < 2; ++i) once();
   cudaEventRecord(e0, nullptr);
-  for (int i = 0; i < iters; ++i) bsb::launch_pointwise(nullptr, M, K, N, (const float*)dA.p, K, (const float*)dW.p, n4, (float*)dO.p, N, e, nullptr, 1, nullptr, 0);
+  for (int i = 0; i < iters; ++i) once();
   cudaEventRecord(e1, nullptr);
   cudaEventSynchronize(e1);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   bsb::set_pointwise_variant(saved);
+  if (!ok) { g_last_error = "tensor-core launch rejected the shape"; return -1.0; }
   if (!stage_end()) return -1.0;
   return (double)ms / iters;
 }
@@ -526,6 +537,8 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "post_tma") t.post_tma = value;
   else if (n == "cnn_chain") t.cnn_chain = value;
   else if (n == "pool_merge") t.pool_merge = value;
+  else if (n == "tc_variant") t.tc_variant = value;
+  else if (n == "tc_mask_hi") t.tc_mask_hi = value;
   else if (n == "post_wide") t.post_wide = value;
   else if (n == "post_l1") t.post_l1 = value;
   else { g_last_error = "unknown tuning switch '" + n + "'"; return 0; }

@@ -12,6 +12,8 @@
 // Shared-memory operand layout (K-major, SWIZZLE_128B): one K chunk = 32 fp32 = one 128-byte row per
 // M/N index; 8 rows form a 1024-byte swizzle atom in which the 16-byte column c of row r is stored at
 // column c ^ (r & 7).  Descriptor: start >> 4, LBO = 1, SBO = 1024 >> 4, version 1, layout 2.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace bsb {
@@ -257,6 +259,242 @@ static bool launch_tc_bn(cudaStream_t s, const TcArgs& a, int npad) {
   return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-specialised, persistent, TMA-fed version (the default tensor-core kernel).
+//
+//   warp 0      TMA producer: per K chunk of 32 floats one bulk tensor copy each for the raw A tile (128 rows, fp32 as
+//               stored by the producing layer), W_hi and W_lo (BN rows) into 128-byte-swizzled stages (SASS: UTMALDG)
+//   warp 1      MMA issuer: per chunk 12 tcgen05.mma kind::tf32 (a_lo*w_hi, a*w_lo, a*w_hi for 4 K steps; the tensor
+//               core truncates the raw fp32 operand to tf32 itself, so the "hi" part of A needs no pass of its own),
+//               tcgen05.commit -> the stage's `empty` barrier, and after a tile's last chunk -> `tmem_full`
+//   warp 2      TMEM allocation (2 accumulator buffers of BN columns: the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4-7   epilogue: tcgen05.ld (one 32-lane quadrant each) -> bias / activations / residual -> 16-byte stores
+//   warps 8-11  splitter: a_lo = a - tf32_trunc(a) for their row of the raw tile (exact), written to the stage's A_lo tile
+// CTAs are persistent (grid = #SMs) and walk the (M tile, N tile) list with a static stride.
+// ---------------------------------------------------------------------------------------------------------
+}  // namespace bsb
+#include <cuda.h>
+namespace bsb {
+
+namespace tc {
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+}  // namespace tc
+
+struct TcMaps { CUtensorMap a, whi, wlo; };
+struct Tc2Args { float* out; int M, K, N, ld_out, tiles_m, tiles_n, nchunks, mask_hi; EpiDevTc e; };
+
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int A_BYTES = 128 * 128;                       // 128 rows x 32 fp32
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;        // A raw | A lo | W hi | W lo
+  static constexpr int NS = (STAGE * 4 <= 220 * 1024) ? 4 : 3;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = NS * STAGE + BAR_BYTES + 1024;     // + slack to align the stages to 1024 bytes
+  static constexpr uint32_t TMEM_COLS = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators
+};
+
+template <int BN>
+__global__ void __launch_bounds__(384, 1) k_pointwise_tc2(const __grid_constant__ TcMaps tm, const Tc2Args a) {
+  using C = Tc2Cfg<BN>;
+  extern __shared__ uint8_t smem_tc2[];
+  const uint32_t raw_base = tc::smem_u32(smem_tc2);
+  const uint32_t sbase = (raw_base + 1023u) & ~1023u;             // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* gen_base = smem_tc2 + (sbase - raw_base);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + C::NS * C::STAGE);
+  uint64_t* full_raw = bars;                    // [NS] TMA bytes landed
+  uint64_t* full_lo = bars + C::NS;             // [NS] 128 splitter threads done
+  uint64_t* empty = bars + 2 * C::NS;           // [NS] the MMAs that read the stage have completed
+  uint64_t* tmem_full = bars + 3 * C::NS;       // [2]
+  uint64_t* tmem_empty = bars + 3 * C::NS + 2;  // [2] 128 epilogue threads done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NS + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < C::NS; ++i) { tc::mbar_init(&full_raw[i], 1); tc::mbar_init(&full_lo[i], 128); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 128); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ntiles = a.tiles_m * a.tiles_n;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / a.tiles_n) * 128, n0 = (tile % a.tiles_n) * BN;
+        for (int c = 0; c < a.nchunks; ++c, ++it) {
+          const int s = it % C::NS;
+          if (it >= C::NS) tc::mbar_wait(&empty[s], (uint32_t)((it / C::NS - 1) & 1));
+          const uint32_t st = sbase + (uint32_t)(s * C::STAGE);
+          tc::mbar_expect_tx(&full_raw[s], (uint32_t)(C::A_BYTES + 2 * C::B_BYTES));
+          tc::tma_load_2d(st, &tm.a, c * 32, m0, &full_raw[s]);
+          tc::tma_load_2d(st + 2 * C::A_BYTES, &tm.whi, c * 32, n0, &full_raw[s]);
+          tc::tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tm.wlo, c * 32, n0, &full_raw[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      if (tcount >= 2) tc::mbar_wait(&tmem_empty[acc], (uint32_t)((tcount / 2 - 1) & 1));      // the epilogue drained this accumulator
+      tc::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const int s = it % C::NS;
+        const uint32_t ph = (uint32_t)((it / C::NS) & 1);
+        tc::mbar_wait(&full_raw[s], ph);
+        tc::mbar_wait(&full_lo[s], ph);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = sbase + (uint32_t)(s * C::STAGE);
+          const uint64_t dA = tc::make_desc(st), dA_lo = tc::make_desc(st + C::A_BYTES);
+          const uint64_t dB_hi = tc::make_desc(st + 2 * C::A_BYTES), dB_lo = tc::make_desc(st + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {                  // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (>>4) address field
+            const uint64_t adv = (uint64_t)(ks * 2);
+            tc::mma_tf32(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (c > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            tc::mma_tf32(tmem_d, dA + adv, dB_lo + adv, idesc, 1u);
+            tc::mma_tf32(tmem_d, dA + adv, dB_hi + adv, idesc, 1u);
+          }
+          tc::mma_commit(&empty[s]);                        // arrives when the MMAs above have finished reading the stage
+          if (c == a.nchunks - 1) tc::mma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue =====
+    const int quad = warp & 3;
+    int tcount = 0;
+    const bool vec = (a.ld_out & 3) == 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const int m0 = (tile / a.tiles_n) * 128, n0 = (tile % a.tiles_n) * BN;
+      tc::mbar_wait(&tmem_full[acc], (uint32_t)((tcount / 2) & 1));
+      tc::tc_fence_after();
+      const int gm = m0 + quad * 32 + lane;
+      constexpr int NCH = (BN + 31) / 32;
+#pragma unroll 1
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int cc = ci * 32;
+        float v[32];
+        tc::tmem_ld32(tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16) + (uint32_t)cc, v);
+        if (gm < a.M) {
+          float* op = a.out + (size_t)gm * a.ld_out + n0 + cc;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int ch = n0 + cc + j;
+            if (cc + j + 3 < BN && ch + 3 < a.N && vec) {
+              *reinterpret_cast<float4*>(op + j) = make_float4(tc_epilogue(v[j], ch, (size_t)gm, a.e), tc_epilogue(v[j + 1], ch + 1, (size_t)gm, a.e),
+                                                               tc_epilogue(v[j + 2], ch + 2, (size_t)gm, a.e), tc_epilogue(v[j + 3], ch + 3, (size_t)gm, a.e));
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (cc + j + t < BN && ch + t < a.N) op[j + t] = tc_epilogue(v[j + t], ch + t, (size_t)gm, a.e);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&tmem_empty[acc]);
+    }
+  } else if (warp >= 8) {
+    // ===== splitter: A_lo = a - tf32_trunc(a), one row (128 bytes) per thread =====
+    const int row = tid - 256;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const int s = it % C::NS;
+        tc::mbar_wait(&full_raw[s], (uint32_t)((it / C::NS) & 1));
+        uint8_t* sA = gen_base + s * C::STAGE;
+        uint8_t* sLo = sA + C::A_BYTES;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const uint32_t off = tc::swz(row, c16);
+          const float4 v = *reinterpret_cast<const float4*>(sA + off);
+          float4 lo;
+          lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(sLo + off) = lo;
+          if (a.mask_hi) {        // measurement switch: do not rely on the tensor core truncating the raw operand
+            float4 hi;
+            hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            *reinterpret_cast<float4*>(sA + off) = hi;
+          }
+        }
+        tc::fence_proxy_async();                 // generic-proxy writes of A_lo -> visible to the tensor core (async proxy)
+        tc::mbar_arrive(&full_lo[s]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, C::TMEM_COLS); }
+}
+
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+    return reinterpret_cast<TcEncodeFn>(p);
+  }();
+  return fn;
+}
+// fp32 matrix [rows][cols], row pitch in floats; box = 32 floats x box_rows, 128-byte swizzle
+static bool tc_make_map(CUtensorMap* m, const float* base, size_t rows, size_t cols, size_t pitch_floats, unsigned box_rows) {
+  TcEncodeFn enc = tc_encode_fn();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch_floats & 3)) return false;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {pitch_floats * 4};
+  const cuuint32_t box[2] = {32, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+static bool launch_tc2_bn(cudaStream_t s, int M, int K, int N, const float* A, int ld_a, const float* w_hi, const float* w_lo, int kpad, int npad,
+                          float* out, int ld_out, const EpiDevTc& e) {
+  TcMaps tm;
+  if (!tc_make_map(&tm.a, A, (size_t)M, (size_t)K, (size_t)ld_a, 128)) return false;
+  if (!tc_make_map(&tm.whi, w_hi, (size_t)npad, (size_t)kpad, (size_t)kpad, BN)) return false;
+  if (!tc_make_map(&tm.wlo, w_lo, (size_t)npad, (size_t)kpad, (size_t)kpad, BN)) return false;
+  Tc2Args a{out, M, K, N, ld_out, ceil_div(M, 128), npad / BN, kpad / 32, tuning().tc_mask_hi, e};
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_pointwise_tc2<BN>), Tc2Cfg<BN>::SMEM)) return false;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(sms, a.tiles_m * a.tiles_n);
+  k_pointwise_tc2<BN><<<grid, 384, Tc2Cfg<BN>::SMEM, s>>>(tm, a);
+  return true;
+}
+
 int pointwise_tc_tile_n(int N) {       // tile width the launcher will use for this N (weights are padded to a multiple of it)
   if (N <= 16) return 16;
   if (N <= 32) return 32;
@@ -273,6 +511,21 @@ bool launch_pointwise_tc(cudaStream_t s, int M, int K, int N, const float* A, in
   const int bn = pointwise_tc_tile_n(N);
   if (npad % bn != 0) return false;
   bool ok = false;
+  if (tuning().tc_variant == 2) {
+    const EpiDevTc ed{e.bias, e.residual, e.ld_res, e.act1, e.act2, e.act3};
+    switch (bn) {
+      case 16: ok = launch_tc2_bn<16>(s, M, K, N, A, ld_a, w_hi, w_lo, kpad, npad, out, ld_out, ed); break;
+      case 32: ok = launch_tc2_bn<32>(s, M, K, N, A, ld_a, w_hi, w_lo, kpad, npad, out, ld_out, ed); break;
+      case 64: ok = launch_tc2_bn<64>(s, M, K, N, A, ld_a, w_hi, w_lo, kpad, npad, out, ld_out, ed); break;
+      case 80: ok = launch_tc2_bn<80>(s, M, K, N, A, ld_a, w_hi, w_lo, kpad, npad, out, ld_out, ed); break;
+      case 96: ok = launch_tc2_bn<96>(s, M, K, N, A, ld_a, w_hi, w_lo, kpad, npad, out, ld_out, ed); break;
+      case 128: ok = launch_tc2_bn<128>(s, M, K, N, A, ld_a, w_hi, w_lo, kpad, npad, out, ld_out, ed); break;
+      default: return false;
+    }
+    if (!ok) return false;
+    count_launch();
+    return true;
+  }
   switch (bn) {
     case 16: ok = launch_tc_bn<16>(s, a, npad); break;
     case 32: ok = launch_tc_bn<32>(s, a, npad); break;

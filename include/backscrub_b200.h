@@ -202,7 +202,8 @@ BSB_API int bsb_resize_u8c3(int device, const uint8_t* src, int sw, int sh, uint
  * act is a TFLite fused-activation code (0 none, 1 relu, 3 relu6). */
 BSB_API int bsb_pointwise(int device, int variant, int M, int K, int N, const float* A, const float* W,
                           const float* bias, int act, float* out);
-/* ms per launch of the exact FFMA pointwise kernel `variant` (0, 2, 3) on an M x K x N problem (CUDA events) */
+/* ms per launch of the pointwise kernel `variant` (0, 2, 3, ...: exact FFMA kernels; 1: the tensor-core kernel selected by the
+ * "tc_variant" tuning switch) on an M x K x N problem (CUDA events, zero data) */
 BSB_API double bsb_time_pointwise(int device, int variant, int M, int K, int N, int iters);
 
 /* ---- introspection (tests, bench) -------------------------------------------------- */
