@@ -151,19 +151,18 @@ __global__ void __launch_bounds__(256, 4) k_post_tma(const __grid_constant__ Pos
                             (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
     }
     tma::mbar_wait(barP, 0);
-    // all-255 / all-0 test of the patch, one 32-bit word per thread (24 words per box row): bytes outside
-    // [coff, coff + ncols) are forced to the neutral value of each test
+    // all-255 / all-0 test of the patch, one 32-bit word per thread, over the box columns [0, coff + ncols) rounded up to
+    // words: a few columns more than the patch.  The classification only selects the code path (the mixed path is
+    // always correct), so a conservative test costs nothing in exactness and needs no per-byte masks.
     bool hi = true, lo = true;
-    for (int i = tid; i < nrows * (PT_PW / 4); i += 256) {
-      const int r = i / (PT_PW / 4), wc = i - r * (PT_PW / 4);
-      const int c0 = wc * 4 - coff;                                   // patch column of the word's first byte
-      if (c0 + 3 < 0 || c0 >= ncols) continue;
-      unsigned keep = 0u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (c0 + k >= 0 && c0 + k < ncols) keep |= 0xffu << (8 * k);
-      const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PT_PW + wc * 4);
-      hi = hi && ((v | ~keep) == 0xffffffffu);
-      lo = lo && ((v & keep) == 0u);
+    {
+      const int wpr = (coff + ncols + 3) >> 2;                        // words per row to look at (<= PT_PW / 4)
+      for (int i = tid; i < nrows * wpr; i += 256) {
+        const int r = i / wpr, wc = i - r * wpr;
+        const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PT_PW + wc * 4);
+        hi = hi && (v == 0xffffffffu);
+        lo = lo && (v == 0u);
+      }
     }
     const int all_hi = __syncthreads_and(hi);
     const int all_lo = all_hi ? 0 : __syncthreads_and(lo);

@@ -90,22 +90,27 @@ BSB_D unsigned blend_px(unsigned g_pair_w, unsigned f_pair_w, unsigned g_single_
 // cv::cvtColor(COLOR_YUV2BGR_YUYV) on 8 pixels: w = 4 words of (Y0 U Y1 V) -> o = 24 bytes of BGR (6 words).
 // BT.601 limited range, 20-bit fixed point (oracle_img.c:or_yuyv_to_bgr, pinned on cv2).
 BSB_D void yuyv8_to_bgr24(const unsigned* w, unsigned* o) {
-#pragma unroll
-  for (int i = 0; i < 6; ++i) o[i] = 0u;
+  // saturate with one VIMNMX.RELU per channel (min(v, 255) then max(.., 0)) and Y - 16 with one VIADDMNMX; the 24 bytes
+  // are assembled with byte permutes (pixel = b | g << 8 | r << 16, then three words per four pixels)
+  unsigned px[8];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int u = (int)((w[k] >> 8) & 255u) - 128, v = (int)(w[k] >> 24) - 128;
     const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int yy = max((int)((w[k] >> (16 * h)) & 255u) - 16, 0) * 1220542;
-      const unsigned px[3] = {bsb_sat_u8((yy + buv) >> 20), bsb_sat_u8((yy + guv) >> 20), bsb_sat_u8((yy + ruv) >> 20)};
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int byte = 6 * k + 3 * h + c;
-        o[byte >> 2] |= px[c] << (8 * (byte & 3));
-      }
+      const int yy = __viaddmax_s32((int)((w[k] >> (16 * h)) & 255u), -16, 0) * 1220542;
+      const unsigned bb = (unsigned)__vimin_s32_relu((yy + buv) >> 20, 255), gg = (unsigned)__vimin_s32_relu((yy + guv) >> 20, 255),
+                     rr = (unsigned)__vimin_s32_relu((yy + ruv) >> 20, 255);
+      px[2 * k + h] = __byte_perm(__byte_perm(bb, gg, 0x0040), rr, 0x0410);      // b | g << 8 | r << 16
     }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {        // four pixels (b0 g0 r0 | b1 g1 r1 | b2 g2 r2 | b3 g3 r3) -> three words
+    const unsigned p0 = px[4 * q], p1 = px[4 * q + 1], p2 = px[4 * q + 2], p3 = px[4 * q + 3];
+    o[3 * q] = __byte_perm(p0, p1, 0x4210);          // b0 g0 r0 b1
+    o[3 * q + 1] = __byte_perm(p1, p2, 0x5421);      // g1 r1 b2 g2
+    o[3 * q + 2] = __byte_perm(p2, p3, 0x6542);      // r2 b3 g3 r3
   }
 }
 // one pixel of a YUYV row: BGR of pixel x (the pair's U / V are shared)
@@ -192,7 +197,7 @@ BSB_D void post_blend16(const unsigned* f, const unsigned* g, const unsigned* m,
         Y[j] = y14 >> 14;
         U[j] = __dp2a_hi(8061u, T[j], 2105344u - 8061u * Y[j]) >> 14;
         V[j] = (int)__dp2a_lo(14369u, T[j], 2105344u - 14369u * Y[j]) >> 14;
-        V[j] = min(max(V[j], 0), 255);
+        V[j] = __vimin_s32_relu(V[j], 255);
       }
       yy[2 * q] = Y[0] | ((unsigned)((V[0] + V[1]) >> 1) << 8) | (Y[1] << 16) | (((U[0] + U[1]) >> 1) << 24);
       yy[2 * q + 1] = Y[2] | ((unsigned)((V[2] + V[3]) >> 1) << 8) | (Y[3] << 16) | (((U[2] + U[3]) >> 1) << 24);

@@ -114,6 +114,8 @@ static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c 
 static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * ((b >> 16) & 0xffu) + (a >> 16) * ((b >> 24) & 0xffu); }
 template <typename T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline void __threadfence() {}
+static inline int __vimin_s32_relu(int a, int b) { int m = a < b ? a : b; return m < 0 ? 0 : m; }
+static inline int __viaddmax_s32(int a, int b, int c) { int s = a + b; return s > c ? s : c; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

@@ -1,4 +1,8 @@
 """debug aid: the smallest calls that reach k_post_tma (mask-only, then all outputs), for compute-sanitizer"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import backscrub_b200 as bs
 from backscrub_b200 import api

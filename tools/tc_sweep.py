@@ -3,7 +3,10 @@
 (ms per launch, useful TFLOP/s = 2*M*K*N / t), plus the accuracy of the tensor-core result against fp64.
     python tools/tc_sweep.py [batch]"""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
