@@ -300,7 +300,7 @@ struct Tc2Cfg {
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;        // A raw | A lo | W hi | W lo
   static constexpr int NS = (STAGE * 4 <= 220 * 1024) ? 4 : 3;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = NS * STAGE + BAR_BYTES + 1024;     // + slack to align the stages to 1024 bytes
+  static constexpr int SMEM = NS * STAGE + BAR_BYTES + 1024 + 1024;   // + bias tile + slack to align the stages to 1024 bytes
   static constexpr uint32_t TMEM_COLS = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators
 };
 
@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(384, 1) k_pointwise_tc2(const __grid_constant_
   uint64_t* tmem_full = bars + 3 * C::NS;       // [2]
   uint64_t* tmem_empty = bars + 3 * C::NS + 2;  // [2] 128 epilogue threads done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NS + 4);
+  float* sbias = reinterpret_cast<float*>(gen_base + C::NS * C::STAGE + C::BAR_BYTES);   // [BN] bias of the current tile (epilogue warps)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -394,6 +395,13 @@ __global__ void __launch_bounds__(384, 1) k_pointwise_tc2(const __grid_constant_
       tc::tc_fence_after();
       const int gm = m0 + quad * 32 + lane;
       constexpr int NCH = (BN + 31) / 32;
+      // bias of this tile's columns -> shared memory once (the 128 epilogue threads only: named barrier 1)
+      for (int i = tid - 128; i < BN; i += 128) sbias[i] = (a.e.bias && n0 + i < a.N) ? __ldg(a.e.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // the activations of the GEMM-heavy graphs (none / relu / relu6 after the bias, then an optional residual add) become
+      // two clamps with +-inf bounds; anything else takes the generic per-element path
+      const bool simple = a.e.act2 == ACT_NONE && a.e.act3 == ACT_NONE && (a.e.act1 == ACT_NONE || a.e.act1 == ACT_RELU || a.e.act1 == ACT_RELU6);
+      const float lo_b = a.e.act1 == ACT_NONE ? -INFINITY : 0.f, hi_b = a.e.act1 == ACT_RELU6 ? 6.f : INFINITY;
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int cc = ci * 32;
@@ -401,12 +409,18 @@ __global__ void __launch_bounds__(384, 1) k_pointwise_tc2(const __grid_constant_
         tc::tmem_ld32(tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16) + (uint32_t)cc, v);
         if (gm < a.M) {
           float* op = a.out + (size_t)gm * a.ld_out + n0 + cc;
+          const float* rp = a.e.residual ? a.e.residual + (size_t)gm * a.e.ld_res + n0 + cc : nullptr;
+          const bool rvec = rp && (a.e.ld_res & 3) == 0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int ch = n0 + cc + j;
-            if (cc + j + 3 < BN && ch + 3 < a.N && vec) {
-              *reinterpret_cast<float4*>(op + j) = make_float4(tc_epilogue(v[j], ch, (size_t)gm, a.e), tc_epilogue(v[j + 1], ch + 1, (size_t)gm, a.e),
-                                                               tc_epilogue(v[j + 2], ch + 2, (size_t)gm, a.e), tc_epilogue(v[j + 3], ch + 3, (size_t)gm, a.e));
+            if (cc + j >= BN || ch >= a.N) break;
+            if (simple && cc + j + 3 < BN && ch + 3 < a.N && vec && (!rp || rvec)) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sbias + cc + j);
+              float4 r = make_float4(fminf(fmaxf(v[j] + b4.x, lo_b), hi_b), fminf(fmaxf(v[j + 1] + b4.y, lo_b), hi_b),
+                                     fminf(fmaxf(v[j + 2] + b4.z, lo_b), hi_b), fminf(fmaxf(v[j + 3] + b4.w, lo_b), hi_b));
+              if (rp) { const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j)); r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
+              *reinterpret_cast<float4*>(op + j) = r;
             } else {
 #pragma unroll
               for (int t = 0; t < 4; ++t)
@@ -415,6 +429,7 @@ __global__ void __launch_bounds__(384, 1) k_pointwise_tc2(const __grid_constant_
           }
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");            // everyone is done with sbias before the next tile refills it
       tc::tc_fence_before();
       tc::mbar_arrive(&tmem_empty[acc]);
     }

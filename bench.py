@@ -302,14 +302,15 @@ def load_peaks():
 
 
 def post_bytes(W, H, ow, oh, B, yuyv_in, bg_per_frame, bg_cache):
-    """Algorithmic HBM bytes of ONE launch of the fused blur+composite kernel over B frames:
+    """Algorithmic HBM bytes of ONE launch of the fused blur+composite kernel over B frames (`bg_cache` is
+    accepted for the record only):
     per frame: camera frame in (3WH as BGR, 2WH when the kernel reads the camera YUYV itself) + RGB composite out (3WH) +
     YUYV out (2WH) + full-resolution mask out (WH) + the small mask (ow*oh);
     background: 3WH per frame for an animated / per-frame background, but ONCE per launch for a still image (every frame
     of the launch blends the same L2-resident image; round 1 counted it per frame, which overstated the fraction)."""
     npx = W * H
     per_frame = (2 if yuyv_in else 3) * npx + 3 * npx + 2 * npx + npx + ow * oh
-    bg = 3 * npx + (2 * npx if bg_cache else 0)
+    bg = 3 * npx          # the cached YUYV copy of the background is this implementation's own extra traffic: not counted
     return B * per_frame + (B * bg if bg_per_frame else bg)
 
 
@@ -500,12 +501,45 @@ def workload_config(wl, args, S, B, lps, world, extra=None):
     return cfg
 
 
+def gpu_for_local_rank(torch, local, world):
+    """Which GPU a local rank drives.  The end-to-end path is bound by each socket's host-memory / PCIe root complex, so
+    for world < #GPUs the ranks are spread round-robin over the sockets (GPU NUMA groups from NVML's CPU affinity:
+    local ranks 0,1,2,3 -> GPUs 0,4,1,5 on a 2 x 4 box) instead of filling socket 0 first.  Every rank computes the same
+    order; with all GPUs in use it is a permutation and changes nothing."""
+    n = torch.cuda.device_count()
+    order = list(range(n))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        groups = {}
+        for d in range(n):
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(d).uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(d)
+            key = tuple(pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64))
+            groups.setdefault(key, []).append(d)
+        lists = [groups[k] for k in sorted(groups, key=lambda k: groups[k][0])]
+        order = []
+        i = 0
+        while len(order) < n:
+            for g in lists:
+                if i < len(g):
+                    order.append(g[i])
+            i += 1
+    except Exception:
+        order = list(range(n))
+    return order[local % n] if world <= n else local % n
+
+
 def run_b200(args, wl):
     import torch
 
     import backscrub_b200 as bs
 
     rank, world, local = dist_env()
+    dev = gpu_for_local_rank(torch, local, world) if world > 1 else 0
     if world > 1:
         import torch.distributed as dist
         # NCCL writes its version banner / debug lines to stdout while the communicator comes up; rank 0's stdout must
@@ -514,14 +548,13 @@ def run_b200(args, wl):
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
             dist.barrier()
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
     full_affinity = bind_near_gpu(torch, dev)
     bound_cpus = len(os.sched_getaffinity(0))
@@ -575,6 +608,7 @@ def run_b200(args, wl):
                 "streams_per_gpu": S, "batch": B, "graph_launches_per_stream_per_step": lps, "frames_per_step": world * S * B * lps,
                 "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)",
                 "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                "gpu_of_rank0": dev,
                 "background_detail": m["bg_desc"], "host_affinity_cpus": bound_cpus,
                 "camera_frames": "read in place as YUYV by the GPU kernels" if m["yuyv_native"] else "YUYV -> BGR on the GPU, then BGR pipeline",
                 "tuning": args.tune or None,
