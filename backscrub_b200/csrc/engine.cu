@@ -207,7 +207,7 @@ bool Engine::plan(std::string* err) {
           auto it = prologue.find(st.in);
           if (it != prologue.end()) { st.in = it->second.x; st.scale = it->second.s; st.in_add = it->second.add; }
           // tensor cores (opt-in): plain GEMM-shaped layers with enough rows and depth to fill a 128 x N x 32 tile pipeline
-          if ((flags_ & 4u) && st.scale < 0 && st.in_add < 0 && ic >= 160 && ic % 4 == 0 && oc >= 8 &&
+          if ((flags_ & 4u) && st.scale < 0 && st.in_add < 0 && ic >= tuning().tc_min_k && ic % 4 == 0 && oc >= 8 &&
               tinfo_[st.in].h * tinfo_[st.in].w >= 1024 && tinfo_[st.in].ld % 4 == 0)
             pack_tc_weights(w, oc, ic, st);
         } else {
@@ -484,6 +484,12 @@ bool Engine::plan(std::string* err) {
     const Step& s0 = steps_[0];
     stem_u8_ok_ = s0.kind == Step::CONV && s0.in == g_.input && s0.K == 3 && s0.N == 16 && s0.dh == 1 && s0.dw == 1 &&
                   consumers[g_.input].size() == 1 && tinfo_[s0.out].ld % 4 == 0 && s0.residual < 0;
+    stem_pw_ok_ = false;
+    if (stem_u8_ok_ && steps_.size() > 1) {
+      const Step& s1 = steps_[1];
+      stem_pw_ok_ = s1.kind == Step::PW && s1.in == s0.out && s1.K == 16 && s1.N == 16 && s1.n4 == 16 && s1.scale < 0 && s1.in_add < 0 &&
+                    s1.residual < 0 && !s1.use_tc && tinfo_[s1.out].ld % 4 == 0;
+    }
   }
   // algorithmic FLOPs (2*MAC of conv / depthwise / fc / tconv), SURVEY.md Appendix A
   flops_ = 0;
@@ -769,7 +775,10 @@ void Engine::enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t st
 
 void Engine::enqueue_cnn(int n, bool from_u8) {
   bool first = true;
-  for (const Step& st : steps_) {
+  bool skip_next = false;
+  for (size_t si = 0; si < steps_.size(); ++si) {
+    const Step& st = steps_[si];
+    if (skip_next) { skip_next = false; continue; }      // the 1x1 conv that ran inside the stem kernel
     const bool fused_stem = first && from_u8 && stem_u8_ok_;
     first = false;
     const TensorInfo& I = tinfo_[st.in];
@@ -781,8 +790,18 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
     switch (st.kind) {
       case Step::CONV:
         if (fused_stem) {
-          launch_stem_u8(stream_, n, filt_u8_, I.h, I.w, scaling_, offset_, wblob_ + st.w_off, st.kh, st.kw, st.sh, st.sw, st.pt, st.pl,
-                         tptr(st.out), O.h, O.w, O.ld, e);
+          // the thread that produced a stem pixel holds its 16 channels: a following plain 16 -> 16 1x1 conv runs there too
+          const Step* pw = (stem_pw_ok_ && tuning().stem_pw && si + 1 < steps_.size()) ? &steps_[si + 1] : nullptr;
+          if (pw) {
+            Epilogue e2;
+            e2.bias = pw->has_bias ? wblob_ + pw->b_off : nullptr; e2.act1 = pw->act1; e2.act2 = pw->act2;
+            launch_stem_u8(stream_, n, filt_u8_, I.h, I.w, scaling_, offset_, wblob_ + st.w_off, st.kh, st.kw, st.sh, st.sw, st.pt, st.pl,
+                           tptr(st.out), O.h, O.w, O.ld, e, wblob_ + pw->w_off, tptr(pw->out), tinfo_[pw->out].ld, &e2);
+            skip_next = true;
+          } else {
+            launch_stem_u8(stream_, n, filt_u8_, I.h, I.w, scaling_, offset_, wblob_ + st.w_off, st.kh, st.kw, st.sh, st.sw, st.pt, st.pl,
+                           tptr(st.out), O.h, O.w, O.ld, e);
+          }
           break;
         }
         launch_conv_direct(stream_, n, tptr(st.in), I.h, I.w, I.c, I.ld, wblob_ + st.w_off, st.N, st.kh, st.kw, st.sh, st.sw,

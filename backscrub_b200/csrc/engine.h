@@ -186,6 +186,7 @@ class Engine {
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
   bool stem_u8_ok_ = false;          // step 0 is a 3->16 dense conv that is the only reader of the graph input
+  bool stem_pw_ok_ = false;          // ... and step 1 is a plain 16 -> 16 1x1 conv of its output (runs inside the stem kernel)
 
   // device memory
   cudaStream_t stream_ = nullptr;

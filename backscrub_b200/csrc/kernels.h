@@ -29,7 +29,9 @@ void launch_conv_direct(cudaStream_t s, int B, const float* in, int ih, int iw, 
 // fmaf(u8, scale, offset) on the fly (identical values, no fp32 input tensor round trip).  oc == 16, ic == 3.
 void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw, float scale, float offset,
                     const float* w_t, int kh, int kw, int stride_h, int stride_w, int pad_t, int pad_l,
-                    float* out, int oh, int ow, int ld_out, const Epilogue& e);
+                    float* out, int oh, int ow, int ld_out, const Epilogue& e,
+                    // optional fused 1x1 conv 16 -> 16 of the stem output (w2_kn: [16][16] k-major; no residual / scale)
+                    const float* w2_kn = nullptr, float* out2 = nullptr, int ld_out2 = 0, const Epilogue* e2 = nullptr);
 
 // 1x1 convolution / fully-connected as a GEMM: out[M][N] = A[M][K] * w_kn[K][N4] (+ epilogue).
 // in_scale (optional): [B][K] per-frame channel scale applied to A on load (folded SE MUL);
@@ -227,7 +229,9 @@ struct Tuning {
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel
+  int tc_min_k = 160;      // smallest input depth of a 1x1 conv that goes to the tensor cores (with BSB_FLAG_TENSOR_CORES)
   int tc_mask_hi = 0;      // tensor-core kernel: clear the low mantissa bits of A explicitly instead of relying on the hardware truncation
+  int stem_pw = 1;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses

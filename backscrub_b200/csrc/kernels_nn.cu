@@ -137,6 +137,9 @@ struct StemArgs {
   int B, ih, iw, kh, kw, sh, sw, pt, pl, oh, ow, ld_out;
   float scale, offset;
   EpiDev e;
+  // optional fused 1x1 conv 16 -> 16 on the stem's output (the thread already holds the pixel's 16 channels):
+  // out2[p][n] = act(sum_k out[p][k] * w2[k][n] + bias2), k ascending — the same chain the stand-alone kernel computes
+  const float* w2; float* out2; int ld_out2; EpiDev e2;
 };
 
 __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
   float* ws = reinterpret_cast<float*>(smem_raw);     // [kh][kw][3][16]
   const int wcount = a.kh * a.kw * 3 * 16;
   for (int i = threadIdx.x; i < wcount; i += blockDim.x) ws[i] = __ldg(a.w + i);
+  if (a.w2) for (int i = threadIdx.x; i < 256; i += blockDim.x) ws[wcount + i] = __ldg(a.w2 + i);
   __syncthreads();
   const long total = (long)a.B * a.oh * a.ow;
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,7 +186,30 @@ __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
     r[q] = valid ? make_float4(epilogue(acc[4 * q], 4 * q, (size_t)pix, a.e), epilogue(acc[4 * q + 1], 4 * q + 1, (size_t)pix, a.e),
                                epilogue(acc[4 * q + 2], 4 * q + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], 4 * q + 3, (size_t)pix, a.e))
                  : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.ld_out == 16) {
+  float4 r2[4];
+  if (a.w2) {
+    // second stage: 16 x 16 weights [k][n] behind the stem weights in shared memory
+    const float* w2s = ws + wcount;
+    float acc2[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc2[n] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float xk = k % 4 == 0 ? r[k / 4].x : (k % 4 == 1 ? r[k / 4].y : (k % 4 == 2 ? r[k / 4].z : r[k / 4].w));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w2s + k * 16 + q * 4);
+        acc2[4 * q] = fmaf(xk, w4.x, acc2[4 * q]); acc2[4 * q + 1] = fmaf(xk, w4.y, acc2[4 * q + 1]);
+        acc2[4 * q + 2] = fmaf(xk, w4.z, acc2[4 * q + 2]); acc2[4 * q + 3] = fmaf(xk, w4.w, acc2[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      r2[q] = valid ? make_float4(epilogue(acc2[4 * q], 4 * q, (size_t)pix, a.e2), epilogue(acc2[4 * q + 1], 4 * q + 1, (size_t)pix, a.e2),
+                                  epilogue(acc2[4 * q + 2], 4 * q + 2, (size_t)pix, a.e2), epilogue(acc2[4 * q + 3], 4 * q + 3, (size_t)pix, a.e2))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (a.ld_out == 16 && (!a.w2 || a.ld_out2 == 16)) {
     // packed output: a thread's 16 channels are 64 contiguous bytes, so four strided float4 stores per thread would
     // touch every sector four times; transpose through shared memory and let the block write 8 KB contiguously
     __shared__ float4 stage[4 * 129];
@@ -196,20 +223,39 @@ __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
       const int j = it * 128 + threadIdx.x;                   // float4 index inside the block's output: pixel j / 4, quad j % 4
       if (blk0 + (j >> 2) < total) dst[j] = stage[(j & 3) * 129 + (j >> 2)];
     }
+    if (a.w2) {
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) stage[q * 129 + threadIdx.x] = r2[q];
+      __syncthreads();
+      float4* dst2 = reinterpret_cast<float4*>(a.out2 + (size_t)blk0 * 16);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int j = it * 128 + threadIdx.x;
+        if (blk0 + (j >> 2) < total) dst2[j] = stage[(j & 3) * 129 + (j >> 2)];
+      }
+    }
     return;
   }
   if (!valid) return;
   float* op = a.out + (size_t)pix * a.ld_out;
 #pragma unroll
   for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(op + 4 * q) = r[q];
+  if (a.w2) {
+    float* op2 = a.out2 + (size_t)pix * a.ld_out2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(op2 + 4 * q) = r2[q];
+  }
 }
 
 void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw, float scale, float offset,
                     const float* w_t, int kh, int kw, int stride_h, int stride_w, int pad_t, int pad_l,
-                    float* out, int oh, int ow, int ld_out, const Epilogue& e) {
-  StemArgs a{in_u8, w_t, out, B, ih, iw, kh, kw, stride_h, stride_w, pad_t, pad_l, oh, ow, ld_out, scale, offset, to_dev(e)};
+                    float* out, int oh, int ow, int ld_out, const Epilogue& e,
+                    const float* w2_kn, float* out2, int ld_out2, const Epilogue* e2) {
+  StemArgs a{in_u8, w_t, out, B, ih, iw, kh, kw, stride_h, stride_w, pad_t, pad_l, oh, ow, ld_out, scale, offset, to_dev(e),
+             w2_kn, out2, ld_out2, e2 ? to_dev(*e2) : EpiDev{nullptr, nullptr, 0, 0, 0, 0}};
   const long total = (long)B * oh * ow;
-  BSB_LAUNCH(k_stem_u8, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * (size_t)kh * kw * 48, s, a);
+  BSB_LAUNCH(k_stem_u8, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * ((size_t)kh * kw * 48 + (w2_kn ? 256 : 0)), s, a);
   count_launch();
 }
 
