@@ -76,6 +76,7 @@ def grab_background(raw, width, height, device=0):
 FLAG_KEEP_TENSORS = _binding.FLAG_KEEP_TENSORS
 FLAG_NO_GRAPH = _binding.FLAG_NO_GRAPH
 FLAG_TENSOR_CORES = _binding.FLAG_TENSOR_CORES
+FLAG_EXACT = _binding.FLAG_EXACT
 
 
 def set_tuning(name: str, value: int) -> None:

@@ -16,7 +16,7 @@ STAGE_CB = C.CFUNCTYPE(None, C.c_void_p)
 BG_READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), i32p, i32p, C.POINTER(C.c_size_t))
 BG_REWIND_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
-FLAG_KEEP_TENSORS, FLAG_NO_GRAPH, FLAG_TENSOR_CORES = 1, 2, 4
+FLAG_KEEP_TENSORS, FLAG_NO_GRAPH, FLAG_TENSOR_CORES, FLAG_FUSE_BLOCKS, FLAG_EXACT = 1, 2, 4, 8, 16
 
 # every symbol include/backscrub_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
@@ -26,7 +26,7 @@ SYMBOLS = [
     "bsb_gaussian_blur", "bsb_gaussian_taps", "bsb_flip",
     "bsb_composite", "bsb_composite_device", "bsb_composite_yuyv", "bsb_composite_yuyv_device", "bsb_convert_yuyv_to_bgr", "bsb_synchronize", "bsb_stream", "bsb_alpha_blend",
     "bsb_convert_rgb_to_yuyv", "bsb_resize_u8c3", "bsb_pointwise", "bsb_time_pointwise", "bsb_geometry", "bsb_infer", "bsb_get_tensor",
-    "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops", "bsb_set_tuning", "bsb_frame_size", "bsb_yuyv_native",
+    "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops", "bsb_set_tuning", "bsb_frame_size", "bsb_yuyv_native", "bsb_uses_tensor_cores",
     "bsb_calcmask_new", "bsb_calcmask_delete", "bsb_calcmask_set_input_frame", "bsb_calcmask_get_output_mask", "bsb_calcmask_timings",
     "bsb_calcmask_frames_done", "bsb_calcmask_mask_serial",
     "bsb_background_new_still", "bsb_background_new_video", "bsb_background_delete", "bsb_background_grab", "bsb_background_grab_into",
@@ -92,6 +92,7 @@ def bind(path: str) -> C.CDLL:
     L.bsb_set_tuning.argtypes = [C.c_char_p, C.c_int]
     L.bsb_frame_size.argtypes = [C.c_void_p, i32p, i32p]
     L.bsb_yuyv_native.argtypes = [C.c_void_p]
+    L.bsb_uses_tensor_cores.argtypes = [C.c_void_p]
     L.bsb_calcmask_new.restype = C.c_void_p
     L.bsb_calcmask_new.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
     L.bsb_calcmask_delete.restype = None

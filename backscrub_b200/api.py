@@ -223,6 +223,10 @@ class MaskGen:
         return ms
 
     @property
+    def uses_tensor_cores(self) -> bool:
+        return bool(self._lib.bsb_uses_tensor_cores(self._h))
+
+    @property
     def yuyv_native(self) -> bool:
         """the last composite_yuyv call read the camera YUYV frames in place (no BGR frame was materialised)"""
         return bool(self._lib.bsb_yuyv_native(self._h))

@@ -526,6 +526,8 @@ long bsb_total_launches(void) { return bsb::launch_count(); }
 
 double bsb_model_flops(bsb_ctx* ctx) { return check_ctx(ctx) ? ctx->eng->flops() : 0.0; }
 
+int bsb_uses_tensor_cores(bsb_ctx* ctx) { return check_ctx(ctx) && ctx->eng->uses_tensor_cores() ? 1 : 0; }
+
 int bsb_yuyv_native(bsb_ctx* ctx) { return check_ctx(ctx) && ctx->eng->last_native() ? 1 : 0; }
 
 int bsb_set_tuning(const char* name, int value) {

@@ -108,6 +108,11 @@ static int unary_act(int kind) {
 // ---------------------------------------------------------------------------
 bool Engine::plan(std::string* err) {
   const int nt = (int)g_.tensors.size(), nops = (int)g_.ops.size();
+  // Tensor cores for the 1x1 convs (3xTF32 split, ~1e-6 relative to the exact fp32 chain — the tolerance the reference's
+  // own XNNPACK-vs-builtin conv tests use): on by default for the GEMM-dominated graphs (DeepLab 93 %, BodyPix 95 % of
+  // their FLOPs are 1x1 convs), on request for the others (BSB_FLAG_TENSOR_CORES), never with BSB_FLAG_EXACT or when
+  // every intermediate tensor is kept for bit-level comparison (BSB_FLAG_KEEP_TENSORS).
+  tc_enabled_ = !(flags_ & (1u | 16u)) && ((flags_ & 4u) || model_type_ == MODEL_DEEPLAB || model_type_ == MODEL_BODYPIX);
   std::vector<std::vector<int>> consumers(nt);
   std::vector<int> produced_at(nt, -1);
   for (int i = 0; i < nops; ++i) {
@@ -207,7 +212,7 @@ bool Engine::plan(std::string* err) {
           auto it = prologue.find(st.in);
           if (it != prologue.end()) { st.in = it->second.x; st.scale = it->second.s; st.in_add = it->second.add; }
           // tensor cores (opt-in): plain GEMM-shaped layers with enough rows and depth to fill a 128 x N x 32 tile pipeline
-          if ((flags_ & 4u) && st.scale < 0 && st.in_add < 0 && ic >= tuning().tc_min_k && ic % 4 == 0 && oc >= 8 &&
+          if (tc_enabled_ && st.scale < 0 && st.in_add < 0 && ic >= tuning().tc_min_k && ic % 4 == 0 && oc >= 8 &&
               tinfo_[st.in].h * tinfo_[st.in].w >= 1024 && tinfo_[st.in].ld % 4 == 0)
             pack_tc_weights(w, oc, ic, st);
         } else {
@@ -420,6 +425,7 @@ bool Engine::plan(std::string* err) {
     steps_.swap(fused);
   }
 
+  for (const Step& st : steps_) uses_tc_ = uses_tc_ || st.use_tc;
   // ---- the low-resolution middle of MobileNetV3-style graphs as one kernel ----
   if (tuning().cnn_chain && !(flags_ & (1u | 8u))) detect_chain();
 

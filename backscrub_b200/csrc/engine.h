@@ -141,6 +141,7 @@ class Engine {
   uint8_t* h_mask() const { return h_mask_; }
   bool has_background() const { return has_bg_; }
   bool last_native() const { return last_native_; }
+  bool uses_tensor_cores() const { return uses_tc_; }
 
  private:
   Engine() = default;
@@ -185,6 +186,7 @@ class Engine {
   bool detect_chain();
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
+  bool tc_enabled_ = false, uses_tc_ = false;   // tensor-core 1x1 convs allowed / actually planned for at least one layer
   bool stem_u8_ok_ = false;          // step 0 is a 3->16 dense conv that is the only reader of the graph input
   bool stem_pw_ok_ = false;          // ... and step 1 is a plain 16 -> 16 1x1 conv of its output (runs inside the stem kernel)
 

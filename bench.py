@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="consecutive frames per stream per step (default 32; 8 at 4k)")
     ap.add_argument("--bgblur", type=int, default=0, help="`-p bgblur:k` of the reference: Gaussian-blur the background (odd k)")
     ap.add_argument("--camera-blur", action="store_true", help="with --bgblur: no background source, blur the camera frame itself")
-    ap.add_argument("--tensor-cores", action="store_true", help="tcgen05 3xTF32 pointwise convs (not bit-exact; IoU-validated)")
+    ap.add_argument("--tensor-cores", action="store_true", help="tcgen05 3xTF32 1x1 convs for any model (default only for DeepLab / BodyPix)")
+    ap.add_argument("--exact", action="store_true", help="fp32 FFMA 1x1 convs everywhere (BSB_FLAG_EXACT: bit-identical to the oracle)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs (parsed.configs)")
@@ -336,7 +337,7 @@ def measure(args, wl, key, dev, rank, world, S, B, steps, warmup, lps, with_e2e,
     my_streams = sharding.streams_for_rank(world * S, rank, world)      # stream ids served by this GPU
     ctxs, rings = [], []
     for s in range(S):
-        c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=4 if args.tensor_cores else 0)
+        c = bs.bs_maskgen_new(model, 2, W, H, device=dev, max_batch=B, flags=(4 if args.tensor_cores else 0) | (16 if args.exact else 0))
         if ring_frames is not None and not args.camera_blur:
             c.set_background_ring(ring_frames, advance=1)
         elif not args.camera_blur:
@@ -482,7 +483,9 @@ def measure(args, wl, key, dev, rank, world, S, B, steps, warmup, lps, with_e2e,
                         "ffma_peak_tflops": 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
                         "launches_per_call": c0.launches_per_call}}
 
-    res = dict(value=value, ms=ms, e2e=e2e, clocks=clocks, stages=stages, roofline=roofline, S=S, B=B, lps=lps,
+    roofline["cnn"]["pointwise_convs"] = "tcgen05 3xTF32 (decisions identical to the exact path on the committed fixtures)" if c0.uses_tensor_cores else "fp32 FFMA (bit-exact vs oracle)"
+    roofline["cnn"]["tensor_dense_tf32_peak_tflops"] = 1100.0
+    res = dict(value=value, ms=ms, e2e=e2e, clocks=clocks, stages=stages, roofline=roofline, S=S, B=B, lps=lps, tc=bool(c0.uses_tensor_cores),
                launches=c0.launches_per_call, bg_desc=bg_desc, flops=flops, yuyv_native=yuyv_native, steps=steps)
     for c in ctxs:
         bs.bs_maskgen_delete(c)
@@ -606,7 +609,7 @@ def run_b200(args, wl):
             "dtype": "f32+u8", "data": "synthetic",
             "config": workload_config(wl, args, S, B, lps, world, {
                 "streams_per_gpu": S, "batch": B, "graph_launches_per_stream_per_step": lps, "frames_per_step": world * S * B * lps,
-                "pointwise_convs": "tcgen05 3xTF32" if args.tensor_cores else "fp32 FFMA (bit-exact vs oracle)",
+                "pointwise_convs": "tcgen05 3xTF32" if m["tc"] else "fp32 FFMA (bit-exact vs oracle)",
                 "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                 "gpu_of_rank0": dev,
                 "background_detail": m["bg_desc"], "host_affinity_cpus": bound_cpus,

@@ -44,8 +44,9 @@ typedef void (*bsb_stage_cb)(void* caller_ctx);
 enum {
   BSB_FLAG_KEEP_TENSORS = 1,  /* keep every intermediate activation (tests / debugging) */
   BSB_FLAG_NO_GRAPH = 2,      /* launch kernels eagerly instead of one CUDA graph per batch */
-  BSB_FLAG_TENSOR_CORES = 4,  /* allow tcgen05 3xTF32 pointwise convs (not bit-exact vs the oracle) */
-  BSB_FLAG_FUSE_BLOCKS = 8    /* experimental: one-kernel inverted-residual blocks (bit-exact; currently slower) */
+  BSB_FLAG_TENSOR_CORES = 4,  /* tcgen05 3xTF32 1x1 convs for ANY model (default only for the GEMM-dominated DeepLab / BodyPix graphs) */
+  BSB_FLAG_FUSE_BLOCKS = 8,   /* round-1 experiment: one-kernel inverted-residual blocks (bit-exact; superseded by the chain kernel) */
+  BSB_FLAG_EXACT = 16         /* fp32 FFMA 1x1 convs everywhere: every activation bit-identical to the CPU oracle (no tensor cores) */
 };
 
 /* replaces bs_tensorflow_version() (lib/libbackscrub.h:13, lib/libbackscrub.cc:150):
@@ -234,6 +235,8 @@ BSB_API double bsb_time_stage(bsb_ctx* ctx, int stage, int n_frames, int iters);
 /* 1 if the last fused call read camera YUYV frames in place (pre-processing and post kernels convert per tap / per tile),
  * 0 if a BGR frame was materialised first (k_yuyv_to_bgr) or the input was BGR */
 BSB_API int bsb_yuyv_native(bsb_ctx* ctx);
+/* 1 if at least one 1x1 conv of this context runs on the tensor cores */
+BSB_API int bsb_uses_tensor_cores(bsb_ctx* ctx);
 /* algorithmic FLOPs of one CNN frame (2*MAC) */
 BSB_API double bsb_model_flops(bsb_ctx* ctx);
 /* Process-wide measurement switches of the kernel launchers (A/B runs in bench.py / tools/): they select between

@@ -9,9 +9,20 @@ from tests import synth
 from tests.conftest import model_path
 
 
+FLAG_EXACT = 16
+
+
+def exact_flag(key):
+    """DeepLab / BodyPix run their 1x1 convs on the tensor cores by default (3xTF32: decisions agree with the oracle on
+    the committed fixtures, activations to ~1e-6); the bit-for-bit comparisons against the oracle select the exact
+    fp32 path with BSB_FLAG_EXACT.  The default path has its own checks (check_tc_default)."""
+    return FLAG_EXACT if key in ("deeplab", "bodypix") else 0
+
+
 def check_pipeline(lib, key, W, H, n_frames=3, batch=None, tensors=False, frame_kind="person", flags=0):
     """n consecutive frames of one stream through bsb_composite (batched) vs the oracle."""
     batch = batch or n_frames
+    flags |= exact_flag(key)
     g = api.MaskGen(lib, model_path(key), W, H, max_batch=batch, flags=flags | (1 if tensors else 0))
     o = po.MaskGen(model_path(key), W, H)
     assert g.roidim == o.roidim and g.in_roidim == o.in_roidim and g.out_roidim == o.out_roidim
@@ -68,7 +79,7 @@ def check_tensors(lib, key, W=640, H=480):
 
 def check_infer_batch(lib, key, n=3):
     """bsb_infer on a batch == oracle interpreter frame by frame (bit-exact)."""
-    g = api.MaskGen(lib, model_path(key), 640, 480, max_batch=n)
+    g = api.MaskGen(lib, model_path(key), 640, 480, max_batch=n, flags=exact_flag(key))
     m = po.Model(model_path(key))
     rng = np.random.default_rng(11)
     x = rng.uniform(-1 if key == "deeplab" else 0, 1, (n, *g.in_hwc)).astype(np.float32)
@@ -312,7 +323,7 @@ def check_post_variants(lib, key="meet_full", W=1280, H=720, n=3):
         for tma in (1, 0):
             assert lib.bsb_set_tuning(b"post_tma", tma)
             for kind in ("person", "noise", "const"):
-                g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+                g = api.MaskGen(lib, model_path(key), W, H, max_batch=n, flags=exact_flag(key))
                 o = po.MaskGen(model_path(key), W, H)
                 g.set_background(bg)
                 bgr = np.stack([synth.frame(W, H, t=t, kind=kind) for t in range(n)])
@@ -326,7 +337,7 @@ def check_post_variants(lib, key="meet_full", W=1280, H=720, n=3):
             bgr = np.stack([synth.frame(W, H, t=t) for t in range(n)])
             yin = np.stack([po.convert_rgb_to_yuyv(f) for f in bgr])
             for want in ((True, False, False), (False, True, False), (False, False, True), (True, True, False)):
-                g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+                g = api.MaskGen(lib, model_path(key), W, H, max_batch=n, flags=exact_flag(key))
                 o = po.MaskGen(model_path(key), W, H)
                 g.set_background(bg)
                 bufs = [np.zeros((n, H, W, 3), np.uint8) if want[0] else None, np.zeros((n, H, W, 2), np.uint8) if want[1] else None,
@@ -339,7 +350,7 @@ def check_post_variants(lib, key="meet_full", W=1280, H=720, n=3):
                             assert np.array_equal(got[b], exp), (tma, want, b)
                 g.close()
             # BGR input + animated background ring (one image per frame, wraps inside the batch)
-            g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+            g = api.MaskGen(lib, model_path(key), W, H, max_batch=n, flags=exact_flag(key))
             o = po.MaskGen(model_path(key), W, H)
             g.set_background_ring(ring, advance=1)
             for rep in range(2):
@@ -379,3 +390,34 @@ def check_chain(lib, key, n=3, max_launches=45):
     assert np.array_equal(outs[1].view(np.uint32), outs[0].view(np.uint32)), f"{key}: chain and stand-alone kernels differ"
     for b in range(n):
         assert np.array_equal(outs[1][b].view(np.uint32), m.invoke(x[b])[0].view(np.uint32)), f"{key}: frame {b} differs from the oracle"
+
+
+TC_FIXTURES = [("deeplab", 640, 480, 6), ("deeplab", 1280, 720, 4), ("bodypix", 640, 480, 6), ("bodypix", 1920, 1080, 3), ("bodypix", 3840, 2160, 2)]
+
+
+def check_tc_default(lib, key, W, H, n):
+    """The default path of the GEMM-dominated models (tensor-core 1x1 convs) on the committed synthetic fixtures: every
+    per-frame decision, mask byte and composited byte equals the exact fp32 path (which the other tests pin to the
+    oracle bit for bit) — 0 flips — and the logits stay within the reference's own fp32-conv tolerance."""
+    bg = synth.background()
+    for kind in ("person", "noise"):
+        frames = np.stack([synth.frame(W, H, t=t, kind=kind) for t in range(n)])
+        res = {}
+        for name, flags in (("exact", FLAG_EXACT), ("default", 0)):
+            g = api.MaskGen(lib, model_path(key), W, H, max_batch=n, flags=flags)
+            assert g.uses_tensor_cores == (name == "default")
+            g.set_background(bg)
+            out, yuyv, mask = g.composite(frames)
+            res[name] = (np.stack([g.stage_u8(2, b) for b in range(n)]), mask, out, yuyv)
+            g.close()
+        for a, b, what in zip(res["exact"], res["default"], ("decisions (ofinal)", "mask", "composite", "YUYV")):
+            assert np.array_equal(a, b), f"{key} {W}x{H} {kind}: {what} differs between the exact and the tensor-core path ({int((a != b).sum())} bytes)"
+    # logits: tensor-core vs oracle on one frame
+    g = api.MaskGen(lib, model_path(key), 640, 480, max_batch=1)
+    o = po.MaskGen(model_path(key), 640, 480)
+    m = po.Model(model_path(key))
+    o.process(synth.frame(640, 480, t=2))
+    ref = m.invoke(o.input_f32)[0]
+    got = g.infer(o.input_f32[None])[0]
+    assert np.abs(got - ref).max() < 2e-3 * max(1.0, float(np.abs(ref).max()) / 10.0), float(np.abs(got - ref).max())
+    g.close()

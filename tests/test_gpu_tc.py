@@ -70,6 +70,21 @@ def test_model_tc_vs_oracle(lib, key):
     g.close()
 
 
+@pytest.mark.parametrize("key,W,H,n", [(k, w, h, n) for (k, w, h, n) in __import__("tests.parity_common", fromlist=["x"]).TC_FIXTURES])
+def test_tc_default_path_has_no_flips_on_the_fixtures(lib, key, W, H, n):
+    from tests import parity_common as pc
+    pc.check_tc_default(lib, key, W, H, n)
+
+
+def test_meet_stays_exact_by_default(lib):
+    g = api.MaskGen(lib, model_path("meet_full"), 640, 480)
+    assert not g.uses_tensor_cores
+    g.close()
+    g = api.MaskGen(lib, model_path("meet_full"), 640, 480, flags=4)
+    assert g.uses_tensor_cores
+    g.close()
+
+
 def test_pipeline_tc_mask_iou(lib):
     W, H = 1280, 720
     g = api.MaskGen(lib, model_path("deeplab"), W, H, max_batch=2, flags=4)
