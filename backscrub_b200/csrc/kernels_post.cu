@@ -62,14 +62,15 @@ struct PostTmaCfg { int has_out, has_yuyv, has_mask, has_bgy; };
 // A TMA box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate raises "illegal
 // instruction"), so the box begins at the patch's first column rounded down to 16 and is 16 columns wider.
 constexpr int PT_RMAX = 24, PT_PCOLS = 80, PT_PW = PT_PCOLS + 16;
-// A CTA owns PT_NT x-adjacent tiles.  The loads of ALL its tiles are issued up front, so while tile 0 is classified,
-// blended and stored, the operands of tile 1 are already landing: the load latency is paid once per CTA, not once per tile.
-// Shared memory: per tile the four TMA tiles + patch + mask staging; one mask-building scratch shared by the tiles
-// (Vs reuses Hs, dead after the vertical resize pass).  ~95 KB per CTA: two CTAs (four tiles in flight) per SM.
-constexpr int PT_NT = 2;
+// A CTA owns PT_NT x-adjacent tiles; the loads of all its tiles are issued up front.  Measured on a B200 (run r2i): two
+// tiles per CTA (95 KB, two CTAs per SM) is SLOWER than one (88.6 vs 65.6 us per 32-frame 720p launch) — the halved warp
+// count costs more than the amortised load latency saves — so PT_NT = 1: ~53 KB per CTA, four CTAs per SM.
+// Shared memory: per tile the TMA tiles + patch (+ mask staging when PT_NT > 1); one mask-building scratch shared by the
+// tiles (Vs reuses Hs, dead after the vertical resize pass; with one tile per CTA the mask staging tile reuses Us).
+constexpr int PT_NT = 1;
 constexpr int PT_OFF_F = 0, PT_OFF_B = 12288, PT_OFF_Y = 24576, PT_OFF_P = 32768;
 constexpr int PT_OFF_M = PT_OFF_P + PT_RMAX * PT_PW;             // mask tile [32][128]
-constexpr int PT_TILE = PT_OFF_M + 4096;                         // bytes of per-tile buffers
+constexpr int PT_TILE = PT_OFF_M + (PT_NT > 1 ? 4096 : 0);       // bytes of per-tile buffers
 constexpr int PT_OFF_HS = PT_NT * PT_TILE;                       // [PT_RMAX][PF_US] u16, later Vs [PF_H][PF_US] u16
 constexpr int PT_HV_BYTES = (PT_RMAX > PF_H ? PT_RMAX : PF_H) * PF_US * 2;
 constexpr int PT_OFF_VS = PT_OFF_HS;
@@ -78,12 +79,13 @@ constexpr int PT_OFF_ROWS = PT_OFF_US + PF_UH * PF_US * 2;       // [PF_UH] uint
 constexpr int PT_OFF_BAR = PT_OFF_ROWS + PF_UH * 16;
 constexpr int PT_SMEM = PT_OFF_BAR + 64;
 static_assert(PT_PW % 16 == 0 && PT_OFF_M % 128 == 0 && PT_TILE % 128 == 0 && PT_OFF_HS % 16 == 0 && PT_OFF_US % 16 == 0 && PT_OFF_ROWS % 16 == 0 &&
-              PT_OFF_BAR % 8 == 0 && PT_NT * 3 * 8 <= 64 && PT_SMEM <= 113 * 1024, "smem layout");
+              PT_OFF_BAR % 8 == 0 && PT_NT * 3 * 8 <= 64 && PT_OFF_US % 128 == 0 && PF_UH * PF_US * 2 >= 4096 &&
+              PT_SMEM <= (PT_NT > 1 ? 113 : 56) * 1024, "smem layout");
 
 struct TileGeo { int tx0, hits_roi, gy_lo, gx_lo, rmin, nrows, cmin, ncols, coff; };
 
 template <bool IN_YUYV>
-__global__ void __launch_bounds__(256, 2) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
+__global__ void __launch_bounds__(256, PT_NT > 1 ? 2 : 4) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned short* Hs = reinterpret_cast<unsigned short*>(smem + PT_OFF_HS);
   unsigned short* Us = reinterpret_cast<unsigned short*>(smem + PT_OFF_US);
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256, 2) k_post_tma(const __grid_constant__ Pos
     uint8_t* sF = tb + PT_OFF_F;            // frame tile [32][384] (BGR) or [32][256] (YUYV); later the blended tile
     uint8_t* sB = tb + PT_OFF_B;            // background tile [32][384]
     uint8_t* sY = tb + PT_OFF_Y;            // YUYV tile [32][256]: cached background YUYV in, result out
-    uint8_t* sM = tb + PT_OFF_M;            // mask tile [32][128]
+    uint8_t* sM = PT_NT > 1 ? tb + PT_OFF_M : smem + PT_OFF_US;   // mask tile [32][128] (one tile per CTA: reuses Us, dead by then)
     uint8_t* sP = tb + PT_OFF_P;            // source patch of the small mask [PT_RMAX][PT_PW]
     uint64_t* barP = bars + 3 * t; uint64_t* barB = barP + 1; uint64_t* barF = barP + 2;
     const int tx0 = g.tx0;
@@ -251,8 +253,10 @@ __global__ void __launch_bounds__(256, 2) k_post_tma(const __grid_constant__ Pos
     uint4* ydst = reinterpret_cast<uint4*>(sY + ly * (PF_W * 2) + lx * 2);
     const uint8_t* out_src = sB;
 
-    tma::mbar_wait(barB, 0);          // every tile waits for all of its loads: shared memory must be quiet at exit
-    if (hits_roi) tma::mbar_wait(barF, 0);
+    tma::mbar_wait(barB, 0);
+    // a background tile does not use its (speculatively loaded) camera tile: only thread 0 waits for it, after the stores
+    // are on their way (shared memory must be quiet when the CTA exits)
+    if (hits_roi && kind != 0) tma::mbar_wait(barF, 0);
     if (kind == 0) {
       // ---- background tile: out = background tile, YUYV = cached YUYV tile, mask = 255.  No per-pixel arithmetic ----
       if (cfg.has_mask) *mdst = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -314,6 +318,7 @@ __global__ void __launch_bounds__(256, 2) k_post_tma(const __grid_constant__ Pos
       if (cfg.has_yuyv) tma::store_3d(&tm.yuyv, sY, txi * 64, ty0, b);
       if (cfg.has_mask) tma::store_3d(&tm.mask, sM, tx0, ty0, b);
       tma::store_commit();
+      if (hits_roi && kind == 0) tma::mbar_wait(barF, 0);
     }
   }
   if (tid == 0) tma::store_wait_read();      // shared memory may be handed to the next CTA only after the engine has read it

@@ -124,7 +124,7 @@ def cpu_path_fps(wl, threads, frames_per_thread, warm=1, bgblur=0, camera_blur=F
     def work(i, lo, hi):
         g, fr = gens[i], frames[i % len(frames)]
         for t in range(lo, hi):
-            g.composite_ex(po.yuyv_to_bgr(fr[t]), None if camera_blur else ring[t % len(ring)], bgblur=bgblur, want_yuyv=True)
+            g.composite_ex(po.yuyv_to_bgr(fr[t]), None if camera_blur else ring[t % len(ring)], bgblur=bgblur, want_yuyv=True, reuse=True)
 
     def run(lo, hi):
         th = [threading.Thread(target=work, args=(i, lo, hi)) for i in range(threads)]

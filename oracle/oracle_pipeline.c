@@ -33,7 +33,14 @@ struct or_maskgen {
   uint8_t* ofinal;      /* oh*ow IIR state */
   uint8_t* mask;        /* H*W, 255 outside roidim */
   uint8_t* tmp_up;      /* roi_h*roi_w */
+  uint8_t* scratch[3];  /* W*H*3 each: frame copy / background / work image of or_composite[_ex] (the reference allocates
+                           cv::Mats per frame, app/deepseg.cc:110,649; kept here so the timed CPU arm scales with threads) */
 };
+
+static uint8_t* scratch_buf(or_maskgen* g, int i) {
+  if (!g->scratch[i]) g->scratch[i] = (uint8_t*)malloc((size_t)g->W * g->H * 3);
+  return g->scratch[i];
+}
 
 /* lib/libbackscrub.cc:116-130 */
 int or_model_type_from_name(const char* path) {
@@ -49,6 +56,7 @@ void or_maskgen_delete(or_maskgen* g) {
   or_model_free(g->model);
   free(g->in_u8_bgr); free(g->in_u8_rgb); free(g->filtered); free(g->input);
   free(g->ofinal); free(g->mask); free(g->tmp_up);
+  free(g->scratch[0]); free(g->scratch[1]); free(g->scratch[2]);
   free(g);
 }
 
@@ -201,16 +209,15 @@ int or_composite(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
   int rc = or_maskgen_process(g, frame_bgr, stride, out_mask);
   if (rc) return rc;
   /* app/background.cc:178-194: resize the raw background to the frame size, every frame */
-  uint8_t* bg = (uint8_t*)malloc(npix * 3);
+  uint8_t* bg = scratch_buf(g, 1);
   or_resize_linear_u8(bg_raw, bw, bh, bstride, bg, g->W, g->H, (size_t)g->W * 3, 3);
   /* the camera frame as a packed buffer (alpha_blend walks data pointers linearly) */
-  uint8_t* fr = (uint8_t*)malloc(npix * 3);
+  uint8_t* fr = scratch_buf(g, 0);
   for (int y = 0; y < g->H; ++y) memcpy(fr + (size_t)y * g->W * 3, frame_bgr + (size_t)y * stride, (size_t)g->W * 3);
   /* app/deepseg.cc:661: raw = alpha_blend(bg, raw, mask) */
   or_alpha_blend(bg, fr, g->mask, out_rgb, npix);
   /* app/deepseg.cc:681 */
   if (out_yuyv) or_convert_rgb_to_yuyv(out_rgb, out_yuyv, g->W, g->H);
-  free(bg); free(fr);
   return 0;
 }
 
@@ -223,9 +230,9 @@ int or_composite_ex(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
   const int ow = o->out_w > 0 ? o->out_w : W, oh = o->out_h > 0 ? o->out_h : H;
   int rc = or_maskgen_process(g, frame_bgr, stride, out_mask);
   if (rc) return rc;
-  uint8_t* fr = (uint8_t*)malloc(npix * 3);
-  uint8_t* bg = (uint8_t*)malloc(npix * 3);
-  uint8_t* cur = (uint8_t*)malloc(npix * 3);
+  uint8_t* fr = scratch_buf(g, 0);
+  uint8_t* bg = scratch_buf(g, 1);
+  uint8_t* cur = scratch_buf(g, 2);
   for (int y = 0; y < H; ++y) memcpy(fr + (size_t)y * W * 3, frame_bgr + (size_t)y * stride, (size_t)W * 3);
   /* app/deepseg.cc:649-655: the grabbed background, else a copy of the camera frame */
   if (bg_raw) or_resize_linear_u8(bg_raw, bw, bh, bstride, bg, W, H, (size_t)W * 3, 3);
@@ -233,13 +240,12 @@ int or_composite_ex(or_maskgen* g, const uint8_t* frame_bgr, size_t stride,
   /* :657-658 (in place in the reference; GaussianBlur clones the source when src == dst) */
   if (o->bgblur_k) {
     memcpy(cur, bg, npix * 3);
-    if (or_gaussian_blur_u8c3(cur, W, H, (size_t)W * 3, bg, (size_t)W * 3, o->bgblur_k)) { free(fr); free(bg); free(cur); return -1; }
+    if (or_gaussian_blur_u8c3(cur, W, H, (size_t)W * 3, bg, (size_t)W * 3, o->bgblur_k)) return -1;
   }
   or_alpha_blend(bg, fr, g->mask, cur, npix);                                   /* :661 */
   if (o->flip_h || o->flip_v) { or_flip_u8c3(cur, bg, W, H, o->flip_h, o->flip_v); memcpy(cur, bg, npix * 3); }   /* :667-673 */
   if (ow != W || oh != H) or_resize_linear_u8(cur, W, H, (size_t)W * 3, out_rgb, ow, oh, (size_t)ow * 3, 3);     /* :677-679 */
   else memcpy(out_rgb, cur, npix * 3);
   if (out_yuyv) or_convert_rgb_to_yuyv(out_rgb, out_yuyv, ow, oh);              /* :681 */
-  free(fr); free(bg); free(cur);
   return 0;
 }

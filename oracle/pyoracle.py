@@ -440,7 +440,7 @@ class MaskGen:
             raise RuntimeError(f"or_composite rc={rc}")
         return out, yuyv, mask
 
-    def composite_ex(self, frame_bgr, bg_raw=None, bgblur=0, flip_h=False, flip_v=False, out_size=None, want_yuyv=True):
+    def composite_ex(self, frame_bgr, bg_raw=None, bgblur=0, flip_h=False, flip_v=False, out_size=None, want_yuyv=True, reuse=False):
         """app/deepseg.cc:640-681 with its options; bg_raw None = blur-the-camera-frame mode."""
         frame_bgr = _cu(frame_bgr)
         ow, oh = out_size if out_size else (self.W, self.H)
@@ -450,9 +450,15 @@ class MaskGen:
             bh, bw = bg_raw.shape[:2]
         else:
             bh = bw = 0
-        out = np.empty((oh, ow, 3), np.uint8)
-        yuyv = np.empty((oh, ow, 2), np.uint8) if want_yuyv else None
-        mask = np.empty((self.H, self.W), np.uint8)
+        # result arrays are kept per context (same-shape calls reuse them when `reuse`): a timed multi-threaded run then does
+        # not spend its time in mmap / page faults of three fresh frame-sized arrays per frame
+        if reuse and getattr(self, "_bufs", None) is not None and self._bufs[0].shape == (oh, ow, 3):
+            out, yuyv_b, mask = self._bufs
+        else:
+            out, yuyv_b, mask = np.empty((oh, ow, 3), np.uint8), np.empty((oh, ow, 2), np.uint8), np.empty((self.H, self.W), np.uint8)
+            if reuse:
+                self._bufs = (out, yuyv_b, mask)
+        yuyv = yuyv_b if want_yuyv else None
         rc = lib().or_composite_ex(self.h, _u(frame_bgr), C.c_size_t(self.W * 3), _u(bg_raw) if bg_raw is not None else None,
                                    bw, bh, C.c_size_t(bw * 3), C.byref(o), _u(out), _u(yuyv) if want_yuyv else None, _u(mask))
         if rc:
