@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--exact", action="store_true", help="fp32 FFMA 1x1 convs everywhere (BSB_FLAG_EXACT: bit-identical to the oracle)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-hugepages", action="store_true", help="end-to-end staging buffers on 2 MB transparent huge pages + cudaHostRegister instead of cudaHostAlloc")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs (parsed.configs)")
     ap.add_argument("--frames", default="person", choices=["person", "noise", "const"], help="synthetic stream kind (SURVEY 8d)")
     ap.add_argument("--launches-per-step", type=int, default=4, help="graph launches per stream per timed step (lengthens the timed window)")
@@ -391,11 +392,36 @@ def measure(args, wl, key, dev, rank, world, S, B, steps, warmup, lps, with_e2e,
     # ---- end to end through the host-buffer C-ABI call (H2D + graph + D2H every step) ----
     e2e = None
     if with_e2e:
-        pin = lambda shape: torch.empty(shape, dtype=torch.uint8).pin_memory()
+        keep = []
+
+        def pin(shape):
+            """page-locked staging buffer allocated (first-touched) on this rank's NUMA node"""
+            if not args.e2e_hugepages:
+                t = torch.empty(shape, dtype=torch.uint8).pin_memory()
+                keep.append(t)
+                return t.numpy()
+            import ctypes
+            import mmap
+            n = int(np.prod(shape))
+            size = (n + (2 << 20) - 1) // (2 << 20) * (2 << 20)
+            mm = mmap.mmap(-1, size, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+            try:
+                mm.madvise(mmap.MADV_HUGEPAGE)
+            except Exception:
+                pass
+            arr = np.frombuffer(mm, dtype=np.uint8, count=n).reshape(shape)
+            arr[...] = 0
+            rt = ctypes.CDLL("libcudart.so.12")
+            rt.cudaHostRegister.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint]
+            rc = rt.cudaHostRegister(arr.ctypes.data, size, 0)
+            if rc != 0:
+                raise RuntimeError(f"cudaHostRegister failed: {rc}")
+            keep.append((mm, rt))
+            return arr
         hb = []
         for s in range(S):
-            h_in = pin((B, H, W, 2)); h_in.numpy()[:] = rings[s]["host"]
-            hb.append(dict(inp=h_in.numpy(), yuyv=pin((B, H, W, 2)).numpy(), keep=h_in))
+            h_in = pin((B, H, W, 2)); h_in[:] = rings[s]["host"]
+            hb.append(dict(inp=h_in, yuyv=pin((B, H, W, 2))))
         e_steps = max(3, steps * lps // 2)
 
         def worker(s, n):
@@ -421,6 +447,7 @@ def measure(args, wl, key, dev, rank, world, S, B, steps, warmup, lps, with_e2e,
         e2e = {"value": world * S * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * B * npx * 2,
                "d2h_bytes_per_step": S * B * npx * 2, "steps": e_steps, "frames_per_step": world * S * B,
                "pcie_gbs_each_direction": world * S * B * e_steps * npx * 2 / dt / 1e9 / world,
+               "host_buffers": "2 MB huge pages + cudaHostRegister" if args.e2e_hugepages else "cudaHostAlloc (torch pin_memory)",
                "input": "camera YUYV frame in pinned host memory (read in place by the GPU kernels; app/deepseg.cc:553 converts it on the CPU)",
                "result": "YUYV frame (what app/deepseg.cc:681-690 writes to the v4l2 loopback device)"}
 

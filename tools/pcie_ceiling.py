@@ -19,6 +19,30 @@ import time
 import torch
 
 
+def cudart():
+    """libcudart through ctypes (torch's own binding does not export cudaMemcpyAsync / cudaHostRegister)"""
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            L = ctypes.CDLL(name)
+            L.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+            L.cudaHostRegister.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint]
+            L.cudaHostUnregister.argtypes = [ctypes.c_void_p]
+            return L
+        except OSError:
+            continue
+    import glob
+    for path in glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")):
+        L = ctypes.CDLL(path)
+        L.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        L.cudaHostRegister.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint]
+        L.cudaHostUnregister.argtypes = [ctypes.c_void_p]
+        return L
+    raise RuntimeError("libcudart not found")
+
+
+RT = None
+
+
 def numa_cpus(dev):
     try:
         import pynvml
@@ -38,7 +62,7 @@ def numa_cpus(dev):
 class HostBuf:
     def __init__(self, nbytes, kind, write_combined=False):
         self.kind, self.nbytes = kind, nbytes
-        rt = torch.cuda.cudart()
+        rt = RT
         if kind == "huge":
             size = (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20)
             self.mm = mmap.mmap(-1, size, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
@@ -50,8 +74,9 @@ class HostBuf:
             self.ptr = ctypes.addressof(buf)
             ctypes.memset(self.ptr, 1, size)                       # first touch on this thread's NUMA node
             r = rt.cudaHostRegister(self.ptr, size, 0)
-            assert int(r) == 0, r
+            assert int(r) == 0, f"cudaHostRegister -> {r}"
             self.t = None
+            self.size = size
         else:
             self.t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
             self.t.fill_(1)
@@ -72,7 +97,7 @@ def run_set(gpus, kind, mb, seconds):
             din = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
             dout = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
             s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            rt = torch.cuda.cudart()
+            rt = RT
 
             def burst(n):
                 for _ in range(n):
@@ -86,6 +111,9 @@ def run_set(gpus, kind, mb, seconds):
                 s1.synchronize(); s2.synchronize()
             dt = time.perf_counter() - t0
             res[dev] = n * nbytes / dt / 1e9
+            for hb in (hin, hout):
+                if hb.kind == "huge":
+                    rt.cudaHostUnregister(hb.ptr)
         except Exception as e:                                         # report, never hang the barrier
             errs.append(f"gpu {dev}: {e}")
             try:
@@ -107,6 +135,9 @@ def main():
     ap.add_argument("--seconds", type=float, default=0.6)
     ap.add_argument("--mb", type=int, default=118)
     a = ap.parse_args()
+    global RT
+    torch.cuda.init()
+    RT = cudart()
     n = torch.cuda.device_count()
     sets = [[0]]
     if n >= 2: sets.append([0, 1])
