@@ -425,6 +425,19 @@ bool Engine::plan(std::string* err) {
     steps_.swap(fused);
   }
 
+  // ---- RESIZE_BILINEAR folded into the 1x1 conv that is its only reader ----
+  if (tuning().up_pw) {
+    for (size_t i = 0; i + 1 < steps_.size(); ++i) {
+      const Step& r = steps_[i]; Step& q = steps_[i + 1];
+      if (r.kind != Step::RESIZE || q.kind != Step::PW || q.in != r.out || q.scale >= 0 || q.in_add >= 0 || q.residual >= 0 || q.use_tc) continue;
+      if (r.out == g_.output || consumers[r.out].size() != 1) continue;
+      if (!upsample_pw_supported(q.K, q.N, q.n4, tinfo_[r.in].ld, tinfo_[q.out].ld)) continue;
+      q.up_from = r.in; q.align_corners = r.align_corners; q.half_pixel = r.half_pixel;
+      q.in = r.in;                                    // liveness: the conv now reads the low-resolution tensor
+      tinfo_[r.out].materialized = false;
+      steps_.erase(steps_.begin() + i);
+    }
+  }
   for (const Step& st : steps_) uses_tc_ = uses_tc_ || st.use_tc;
   // ---- the low-resolution middle of MobileNetV3-style graphs as one kernel ----
   if (tuning().cnn_chain && !(flags_ & (1u | 8u))) detect_chain();
@@ -814,6 +827,12 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
                            st.dh, st.dw, st.pt, st.pl, tptr(st.out), O.h, O.w, O.ld, e);
         break;
       case Step::PW:
+        if (st.up_from >= 0) {
+          const TensorInfo& S = tinfo_[st.up_from];
+          launch_upsample_pw(stream_, n, tptr(st.up_from), S.h, S.w, st.K, S.ld, st.align_corners, st.half_pixel, wblob_ + st.w_off, st.n4, st.N,
+                             tptr(st.out), O.h, O.w, O.ld, e);
+          break;
+        }
         if (st.use_tc && launch_pointwise_tc(stream_, n * I.h * I.w, st.K, st.N, tptr(st.in), I.ld, wblob_ + st.tc_hi_off, wblob_ + st.tc_lo_off,
                                              st.kpad, st.npad, tptr(st.out), O.ld, e))
           break;

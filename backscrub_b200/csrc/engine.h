@@ -41,6 +41,7 @@ struct Step {
   int elt_mode = 0;
   bool align_corners = false, half_pixel = false;
   int copy_off = 0;
+  int up_from = -1;           // PW: >= 0 -> the input is RESIZE_BILINEAR(up_from), interpolated on the fly (k_upsample_pw)
   bool use_tc = false; size_t tc_hi_off = 0, tc_lo_off = 0; int kpad = 0, npad = 0;   // tensor-core pointwise
   // POOL: optional fused fully-connected chain (squeeze-excite) after the global average pool
   struct Fc { size_t w_off = 0, b_off = 0; bool has_bias = false; int K = 0, N = 0, n4 = 0, act1 = 0, act2 = 0; };

@@ -119,6 +119,12 @@ void launch_chain(cudaStream_t s, int B, int h, int w, const ChainOp* d_ops, int
 void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                             float* out, int oh, int ow, int ld_out, bool align_corners, bool half_pixel);
 
+// RESIZE_BILINEAR + the 1x1 conv that consumes it, fused (N <= 24 output channels; the up-sampled tensor is never
+// materialised; same arithmetic per output as the two stand-alone kernels)
+bool upsample_pw_supported(int K, int N, int n4, int ld_in, int ld_out);
+void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, int K, int ld_in, bool align_corners, bool half_pixel,
+                        const float* w_kn, int n4, int N, float* out, int oh, int ow, int ld_out, const Epilogue& e);
+
 // Convolution2DTransposeBias k2x2 s2 (lib/transpose_conv_bias.cc:37-114).  w: OHWI [oc][2][2][ic].
 void launch_tconv2x2(cudaStream_t s, int B, const float* in, int ih, int iw, int ic, int ld_in,
                      const float* w, const float* bias, int oc, float* out, int oh, int ow, int ld_out, int act2);
@@ -231,6 +237,7 @@ struct Tuning {
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel
   int tc_min_k = 16;       // smallest input depth of a 1x1 conv that goes to the tensor cores (with BSB_FLAG_TENSOR_CORES)
   int tc_mask_hi = 0;      // tensor-core kernel: clear the low mantissa bits of A explicitly instead of relying on the hardware truncation
+  int up_pw = 1;           // fuse RESIZE_BILINEAR into the 1x1 conv that consumes it
   int stem_pw = 1;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)

@@ -143,8 +143,8 @@ BSB_D void chain_fc(const float* in, const FcLayer& f, float* out, float* stage,
 // A lane keeps its channel, so its KS*KS taps live in registers; a thread produces 4 consecutive pixels of a row from
 // KS x (KS + 3) loads.  Out-of-image taps read the halo's zeros: fmaf(+0, w, acc) leaves acc unchanged bit for bit (an
 // accumulator that starts at +0 can never become -0 by adding zeros), so skipping them as the oracle does gives the same bits.
-template <int KS>
-BSB_D void chain_dw_slice(const float* E, const float* wds, const ChainOp& op, int c0, int cw, int h, int w, float* D) {
+template <int KS, int ACT2>
+BSB_D void chain_dw_slice_t(const float* E, const float* wds, const ChainOp& op, int c0, int cw, int h, int w, float* D) {
   const int j = threadIdx.x & 31;
   if (j >= cw) return;
   float wr[KS * KS];
@@ -152,6 +152,7 @@ BSB_D void chain_dw_slice(const float* E, const float* wds, const ChainOp& op, i
   for (int t = 0; t < KS * KS; ++t) wr[t] = wds[t * 32 + j];
   const float bias = op.bd ? __ldg(op.bd + c0 + j) : 0.f;
   const int ew = w + 2 * CH_PAD, strips = (w + 3) / 4;
+  const bool full = (w & 3) == 0;                 // every strip has 4 pixels and its KS + 3 columns lie inside the haloed grid
   for (int sidx = threadIdx.x >> 5; sidx < h * strips; sidx += blockDim.x >> 5) {
     const int oy = sidx / strips, ox0 = (sidx - oy * strips) * 4;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -160,8 +161,13 @@ BSB_D void chain_dw_slice(const float* E, const float* wds, const ChainOp& op, i
 #pragma unroll
     for (int fy = 0; fy < KS; ++fy) {
       float v[KS + 3];
+      if (full) {
 #pragma unroll
-      for (int c = 0; c < KS + 3; ++c) v[c] = (ox0 - op.pl + CH_PAD + c < ew) ? e0[((size_t)fy * ew + c) * CH_ELD] : 0.f;
+        for (int c = 0; c < KS + 3; ++c) v[c] = e0[((size_t)fy * ew + c) * CH_ELD];
+      } else {
+#pragma unroll
+        for (int c = 0; c < KS + 3; ++c) v[c] = (ox0 - op.pl + CH_PAD + c < ew) ? e0[((size_t)fy * ew + c) * CH_ELD] : 0.f;
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -169,8 +175,23 @@ BSB_D void chain_dw_slice(const float* E, const float* wds, const ChainOp& op, i
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (ox0 + q < w) D[(size_t)(oy * w + ox0 + q) * CH_DLD + c0 + j] = chain_act2(acc[q] + bias, op.dact1, op.dact2);
+      if (ox0 + q < w) {
+        const float r = acc[q] + bias;
+        D[(size_t)(oy * w + ox0 + q) * CH_DLD + c0 + j] = ACT2 >= 0 ? bsb_act(r, ACT2) : chain_act2(r, op.dact1, op.dact2);
+      }
   }
+}
+
+// depthwise KS x KS, stride 1, SAME, of one 32-channel slice: E (zero-haloed (h+4) x (w+4) grid of [32]) -> D[:, c0 : c0 + cw].
+// A lane keeps its channel, so its KS*KS taps live in registers; a thread produces 4 consecutive pixels of a row from
+// KS x (KS + 3) loads.  Out-of-image taps read the halo's zeros: fmaf(+0, w, acc) leaves acc unchanged bit for bit (an
+// accumulator that starts at +0 can never become -0 by adding zeros), so skipping them as the oracle does gives the same bits.
+template <int KS>
+BSB_D void chain_dw_slice(const float* E, const float* wds, const ChainOp& op, int c0, int cw, int h, int w, float* D) {
+  if (op.dact1 == ACT_NONE && op.dact2 == ACT_HARD_SWISH) chain_dw_slice_t<KS, ACT_HARD_SWISH>(E, wds, op, c0, cw, h, w, D);
+  else if (op.dact1 == ACT_NONE && op.dact2 == ACT_RELU6) chain_dw_slice_t<KS, ACT_RELU6>(E, wds, op, c0, cw, h, w, D);
+  else if (op.dact1 == ACT_NONE && op.dact2 == ACT_RELU) chain_dw_slice_t<KS, ACT_RELU>(E, wds, op, c0, cw, h, w, D);
+  else chain_dw_slice_t<KS, -1>(E, wds, op, c0, cw, h, w, D);
 }
 
 }  // namespace

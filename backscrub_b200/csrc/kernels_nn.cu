@@ -1119,6 +1119,97 @@ __global__ void __launch_bounds__(256) k_resize_bilinear(const float* in, int B,
   }
 }
 
+// RESIZE_BILINEAR fused into the 1x1 conv that consumes it: one thread = one output pixel and ALL its output channels
+// (N <= 24); the interpolated input value (the exact expression of k_resize_bilinear above) is formed per channel in
+// registers and fed straight into the k-ascending fmaf chains, so the up-sampled tensor is never written or re-read.
+struct UpPwArgs {
+  const float* in; const float* w; float* out;
+  int B, ih, iw, K, ld_in, oh, ow, N, n4, ld_out;
+  float hs, ws; bool half_pixel;
+  EpiDev e;
+};
+
+template <int NQ>     // output channel quads: n4 = 4 * NQ
+__global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a) {
+  BSB_DYN_SMEM(smem_raw);
+  float* Ws = reinterpret_cast<float*>(smem_raw);            // [K][n4]
+  for (int i = threadIdx.x * 4; i < a.K * a.n4; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(Ws + i) = __ldg(reinterpret_cast<const float4*>(a.w + i));
+  __syncthreads();
+  const long total = (long)a.B * a.oh * a.ow;
+  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int x = (int)(pix % a.ow), y = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
+  float fy, fx; int y0, y1, x0, x1;
+  interp((float)y, a.hs, a.half_pixel, a.ih, &fy, &y0, &y1);
+  interp((float)x, a.ws, a.half_pixel, a.iw, &fx, &x0, &x1);
+  const float dy = fy - (float)y0, dx = fx - (float)x0;
+  const float wy0 = 1.f - dy, wx0 = 1.f - dx;
+  const float* inb = a.in + (size_t)b * a.ih * a.iw * a.ld_in;
+  const float* p00 = inb + ((size_t)y0 * a.iw + x0) * a.ld_in;
+  const float* p10 = inb + ((size_t)y1 * a.iw + x0) * a.ld_in;
+  const float* p01 = inb + ((size_t)y0 * a.iw + x1) * a.ld_in;
+  const float* p11 = inb + ((size_t)y1 * a.iw + x1) * a.ld_in;
+  float acc[NQ * 4];
+#pragma unroll
+  for (int n = 0; n < NQ * 4; ++n) acc[n] = 0.f;
+  for (int k = 0; k < a.K; k += 4) {
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(p00 + k)), v10 = __ldg(reinterpret_cast<const float4*>(p10 + k));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(p01 + k)), v11 = __ldg(reinterpret_cast<const float4*>(p11 + k));
+    float r[4];
+    r[0] = ((v00.x * wy0 * wx0 + v10.x * dy * wx0) + v01.x * wy0 * dx) + v11.x * dy * dx;
+    r[1] = ((v00.y * wy0 * wx0 + v10.y * dy * wx0) + v01.y * wy0 * dx) + v11.y * dy * dx;
+    r[2] = ((v00.z * wy0 * wx0 + v10.z * dy * wx0) + v01.z * wy0 * dx) + v11.z * dy * dx;
+    r[3] = ((v00.w * wy0 * wx0 + v10.w * dy * wx0) + v01.w * wy0 * dx) + v11.w * dy * dx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* wr = Ws + (size_t)(k + j) * a.n4;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * q);
+        acc[4 * q] = fmaf(r[j], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(r[j], w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(r[j], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(r[j], w4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  float* op = a.out + (size_t)pix * a.ld_out;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int n0 = 4 * q;
+    if (n0 + 3 < a.N) {
+      *reinterpret_cast<float4*>(op + n0) = make_float4(epilogue(acc[n0], n0, (size_t)pix, a.e), epilogue(acc[n0 + 1], n0 + 1, (size_t)pix, a.e),
+                                                        epilogue(acc[n0 + 2], n0 + 2, (size_t)pix, a.e), epilogue(acc[n0 + 3], n0 + 3, (size_t)pix, a.e));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (n0 + j < a.N) op[n0 + j] = epilogue(acc[n0 + j], n0 + j, (size_t)pix, a.e);
+    }
+  }
+}
+
+bool upsample_pw_supported(int K, int N, int n4, int ld_in, int ld_out) {
+  return K % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && n4 % 4 == 0 && n4 >= 4 && n4 <= 24 && N <= n4 && (size_t)K * n4 * 4 <= 48 * 1024;
+}
+
+void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, int K, int ld_in, bool align_corners, bool half_pixel,
+                        const float* w_kn, int n4, int N, float* out, int oh, int ow, int ld_out, const Epilogue& e) {
+  float hs = (float)ih / (float)oh, ws = (float)iw / (float)ow;
+  if (align_corners && oh > 1) hs = (float)(ih - 1) / (float)(oh - 1);
+  if (align_corners && ow > 1) ws = (float)(iw - 1) / (float)(ow - 1);
+  UpPwArgs a{in, w_kn, out, B, ih, iw, K, ld_in, oh, ow, N, n4, ld_out, hs, ws, half_pixel, to_dev(e)};
+  const long total = (long)B * oh * ow;
+  const dim3 grid((unsigned)((total + 127) / 128)), block(128);
+  const size_t smem = sizeof(float) * (size_t)K * n4;
+  switch (n4 / 4) {
+    case 1: BSB_LAUNCH(k_upsample_pw<1>, grid, block, smem, s, a); break;
+    case 2: BSB_LAUNCH(k_upsample_pw<2>, grid, block, smem, s, a); break;
+    case 3: BSB_LAUNCH(k_upsample_pw<3>, grid, block, smem, s, a); break;
+    case 4: BSB_LAUNCH(k_upsample_pw<4>, grid, block, smem, s, a); break;
+    case 5: BSB_LAUNCH(k_upsample_pw<5>, grid, block, smem, s, a); break;
+    default: BSB_LAUNCH(k_upsample_pw<6>, grid, block, smem, s, a); break;
+  }
+  count_launch();
+}
+
 void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int iw, int c, int ld_in,
                             float* out, int oh, int ow, int ld_out, bool align_corners, bool half_pixel) {
   float hs = (float)ih / (float)oh, ws = (float)iw / (float)ow;
