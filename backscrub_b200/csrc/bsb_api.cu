@@ -541,6 +541,7 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "pool_merge") t.pool_merge = value;
   else if (n == "stem_pw") t.stem_pw = value;
   else if (n == "up_pw") t.up_pw = value;
+  else if (n == "head") t.head = value;
   else if (n == "tc_variant") t.tc_variant = value;
   else if (n == "tc_mask_hi") t.tc_mask_hi = value;
   else if (n == "tc_min_k") t.tc_min_k = value;

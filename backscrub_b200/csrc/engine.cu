@@ -441,6 +441,8 @@ bool Engine::plan(std::string* err) {
   for (const Step& st : steps_) uses_tc_ = uses_tc_ || st.use_tc;
   // ---- the low-resolution middle of MobileNetV3-style graphs as one kernel ----
   if (tuning().cnn_chain && !(flags_ & (1u | 8u))) detect_chain();
+  // ---- decoder stages (1x1 -> depthwise + residual [-> transposed conv]) as one kernel each ----
+  if (tuning().head && !(flags_ & (1u | 8u))) detect_heads();
 
   // ---- liveness + arena (floats; every tensor is max_batch frames) ----
   const int ns = (int)steps_.size();
@@ -521,6 +523,37 @@ bool Engine::plan(std::string* err) {
     else if (O.kind == OP_CUSTOM) flops_ += 2.0 * out.count() * w.shape[3];
   }
   return true;
+}
+
+void Engine::detect_heads() {
+  auto reads = [&](const Step& r, int t) { return r.in == t || r.in2 == t || r.scale == t || r.in_add == t || r.residual == t; };
+  for (size_t i = 0; i + 1 < steps_.size(); ++i) {
+    const Step& P = steps_[i]; const Step& D = steps_[i + 1];
+    if (P.kind != Step::PW || P.use_tc || P.up_from >= 0 || P.residual >= 0 || P.K != P.N || (P.N != 16 && P.N != 24) || P.n4 != P.N) continue;
+    if (D.kind != Step::DW || D.in != P.out || D.residual != P.out || D.kh != 3 || D.kw != 3 || D.sh != 1 || D.sw != 1 || D.dh != 1 || D.dw != 1) continue;
+    if (tinfo_[D.out].c != P.N || P.out == g_.output || D.out == g_.output) continue;
+    bool only_d = true;                                         // t (the 1x1 output) must be private to the depthwise step
+    for (size_t k = 0; k < steps_.size(); ++k) if (k != i + 1 && reads(steps_[k], P.out)) only_d = false;
+    if (!only_d) continue;
+    HeadPlan hp; hp.p = P; hp.d = D;
+    if (i + 2 < steps_.size()) {
+      const Step& T = steps_[i + 2];
+      bool only_t = T.kind == Step::TCONV && T.in == D.out && T.K == P.N && T.N <= 2 && tinfo_[T.out].ld == T.N;
+      for (size_t k = 0; k < steps_.size() && only_t; ++k) if (k != i + 2 && reads(steps_[k], D.out)) only_t = false;
+      if (only_t) { hp.t = T; hp.has_t = true; }
+    }
+    const int ld_add = P.in_add >= 0 ? tinfo_[P.in_add].ld : 4;
+    const int out_t = hp.has_t ? hp.t.out : D.out;
+    if (!head_supported(P.N, tinfo_[P.in].ld, ld_add, tinfo_[out_t].ld, hp.has_t ? hp.t.N : 0, hp.has_t)) continue;
+    Step h; h.kind = Step::HEAD; h.op_index = P.op_index; h.in = P.in; h.scale = P.scale; h.in_add = P.in_add; h.out = out_t;
+    h.block = (int)heads_.size();
+    heads_.push_back(hp);
+    tinfo_[P.out].materialized = false;
+    if (hp.has_t) tinfo_[D.out].materialized = false;
+    const size_t n_erase = hp.has_t ? 3 : 2;
+    steps_.erase(steps_.begin() + i, steps_.begin() + i + n_erase);
+    steps_.insert(steps_.begin() + i, h);
+  }
 }
 
 // Find   DW(strided, from a larger tensor) -> SE -> PW(scaled)  { -> PW(expand) -> DW -> SE -> PW(scaled [+ residual]) }*
@@ -883,6 +916,16 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
         a.w2 = wblob_ + fb.project.w_off; a.b2 = fb.project.has_bias ? wblob_ + fb.project.b_off : nullptr; a.n4_2 = fb.project.n4;
         a.a2a = fb.project.act1; a.a2b = fb.project.act2; a.residual = fb.project.residual >= 0 ? 1 : 0; a.a3 = fb.project.act3;
         launch_mb_block(stream_, n, a);
+        break;
+      }
+      case Step::HEAD: {
+        const HeadPlan& hp = heads_[st.block];
+        const Step& P = hp.p; const Step& D = hp.d; const Step& T = hp.t;
+        launch_head(stream_, P.N, tptr(P.in), I.ld, P.scale >= 0 ? tptr(P.scale) : nullptr, P.in_add >= 0 ? tptr(P.in_add) : nullptr,
+                    P.in_add >= 0 ? tinfo_[P.in_add].ld : 0, wblob_ + P.w_off, P.has_bias ? wblob_ + P.b_off : nullptr, P.act1, P.act2,
+                    wblob_ + D.w_off, D.has_bias ? wblob_ + D.b_off : nullptr, D.act1, D.act2, D.act3,
+                    hp.has_t ? wblob_ + T.w_off : nullptr, hp.has_t ? wblob_ + T.b_off : nullptr, hp.has_t ? T.N : 0, hp.has_t ? T.act2 : 0,
+                    tptr(st.out), O.ld, n, I.h, I.w, D.pt, D.pl);
         break;
       }
       case Step::CHAIN: {

@@ -30,7 +30,7 @@ struct TensorInfo {
 };
 
 struct Step {
-  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY, BLOCK, CHAIN } kind = ELT;
+  enum Kind { CONV, PW, DW, POOL, RESIZE, TCONV, ELT, COPY, BLOCK, CHAIN, HEAD } kind = ELT;
   int block = -1;             // BLOCK: index into Engine::blocks_ (the four fused sub-steps); CHAIN: index into Engine::chains_
   int op_index = -1;
   int in = -1, in2 = -1, out = -1, scale = -1, in_add = -1, residual = -1;
@@ -185,6 +185,10 @@ class Engine {
   struct ChainPlan { int h = 0, w = 0; std::vector<Step> seq; std::vector<int> types; ChainOp* d_ops = nullptr; int n_ops = 0; };
   std::vector<ChainPlan> chains_;
   bool detect_chain();
+  // decoder stage run by one kernel (k_head): 1x1 conv -> depthwise 3x3 + residual [-> transposed conv]
+  struct HeadPlan { Step p, d, t; bool has_t = false; };
+  std::vector<HeadPlan> heads_;
+  void detect_heads();
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
   bool tc_enabled_ = false, uses_tc_ = false;   // tensor-core 1x1 convs allowed / actually planned for at least one layer

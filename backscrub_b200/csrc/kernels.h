@@ -125,6 +125,13 @@ bool upsample_pw_supported(int K, int N, int n4, int ld_in, int ld_out);
 void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, int K, int ld_in, bool align_corners, bool half_pixel,
                         const float* w_kn, int n4, int N, float* out, int oh, int ow, int ld_out, const Epilogue& e);
 
+// Decoder stage in one kernel: 1x1 conv (optional SE scale / skip add on its operand) -> depthwise 3x3 + residual of its
+// own input -> optionally Convolution2DTransposeBias k2 s2.  C = 16 or 24.  Same arithmetic per output as the stand-alone kernels.
+bool head_supported(int C, int ld_x, int ld_add, int ld_out, int oc, bool tconv);
+void launch_head(cudaStream_t s, int C, const float* x, int ld_x, const float* sv, const float* add, int ld_add,
+                 const float* wp, const float* bp, int actp1, int actp2, const float* wd, const float* bd, int actd1, int actd2, int actr,
+                 const float* wt, const float* bt, int oc, int actt, float* out, int ld_out, int B, int h, int w, int pt, int pl);
+
 // Convolution2DTransposeBias k2x2 s2 (lib/transpose_conv_bias.cc:37-114).  w: OHWI [oc][2][2][ic].
 void launch_tconv2x2(cudaStream_t s, int B, const float* in, int ih, int iw, int ic, int ld_in,
                      const float* w, const float* bias, int oc, float* out, int oh, int ow, int ld_out, int act2);
@@ -237,8 +244,9 @@ struct Tuning {
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel
   int tc_min_k = 16;       // smallest input depth of a 1x1 conv that goes to the tensor cores (with BSB_FLAG_TENSOR_CORES)
   int tc_mask_hi = 0;      // tensor-core kernel: clear the low mantissa bits of A explicitly instead of relying on the hardware truncation
+  int head = 1;            // decoder stages (1x1 -> depthwise 3x3 + residual [-> transposed conv]) in one kernel
   int up_pw = 1;           // fuse RESIZE_BILINEAR into the 1x1 conv that consumes it
-  int stem_pw = 1;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel
+  int stem_pw = 0;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel (measured slower: 78.9 vs 40 + 30 us; off)
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses

@@ -1129,16 +1129,19 @@ struct UpPwArgs {
   EpiDev e;
 };
 
-template <int NQ>     // output channel quads: n4 = 4 * NQ
-__global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a) {
+template <int NQ>     // output channel quads per thread; a pixel is shared by n4 / (4 * NQ) threads
+__global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a, int groups) {
   BSB_DYN_SMEM(smem_raw);
   float* Ws = reinterpret_cast<float*>(smem_raw);            // [K][n4]
   for (int i = threadIdx.x * 4; i < a.K * a.n4; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(Ws + i) = __ldg(reinterpret_cast<const float4*>(a.w + i));
   __syncthreads();
-  const long total = (long)a.B * a.oh * a.ow;
-  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
+  const long total = (long)a.B * a.oh * a.ow * groups;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int grp = (int)(idx % groups);
+  const long pix = idx / groups;
+  const int nbase = grp * NQ * 4;
   const int x = (int)(pix % a.ow), y = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
   float fy, fx; int y0, y1, x0, x1;
   interp((float)y, a.hs, a.half_pixel, a.ih, &fy, &y0, &y1);
@@ -1163,7 +1166,7 @@ __global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a) {
     r[3] = ((v00.w * wy0 * wx0 + v10.w * dy * wx0) + v01.w * wy0 * dx) + v11.w * dy * dx;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float* wr = Ws + (size_t)(k + j) * a.n4;
+      const float* wr = Ws + (size_t)(k + j) * a.n4 + nbase;
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * q);
@@ -1175,13 +1178,13 @@ __global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a) {
   float* op = a.out + (size_t)pix * a.ld_out;
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    const int n0 = 4 * q;
+    const int n0 = nbase + 4 * q;
     if (n0 + 3 < a.N) {
-      *reinterpret_cast<float4*>(op + n0) = make_float4(epilogue(acc[n0], n0, (size_t)pix, a.e), epilogue(acc[n0 + 1], n0 + 1, (size_t)pix, a.e),
-                                                        epilogue(acc[n0 + 2], n0 + 2, (size_t)pix, a.e), epilogue(acc[n0 + 3], n0 + 3, (size_t)pix, a.e));
+      *reinterpret_cast<float4*>(op + n0) = make_float4(epilogue(acc[4 * q], n0, (size_t)pix, a.e), epilogue(acc[4 * q + 1], n0 + 1, (size_t)pix, a.e),
+                                                        epilogue(acc[4 * q + 2], n0 + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], n0 + 3, (size_t)pix, a.e));
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (n0 + j < a.N) op[n0 + j] = epilogue(acc[n0 + j], n0 + j, (size_t)pix, a.e);
+      for (int j = 0; j < 4; ++j) if (n0 + j < a.N) op[n0 + j] = epilogue(acc[4 * q + j], n0 + j, (size_t)pix, a.e);
     }
   }
 }
@@ -1196,16 +1199,22 @@ void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, 
   if (align_corners && oh > 1) hs = (float)(ih - 1) / (float)(oh - 1);
   if (align_corners && ow > 1) ws = (float)(iw - 1) / (float)(ow - 1);
   UpPwArgs a{in, w_kn, out, B, ih, iw, K, ld_in, oh, ow, N, n4, ld_out, hs, ws, half_pixel, to_dev(e)};
-  const long total = (long)B * oh * ow;
-  const dim3 grid((unsigned)((total + 127) / 128)), block(128);
+  const long pixels = (long)B * oh * ow;
   const size_t smem = sizeof(float) * (size_t)K * n4;
-  switch (n4 / 4) {
-    case 1: BSB_LAUNCH(k_upsample_pw<1>, grid, block, smem, s, a); break;
-    case 2: BSB_LAUNCH(k_upsample_pw<2>, grid, block, smem, s, a); break;
-    case 3: BSB_LAUNCH(k_upsample_pw<3>, grid, block, smem, s, a); break;
-    case 4: BSB_LAUNCH(k_upsample_pw<4>, grid, block, smem, s, a); break;
-    case 5: BSB_LAUNCH(k_upsample_pw<5>, grid, block, smem, s, a); break;
-    default: BSB_LAUNCH(k_upsample_pw<6>, grid, block, smem, s, a); break;
+  const int quads = n4 / 4;
+  // a pixel's output quads are split over threads until the grid fills the GPU a few times over (the interpolation is
+  // recomputed per thread; it is cheap next to the K x 4 fmaf chains)
+  int nq = quads;
+  while (nq > 1 && (nq % 2 == 0 || nq % 3 == 0) && pixels * (quads / nq) < 148L * 2048) nq = (nq % 2 == 0) ? nq / 2 : nq / 3;
+  const int groups = quads / nq;
+  const dim3 grid((unsigned)((pixels * groups + 127) / 128)), block(128);
+  switch (nq) {
+    case 1: BSB_LAUNCH(k_upsample_pw<1>, grid, block, smem, s, a, groups); break;
+    case 2: BSB_LAUNCH(k_upsample_pw<2>, grid, block, smem, s, a, groups); break;
+    case 3: BSB_LAUNCH(k_upsample_pw<3>, grid, block, smem, s, a, groups); break;
+    case 4: BSB_LAUNCH(k_upsample_pw<4>, grid, block, smem, s, a, groups); break;
+    case 5: BSB_LAUNCH(k_upsample_pw<5>, grid, block, smem, s, a, groups); break;
+    default: BSB_LAUNCH(k_upsample_pw<6>, grid, block, smem, s, a, groups); break;
   }
   count_launch();
 }
@@ -1218,6 +1227,145 @@ void launch_resize_bilinear(cudaStream_t s, int B, const float* in, int ih, int 
   const long total = (long)B * oh * ow * ((c + 3) / 4);
   BSB_LAUNCH(k_resize_bilinear<4>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
              in, B, ih, iw, c, ld_in, out, oh, ow, ld_out, hs, ws, half_pixel);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// Decoder stage of the MobileNetV3-style graphs in one kernel (C = 16 or 24 channels):
+//     t = act_p( (x * sv + add) . Wp + bp )            1x1 conv with the squeeze-excite scale / skip add on its operand
+//     u = act_r( t + act_d( dw3x3(t) + bd ) )          depthwise 3x3 (stride 1) + residual of its own input
+//     out = u                                          ... or, for the last stage,
+//     out = act_t( tconv2x2( u ) + bt )                Convolution2DTransposeBias k2 s2 (lib/transpose_conv_bias.cc:37-114)
+// One CTA = a 32 x 8 pixel tile: phase A computes t for the tile and its 1-pixel ring into shared memory (a pixel and all
+// its C channels per thread: the k-ascending fmaf chains of the stand-alone 1x1 kernel); phase B = one thread per pixel:
+// 9 taps x C from shared memory in (fy, fx) order skipping out-of-image taps, residual, then the 2x2 x oc transposed
+// conv straight from registers.  t and u never touch global memory.
+// ---------------------------------------------------------------------------
+struct HeadArgs {
+  const float* x; int ld_x; const float* sv; const float* add; int ld_add;     // sv: [B][C] or null; add: same shape as x or null
+  const float* wp; const float* bp; int actp1, actp2;                             // [C][n4 = C]
+  const float* wd; const float* bd; int actd1, actd2, actr;                       // [3][3][C]
+  const float* wt; const float* bt; int oc, actt;                                 // OHWI [oc][2][2][C]; null -> no transposed conv
+  float* out; int ld_out;                                                          // [B][h][w][ld_out] or [B][2h][2w][oc]
+  int B, h, w, pt, pl;
+};
+constexpr int HD_TW = 32, HD_TH = 8, HD_SW = HD_TW + 2, HD_SH = HD_TH + 2;
+
+template <int C>
+__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+  __shared__ __align__(16) float ts[HD_SH * HD_SW * C];
+  __shared__ __align__(16) float wps[C * C];
+  __shared__ __align__(16) float wds[9 * C];
+  __shared__ __align__(16) float wts[2 * 4 * C];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * HD_TW, y0 = blockIdx.y * HD_TH, b = blockIdx.z;
+  for (int i = tid; i < C * C; i += 256) wps[i] = __ldg(a.wp + i);
+  for (int i = tid; i < 9 * C; i += 256) wds[i] = __ldg(a.wd + i);
+  if (a.wt) for (int i = tid; i < a.oc * 4 * C; i += 256) wts[i] = __ldg(a.wt + i);
+  __syncthreads();
+  const float* xb = a.x + (size_t)b * a.h * a.w * a.ld_x;
+  const float* ab = a.add ? a.add + (size_t)b * a.h * a.w * a.ld_add : nullptr;
+  const float* svb = a.sv ? a.sv + (size_t)b * C : nullptr;
+  // ---- A: t on the (TH + 2) x (TW + 2) ring-extended tile ----
+  for (int i = tid; i < HD_SH * HD_SW; i += 256) {
+    const int sy = i / HD_SW, sx = i - sy * HD_SW;
+    const int gy = y0 + sy - 1, gx = x0 + sx - 1;
+    if (gy < 0 || gy >= a.h || gx < 0 || gx >= a.w) continue;          // never read: phase B skips out-of-image taps
+    const size_t pix = (size_t)gy * a.w + gx;
+    float acc[C];
+#pragma unroll
+    for (int n = 0; n < C; ++n) acc[n] = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; k += 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(xb + pix * a.ld_x + k));
+      if (svb) { const float4 sc = __ldg(reinterpret_cast<const float4*>(svb + k)); v.x = v.x * sc.x; v.y = v.y * sc.y; v.z = v.z * sc.z; v.w = v.w * sc.w; }
+      if (ab) { const float4 ad = __ldg(reinterpret_cast<const float4*>(ab + pix * a.ld_add + k)); v.x = v.x + ad.x; v.y = v.y + ad.y; v.z = v.z + ad.z; v.w = v.w + ad.w; }
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wps + (k + j) * C + 4 * q);
+          acc[4 * q] = fmaf(vv[j], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(vv[j], w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(vv[j], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(vv[j], w4.w, acc[4 * q + 3]);
+        }
+    }
+    float* tp = ts + (size_t)i * C;
+#pragma unroll
+    for (int n = 0; n < C; ++n) tp[n] = bsb_act(bsb_act(acc[n] + (a.bp ? __ldg(a.bp + n) : 0.f), a.actp1), a.actp2);
+  }
+  __syncthreads();
+  // ---- B: depthwise 3x3 + residual (+ transposed conv) ----
+  const int lx = tid & (HD_TW - 1), ly = tid >> 5;
+  const int gx = x0 + lx, gy = y0 + ly;
+  if (gx >= a.w || gy >= a.h) return;
+  float u[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) u[c] = 0.f;
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+    const int iy = gy - a.pt + fy;
+    if (iy < 0 || iy >= a.h) continue;
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx) {
+      const int ix = gx - a.pl + fx;
+      if (ix < 0 || ix >= a.w) continue;
+      const float* tp = ts + (size_t)((iy - y0 + 1) * HD_SW + (ix - x0 + 1)) * C;
+      const float* wp = wds + (fy * 3 + fx) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) u[c] = fmaf(tp[c], wp[c], u[c]);
+    }
+  }
+  {
+    const float* tc = ts + (size_t)((ly + 1) * HD_SW + lx + 1) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float d = bsb_act(bsb_act(u[c] + (a.bd ? __ldg(a.bd + c) : 0.f), a.actd1), a.actd2);
+      u[c] = bsb_act(d + tc[c], a.actr);                      // ADD(t, act(dw(t))): the planner folded it as residual of the depthwise step
+    }
+  }
+  if (!a.wt) {
+    float* op = a.out + (((size_t)b * a.h + gy) * a.w + gx) * a.ld_out;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) *reinterpret_cast<float4*>(op + c) = make_float4(u[c], u[c + 1], u[c + 2], u[c + 3]);
+    return;
+  }
+  const int oh = 2 * a.h, ow = 2 * a.w;
+#pragma unroll
+  for (int fy = 0; fy < 2; ++fy) {
+    float r[2][2];
+#pragma unroll
+    for (int fx = 0; fx < 2; ++fx)
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        r[fx][o] = 0.f;
+        if (o >= a.oc) continue;
+        const float* wq = wts + ((o * 2 + fy) * 2 + fx) * C;
+        float acc = __ldg(a.bt + o);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc = fmaf(u[c], wq[c], acc);
+        r[fx][o] = bsb_act(acc, a.actt);
+      }
+    float* op = a.out + (((size_t)b * oh + 2 * gy + fy) * ow + 2 * gx) * a.oc;
+    if (a.oc == 2) *reinterpret_cast<float4*>(op) = make_float4(r[0][0], r[0][1], r[1][0], r[1][1]);
+    else *reinterpret_cast<float2*>(op) = make_float2(r[0][0], r[1][0]);
+  }
+}
+
+bool head_supported(int C, int ld_x, int ld_add, int ld_out, int oc, bool tconv) {
+  if (C != 16 && C != 24) return false;
+  if (ld_x % 4 || ld_add % 4) return false;
+  if (tconv) return oc >= 1 && oc <= 2;
+  return ld_out % 4 == 0;
+}
+
+void launch_head(cudaStream_t s, int C, const float* x, int ld_x, const float* sv, const float* add, int ld_add,
+                 const float* wp, const float* bp, int actp1, int actp2, const float* wd, const float* bd, int actd1, int actd2, int actr,
+                 const float* wt, const float* bt, int oc, int actt, float* out, int ld_out, int B, int h, int w, int pt, int pl) {
+  HeadArgs a{x, ld_x, sv, add, ld_add, wp, bp, actp1, actp2, wd, bd, actd1, actd2, actr, wt, bt, oc, actt, out, ld_out, B, h, w, pt, pl};
+  const dim3 grid((unsigned)ceil_div(w, HD_TW), (unsigned)ceil_div(h, HD_TH), (unsigned)B);
+  if (C == 16) BSB_LAUNCH(k_head<16>, grid, dim3(256), 0, s, a);
+  else BSB_LAUNCH(k_head<24>, grid, dim3(256), 0, s, a);
   count_launch();
 }
 

@@ -58,6 +58,11 @@ def test_chain_kernel(lib, key):
     pc.check_chain(lib, key, n=2)
 
 
+@pytest.mark.parametrize("key", ["meet_lite", "mlkit"])
+def test_fusion_switches(lib, key):
+    pc.check_fusion_switches(lib, key, n=2)
+
+
 def test_infer_batch(lib):
     pc.check_infer_batch(lib, "meet_lite", n=3)
 

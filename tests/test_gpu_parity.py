@@ -77,6 +77,11 @@ def test_chain_kernel(lib, key, n):
     pc.check_chain(lib, key, n=n)
 
 
+@pytest.mark.parametrize("key", ["meet_full", "meet_lite", "mlkit", "bodypix"])
+def test_fusion_switches(lib, key):
+    pc.check_fusion_switches(lib, key, n=3)
+
+
 def test_mask_only_and_callbacks(lib):
     pc.check_mask_only_and_callbacks(lib, "mlkit")
 
