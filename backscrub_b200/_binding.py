@@ -24,7 +24,7 @@ SYMBOLS = [
     "bsb_maskgen_delete", "bsb_maskgen_process", "bsb_set_background", "bsb_get_background",
     "bsb_set_background_ring", "bsb_set_background_cursor", "bsb_set_bgblur", "bsb_set_output", "bsb_output_size",
     "bsb_gaussian_blur", "bsb_gaussian_taps", "bsb_flip",
-    "bsb_composite", "bsb_composite_device", "bsb_composite_yuyv", "bsb_composite_yuyv_device", "bsb_convert_yuyv_to_bgr", "bsb_synchronize", "bsb_stream", "bsb_alpha_blend",
+    "bsb_composite", "bsb_composite_device", "bsb_composite_yuyv", "bsb_composite_yuyv_device", "bsb_composite_mjpg", "bsb_decode_mjpg", "bsb_convert_yuyv_to_bgr", "bsb_synchronize", "bsb_stream", "bsb_alpha_blend",
     "bsb_convert_rgb_to_yuyv", "bsb_resize_u8c3", "bsb_pointwise", "bsb_time_pointwise", "bsb_geometry", "bsb_infer", "bsb_get_tensor",
     "bsb_get_stage_u8", "bsb_reset_state", "bsb_time_stage", "bsb_launches_per_call", "bsb_total_launches", "bsb_model_flops", "bsb_set_tuning", "bsb_frame_size", "bsb_yuyv_native", "bsb_uses_tensor_cores",
     "bsb_calcmask_new", "bsb_calcmask_delete", "bsb_calcmask_set_input_frame", "bsb_calcmask_get_output_mask", "bsb_calcmask_timings",
@@ -66,6 +66,9 @@ def bind(path: str) -> C.CDLL:
                                        C.c_void_p, C.c_size_t, C.c_int]
     L.bsb_composite_yuyv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     L.bsb_composite_yuyv_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    L.bsb_composite_mjpg.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                     C.c_void_p, C.c_size_t]
+    L.bsb_decode_mjpg.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.bsb_convert_yuyv_to_bgr.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.bsb_synchronize.argtypes = [C.c_void_p]
     L.bsb_stream.restype = C.c_void_p

@@ -165,6 +165,28 @@ class MaskGen:
         self.composite_yuyv_into(yuyv_frames, out, yuyv, mask)
         return out, yuyv, mask
 
+    def decode_mjpg(self, jpeg: bytes) -> np.ndarray:
+        """one MJPG camera frame -> BGR, decoded on the GPU (NVJPG); what composite_mjpg feeds the pipeline"""
+        buf = np.frombuffer(jpeg, np.uint8)
+        out = np.empty((self.height, self.width, 3), np.uint8)
+        if not self._lib.bsb_decode_mjpg(self._h, _ptr(buf), buf.size, _ptr(out)):
+            self._fail("bsb_decode_mjpg")
+        return out
+
+    def composite_mjpg(self, jpegs):
+        """MJPG camera ingest (app/deepseg.cc:548-553): a list of JPEG byte strings -> (out, yuyv, mask)"""
+        bufs = [np.frombuffer(j, np.uint8) for j in jpegs]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        out = np.empty((n, self.out_height, self.out_width, 3), np.uint8)
+        yuyv = np.empty((n, self.out_height, self.out_width, 2), np.uint8)
+        mask = np.empty((n, self.height, self.width), np.uint8)
+        opx = self.out_width * self.out_height
+        if not self._lib.bsb_composite_mjpg(self._h, n, ptrs, sizes, _ptr(out), opx * 3, _ptr(yuyv), opx * 2, _ptr(mask), self.height * self.width):
+            self._fail("bsb_composite_mjpg")
+        return out, yuyv, mask
+
     def composite_device(self, n, d_frames, d_out=0, d_yuyv=0, d_mask=0, sync=False):
         """Fused path on DEVICE pointers (ints, e.g. torch.Tensor.data_ptr()); tightly packed frames."""
         fb, npx, opx = self.height * self.width * 3, self.height * self.width, self.out_width * self.out_height

@@ -8,11 +8,18 @@
 #include "../../include/backscrub_b200.h"
 #include "engine.h"
 
+#ifndef BSB_EMU
+#include <dlfcn.h>
+#include <nvjpeg.h>       // types only: the library is dlopen()ed so the product links against cudart alone
+#include <mutex>
+#endif
+
 using bsb::Engine;
 
 struct bsb_ctx {
   Engine* eng = nullptr;
   bsb::Callbacks cb;
+  void* jpeg_state = nullptr;      // nvjpegJpegState_t of this context (MJPG ingest), created on first use
 };
 
 namespace {
@@ -40,6 +47,64 @@ bool check_ctx(bsb_ctx* ctx) {
   } while (0)
 
 }  // namespace
+
+// ---- NVJPG (MJPG camera ingest) --------------------------------------------------------------------------
+#ifndef BSB_EMU
+namespace {
+struct NvJpegApi {
+  void* lib = nullptr;
+  nvjpegHandle_t handle = nullptr;
+  nvjpegStatus_t (*create)(nvjpegHandle_t*) = nullptr;
+  nvjpegStatus_t (*state_create)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+  nvjpegStatus_t (*state_destroy)(nvjpegJpegState_t) = nullptr;
+  nvjpegStatus_t (*info)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
+  nvjpegStatus_t (*decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t, nvjpegImage_t*, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+NvJpegApi& nvjpeg_api() {
+  static NvJpegApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so"}) { api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL); if (api.lib) break; }
+    if (!api.lib) return;
+    api.create = reinterpret_cast<decltype(api.create)>(dlsym(api.lib, "nvjpegCreateSimple"));
+    api.state_create = reinterpret_cast<decltype(api.state_create)>(dlsym(api.lib, "nvjpegJpegStateCreate"));
+    api.state_destroy = reinterpret_cast<decltype(api.state_destroy)>(dlsym(api.lib, "nvjpegJpegStateDestroy"));
+    api.info = reinterpret_cast<decltype(api.info)>(dlsym(api.lib, "nvjpegGetImageInfo"));
+    api.decode = reinterpret_cast<decltype(api.decode)>(dlsym(api.lib, "nvjpegDecode"));
+    if (!api.create || !api.state_create || !api.state_destroy || !api.info || !api.decode) return;
+    api.ok = api.create(&api.handle) == NVJPEG_STATUS_SUCCESS;
+  });
+  return api;
+}
+// decode one JPEG into `d_bgr` (W x H x 3 device buffer) on the context's stream; "" on success
+std::string jpeg_decode(bsb_ctx* ctx, const uint8_t* jpeg, size_t size, uint8_t* d_bgr) {
+  NvJpegApi& api = nvjpeg_api();
+  if (!api.ok) return "libnvjpeg is not available (MJPG ingest needs the CUDA toolkit's NVJPG library)";
+  Engine* e = ctx->eng;
+  if (!ctx->jpeg_state) {
+    nvjpegJpegState_t st = nullptr;
+    if (api.state_create(api.handle, &st) != NVJPEG_STATUS_SUCCESS) return "nvjpegJpegStateCreate failed";
+    ctx->jpeg_state = st;
+  }
+  int ncomp = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+  nvjpegChromaSubsampling_t sub;
+  if (!jpeg || api.info(api.handle, jpeg, size, &ncomp, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS) return "not a decodable JPEG image";
+  if (ws[0] != e->W() || hs[0] != e->H()) return "JPEG frame size differs from the context's frame size";
+  nvjpegImage_t img{};
+  img.channel[0] = d_bgr; img.pitch[0] = (size_t)e->W() * 3;
+  if (api.decode(api.handle, static_cast<nvjpegJpegState_t>(ctx->jpeg_state), jpeg, size, NVJPEG_OUTPUT_BGRI, &img, e->stream()) != NVJPEG_STATUS_SUCCESS)
+    return "nvjpegDecode failed";
+  return "";
+}
+}  // namespace
+static void bsb_jpeg_release(bsb_ctx* ctx) {
+  if (ctx->jpeg_state && nvjpeg_api().ok) nvjpeg_api().state_destroy(static_cast<nvjpegJpegState_t>(ctx->jpeg_state));
+  ctx->jpeg_state = nullptr;
+}
+#else
+static void bsb_jpeg_release(bsb_ctx*) {}
+#endif
 
 extern "C" {
 
@@ -75,6 +140,7 @@ bsb_ctx* bsb_maskgen_new(const char* modelname, size_t threads, size_t width, si
 
 void bsb_maskgen_delete(bsb_ctx* ctx) {
   if (!ctx) return;
+  bsb_jpeg_release(ctx);
   delete ctx->eng;
   delete ctx;
 }
@@ -237,6 +303,60 @@ int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_frames, s
   API_CUDA(cudaStreamSynchronize(e->stream()));
   API_CUDA(cudaGetLastError());
   return 1;
+}
+
+int bsb_decode_mjpg(bsb_ctx* ctx, const uint8_t* jpeg, size_t jpeg_size, uint8_t* bgr_out) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+#ifdef BSB_EMU
+  (void)jpeg; (void)jpeg_size; (void)bgr_out;
+  report(cbp, "error: MJPG ingest needs a GPU (NVJPG)"); return 0;
+#else
+  Engine* e = ctx->eng;
+  if (!bgr_out) { report(cbp, "error: null buffer"); return 0; }
+  API_CUDA(cudaSetDevice(e->device()));
+  const std::string err = jpeg_decode(ctx, jpeg, jpeg_size, e->d_frames());
+  if (!err.empty()) { report(cbp, "error: " + err); return 0; }
+  API_CUDA(cudaMemcpyAsync(bgr_out, e->d_frames(), (size_t)e->W() * e->H() * 3, cudaMemcpyDeviceToHost, e->stream()));
+  API_CUDA(cudaStreamSynchronize(e->stream()));
+  return 1;
+#endif
+}
+
+int bsb_composite_mjpg(bsb_ctx* ctx, int n_frames, const uint8_t* const* jpegs, const size_t* jpeg_sizes, uint8_t* out, size_t out_stride,
+                       uint8_t* out_yuyv, size_t yuyv_stride, uint8_t* out_mask, size_t mask_stride) {
+  if (!check_ctx(ctx)) return 0;
+  const bsb::Callbacks* cbp = &ctx->cb;
+#ifdef BSB_EMU
+  (void)n_frames; (void)jpegs; (void)jpeg_sizes; (void)out; (void)out_stride; (void)out_yuyv; (void)yuyv_stride; (void)out_mask; (void)mask_stride;
+  report(cbp, "error: MJPG ingest needs a GPU (NVJPG)"); return 0;
+#else
+  Engine* e = ctx->eng;
+  const size_t row = (size_t)e->W() * 3, fbytes = row * e->H(), npix = (size_t)e->W() * e->H();
+  const size_t opix = (size_t)e->out_w() * e->out_h(), obytes = opix * 3;
+  if (n_frames < 1 || n_frames > e->max_batch()) { report(cbp, "error: n_frames out of range (1..max_batch)"); return 0; }
+  if (!jpegs || !jpeg_sizes) { report(cbp, "error: invalid frame"); return 0; }
+  if (out_yuyv && (e->out_w() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
+  API_CUDA(cudaSetDevice(e->device()));
+  for (int b = 0; b < n_frames; ++b) {
+    const std::string derr = jpeg_decode(ctx, jpegs[b], jpeg_sizes[b], e->d_frames() + (size_t)b * fbytes);
+    if (!derr.empty()) { report(cbp, "error: " + derr); return 0; }
+  }
+  std::string err;
+  if (!e->run(n_frames, e->d_frames(), row, fbytes, out ? e->d_out() : nullptr, obytes, out_yuyv ? e->d_yuyv() : nullptr, opix * 2,
+              out_mask ? e->d_mask() : nullptr, npix, false, &err)) {
+    report(cbp, "error: failed to process video frame: " + err); return 0;
+  }
+  if (out) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out + (size_t)b * out_stride, e->d_out() + b * obytes, obytes, cudaMemcpyDeviceToHost, e->stream()));
+  if (out_yuyv) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + b * opix * 2, opix * 2, cudaMemcpyDeviceToHost, e->stream()));
+  if (out_mask) for (int b = 0; b < n_frames; ++b)
+    API_CUDA(cudaMemcpyAsync(out_mask + (size_t)b * mask_stride, e->d_mask() + b * npix, npix, cudaMemcpyDeviceToHost, e->stream()));
+  API_CUDA(cudaStreamSynchronize(e->stream()));
+  API_CUDA(cudaGetLastError());
+  return 1;
+#endif
 }
 
 int bsb_composite_yuyv_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_yuyv_frames, uint8_t* d_out, size_t out_stride,

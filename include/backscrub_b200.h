@@ -132,6 +132,16 @@ BSB_API int bsb_composite_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_fr
 BSB_API int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_frames, size_t in_stride,
                                uint8_t* out, size_t out_stride, uint8_t* out_yuyv, size_t yuyv_stride,
                                uint8_t* out_mask, size_t mask_stride);
+/* MJPG camera ingest (app/deepseg.cc:548-553: the capture is opened with FOURCC MJPG and cv::VideoCapture decodes each
+ * JPEG to BGR): `n_frames` JPEG images (pointer + size each, HOST memory) are decoded on the GPU by NVJPG (libnvjpeg,
+ * loaded at run time; a library decoder for a wire format either side of the path, like FFmpeg is for the reference)
+ * straight into the context's BGR frame buffer, then the fused call runs as in bsb_composite.  Decoded pixels may differ
+ * from libjpeg's by a few LSB (different IDCT / chroma up-sampling), so bsb_decode_mjpg returns the frame the pipeline saw.
+ * Returns 0 with an error message if libnvjpeg is not available. */
+BSB_API int bsb_composite_mjpg(bsb_ctx* ctx, int n_frames, const uint8_t* const* jpegs, const size_t* jpeg_sizes,
+                               uint8_t* out, size_t out_stride, uint8_t* out_yuyv, size_t yuyv_stride, uint8_t* out_mask, size_t mask_stride);
+/* the decode step alone: one JPEG -> W x H x 3 BGR (tightly packed HOST buffer) */
+BSB_API int bsb_decode_mjpg(bsb_ctx* ctx, const uint8_t* jpeg, size_t jpeg_size, uint8_t* bgr_out);
 /* DEVICE pointers, asynchronous unless `sync`. */
 BSB_API int bsb_composite_yuyv_device(bsb_ctx* ctx, int n_frames, const uint8_t* d_yuyv_frames,
                                       uint8_t* d_out, size_t out_stride, uint8_t* d_yuyv, size_t yuyv_stride,

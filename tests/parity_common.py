@@ -440,7 +440,7 @@ def check_fusion_switches(lib, key, n=2):
     g.close()
     for b in range(n):
         assert np.array_equal(base[b].view(np.uint32), m.invoke(x[b])[0].view(np.uint32)), f"{key}: frame {b} differs from the oracle"
-    defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 1}
+    defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 0}
     for sw, dflt in defaults.items():
         try:
             assert lib.bsb_set_tuning(sw, 1 - dflt)
@@ -455,3 +455,36 @@ def check_fusion_switches(lib, key, n=2):
         assert np.array_equal(got.view(np.uint32), base.view(np.uint32)), f"{key}: flipping {sw.decode()} changes the CNN output"
         for a, b in zip(out, ref_out):
             assert np.array_equal(a, b), f"{key}: flipping {sw.decode()} changes the composite"
+
+
+def check_mjpg_ingest(lib, key="meet_lite", W=640, H=480, n=2):
+    """MJPG camera ingest (app/deepseg.cc:548-553): JPEG frames decoded on the GPU (NVJPG) feed the fused path.  The
+    decoder is a library either side of the path (the reference uses libjpeg behind cv::VideoCapture); what is checked:
+    the decoded frame is the same picture as libjpeg's (cv2.imdecode) up to IDCT / up-sampling rounding, and everything
+    downstream of the decoded frame is bit-exact against the oracle."""
+    import cv2
+    import pytest
+    g = api.MaskGen(lib, model_path(key), W, H, max_batch=n, flags=exact_flag(key))
+    o = po.MaskGen(model_path(key), W, H)
+    bg = synth.background()
+    g.set_background(bg)
+    frames = [synth.frame(W, H, t=t) for t in range(n)]
+    params = [int(cv2.IMWRITE_JPEG_QUALITY), 92]
+    if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        params += [int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR), int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422)]      # what UVC cameras send
+    jpgs = [cv2.imencode(".jpg", f, params)[1].tobytes() for f in frames]
+    dec = [g.decode_mjpg(j) for j in jpgs]
+    for d, j in zip(dec, jpgs):
+        ref = cv2.imdecode(np.frombuffer(j, np.uint8), cv2.IMREAD_COLOR)
+        diff = np.abs(d.astype(np.int16) - ref.astype(np.int16))
+        assert diff.max() <= 6 and diff.mean() < 0.75, (int(diff.max()), float(diff.mean()))
+    out, yuyv, mask = g.composite_mjpg(jpgs)
+    for b in range(n):
+        ro, ry, rm = o.composite(dec[b], bg)
+        assert np.array_equal(mask[b], rm) and np.array_equal(out[b], ro) and np.array_equal(yuyv[b], ry), b
+    small = cv2.imencode(".jpg", synth.frame(W // 2, H // 2))[1].tobytes()
+    with pytest.raises(api.BackscrubError, match="frame size"):
+        g.composite_mjpg([small])
+    with pytest.raises(api.BackscrubError, match="JPEG"):
+        g.composite_mjpg([b"\x00\x01not a jpeg at all" * 8])
+    g.close()

@@ -82,6 +82,11 @@ def test_fusion_switches(lib, key):
     pc.check_fusion_switches(lib, key, n=3)
 
 
+def test_mjpg_ingest(lib):
+    pc.check_mjpg_ingest(lib, "meet_lite", 640, 480, n=2)
+    pc.check_mjpg_ingest(lib, "meet_full", 1280, 720, n=1)
+
+
 def test_mask_only_and_callbacks(lib):
     pc.check_mask_only_and_callbacks(lib, "mlkit")
 
