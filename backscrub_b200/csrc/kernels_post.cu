@@ -58,270 +58,257 @@ BSB_D void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensorm
 struct PostMaps { CUtensorMap frame, bg, bgy, out, yuyv, mask, ofinal; };
 struct PostTmaCfg { int has_out, has_yuyv, has_mask, has_bgy; };
 
-// patch of the small mask a 36 x 132 halo tile can touch: rows <= PT_RMAX, columns <= PT_PCOLS (up-scales >= ~1.75x).
-// A TMA box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate raises "illegal
-// instruction"), so the box begins at the patch's first column rounded down to 16 and is 16 columns wider.
-constexpr int PT_RMAX = 24, PT_PCOLS = 80, PT_PW = PT_PCOLS + 16;
-// A CTA owns PT_NT x-adjacent tiles; the loads of all its tiles are issued up front.  Measured on a B200 (run r2i): two
-// tiles per CTA (95 KB, two CTAs per SM) is SLOWER than one (88.6 vs 65.6 us per 32-frame 720p launch) — the halved warp
-// count costs more than the amortised load latency saves — so PT_NT = 1: ~53 KB per CTA, four CTAs per SM.
-// Shared memory: per tile the TMA tiles + patch (+ mask staging when PT_NT > 1); one mask-building scratch shared by the
-// tiles (Vs reuses Hs, dead after the vertical resize pass; with one tile per CTA the mask staging tile reuses Us).
-constexpr int PT_NT = 1;
-constexpr int PT_OFF_F = 0, PT_OFF_B = 12288, PT_OFF_Y = 24576, PT_OFF_P = 32768;
-constexpr int PT_OFF_M = PT_OFF_P + PT_RMAX * PT_PW;             // mask tile [32][128]
-constexpr int PT_TILE = PT_OFF_M + (PT_NT > 1 ? 4096 : 0);       // bytes of per-tile buffers
-constexpr int PT_OFF_HS = PT_NT * PT_TILE;                       // [PT_RMAX][PF_US] u16, later Vs [PF_H][PF_US] u16
-constexpr int PT_HV_BYTES = (PT_RMAX > PF_H ? PT_RMAX : PF_H) * PF_US * 2;
-constexpr int PT_OFF_VS = PT_OFF_HS;
-constexpr int PT_OFF_US = PT_OFF_HS + PT_HV_BYTES;               // [PF_UH][PF_US] u16
-constexpr int PT_OFF_ROWS = PT_OFF_US + PF_UH * PF_US * 2;       // [PF_UH] uint4
-constexpr int PT_OFF_BAR = PT_OFF_ROWS + PF_UH * 16;
-constexpr int PT_SMEM = PT_OFF_BAR + 64;
-static_assert(PT_PW % 16 == 0 && PT_OFF_M % 128 == 0 && PT_TILE % 128 == 0 && PT_OFF_HS % 16 == 0 && PT_OFF_US % 16 == 0 && PT_OFF_ROWS % 16 == 0 &&
-              PT_OFF_BAR % 8 == 0 && PT_NT * 3 * 8 <= 64 && PT_OFF_US % 128 == 0 && PF_UH * PF_US * 2 >= 4096 &&
-              PT_SMEM <= (PT_NT > 1 ? 113 : 56) * 1024, "smem layout");
+// Tile geometry.  A CTA owns one TW x 32 tile (TW = 64 or 128), one thread per 16 pixels of a row.  Measured on a B200:
+//   * two 128-wide tiles per CTA (95 KB, two CTAs per SM) is SLOWER than one (88.6 vs 65.6 us per 32-frame 720p launch,
+//     run r2i): the halved warp count costs more than the amortised load latency saves;
+//   * the stage is a dependent chain per CTA (patch -> classify -> tiles -> arithmetic -> stores), so what hides latency
+//     is the number of independent chains per SM: a 64-wide tile needs ~27 KB and 128 threads, eight CTAs per SM instead
+//     of four with the same number of resident warps (tuning switch post_tile, see DESIGN.md for the measured numbers).
+// The patch of the small mask a (TW + 4) x 36 halo tile can touch has <= PT_RMAX rows and <= PCOLS columns (up-scales
+// >= ~1.75x).  A TMA box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate raises
+// "illegal instruction"), so the box begins at the patch's first column rounded down to 16 and is 16 columns wider.
+constexpr int PT_RMAX = 24;
+template <int TW> struct PtL {
+  static constexpr int NT = TW * PF_H / PF_PX;                   // threads
+  static constexpr int UW = TW + 4, US = TW + 8;                 // halo tile width, its row stride (u16 elements)
+  static constexpr int PCOLS = TW == 128 ? 80 : 48, PW = PCOLS + 16;
+  static constexpr int F_BYTES = TW * PF_H * 3, Y_BYTES = TW * PF_H * 2, M_BYTES = TW * PF_H;
+  static constexpr int OFF_F = 0, OFF_B = F_BYTES, OFF_Y = 2 * F_BYTES, OFF_P = 2 * F_BYTES + Y_BYTES;
+  static constexpr int OFF_HS = OFF_P + PT_RMAX * PW;            // Hs [PT_RMAX][US] u16, later Vs [PF_H][US] u16
+  static constexpr int HV_BYTES = (PT_RMAX > PF_H ? PT_RMAX : PF_H) * US * 2;
+  static constexpr int OFF_ROWS = OFF_HS + PT_RMAX * US * 2;     // [PF_UH] uint4 in the part of Vs that Hs does not use
+  static constexpr int OFF_US = OFF_HS + HV_BYTES;               // Us [PF_UH][US] u16, later the mask staging tile
+  static constexpr int OFF_BAR = OFF_US + PF_UH * US * 2;
+  static constexpr int SMEM = OFF_BAR + 32;
+  static constexpr int CTAS = TW == 128 ? 4 : 8;
+  static_assert(PW % 16 == 0 && OFF_P % 128 == 0 && OFF_HS % 16 == 0 && OFF_US % 128 == 0 && OFF_ROWS % 16 == 0 && OFF_BAR % 8 == 0 &&
+                (PF_H - PT_RMAX) * US * 2 >= PF_UH * 16 && PF_UH * US * 2 >= M_BYTES && US % 8 == 0 && NT % 64 == 0 && NT >= PF_UH &&
+                (SMEM + 1024) * CTAS <= 228 * 1024, "smem layout");
+};
 
-struct TileGeo { int tx0, hits_roi, gy_lo, gx_lo, rmin, nrows, cmin, ncols, coff; };
-
-template <bool IN_YUYV>
-__global__ void __launch_bounds__(256, PT_NT > 1 ? 2 : 4) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
+template <bool IN_YUYV, int TW>
+__global__ void __launch_bounds__(PtL<TW>::NT, PtL<TW>::CTAS) k_post_tma(const __grid_constant__ PostMaps tm, const PostArgs a, const PostTmaCfg cfg) {
+  using L = PtL<TW>;
+  constexpr int NT = L::NT, UW = L::UW, US = L::US, PW = L::PW;
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned short* Hs = reinterpret_cast<unsigned short*>(smem + PT_OFF_HS);
-  unsigned short* Us = reinterpret_cast<unsigned short*>(smem + PT_OFF_US);
-  unsigned short* Vs = reinterpret_cast<unsigned short*>(smem + PT_OFF_VS);
-  uint4* rows = reinterpret_cast<uint4*>(smem + PT_OFF_ROWS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PT_OFF_BAR);      // per tile: patch | background (+ its YUYV) | camera tile
+  unsigned short* Hs = reinterpret_cast<unsigned short*>(smem + L::OFF_HS);
+  unsigned short* Us = reinterpret_cast<unsigned short*>(smem + L::OFF_US);
+  unsigned short* Vs = Hs;
+  uint4* rows = reinterpret_cast<uint4*>(smem + L::OFF_ROWS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);      // patch | background (+ its YUYV) | camera tile
+  uint8_t* sF = smem + L::OFF_F;          // frame tile [32][3 TW] (BGR) or [32][2 TW] (YUYV); later the blended tile
+  uint8_t* sB = smem + L::OFF_B;          // background tile [32][3 TW]
+  uint8_t* sY = smem + L::OFF_Y;          // YUYV tile [32][2 TW]: cached background YUYV in, result out
+  uint8_t* sM = smem + L::OFF_US;         // mask tile [32][TW] (reuses Us, dead by then)
+  uint8_t* sP = smem + L::OFF_P;          // source patch of the small mask [PT_RMAX][PW]
+  uint64_t* barP = bars; uint64_t* barB = bars + 1; uint64_t* barF = bars + 2;
 
   const int b = blockIdx.z;
-  const int ty0 = blockIdx.y * PF_H;
+  const int ty0 = blockIdx.y * PF_H, tx0 = blockIdx.x * TW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (int i = 0; i < 3 * PT_NT; ++i) tma::mbar_init(bars + i, 1);
+    tma::mbar_init(barP, 1); tma::mbar_init(barB, 1); tma::mbar_init(barF, 1);
     tma::fence_barrier_init();
   }
   __syncthreads();
 
-  // ---- geometry of every tile, and all the loads, up front ----
-  TileGeo G[PT_NT];
-#pragma unroll
-  for (int t = 0; t < PT_NT; ++t) {
-    TileGeo& g = G[t];
-    g.tx0 = (blockIdx.x * PT_NT + t) * PF_W;
-    g.hits_roi = g.tx0 < a.W && g.tx0 < a.roi_x + a.roi_w && g.tx0 + PF_W > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
-    g.gy_lo = g.gx_lo = g.rmin = g.nrows = g.cmin = g.ncols = g.coff = 0;
-    if (g.hits_roi) {
-      // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
-      g.gy_lo = ty0 - a.roi_y - 2; g.gx_lo = g.tx0 - a.roi_x - 2;
-      const int gy_hi = g.gy_lo + PF_UH - 1, gx_hi = g.gx_lo + PF_UW - 1;
-      const int gy_min = g.gy_lo < 0 ? 0 : min(g.gy_lo, a.roi_h - 1);
-      const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
-      const int gx_min = g.gx_lo < 0 ? 0 : min(g.gx_lo, a.roi_w - 1);
-      const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
-      g.rmin = __ldg(a.tab.yofs0 + gy_min);
-      g.nrows = __ldg(a.tab.yofs1 + gy_max) - g.rmin + 1;
-      g.cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
-      g.ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - g.cmin + 1;
-      g.coff = (a.out_x + g.cmin) & 15;                 // the patch's first column inside the 16-byte aligned box
+  // ---- geometry of the tile, and all the loads, up front ----
+  const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + TW > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+  int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0, coff = 0;
+  if (hits_roi) {
+    // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
+    gy_lo = ty0 - a.roi_y - 2; gx_lo = tx0 - a.roi_x - 2;
+    const int gy_hi = gy_lo + PF_UH - 1, gx_hi = gx_lo + UW - 1;
+    const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
+    const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
+    const int gx_min = gx_lo < 0 ? 0 : min(gx_lo, a.roi_w - 1);
+    const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
+    rmin = __ldg(a.tab.yofs0 + gy_min);
+    nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
+    cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
+    ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
+    coff = (a.out_x + cmin) & 15;                       // the patch's first column inside the 16-byte aligned box
+  }
+  if (tid == 0) {
+    if (hits_roi) {
+      tma::mbar_expect_tx(barP, PT_RMAX * PW);
+      tma::load_3d(sP, &tm.ofinal, a.out_x + cmin - coff, a.out_y + rmin, b, barP);
     }
-    if (tid == 0 && g.tx0 < a.W) {
-      uint8_t* tb = smem + t * PT_TILE;
-      uint64_t* barP = bars + 3 * t; uint64_t* barB = barP + 1; uint64_t* barF = barP + 2;
-      const int txi = blockIdx.x * PT_NT + t;
-      if (g.hits_roi) {
-        tma::mbar_expect_tx(barP, PT_RMAX * PT_PW);
-        tma::load_3d(tb + PT_OFF_P, &tm.ofinal, a.out_x + g.cmin - g.coff, a.out_y + g.rmin, b, barP);
-      }
-      // the background tile (L2-resident for a still image) and its cached YUYV: a background tile needs nothing else,
-      // a mixed tile has its second operand early
-      int bgi = 0;
-      if (a.bg_cursor) bgi = (int)(((unsigned)__ldg(a.bg_cursor) + (unsigned)b * (unsigned)a.bg_advance) % (unsigned)a.bg_count);
-      else if (a.bg_stride) bgi = b;
-      tma::mbar_expect_tx(barB, 12288u + (cfg.has_bgy ? 8192u : 0u));
-      tma::load_3d(tb + PT_OFF_B, &tm.bg, txi * 96, ty0, bgi, barB);
-      if (cfg.has_bgy) tma::load_3d(tb + PT_OFF_Y, &tm.bgy, txi * 64, ty0, bgi, barB);
-      // ... and the camera tile when the tile can contain a person at all: waiting for the classification first would put a
-      // second memory round trip on the critical path of every person / mixed tile
-      if (g.hits_roi) {
-        tma::mbar_expect_tx(barF, IN_YUYV ? 8192u : 12288u);
-        tma::load_3d(tb + PT_OFF_F, &tm.frame, txi * (IN_YUYV ? 64 : 96), ty0, b, barF);
-      }
+    // the background tile (L2-resident for a still image) and its cached YUYV: a background tile needs nothing else,
+    // a mixed tile has its second operand early
+    int bgi = 0;
+    if (a.bg_cursor) bgi = (int)(((unsigned)__ldg(a.bg_cursor) + (unsigned)b * (unsigned)a.bg_advance) % (unsigned)a.bg_count);
+    else if (a.bg_stride) bgi = b;
+    tma::mbar_expect_tx(barB, (unsigned)L::F_BYTES + (cfg.has_bgy ? (unsigned)L::Y_BYTES : 0u));
+    tma::load_3d(sB, &tm.bg, blockIdx.x * (TW * 3 / 4), ty0, bgi, barB);
+    if (cfg.has_bgy) tma::load_3d(sY, &tm.bgy, blockIdx.x * (TW / 2), ty0, bgi, barB);
+    // ... and the camera tile when the tile can contain a person at all: waiting for the classification first would put a
+    // second memory round trip on the critical path of every person / mixed tile
+    if (hits_roi) {
+      tma::mbar_expect_tx(barF, IN_YUYV ? (unsigned)L::Y_BYTES : (unsigned)L::F_BYTES);
+      tma::load_3d(sF, &tm.frame, blockIdx.x * (IN_YUYV ? TW / 2 : TW * 3 / 4), ty0, b, barF);
     }
   }
 
-  const int lx = (tid & 7) * PF_PX, ly = tid >> 3;
+  const int lx = (tid % (TW / PF_PX)) * PF_PX, ly = tid / (TW / PF_PX);
   const int y = ty0 + ly;
 
-#pragma unroll 1
-  for (int t = 0; t < PT_NT; ++t) {
-    const TileGeo g = G[t];
-    if (g.tx0 >= a.W) break;                                   // odd number of tile columns: the last CTA has one tile
-    uint8_t* tb = smem + t * PT_TILE;
-    uint8_t* sF = tb + PT_OFF_F;            // frame tile [32][384] (BGR) or [32][256] (YUYV); later the blended tile
-    uint8_t* sB = tb + PT_OFF_B;            // background tile [32][384]
-    uint8_t* sY = tb + PT_OFF_Y;            // YUYV tile [32][256]: cached background YUYV in, result out
-    uint8_t* sM = PT_NT > 1 ? tb + PT_OFF_M : smem + PT_OFF_US;   // mask tile [32][128] (one tile per CTA: reuses Us, dead by then)
-    uint8_t* sP = tb + PT_OFF_P;            // source patch of the small mask [PT_RMAX][PT_PW]
-    uint64_t* barP = bars + 3 * t; uint64_t* barB = barP + 1; uint64_t* barF = barP + 2;
-    const int tx0 = g.tx0;
-    const bool hits_roi = g.hits_roi != 0;
-    const int gy_lo = g.gy_lo, gx_lo = g.gx_lo, rmin = g.rmin, nrows = g.nrows, cmin = g.cmin, ncols = g.ncols, coff = g.coff;
-
-    int tile_const = -1;
-    if (hits_roi) {
-      if (tid >= 192 && tid < 192 + PF_UH) {          // row parameters of the vertical resize pass (used by mixed tiles)
-        const int uy = tid - 192;
-        int gy = gy_lo + uy;
-        gy = gy < 0 ? -gy : gy; gy = gy >= a.roi_h ? 2 * a.roi_h - 2 - gy : gy;     // reflect-101 (single fold)
-        gy = min(max(gy, 0), a.roi_h - 1);
-        rows[uy] = make_uint4((unsigned)__ldg(a.tab.yofs0 + gy), (unsigned)__ldg(a.tab.yofs1 + gy),
-                              (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
-      }
-      tma::mbar_wait(barP, 0);
-      // all-255 / all-0 test of the patch, one 32-bit word per thread, over the box columns [0, coff + ncols) rounded up to
-      // words: a few columns more than the patch.  The classification only selects the code path (the mixed path is
-      // always correct), so a conservative test costs nothing in exactness and needs no per-byte masks.
-      bool hi = true, lo = true;
-      {
-        const int wpr = (coff + ncols + 3) >> 2;                        // words per row to look at (<= PT_PW / 4)
-        for (int i = tid; i < nrows * wpr; i += 256) {
-          const int r = i / wpr, wc = i - r * wpr;
-          const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PT_PW + wc * 4);
-          hi = hi && (v == 0xffffffffu);
-          lo = lo && (v == 0u);
-        }
-      }
-      const int all_hi = __syncthreads_and(hi);
-      const int all_lo = all_hi ? 0 : __syncthreads_and(lo);
-      tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
+  int tile_const = -1;
+  if (hits_roi) {
+    if (tid < PF_UH) {                                // row parameters of the vertical resize pass (used by mixed tiles)
+      const int uy = tid;
+      int gy = gy_lo + uy;
+      gy = gy < 0 ? -gy : gy; gy = gy >= a.roi_h ? 2 * a.roi_h - 2 - gy : gy;     // reflect-101 (single fold)
+      gy = min(max(gy, 0), a.roi_h - 1);
+      rows[uy] = make_uint4((unsigned)__ldg(a.tab.yofs0 + gy), (unsigned)__ldg(a.tab.yofs1 + gy),
+                            (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
     }
-    const bool inside = tx0 >= a.roi_x && min(tx0 + PF_W, a.W) <= a.roi_x + a.roi_w && ty0 >= a.roi_y && min(ty0 + PF_H, a.H) <= a.roi_y + a.roi_h;
-    const int kind = (!hits_roi || tile_const == 255) ? 0 : ((tile_const == 0 && inside) ? 1 : 2);   // background / person / mixed
-
-    if (kind == 2 && tile_const < 0) {
-      // ---- A1: horizontal pass of cv::resize on the patch rows (see k_post_fast) ----
-      {
-        const int phase = tid >> 7;
-        for (int ux = tid & 127; ux < PF_UW; ux += 128) {
-          int gx = gx_lo + ux;
-          gx = gx < 0 ? -gx : gx; gx = gx >= a.roi_w ? 2 * a.roi_w - 2 - gx : gx;
-          gx = min(max(gx, 0), a.roi_w - 1);
-          const uint2 xc = __ldg(a.tab.xcol + gx);
-          const int sx = (int)(xc.x & 0xffffu) - cmin + coff, sx1 = (int)(xc.x >> 16) - cmin + coff;
-          const int a0 = (int)(short)(xc.y & 0xffffu), a1 = (int)(short)(xc.y >> 16);
-          const uint8_t* pr = sP + phase * PT_PW;
-          unsigned short* hp = Hs + phase * PF_US + ux;
-          for (int r = phase; r < nrows; r += 2) {
-            *hp = (unsigned short)(((int)pr[sx] * a0 + (int)pr[sx1] * a1) >> 4);
-            pr += 2 * PT_PW; hp += 2 * PF_US;
-          }
-        }
+    tma::mbar_wait(barP, 0);
+    // all-255 / all-0 test of the patch, one 32-bit word per thread, over the box columns [0, coff + ncols) rounded up to
+    // words: a few columns more than the patch.  The classification only selects the code path (the mixed path is
+    // always correct), so a conservative test costs nothing in exactness and needs no per-byte masks.
+    bool hi = true, lo = true;
+    {
+      const int wpr = (coff + ncols + 3) >> 2;                        // words per row to look at (<= PW / 4)
+      for (int i = tid; i < nrows * wpr; i += NT) {
+        const int r = i / wpr, wc = i - r * wpr;
+        const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PW + wc * 4);
+        hi = hi && (v == 0xffffffffu);
+        lo = lo && (v == 0u);
       }
-      __syncthreads();
-      // ---- A2: vertical pass -> upsampled tile ----
-      for (int uy = warp; uy < PF_UH; uy += 8) {
-        const uint4 rp = rows[uy];
-        const unsigned short* h0 = Hs + ((int)rp.x - rmin) * PF_US + lane;
-        const unsigned short* h1 = Hs + ((int)rp.y - rmin) * PF_US + lane;
-        unsigned short* up = Us + uy * PF_US + lane;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          up[32 * k] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[32 * k]) + __umulhi(rp.w, (unsigned)h1[32 * k]) + 2u) >> 2);
-        if (lane < PF_UW - 128)
-          up[128] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[128]) + __umulhi(rp.w, (unsigned)h1[128]) + 2u) >> 2);
-      }
-      __syncthreads();
-      // ---- B: vertical 5-sums, two columns per word, sliding window over 8 rows ----
-      for (int it = tid; it < (PF_UW / 2) * 4; it += 256) {
-        const int pair = it % (PF_UW / 2), seg = it / (PF_UW / 2);
-        const unsigned* up = reinterpret_cast<const unsigned*>(Us + (seg * 8) * PF_US) + pair;
-        unsigned* vp = reinterpret_cast<unsigned*>(Vs + (seg * 8) * PF_US) + pair;
-        unsigned u[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) u[k] = up[k * (PF_US / 2)];
-        unsigned v = u[0] + u[1] + u[2] + u[3] + u[4];
-        vp[0] = v;
-#pragma unroll
-        for (int k = 1; k < 8; ++k) { v = v + u[k + 4] - u[k - 1]; vp[k * (PF_US / 2)] = v; }
-      }
-      __syncthreads();
     }
-
-    const int x0 = tx0 + lx;
-    uint4* mdst = reinterpret_cast<uint4*>(sM + ly * PF_W + lx);
-    uint4* ydst = reinterpret_cast<uint4*>(sY + ly * (PF_W * 2) + lx * 2);
-    const uint8_t* out_src = sB;
-
-    tma::mbar_wait(barB, 0);
-    // a background tile does not use its (speculatively loaded) camera tile: only thread 0 waits for it, after the stores
-    // are on their way (shared memory must be quiet when the CTA exits)
-    if (hits_roi && kind != 0) tma::mbar_wait(barF, 0);
-    if (kind == 0) {
-      // ---- background tile: out = background tile, YUYV = cached YUYV tile, mask = 255.  No per-pixel arithmetic ----
-      if (cfg.has_mask) *mdst = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (cfg.has_yuyv && !cfg.has_bgy) {
-        const uint4* gq = reinterpret_cast<const uint4*>(sB + ly * (PF_W * 3) + lx * 3);
-        const uint4 g0 = gq[0], g1 = gq[1], g2 = gq[2];
-        const unsigned gg[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
-        unsigned m[PF_PX], o[12], yy[8];
-#pragma unroll
-        for (int i = 0; i < PF_PX; ++i) m[i] = 255u;
-        post_blend16<false, true>(gg, gg, m, o, yy);
-        ydst[0] = make_uint4(yy[0], yy[1], yy[2], yy[3]); ydst[1] = make_uint4(yy[4], yy[5], yy[6], yy[7]);
-      }
-    } else {
-      unsigned m[PF_PX];
-      if (kind == 1) {
-#pragma unroll
-        for (int i = 0; i < PF_PX; ++i) m[i] = 0u;
-      } else {
-        const bool row_in = y >= a.roi_y && y < a.roi_y + a.roi_h;
-        post_mask16(a, row_in, tile_const, x0, Vs + ly * PF_US + lx, m);
-      }
-      unsigned f[12], gg[12];
-      if (IN_YUYV) {
-        const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (PF_W * 2) + lx * 2);
-        const uint4 w0 = fq[0], w1 = fq[1];
-        const unsigned wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
-        yuyv8_to_bgr24(wa, f); yuyv8_to_bgr24(wb, f + 6);
-      } else {
-        const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (PF_W * 3) + lx * 3);
-        const uint4 f0 = fq[0], f1 = fq[1], f2 = fq[2];
-        f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
-        f[8] = f2.x; f[9] = f2.y; f[10] = f2.z; f[11] = f2.w;
-      }
-      if (kind == 2) {
-        const uint4* gq = reinterpret_cast<const uint4*>(sB + ly * (PF_W * 3) + lx * 3);
-        const uint4 g0 = gq[0], g1 = gq[1], g2 = gq[2];
-        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
-        gg[8] = g2.x; gg[9] = g2.y; gg[10] = g2.z; gg[11] = g2.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) gg[i] = f[i];
-      }
-      unsigned o[12], yy[8];
-      post_blend16<true, true>(f, gg, m, o, yy);
-      if (IN_YUYV) __syncthreads();                     // the YUYV tile is fully consumed before the (wider) BGR tile overwrites it
-      uint4* odst = reinterpret_cast<uint4*>(sF + ly * (PF_W * 3) + lx * 3);
-      odst[0] = make_uint4(o[0], o[1], o[2], o[3]); odst[1] = make_uint4(o[4], o[5], o[6], o[7]); odst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-      ydst[0] = make_uint4(yy[0], yy[1], yy[2], yy[3]); ydst[1] = make_uint4(yy[4], yy[5], yy[6], yy[7]);
-      *mdst = make_uint4(m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24), m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24),
-                         m[8] | (m[9] << 8) | (m[10] << 16) | (m[11] << 24), m[12] | (m[13] << 8) | (m[14] << 16) | (m[15] << 24));
-      out_src = sF;
-    }
-    tma::fence_proxy_async();          // generic-proxy writes of the staging tiles -> visible to the TMA engine
-    __syncthreads();                   // (also: the shared mask-building scratch is free for the next tile)
-    if (tid == 0) {
-      const int txi = blockIdx.x * PT_NT + t;
-      if (cfg.has_out) tma::store_3d(&tm.out, out_src, txi * 96, ty0, b);
-      if (cfg.has_yuyv) tma::store_3d(&tm.yuyv, sY, txi * 64, ty0, b);
-      if (cfg.has_mask) tma::store_3d(&tm.mask, sM, tx0, ty0, b);
-      tma::store_commit();
-      if (hits_roi && kind == 0) tma::mbar_wait(barF, 0);
-    }
+    const int all_hi = __syncthreads_and(hi);
+    const int all_lo = all_hi ? 0 : __syncthreads_and(lo);
+    tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
   }
-  if (tid == 0) tma::store_wait_read();      // shared memory may be handed to the next CTA only after the engine has read it
+  const bool inside = tx0 >= a.roi_x && min(tx0 + TW, a.W) <= a.roi_x + a.roi_w && ty0 >= a.roi_y && min(ty0 + PF_H, a.H) <= a.roi_y + a.roi_h;
+  const int kind = (!hits_roi || tile_const == 255) ? 0 : ((tile_const == 0 && inside) ? 1 : 2);   // background / person / mixed
+
+  if (kind == 2 && tile_const < 0) {
+    // ---- A1: horizontal pass of cv::resize on the patch rows (see k_post_fast) ----
+    {
+      constexpr int HALF = NT / 2;
+      const int phase = tid / HALF;
+      for (int ux = tid % HALF; ux < UW; ux += HALF) {
+        int gx = gx_lo + ux;
+        gx = gx < 0 ? -gx : gx; gx = gx >= a.roi_w ? 2 * a.roi_w - 2 - gx : gx;
+        gx = min(max(gx, 0), a.roi_w - 1);
+        const uint2 xc = __ldg(a.tab.xcol + gx);
+        const int sx = (int)(xc.x & 0xffffu) - cmin + coff, sx1 = (int)(xc.x >> 16) - cmin + coff;
+        const int a0 = (int)(short)(xc.y & 0xffffu), a1 = (int)(short)(xc.y >> 16);
+        const uint8_t* pr = sP + phase * PW;
+        unsigned short* hp = Hs + phase * US + ux;
+        for (int r = phase; r < nrows; r += 2) {
+          *hp = (unsigned short)(((int)pr[sx] * a0 + (int)pr[sx1] * a1) >> 4);
+          pr += 2 * PW; hp += 2 * US;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- A2: vertical pass -> upsampled tile ----
+    for (int uy = warp; uy < PF_UH; uy += NT / 32) {
+      const uint4 rp = rows[uy];
+      const unsigned short* h0 = Hs + ((int)rp.x - rmin) * US + lane;
+      const unsigned short* h1 = Hs + ((int)rp.y - rmin) * US + lane;
+      unsigned short* up = Us + uy * US + lane;
+#pragma unroll
+      for (int k = 0; k < TW / 32; ++k)
+        up[32 * k] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[32 * k]) + __umulhi(rp.w, (unsigned)h1[32 * k]) + 2u) >> 2);
+      if (lane < UW - TW)
+        up[TW] = (unsigned short)((__umulhi(rp.z, (unsigned)h0[TW]) + __umulhi(rp.w, (unsigned)h1[TW]) + 2u) >> 2);
+    }
+    __syncthreads();
+    // ---- B: vertical 5-sums, two columns per word, sliding window over 8 rows (Vs overwrites Hs and the row table) ----
+    for (int it = tid; it < (UW / 2) * 4; it += NT) {
+      const int pair = it % (UW / 2), seg = it / (UW / 2);
+      const unsigned* up = reinterpret_cast<const unsigned*>(Us + (seg * 8) * US) + pair;
+      unsigned* vp = reinterpret_cast<unsigned*>(Vs + (seg * 8) * US) + pair;
+      unsigned u[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) u[k] = up[k * (US / 2)];
+      unsigned v = u[0] + u[1] + u[2] + u[3] + u[4];
+      vp[0] = v;
+#pragma unroll
+      for (int k = 1; k < 8; ++k) { v = v + u[k + 4] - u[k - 1]; vp[k * (US / 2)] = v; }
+    }
+    __syncthreads();
+  }
+
+  const int x0 = tx0 + lx;
+  uint4* mdst = reinterpret_cast<uint4*>(sM + ly * TW + lx);
+  uint4* ydst = reinterpret_cast<uint4*>(sY + ly * (TW * 2) + lx * 2);
+  const uint8_t* out_src = sB;
+
+  tma::mbar_wait(barB, 0);
+  // a background tile does not use its (speculatively loaded) camera tile: only thread 0 waits for it, after the stores
+  // are on their way (shared memory must be quiet when the CTA exits)
+  if (hits_roi && kind != 0) tma::mbar_wait(barF, 0);
+  if (kind == 0) {
+    // ---- background tile: out = background tile, YUYV = cached YUYV tile, mask = 255.  No per-pixel arithmetic ----
+    if (cfg.has_mask) *mdst = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (cfg.has_yuyv && !cfg.has_bgy) {
+      const uint4* gq = reinterpret_cast<const uint4*>(sB + ly * (TW * 3) + lx * 3);
+      const uint4 g0 = gq[0], g1 = gq[1], g2 = gq[2];
+      const unsigned gg[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
+      unsigned m[PF_PX], o[12], yy[8];
+#pragma unroll
+      for (int i = 0; i < PF_PX; ++i) m[i] = 255u;
+      post_blend16<false, true>(gg, gg, m, o, yy);
+      ydst[0] = make_uint4(yy[0], yy[1], yy[2], yy[3]); ydst[1] = make_uint4(yy[4], yy[5], yy[6], yy[7]);
+    }
+  } else {
+    unsigned m[PF_PX];
+    if (kind == 1) {
+#pragma unroll
+      for (int i = 0; i < PF_PX; ++i) m[i] = 0u;
+    } else {
+      const bool row_in = y >= a.roi_y && y < a.roi_y + a.roi_h;
+      post_mask16(a, row_in, tile_const, x0, Vs + ly * US + lx, m);
+    }
+    unsigned f[12], gg[12];
+    if (IN_YUYV) {
+      const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (TW * 2) + lx * 2);
+      const uint4 w0 = fq[0], w1 = fq[1];
+      const unsigned wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
+      yuyv8_to_bgr24(wa, f); yuyv8_to_bgr24(wb, f + 6);
+    } else {
+      const uint4* fq = reinterpret_cast<const uint4*>(sF + ly * (TW * 3) + lx * 3);
+      const uint4 f0 = fq[0], f1 = fq[1], f2 = fq[2];
+      f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
+      f[8] = f2.x; f[9] = f2.y; f[10] = f2.z; f[11] = f2.w;
+    }
+    if (kind == 2) {
+      const uint4* gq = reinterpret_cast<const uint4*>(sB + ly * (TW * 3) + lx * 3);
+      const uint4 g0 = gq[0], g1 = gq[1], g2 = gq[2];
+      gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+      gg[8] = g2.x; gg[9] = g2.y; gg[10] = g2.z; gg[11] = g2.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) gg[i] = f[i];
+    }
+    unsigned o[12], yy[8];
+    post_blend16<true, true>(f, gg, m, o, yy);
+    // the YUYV camera tile is fully consumed before the (wider) BGR tile overwrites it; the mask staging tile reuses Us,
+    // whose last readers (phase B) are behind a barrier already
+    if (IN_YUYV) __syncthreads();
+    uint4* odst = reinterpret_cast<uint4*>(sF + ly * (TW * 3) + lx * 3);
+    odst[0] = make_uint4(o[0], o[1], o[2], o[3]); odst[1] = make_uint4(o[4], o[5], o[6], o[7]); odst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    ydst[0] = make_uint4(yy[0], yy[1], yy[2], yy[3]); ydst[1] = make_uint4(yy[4], yy[5], yy[6], yy[7]);
+    *mdst = make_uint4(m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24), m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24),
+                       m[8] | (m[9] << 8) | (m[10] << 16) | (m[11] << 24), m[12] | (m[13] << 8) | (m[14] << 16) | (m[15] << 24));
+    out_src = sF;
+  }
+  tma::fence_proxy_async();            // generic-proxy writes of the staging tiles -> visible to the TMA engine
+  __syncthreads();
+  if (tid == 0) {
+    if (cfg.has_out) tma::store_3d(&tm.out, out_src, blockIdx.x * (TW * 3 / 4), ty0, b);
+    if (cfg.has_yuyv) tma::store_3d(&tm.yuyv, sY, blockIdx.x * (TW / 2), ty0, b);
+    if (cfg.has_mask) tma::store_3d(&tm.mask, sM, tx0, ty0, b);
+    tma::store_commit();
+    if (hits_roi && kind == 0) tma::mbar_wait(barF, 0);
+    tma::store_wait_read();            // shared memory may be handed to the next CTA only after the engine has read it
+  }
 }
 
 // ---- host side: tensor maps --------------------------------------------------------------------------------
@@ -352,21 +339,24 @@ static bool make_map(CUtensorMap* m, const void* base, bool words, size_t row_by
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static bool build_post_maps(const PostArgs& a, PostMaps* tm) {
+static bool build_post_maps(const PostArgs& a, PostMaps* tm, int TW) {
+  const unsigned bw3 = (unsigned)TW * 3, bw2 = (unsigned)TW * 2, pw = TW == 128 ? (unsigned)PtL<128>::PW : (unsigned)PtL<64>::PW;
   const size_t W = (size_t)a.W, H = (size_t)a.H, B = (size_t)a.B;
   const size_t nbg = a.bg_cursor ? (size_t)a.bg_count : (a.bg_stride ? B : 1);
   bool ok = true;
-  if (a.yuyv_in) ok = ok && make_map(&tm->frame, a.yuyv_in, true, W * 2, H, B, W * 2, a.yuyv_in_stride, 256, PF_H);
-  else ok = ok && make_map(&tm->frame, a.frames, true, W * 3, H, B, a.frame_pitch, a.frame_stride, 384, PF_H);
-  ok = ok && make_map(&tm->bg, a.bg, true, W * 3, H, nbg, a.bg_pitch, a.bg_stride ? a.bg_stride : a.bg_pitch * H, 384, PF_H);
+  if (a.yuyv_in) ok = ok && make_map(&tm->frame, a.yuyv_in, true, W * 2, H, B, W * 2, a.yuyv_in_stride, bw2, PF_H);
+  else ok = ok && make_map(&tm->frame, a.frames, true, W * 3, H, B, a.frame_pitch, a.frame_stride, bw3, PF_H);
+  ok = ok && make_map(&tm->bg, a.bg, true, W * 3, H, nbg, a.bg_pitch, a.bg_stride ? a.bg_stride : a.bg_pitch * H, bw3, PF_H);
   // unused maps still have to be valid descriptors: alias them to a live one
-  if (a.bg_yuyv) ok = ok && make_map(&tm->bgy, a.bg_yuyv, true, W * 2, H, nbg, W * 2, W * 2 * H, 256, PF_H); else tm->bgy = tm->bg;
-  if (a.out) ok = ok && make_map(&tm->out, a.out, true, W * 3, H, B, a.out_pitch, a.out_stride, 384, PF_H); else tm->out = tm->bg;
-  if (a.yuyv) ok = ok && make_map(&tm->yuyv, a.yuyv, true, W * 2, H, B, W * 2, a.yuyv_stride, 256, PF_H); else tm->yuyv = tm->bg;
-  if (a.mask) ok = ok && make_map(&tm->mask, a.mask, false, W, H, B, W, a.mask_stride, PF_W, PF_H); else tm->mask = tm->bg;
-  ok = ok && make_map(&tm->ofinal, a.ofinal, false, (size_t)a.ow, (size_t)a.oh, B, (size_t)a.opitch, (size_t)a.opitch * a.oh, PT_PW, PT_RMAX);
+  if (a.bg_yuyv) ok = ok && make_map(&tm->bgy, a.bg_yuyv, true, W * 2, H, nbg, W * 2, W * 2 * H, bw2, PF_H); else tm->bgy = tm->bg;
+  if (a.out) ok = ok && make_map(&tm->out, a.out, true, W * 3, H, B, a.out_pitch, a.out_stride, bw3, PF_H); else tm->out = tm->bg;
+  if (a.yuyv) ok = ok && make_map(&tm->yuyv, a.yuyv, true, W * 2, H, B, W * 2, a.yuyv_stride, bw2, PF_H); else tm->yuyv = tm->bg;
+  if (a.mask) ok = ok && make_map(&tm->mask, a.mask, false, W, H, B, W, a.mask_stride, (unsigned)TW, PF_H); else tm->mask = tm->bg;
+  ok = ok && make_map(&tm->ofinal, a.ofinal, false, (size_t)a.ow, (size_t)a.oh, B, (size_t)a.opitch, (size_t)a.opitch * a.oh, pw, PT_RMAX);
   return ok;
 }
+
+static int post_tile_width() { return tuning().post_tile == 128 ? 128 : 64; }
 
 static bool post_tma_shape_ok(const PostArgs& a) {
   if (!tuning().post_tma || !encode_fn()) return false;
@@ -381,29 +371,35 @@ static bool post_tma_shape_ok(const PostArgs& a) {
   if (!(a.out || a.yuyv || a.mask) || !al16(a.ofinal) || a.opitch % 16) return false;
   if (a.ow > 32000 || a.oh > 32000 || a.roi_w < 8 || a.roi_h < 8) return false;
   const double scale_y = (double)a.out_h / (double)a.roi_h, scale_x = (double)a.out_w / (double)a.roi_w;
-  if ((int)(PF_UH * scale_y) + 3 > PT_RMAX || (int)(PF_UW * scale_x) + 4 > PT_PCOLS) return false;
+  const int tw = post_tile_width();
+  if ((int)(PF_UH * scale_y) + 3 > PT_RMAX || (int)((tw + 4) * scale_x) + 4 > (tw == 128 ? PtL<128>::PCOLS : PtL<64>::PCOLS)) return false;
   return true;
 }
 
 bool post_tma_eligible(const PostArgs& a) {
   PostMaps tm;
-  return post_tma_shape_ok(a) && build_post_maps(a, &tm);
+  return post_tma_shape_ok(a) && build_post_maps(a, &tm, post_tile_width());
+}
+
+template <bool IN_YUYV, int TW>
+static bool launch_post_tma_t(cudaStream_t s, const PostMaps& tm, const PostArgs& a, const PostTmaCfg& cfg) {
+  using L = PtL<TW>;
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_post_tma<IN_YUYV, TW>), L::SMEM)) return false;
+  const dim3 grid((unsigned)ceil_div(a.W, TW), (unsigned)ceil_div(a.H, PF_H), (unsigned)a.B);
+  k_post_tma<IN_YUYV, TW><<<grid, L::NT, L::SMEM, s>>>(tm, a, cfg);
+  return true;
 }
 
 bool launch_post_tma(cudaStream_t s, const PostArgs& a) {
   PostMaps tm;
-  if (!post_tma_shape_ok(a) || !build_post_maps(a, &tm)) return false;
-  PostTmaCfg cfg{a.out ? 1 : 0, a.yuyv ? 1 : 0, a.mask ? 1 : 0, a.bg_yuyv ? 1 : 0};
-  const dim3 grid((unsigned)ceil_div(ceil_div(a.W, PF_W), PT_NT), (unsigned)ceil_div(a.H, PF_H), (unsigned)a.B);
-  if (a.yuyv_in) {
-    if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_post_tma<true>), PT_SMEM)) return false;
-    k_post_tma<true><<<grid, 256, PT_SMEM, s>>>(tm, a, cfg);
-  } else {
-    if (!ensure_dyn_smem(reinterpret_cast<const void*>(k_post_tma<false>), PT_SMEM)) return false;
-    k_post_tma<false><<<grid, 256, PT_SMEM, s>>>(tm, a, cfg);
-  }
-  count_launch();
-  return true;
+  const int tw = post_tile_width();
+  if (!post_tma_shape_ok(a) || !build_post_maps(a, &tm, tw)) return false;
+  const PostTmaCfg cfg{a.out ? 1 : 0, a.yuyv ? 1 : 0, a.mask ? 1 : 0, a.bg_yuyv ? 1 : 0};
+  bool ok;
+  if (a.yuyv_in) ok = tw == 128 ? launch_post_tma_t<true, 128>(s, tm, a, cfg) : launch_post_tma_t<true, 64>(s, tm, a, cfg);
+  else ok = tw == 128 ? launch_post_tma_t<false, 128>(s, tm, a, cfg) : launch_post_tma_t<false, 64>(s, tm, a, cfg);
+  if (ok) count_launch();
+  return ok;
 }
 
 #else   // BSB_EMU: TMA cannot be emulated; the emulator build always takes k_post_fast / k_post

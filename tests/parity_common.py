@@ -477,7 +477,9 @@ def check_mjpg_ingest(lib, key="meet_lite", W=640, H=480, n=2):
     for d, j in zip(dec, jpgs):
         ref = cv2.imdecode(np.frombuffer(j, np.uint8), cv2.IMREAD_COLOR)
         diff = np.abs(d.astype(np.int16) - ref.astype(np.int16))
-        assert diff.max() <= 6 and diff.mean() < 0.75, (int(diff.max()), float(diff.mean()))
+        # NVJPG replicates the sub-sampled chroma where libjpeg interpolates it ("fancy up-sampling"): isolated pixels on
+        # sharp colour edges differ by tens of levels, the picture as a whole by well under one (measured: max 29, mean 0.70)
+        assert diff.mean() < 1.0 and (diff > 8).mean() < 0.01 and diff.max() <= 64, (int(diff.max()), float(diff.mean()), float((diff > 8).mean()))
     out, yuyv, mask = g.composite_mjpg(jpgs)
     for b in range(n):
         ro, ry, rm = o.composite(dec[b], bg)
