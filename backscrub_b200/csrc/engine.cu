@@ -788,7 +788,6 @@ bool Engine::upload(std::string* err) {
   CUDA_OK(cudaMallocHost((void**)&h_mask_, fpx));
   if (!upload_resize_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
   if (!upload_resize_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
-  if (tab_up_.area2x2) { *err = "mask upsample degenerated to a 2x down-scale"; return false; }
   if (!refresh_bg_yuyv(err)) return false;
   CUDA_OK(cudaDeviceSynchronize());
   return true;
@@ -965,7 +964,7 @@ PostArgs Engine::post_args(int n, const uint8_t* d_frames, size_t pitch, size_t 
   a.ofinal = ofinal_; a.ow = ow_; a.oh = oh_; a.opitch = opitch_;
   a.out_x = out_roidim_[0]; a.out_y = out_roidim_[1]; a.out_w = out_roidim_[2]; a.out_h = out_roidim_[3];
   a.roi_x = roidim_[0]; a.roi_y = roidim_[1]; a.roi_w = roidim_[2]; a.roi_h = roidim_[3];
-  a.tab = tab_up_.tab; a.area2x2 = false;
+  a.tab = tab_up_.tab; a.area2x2 = tab_up_.area2x2;
   a.out_pitch = (size_t)W_ * 3;
   if (!tail) {
     a.out = d_out; a.out_stride = out_stride;

@@ -273,6 +273,12 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
       const int uy = i / PT_UW, ux = i % PT_UW;
       const int gy = bsb_reflect101(ty0 - a.roi_y - 2 + uy, a.roi_h);
       const int gx = bsb_reflect101(tx0 - a.roi_x - 2 + ux, a.roi_w);
+      if (a.area2x2) {      // exact 2x down-scale: cv::resize takes its INTER_AREA 2x2 mean ((a + b + c + d + 2) >> 2)
+        const uint8_t* s0 = src + (size_t)(2 * gy) * a.opitch + 2 * gx;
+        const uint8_t* s1 = s0 + a.opitch;
+        Us[uy * PT_US + ux] = (uint8_t)(((int)s0[0] + s0[1] + s1[0] + s1[1] + 2) >> 2);
+        continue;
+      }
       const int sx = __ldg(a.tab.xofs + gx), sx1 = min(sx + 1, a.out_w - 1);
       const int a0 = __ldg(a.tab.xw + 2 * gx), a1 = __ldg(a.tab.xw + 2 * gx + 1);
       const int b0 = __ldg(a.tab.yw + 2 * gy), b1 = __ldg(a.tab.yw + 2 * gy + 1);
@@ -540,7 +546,7 @@ __global__ void __launch_bounds__(256, 4) k_post_fast(PostArgs a) {
 
 static bool post_fast_ok(const PostArgs& a) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (a.W % 16 != 0) return false;
+  if (a.W % 16 != 0 || a.area2x2) return false;
   if (!al16(a.frames) || !al16(a.bg) || a.frame_pitch % 16 || a.frame_stride % 16 || a.bg_pitch % 16 || a.bg_stride % 16) return false;
   if (a.out && (!al16(a.out) || a.out_pitch % 16 || a.out_stride % 16)) return false;
   if (a.yuyv && (!al16(a.yuyv) || a.yuyv_stride % 16)) return false;

@@ -41,6 +41,8 @@ def test_pipeline_ragged_geometry(lib):
     """odd sizes: ROI not tile-aligned, width not a multiple of 16, letter-boxed model input."""
     pc.check_pipeline(lib, "meet_lite", 324, 250, n_frames=2)
     pc.check_pipeline(lib, "mlkit", 322, 182, n_frames=1)
+    # frame exactly half the model output: cv::resize of the mask takes its INTER_AREA 2x2 path (lib/libbackscrub.cc:366)
+    pc.check_pipeline(lib, "meet_full", 128, 72, n_frames=2)
 
 
 @pytest.mark.parametrize("key", ["mlkit", "meet_full", "bodypix"])

@@ -37,6 +37,7 @@ def test_pipeline_ragged_geometry(lib):
     pc.check_pipeline(lib, "meet_lite", 324, 250, n_frames=2)
     pc.check_pipeline(lib, "mlkit", 322, 182, n_frames=2)
     pc.check_pipeline(lib, "meet_full", 720, 1280, n_frames=1)     # portrait: letter-boxed input
+    pc.check_pipeline(lib, "meet_full", 128, 72, n_frames=2)       # mask resize is an exact 2x down-scale (INTER_AREA path)
 
 
 def test_pipeline_fused_blocks(lib):
