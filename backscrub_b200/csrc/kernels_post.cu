@@ -79,7 +79,8 @@ template <int TW> struct PtL {
   static constexpr int OFF_ROWS = OFF_HS + PT_RMAX * US * 2;     // [PF_UH] uint4 in the part of Vs that Hs does not use
   static constexpr int OFF_US = OFF_HS + HV_BYTES;               // Us [PF_UH][US] u16, later the mask staging tile
   static constexpr int OFF_BAR = OFF_US + PF_UH * US * 2;
-  static constexpr int SMEM = OFF_BAR + 32;
+  static constexpr int OFF_GEO = OFF_BAR + 32;                   // 12 ints of tile geometry / classification
+  static constexpr int SMEM = OFF_GEO + 48;
   static constexpr int CTAS = TW == 128 ? 4 : 8;
   static_assert(PW % 16 == 0 && OFF_P % 128 == 0 && OFF_HS % 16 == 0 && OFF_US % 128 == 0 && OFF_ROWS % 16 == 0 && OFF_BAR % 8 == 0 &&
                 (PF_H - PT_RMAX) * US * 2 >= PF_UH * 16 && PF_UH * US * 2 >= M_BYTES && US % 8 == 0 && NT % 64 == 0 && NT >= PF_UH &&
@@ -106,32 +107,29 @@ __global__ void __launch_bounds__(PtL<TW>::NT, PtL<TW>::CTAS) k_post_tma(const _
   const int b = blockIdx.z;
   const int ty0 = blockIdx.y * PF_H, tx0 = blockIdx.x * TW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* geo = reinterpret_cast<int*>(smem + L::OFF_GEO);                 // tile geometry, published by thread 0
 
+  // ---- thread 0: geometry of the tile and ALL the loads, before anybody else does anything.  The geometry is uniform
+  //      over the CTA: computing it once and publishing it through shared memory takes ~25 instructions off every other
+  //      warp (the stage is half issue-bound, profiles/r2_ncu_k_post_tma.txt) ----
   if (tid == 0) {
     tma::mbar_init(barP, 1); tma::mbar_init(barB, 1); tma::mbar_init(barF, 1);
     tma::fence_barrier_init();
-  }
-  __syncthreads();
-
-  // ---- geometry of the tile, and all the loads, up front ----
-  const bool hits_roi = tx0 < a.roi_x + a.roi_w && tx0 + TW > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
-  int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0, coff = 0;
-  if (hits_roi) {
-    // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
-    gy_lo = ty0 - a.roi_y - 2; gx_lo = tx0 - a.roi_x - 2;
-    const int gy_hi = gy_lo + PF_UH - 1, gx_hi = gx_lo + UW - 1;
-    const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
-    const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
-    const int gx_min = gx_lo < 0 ? 0 : min(gx_lo, a.roi_w - 1);
-    const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
-    rmin = __ldg(a.tab.yofs0 + gy_min);
-    nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
-    cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
-    ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
-    coff = (a.out_x + cmin) & 15;                       // the patch's first column inside the 16-byte aligned box
-  }
-  if (tid == 0) {
-    if (hits_roi) {
+    const bool hit = tx0 < a.roi_x + a.roi_w && tx0 + TW > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+    int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0, coff = 0;
+    if (hit) {
+      // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
+      gy_lo = ty0 - a.roi_y - 2; gx_lo = tx0 - a.roi_x - 2;
+      const int gy_hi = gy_lo + PF_UH - 1, gx_hi = gx_lo + UW - 1;
+      const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
+      const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
+      const int gx_min = gx_lo < 0 ? 0 : min(gx_lo, a.roi_w - 1);
+      const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
+      rmin = __ldg(a.tab.yofs0 + gy_min);
+      nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
+      cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
+      ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
+      coff = (a.out_x + cmin) & 15;                     // the patch's first column inside the 16-byte aligned box
       tma::mbar_expect_tx(barP, PT_RMAX * PW);
       tma::load_3d(sP, &tm.ofinal, a.out_x + cmin - coff, a.out_y + rmin, b, barP);
     }
@@ -145,45 +143,59 @@ __global__ void __launch_bounds__(PtL<TW>::NT, PtL<TW>::CTAS) k_post_tma(const _
     if (cfg.has_bgy) tma::load_3d(sY, &tm.bgy, blockIdx.x * (TW / 2), ty0, bgi, barB);
     // ... and the camera tile when the tile can contain a person at all: waiting for the classification first would put a
     // second memory round trip on the critical path of every person / mixed tile
-    if (hits_roi) {
+    if (hit) {
       tma::mbar_expect_tx(barF, IN_YUYV ? (unsigned)L::Y_BYTES : (unsigned)L::F_BYTES);
       tma::load_3d(sF, &tm.frame, blockIdx.x * (IN_YUYV ? TW / 2 : TW * 3 / 4), ty0, b, barF);
     }
+    const bool inside = tx0 >= a.roi_x && min(tx0 + TW, a.W) <= a.roi_x + a.roi_w && ty0 >= a.roi_y && min(ty0 + PF_H, a.H) <= a.roi_y + a.roi_h;
+    *reinterpret_cast<int4*>(geo) = make_int4(hit ? 1 : 0, gy_lo, gx_lo, rmin);
+    *reinterpret_cast<int4*>(geo + 4) = make_int4(nrows, cmin, ncols, coff);
+    geo[8] = inside ? 1 : 0;
   }
+  __syncthreads();
+  const int4 g0 = *reinterpret_cast<const int4*>(geo), g1 = *reinterpret_cast<const int4*>(geo + 4);
+  const bool hits_roi = g0.x != 0;
+  const int gy_lo = g0.y, gx_lo = g0.z, rmin = g0.w, nrows = g1.x, cmin = g1.y, ncols = g1.z, coff = g1.w;
 
   const int lx = (tid % (TW / PF_PX)) * PF_PX, ly = tid / (TW / PF_PX);
   const int y = ty0 + ly;
 
-  int tile_const = -1;
+  int tile_const = -1, kind = 0;                         // background / person / mixed
   if (hits_roi) {
-    if (tid < PF_UH) {                                // row parameters of the vertical resize pass (used by mixed tiles)
-      const int uy = tid;
+    if (warp == 0) {
+      // warp 0 alone waits for the patch and classifies it: all-255 / all-0 test, one 32-bit word per lane, over the box
+      // columns [0, coff + ncols) rounded up to words — a few columns more than the patch.  The classification only
+      // selects the code path (the mixed path is always correct), so a conservative test costs nothing in exactness and
+      // needs no per-byte masks.
+      tma::mbar_wait(barP, 0);
+      constexpr int WP2 = PW / 4 <= 16 ? 16 : 32;                      // words per patch row, rounded up to a power of two
+      const int wpr = (coff + ncols + 3) >> 2;                         // words per row to look at (<= PW / 4)
+      const int wc = lane % WP2;
+      bool hi = true, lo = true;
+      if (wc < wpr) {
+        for (int r = lane / WP2; r < nrows; r += 32 / WP2) {
+          const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PW + wc * 4);
+          hi = hi && (v == 0xffffffffu);
+          lo = lo && (v == 0u);
+        }
+      }
+      const bool all_hi = __all_sync(0xffffffffu, hi), all_lo = __all_sync(0xffffffffu, lo);
+      if (lane == 0) {
+        const int tc = all_hi ? 255 : (all_lo ? 0 : -1);
+        *reinterpret_cast<int2*>(geo + 10) = make_int2(tc, tc == 255 ? 0 : ((tc == 0 && geo[8]) ? 1 : 2));
+      }
+    } else if (tid - 32 < PF_UH) {                    // row parameters of the vertical resize pass (used by mixed tiles)
+      const int uy = tid - 32;
       int gy = gy_lo + uy;
       gy = gy < 0 ? -gy : gy; gy = gy >= a.roi_h ? 2 * a.roi_h - 2 - gy : gy;     // reflect-101 (single fold)
       gy = min(max(gy, 0), a.roi_h - 1);
       rows[uy] = make_uint4((unsigned)__ldg(a.tab.yofs0 + gy), (unsigned)__ldg(a.tab.yofs1 + gy),
                             (unsigned)(int)__ldg(a.tab.yw + 2 * gy) << 16, (unsigned)(int)__ldg(a.tab.yw + 2 * gy + 1) << 16);
     }
-    tma::mbar_wait(barP, 0);
-    // all-255 / all-0 test of the patch, one 32-bit word per thread, over the box columns [0, coff + ncols) rounded up to
-    // words: a few columns more than the patch.  The classification only selects the code path (the mixed path is
-    // always correct), so a conservative test costs nothing in exactness and needs no per-byte masks.
-    bool hi = true, lo = true;
-    {
-      const int wpr = (coff + ncols + 3) >> 2;                        // words per row to look at (<= PW / 4)
-      for (int i = tid; i < nrows * wpr; i += NT) {
-        const int r = i / wpr, wc = i - r * wpr;
-        const unsigned v = *reinterpret_cast<const unsigned*>(sP + r * PW + wc * 4);
-        hi = hi && (v == 0xffffffffu);
-        lo = lo && (v == 0u);
-      }
-    }
-    const int all_hi = __syncthreads_and(hi);
-    const int all_lo = all_hi ? 0 : __syncthreads_and(lo);
-    tile_const = all_hi ? 255 : (all_lo ? 0 : -1);
+    __syncthreads();
+    const int2 tk = *reinterpret_cast<const int2*>(geo + 10);
+    tile_const = tk.x; kind = tk.y;
   }
-  const bool inside = tx0 >= a.roi_x && min(tx0 + TW, a.W) <= a.roi_x + a.roi_w && ty0 >= a.roi_y && min(ty0 + PF_H, a.H) <= a.roi_y + a.roi_h;
-  const int kind = (!hits_roi || tile_const == 255) ? 0 : ((tile_const == 0 && inside) ? 1 : 2);   // background / person / mixed
 
   if (kind == 2 && tile_const < 0) {
     // ---- A1: horizontal pass of cv::resize on the patch rows (see k_post_fast) ----
@@ -240,9 +252,11 @@ __global__ void __launch_bounds__(PtL<TW>::NT, PtL<TW>::CTAS) k_post_tma(const _
   uint4* ydst = reinterpret_cast<uint4*>(sY + ly * (TW * 2) + lx * 2);
   const uint8_t* out_src = sB;
 
-  tma::mbar_wait(barB, 0);
-  // a background tile does not use its (speculatively loaded) camera tile: only thread 0 waits for it, after the stores
-  // are on their way (shared memory must be quiet when the CTA exits)
+  // a background tile with a cached YUYV copy is moved by the copy engine alone: only thread 0 (which issues the stores)
+  // waits for the background tiles, and for the (speculatively loaded, unused) camera tile after the stores are on their
+  // way — shared memory must be quiet when the CTA exits
+  const bool engine_only = kind == 0 && !(cfg.has_yuyv && !cfg.has_bgy);
+  if (!engine_only) tma::mbar_wait(barB, 0);
   if (hits_roi && kind != 0) tma::mbar_wait(barF, 0);
   if (kind == 0) {
     // ---- background tile: out = background tile, YUYV = cached YUYV tile, mask = 255.  No per-pixel arithmetic ----
@@ -302,6 +316,7 @@ __global__ void __launch_bounds__(PtL<TW>::NT, PtL<TW>::CTAS) k_post_tma(const _
   tma::fence_proxy_async();            // generic-proxy writes of the staging tiles -> visible to the TMA engine
   __syncthreads();
   if (tid == 0) {
+    if (engine_only) tma::mbar_wait(barB, 0);
     if (cfg.has_out) tma::store_3d(&tm.out, out_src, blockIdx.x * (TW * 3 / 4), ty0, b);
     if (cfg.has_yuyv) tma::store_3d(&tm.yuyv, sY, blockIdx.x * (TW / 2), ty0, b);
     if (cfg.has_mask) tma::store_3d(&tm.mask, sM, tx0, ty0, b);

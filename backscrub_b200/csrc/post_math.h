@@ -90,18 +90,22 @@ BSB_D unsigned blend_px(unsigned g_pair_w, unsigned f_pair_w, unsigned g_single_
 // cv::cvtColor(COLOR_YUV2BGR_YUYV) on 8 pixels: w = 4 words of (Y0 U Y1 V) -> o = 24 bytes of BGR (6 words).
 // BT.601 limited range, 20-bit fixed point (oracle_img.c:or_yuyv_to_bgr, pinned on cv2).
 BSB_D void yuyv8_to_bgr24(const unsigned* w, unsigned* o) {
-  // saturate with one VIMNMX.RELU per channel (min(v, 255) then max(.., 0)) and Y - 16 with one VIADDMNMX; the 24 bytes
+  // saturate with one VIMNMX.RELU per channel (min(v, 255) then max(.., 0)); the 24 bytes
   // are assembled with byte permutes (pixel = b | g << 8 | r << 16, then three words per four pixels)
+  // All the constant terms are folded so that every channel is ONE multiply-add from the raw bytes:
+  //   C (Y' - 16) + K (X - 128) + 2^19  ==  C max(Y, 16) + K X + (2^19 - 128 K - 16 C)      (exact in int32: |.| < 2^30)
+  constexpr int CY = 1220542, KRV = 1673527, KGV = -852492, KGU = -409993, KBU = 2116026;
+  constexpr int CR = (1 << 19) - 128 * KRV - 16 * CY, CG = (1 << 19) - 128 * (KGV + KGU) - 16 * CY, CB = (1 << 19) - 128 * KBU - 16 * CY;
   unsigned px[8];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int u = (int)((w[k] >> 8) & 255u) - 128, v = (int)(w[k] >> 24) - 128;
-    const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
+    const int u = (int)__byte_perm(w[k], 0u, 0x4441), v = (int)(w[k] >> 24);
+    const int ruv = KRV * v + CR, guv = KGV * v + (KGU * u + CG), buv = KBU * u + CB;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int yy = __viaddmax_s32((int)((w[k] >> (16 * h)) & 255u), -16, 0) * 1220542;
-      const unsigned bb = (unsigned)__vimin_s32_relu((yy + buv) >> 20, 255), gg = (unsigned)__vimin_s32_relu((yy + guv) >> 20, 255),
-                     rr = (unsigned)__vimin_s32_relu((yy + ruv) >> 20, 255);
+      const int yc = max((int)__byte_perm(w[k], 0u, h ? 0x4442 : 0x4440), 16);
+      const unsigned bb = (unsigned)__vimin_s32_relu((CY * yc + buv) >> 20, 255), gg = (unsigned)__vimin_s32_relu((CY * yc + guv) >> 20, 255),
+                     rr = (unsigned)__vimin_s32_relu((CY * yc + ruv) >> 20, 255);
       px[2 * k + h] = __byte_perm(__byte_perm(bb, gg, 0x0040), rr, 0x0410);      // b | g << 8 | r << 16
     }
   }
