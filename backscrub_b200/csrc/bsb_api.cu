@@ -666,6 +666,7 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "tc_mask_hi") t.tc_mask_hi = value;
   else if (n == "tc_min_k") t.tc_min_k = value;
   else if (n == "post_tile") t.post_tile = value;
+  else if (n == "sub_batch_mb") t.sub_batch_mb = value;
   else if (n == "post_wide") t.post_wide = value;
   else if (n == "post_l1") t.post_l1 = value;
   else { g_last_error = "unknown tuning switch '" + n + "'"; return 0; }

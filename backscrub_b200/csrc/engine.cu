@@ -443,6 +443,7 @@ bool Engine::plan(std::string* err) {
   if (tuning().cnn_chain && !(flags_ & (1u | 8u))) detect_chain();
   // ---- decoder stages (1x1 -> depthwise + residual [-> transposed conv]) as one kernel each ----
   if (tuning().head && !(flags_ & (1u | 8u))) detect_heads();
+  find_segments();
 
   // ---- liveness + arena (floats; every tensor is max_batch frames) ----
   const int ns = (int)steps_.size();
@@ -457,6 +458,22 @@ bool Engine::plan(std::string* err) {
     tinfo_[r].materialized = true;
     tinfo_[r].first_def = std::min(tinfo_[r].first_def, s);
     use(st.out, s);
+  }
+  // a sub-batched segment runs its steps once per frame group: every tensor it touches must stay allocated from the
+  // segment's first step to its last (a buffer recycled inside the segment would be overwritten by group g while group
+  // g + 1 still has to read it)
+  for (int s0 = 0; s0 < ns; ++s0) {
+    if (s0 >= (int)seg_len_.size() || seg_len_[s0] <= 0) continue;
+    const int s1 = s0 + seg_len_[s0] - 1;
+    for (int s = s0; s <= s1; ++s) {
+      const Step& st = steps_[s];
+      for (int t : {st.in, st.in2, st.scale, st.in_add, st.residual, st.up_from, st.out}) {
+        if (t < 0) continue;
+        const int r = root(t);
+        tinfo_[r].last_use = std::max(tinfo_[r].last_use, s1);
+        if (tinfo_[r].first_def > s0 && tinfo_[r].first_def <= s1) tinfo_[r].first_def = s0;
+      }
+    }
   }
   tinfo_[root(g_.output)].last_use = 1 << 30;
   tinfo_[g_.input].last_use = std::max(tinfo_[g_.input].last_use, 0);
@@ -787,7 +804,27 @@ bool Engine::upload(std::string* err) {
   out_cap_ = B * fpx * 3; yuyv_cap_ = B * fpx * 2;
   CUDA_OK(cudaMallocHost((void**)&h_mask_, fpx));
   if (!upload_resize_tab(build_resize_tab(roidim_[2], roidim_[3], in_roidim_[2], in_roidim_[3]), &tab_in_, err)) return false;
-  if (!upload_resize_tab(build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]), &tab_up_, err)) return false;
+  {
+    const HostResizeTab up = build_resize_tab(out_roidim_[2], out_roidim_[3], roidim_[2], roidim_[3]);
+    if (!upload_resize_tab(up, &tab_up_, err)) return false;
+    // patch geometry of the post stage's tiles (k_post_tma): yofs / xofs are monotonic, so the extremes of a halo tile
+    // give the rows / columns of the small mask it touches
+    const int roi_x = roidim_[0], roi_y = roidim_[1], roi_w = roidim_[2], roi_h = roidim_[3], sw = out_roidim_[2];
+    auto span = [&](int lo, int len, int n, const std::vector<int>& first, const std::vector<int>& last, int last_plus, int last_max) {
+      const int hi = lo + len - 1;
+      const int i0 = lo < 0 ? 0 : std::min(lo, n - 1), i1 = hi >= n ? n - 1 : std::max(hi, 0);
+      const int a0 = first[i0], a1 = std::min(last[i1] + last_plus, last_max);
+      return make_int2(a0, a1 - a0 + 1);
+    };
+    geo_nty_ = (H_ + 31) / 32; geo_ntx64_ = (W_ + 63) / 64;
+    const int ntx128 = (W_ + 127) / 128;
+    std::vector<int2> geo((size_t)geo_nty_ + geo_ntx64_ + ntx128);
+    for (int ty = 0; ty < geo_nty_; ++ty) geo[ty] = span(ty * 32 - roi_y - 2, 36, roi_h, up.yofs0, up.yofs1, 0, 1 << 30);
+    for (int tx = 0; tx < geo_ntx64_; ++tx) geo[geo_nty_ + tx] = span(tx * 64 - roi_x - 2, 68, roi_w, up.xofs, up.xofs, 1, sw - 1);
+    for (int tx = 0; tx < ntx128; ++tx) geo[geo_nty_ + geo_ntx64_ + tx] = span(tx * 128 - roi_x - 2, 132, roi_w, up.xofs, up.xofs, 1, sw - 1);
+    CUDA_OK(cudaMalloc((void**)&d_tile_geo_, geo.size() * sizeof(int2)));
+    CUDA_OK(cudaMemcpy(d_tile_geo_, geo.data(), geo.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
   if (!refresh_bg_yuyv(err)) return false;
   CUDA_OK(cudaDeviceSynchronize());
   return true;
@@ -801,7 +838,7 @@ Engine::~Engine() {
   for (void* p : {(void*)wblob_, (void*)arena_, (void*)lut_, (void*)rowsum_, (void*)in_u8_, (void*)filt_u8_, (void*)state_, (void*)ofinal_,
                   (void*)d_frames_, (void*)d_out_, (void*)d_yuyv_, (void*)d_mask_, (void*)d_bg_, (void*)d_bg_raw_, (void*)d_yuyv_in_,
                   tab_in_.blob, tab_up_.blob, tab_bg_.blob, tab_out_.blob, (void*)d_bg_cursor_, (void*)d_bg_eff_, (void*)d_bg_frames_,
-                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_, (void*)d_bg_yuyv_, (void*)pool_counters_})
+                  (void*)d_gauss_tmp_, (void*)d_stage_a_, (void*)d_stage_b_, (void*)d_stage_c_, (void*)d_bg_yuyv_, (void*)pool_counters_, (void*)d_tile_geo_})
     if (p) cudaFree(p);
   for (ChainPlan& cp : chains_) if (cp.d_ops) cudaFree(cp.d_ops);
   if (h_mask_) cudaFreeHost(h_mask_);
@@ -824,12 +861,66 @@ void Engine::enqueue_pre(int n, const uint8_t* d_frames, size_t pitch, size_t st
   launch_bilateral_norm(stream_, n, in_u8_, mw_, mh_, lut_, lut_ + 768, scaling_, offset_, f32, filt_u8_);
 }
 
+// Frames per pass of a sub-batched segment: the segment's largest tensor, in and out, should stay L2-resident
+// (tuning().sub_batch_mb megabytes per tensor; 0 = off).
+static int sub_batch_frames(size_t frame_bytes, int n) {
+  const size_t budget = (size_t)tuning().sub_batch_mb << 20;
+  if (!budget || !frame_bytes) return n;
+  const size_t f = std::max<size_t>(1, budget / frame_bytes);
+  return (int)std::min<size_t>(f, (size_t)n);
+}
+
 void Engine::enqueue_cnn(int n, bool from_u8) {
   bool first = true;
   bool skip_next = false;
   for (size_t si = 0; si < steps_.size(); ++si) {
+    if (si < seg_len_.size() && seg_len_[si] > 0) {
+      const int sub = sub_batch_frames(seg_frame_bytes_[si], n);
+      if (sub < n) {
+        const size_t end = si + (size_t)seg_len_[si];
+        for (int f0 = 0; f0 < n; f0 += sub) {
+          frame_off_ = f0;
+          for (size_t k = si; k < end; ++k) run_step(k, std::min(sub, n - f0), from_u8, &first, &skip_next);
+        }
+        frame_off_ = 0;
+        si = end - 1;
+        continue;
+      }
+    }
+    run_step(si, n, from_u8, &first, &skip_next);
+  }
+}
+
+// Segments: maximal runs of plain per-frame steps (1x1 conv, depthwise, element-wise, copy, resize) that touch a tensor
+// of more than 1 MB per frame.  Everything in such a run depends only on its own frame, so the run can be executed
+// frame-group by frame-group.
+void Engine::find_segments() {
+  seg_len_.assign(steps_.size(), 0);
+  seg_frame_bytes_.assign(steps_.size(), 0);
+  auto plain = [&](const Step& st) {
+    return st.kind == Step::PW || st.kind == Step::DW || st.kind == Step::ELT || st.kind == Step::COPY || st.kind == Step::RESIZE;
+  };
+  auto fbytes = [&](const Step& st) {
+    size_t m = 0;
+    for (int t : {st.in, st.in2, st.in_add, st.residual, st.out, st.up_from})
+      if (t >= 0) m = std::max(m, tinfo_[tinfo_[t].alias_parent >= 0 ? tinfo_[t].alias_parent : t].frame_elems * sizeof(float));
+    return m;
+  };
+  for (size_t i = 0; i < steps_.size();) {
+    if (!plain(steps_[i])) { ++i; continue; }
+    size_t j = i, big = 0;
+    while (j < steps_.size() && plain(steps_[j])) { big = std::max(big, fbytes(steps_[j])); ++j; }
+    if (big > ((size_t)1 << 20) && j - i >= 2) { seg_len_[i] = (int)(j - i); seg_frame_bytes_[i] = big; }
+    i = j;
+  }
+}
+
+void Engine::run_step(size_t si, int n, bool from_u8, bool* first_p, bool* skip_next_p) {
+  bool& first = *first_p;
+  bool& skip_next = *skip_next_p;
+  {
     const Step& st = steps_[si];
-    if (skip_next) { skip_next = false; continue; }      // the 1x1 conv that ran inside the stem kernel
+    if (skip_next) { skip_next = false; return; }        // the 1x1 conv that ran inside the stem kernel
     const bool fused_stem = first && from_u8 && stem_u8_ok_;
     first = false;
     const TensorInfo& I = tinfo_[st.in];
@@ -974,6 +1065,7 @@ PostArgs Engine::post_args(int n, const uint8_t* d_frames, size_t pitch, size_t 
     a.yuyv = nullptr; a.yuyv_stride = 0;
   }
   a.mask = d_mask; a.mask_stride = mask_stride;
+  a.geo_rows = d_tile_geo_; a.geo_cols64 = d_tile_geo_ + geo_nty_; a.geo_cols128 = d_tile_geo_ + geo_nty_ + geo_ntx64_;
   return a;
 }
 

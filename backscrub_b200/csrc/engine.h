@@ -161,10 +161,17 @@ class Engine {
   void enqueue_decision(int n);
   void enqueue_post(int n, const uint8_t* d_frames, size_t pitch, size_t stride, uint8_t* d_out, size_t out_stride,
                     uint8_t* d_yuyv, size_t yuyv_stride, uint8_t* d_mask, size_t mask_stride, const uint8_t* d_yuyv_in = nullptr);
+  // base of tensor t for the frames [frame_off_, ...) of the batch (frame_off_ != 0 only inside a sub-batched segment)
   float* tptr(int t) const {
     const TensorInfo& I = tinfo_[t];
-    return I.alias_parent >= 0 ? arena_ + tinfo_[I.alias_parent].offset + I.alias_off : arena_ + I.offset;
+    if (I.alias_parent >= 0) {
+      const TensorInfo& P = tinfo_[I.alias_parent];
+      return arena_ + P.offset + (size_t)frame_off_ * P.frame_elems + I.alias_off;
+    }
+    return arena_ + I.offset + (size_t)frame_off_ * I.frame_elems;
   }
+  void run_step(size_t si, int n, bool from_u8, bool* first, bool* skip_next);
+  void find_segments();
 
   Graph g_;
   int model_type_ = 0;
@@ -178,6 +185,13 @@ class Engine {
 
   std::vector<TensorInfo> tinfo_;
   std::vector<Step> steps_;
+  // L2-resident execution of the wide layers (DeepLab / BodyPix expand -> depthwise -> project): a run of per-frame steps
+  // whose tensors are too large for the L2 at the full batch is executed a few frames at a time, so that each step finds
+  // its input where the previous one left it instead of streaming it through HBM.  seg_len_[si] > 0: steps
+  // [si, si + seg_len_[si]) form a segment whose largest tensor has seg_frame_bytes_[si] bytes per frame.
+  std::vector<int> seg_len_;
+  std::vector<size_t> seg_frame_bytes_;
+  int frame_off_ = 0;
   struct FusedBlock { Step expand, dw, pool, project; };
   std::vector<FusedBlock> blocks_;
   // the low-resolution middle of the graph run by one kernel (kernels_chain.cu): the original steps in order, each
@@ -231,6 +245,8 @@ class Engine {
   bool flip_h_ = false, flip_v_ = false;
   int out_w_ = 0, out_h_ = 0;
   uint8_t* d_stage_a_ = nullptr, *d_stage_b_ = nullptr, *d_stage_c_ = nullptr;
+  int2* d_tile_geo_ = nullptr;       // k_post_tma patch geometry per tile row | per 64-wide tile column | per 128-wide tile column
+  int geo_nty_ = 0, geo_ntx64_ = 0;
   uint8_t* d_bg_yuyv_ = nullptr;     // YUYV of the effective background (ring): all-background tiles are copies
   size_t bg_yuyv_cap_ = 0;
   bool bg_yuyv_valid_ = false;

@@ -195,6 +195,9 @@ struct PostArgs {
   // converted to YUYV, same indexing as `bg` with W*2-byte rows, so all-background tiles are pure copies.
   const uint8_t* yuyv_in; size_t yuyv_in_stride;
   const uint8_t* bg_yuyv;
+  // per tile row / tile column: the patch of the small mask a (TW + 4) x 36 halo tile touches, {first, count}
+  // (precomputed once per context from `tab`: the patch request is the head of every CTA's critical path)
+  const int2* geo_rows; const int2* geo_cols64; const int2* geo_cols128;
 };
 void launch_post(cudaStream_t s, const PostArgs& a);
 // true if launch_post will take the TMA kernel for these arguments (the only one that can read a.yuyv_in)
@@ -250,6 +253,7 @@ struct Tuning {
   int stem_pw = 0;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel (measured slower: 78.9 vs 40 + 30 us; off)
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
+  int sub_batch_mb = 16;   // engine: wide-layer segments run in frame groups whose largest tensor is <= this many MB (0 = off)
   int post_tile = 64;      // k_post_tma: tile width (64: eight CTAs per SM, 128: four)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses
   int post_l1 = 1;         // k_post_fast: frame loads allocate in L1

@@ -116,25 +116,20 @@ __global__ void __launch_bounds__(PtL<TW>::NT, PtL<TW>::CTAS) k_post_tma(const _
     tma::mbar_init(barP, 1); tma::mbar_init(barB, 1); tma::mbar_init(barF, 1);
     tma::fence_barrier_init();
     const bool hit = tx0 < a.roi_x + a.roi_w && tx0 + TW > a.roi_x && ty0 < a.roi_y + a.roi_h && ty0 + PF_H > a.roi_y;
+    // the patch of the small mask this tile touches comes from two per-context tables (engine.cu): two independent
+    // loads whose addresses need nothing but the block index, then the patch request — the head of the CTA's critical
+    // path — goes out first ...
     int gy_lo = 0, gx_lo = 0, rmin = 0, nrows = 0, cmin = 0, ncols = 0, coff = 0;
     if (hit) {
-      // patch geometry (k_post_fast: yofs / xofs are monotonic, so the extremes of the tile give the patch)
+      const int2 gr = __ldg(a.geo_rows + blockIdx.y), gc = __ldg((TW == 64 ? a.geo_cols64 : a.geo_cols128) + blockIdx.x);
       gy_lo = ty0 - a.roi_y - 2; gx_lo = tx0 - a.roi_x - 2;
-      const int gy_hi = gy_lo + PF_UH - 1, gx_hi = gx_lo + UW - 1;
-      const int gy_min = gy_lo < 0 ? 0 : min(gy_lo, a.roi_h - 1);
-      const int gy_max = gy_hi >= a.roi_h ? a.roi_h - 1 : max(gy_hi, 0);
-      const int gx_min = gx_lo < 0 ? 0 : min(gx_lo, a.roi_w - 1);
-      const int gx_max = gx_hi >= a.roi_w ? a.roi_w - 1 : max(gx_hi, 0);
-      rmin = __ldg(a.tab.yofs0 + gy_min);
-      nrows = __ldg(a.tab.yofs1 + gy_max) - rmin + 1;
-      cmin = (int)(__ldg(&a.tab.xcol[gx_min].x) & 0xffffu);
-      ncols = (int)(__ldg(&a.tab.xcol[gx_max].x) >> 16) - cmin + 1;
+      rmin = gr.x; nrows = gr.y; cmin = gc.x; ncols = gc.y;
       coff = (a.out_x + cmin) & 15;                     // the patch's first column inside the 16-byte aligned box
       tma::mbar_expect_tx(barP, PT_RMAX * PW);
       tma::load_3d(sP, &tm.ofinal, a.out_x + cmin - coff, a.out_y + rmin, b, barP);
     }
-    // the background tile (L2-resident for a still image) and its cached YUYV: a background tile needs nothing else,
-    // a mixed tile has its second operand early
+    // ... then the big tiles: the background tile (L2-resident for a still image) and its cached YUYV (a background
+    // tile needs nothing else, a mixed tile has its second operand early) ...
     int bgi = 0;
     if (a.bg_cursor) bgi = (int)(((unsigned)__ldg(a.bg_cursor) + (unsigned)b * (unsigned)a.bg_advance) % (unsigned)a.bg_count);
     else if (a.bg_stride) bgi = b;
@@ -376,7 +371,7 @@ static int post_tile_width() { return tuning().post_tile == 128 ? 128 : 64; }
 static bool post_tma_shape_ok(const PostArgs& a) {
   if (!tuning().post_tma || !encode_fn()) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (a.B < 1 || a.W % 16 != 0 || a.area2x2 || a.tab.xcol == nullptr) return false;
+  if (a.B < 1 || a.W % 16 != 0 || a.area2x2 || a.tab.xcol == nullptr || a.geo_rows == nullptr) return false;
   if (a.yuyv_in) { if (!al16(a.yuyv_in) || a.yuyv_in_stride % 16) return false; }
   else if (!al16(a.frames) || a.frame_pitch % 16 || a.frame_stride % 16) return false;
   if (!al16(a.bg) || a.bg_pitch % 16 || a.bg_stride % 16 || (a.bg_yuyv && !al16(a.bg_yuyv))) return false;

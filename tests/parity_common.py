@@ -457,6 +457,34 @@ def check_fusion_switches(lib, key, n=2):
             assert np.array_equal(a, b), f"{key}: flipping {sw.decode()} changes the composite"
 
 
+def check_sub_batch(lib, key="deeplab", n=3, W=640, H=480):
+    """Wide-layer segments executed a few frames at a time (engine.cu: find_segments / sub_batch_frames) produce the same
+    bits as the whole batch at once, for any group size — including groups that do not divide the batch."""
+    m = po.Model(model_path(key))
+    rng = np.random.default_rng(11)
+    x = None
+    frames = np.stack([synth.frame(W, H, t=t) for t in range(n)])
+    results = {}
+    try:
+        for mb in (0, 1, 8):            # off / one frame per group / two-ish frames per group (3 frames: groups of 2 + 1)
+            assert lib.bsb_set_tuning(b"sub_batch_mb", mb)
+            g = api.MaskGen(lib, model_path(key), W, H, max_batch=n, flags=exact_flag(key))
+            g.set_background(synth.background())
+            if x is None:
+                x = rng.uniform(-1 if key == "deeplab" else 0, 1, (n, *g.in_hwc)).astype(np.float32)
+            results[mb] = (g.infer(x), g.composite(frames), g.launches_per_call)
+            g.close()
+    finally:
+        lib.bsb_set_tuning(b"sub_batch_mb", 16)
+    base = results[0]
+    assert np.array_equal(base[0][0].view(np.uint32), m.invoke(x[0])[0].view(np.uint32)), f"{key}: differs from the oracle"
+    assert results[1][2] > base[2], (key, "no segment was split", results[1][2], base[2])
+    for mb in (1, 8):
+        assert np.array_equal(results[mb][0].view(np.uint32), base[0].view(np.uint32)), f"{key}: sub_batch_mb={mb} changes the CNN output"
+        for a, b in zip(results[mb][1], base[1]):
+            assert np.array_equal(a, b), f"{key}: sub_batch_mb={mb} changes the composite"
+
+
 def check_mjpg_ingest(lib, key="meet_lite", W=640, H=480, n=2):
     """MJPG camera ingest (app/deepseg.cc:548-553): JPEG frames decoded on the GPU (NVJPG) feed the fused path.  The
     decoder is a library either side of the path (the reference uses libjpeg behind cv::VideoCapture); what is checked:

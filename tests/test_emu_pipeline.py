@@ -65,6 +65,10 @@ def test_fusion_switches(lib, key):
     pc.check_fusion_switches(lib, key, n=2)
 
 
+def test_sub_batched_segments(lib):
+    pc.check_sub_batch(lib, "deeplab", n=3)
+
+
 def test_infer_batch(lib):
     pc.check_infer_batch(lib, "meet_lite", n=3)
 

@@ -40,6 +40,11 @@ def test_pipeline_ragged_geometry(lib):
     pc.check_pipeline(lib, "meet_full", 128, 72, n_frames=2)       # mask resize is an exact 2x down-scale (INTER_AREA path)
 
 
+@pytest.mark.parametrize("key", ["deeplab", "bodypix"])
+def test_sub_batched_segments(lib, key):
+    pc.check_sub_batch(lib, key, n=3)
+
+
 def test_pipeline_fused_blocks(lib):
     pc.check_pipeline(lib, "mlkit", 640, 480, n_frames=3, flags=8)
     pc.check_pipeline(lib, "meet_full", 1280, 720, n_frames=3, flags=8)
