@@ -253,7 +253,7 @@ struct Tuning {
   int stem_pw = 0;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel (measured slower: 78.9 vs 40 + 30 us; off)
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
-  int sub_batch_mb = 16;   // engine: wide-layer segments run in frame groups whose largest tensor is <= this many MB (0 = off)
+  int sub_batch_mb = 0;    // engine: wide-layer segments run in frame groups whose largest tensor is <= this many MB (0 = off; measured slower, run r2t)
   int post_tile = 64;      // k_post_tma: tile width (64: eight CTAs per SM, 128: four)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses
   int post_l1 = 1;         // k_post_fast: frame loads allocate in L1

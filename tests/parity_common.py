@@ -475,7 +475,7 @@ def check_sub_batch(lib, key="deeplab", n=3, W=640, H=480):
             results[mb] = (g.infer(x), g.composite(frames), g.launches_per_call)
             g.close()
     finally:
-        lib.bsb_set_tuning(b"sub_batch_mb", 16)
+        lib.bsb_set_tuning(b"sub_batch_mb", 0)
     base = results[0]
     assert np.array_equal(base[0][0].view(np.uint32), m.invoke(x[0])[0].view(np.uint32)), f"{key}: differs from the oracle"
     assert results[1][2] > base[2], (key, "no segment was split", results[1][2], base[2])
