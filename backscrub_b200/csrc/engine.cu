@@ -897,6 +897,7 @@ void Engine::enqueue_cnn(int n, bool from_u8) {
 void Engine::find_segments() {
   seg_len_.assign(steps_.size(), 0);
   seg_frame_bytes_.assign(steps_.size(), 0);
+  if (tuning().sub_batch_mb <= 0) return;       // off: no segments, the arena recycles buffers step by step as before
   auto plain = [&](const Step& st) {
     return st.kind == Step::PW || st.kind == Step::DW || st.kind == Step::ELT || st.kind == Step::COPY || st.kind == Step::RESIZE;
   };
