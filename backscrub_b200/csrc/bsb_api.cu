@@ -656,6 +656,7 @@ int bsb_set_tuning(const char* name, int value) {
   const std::string n(name);
   if (n == "pw_variant") t.pw_variant = value;
   else if (n == "dw_plane") t.dw_plane = value;
+  else if (n == "dec_up") t.dec_up = value;
   else if (n == "post_tma") t.post_tma = value;
   else if (n == "cnn_chain") t.cnn_chain = value;
   else if (n == "pool_merge") t.pool_merge = value;

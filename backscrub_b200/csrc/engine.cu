@@ -444,6 +444,11 @@ bool Engine::plan(std::string* err) {
   // ---- decoder stages (1x1 -> depthwise + residual [-> transposed conv]) as one kernel each ----
   if (tuning().head && !(flags_ & (1u | 8u))) detect_heads();
   find_segments();
+  dec_up_step_ = -1;
+  if (tuning().dec_up && model_type_ == MODEL_DEEPLAB && !(flags_ & 1u) && !steps_.empty()) {
+    const Step& last = steps_.back();
+    if (last.kind == Step::RESIZE && last.out == g_.output && tinfo_[last.out].c == 21 && tinfo_[last.in].c == 21) dec_up_step_ = (int)steps_.size() - 1;
+  }
 
   // ---- liveness + arena (floats; every tensor is max_batch frames) ----
   const int ns = (int)steps_.size();
@@ -922,6 +927,7 @@ void Engine::run_step(size_t si, int n, bool from_u8, bool* first_p, bool* skip_
   {
     const Step& st = steps_[si];
     if (skip_next) { skip_next = false; return; }        // the 1x1 conv that ran inside the stem kernel
+    if (from_u8 && (int)si == dec_up_step_) return;      // pipeline call: the decision kernel interpolates on the fly
     const bool fused_stem = first && from_u8 && stem_u8_ok_;
     first = false;
     const TensorInfo& I = tinfo_[st.in];
@@ -1032,6 +1038,12 @@ void Engine::run_step(size_t si, int n, bool from_u8, bool* first_p, bool* skip_
 }
 
 void Engine::enqueue_decision(int n) {
+  if (dec_up_step_ >= 0) {
+    const Step& st = steps_[dec_up_step_];
+    const TensorInfo& I = tinfo_[st.in];
+    launch_decision_up_iir(stream_, n, tptr(st.in), I.h, I.w, I.ld, st.align_corners, st.half_pixel, oh_, ow_, state_, ofinal_, opitch_);
+    return;
+  }
   launch_decision_iir(stream_, model_type_, n, tptr(g_.output), oh_, ow_, oc_, state_, ofinal_, opitch_);
 }
 

@@ -209,6 +209,7 @@ class Engine {
   size_t arena_elems_ = 0;
   bool tc_enabled_ = false, uses_tc_ = false;   // tensor-core 1x1 convs allowed / actually planned for at least one layer
   bool stem_u8_ok_ = false;          // step 0 is a 3->16 dense conv that is the only reader of the graph input
+  int dec_up_step_ = -1;             // DeepLab: index of the final RESIZE_BILINEAR step the decision kernel performs itself (pipeline calls)
   bool stem_pw_ok_ = false;          // ... and step 1 is a plain 16 -> 16 1x1 conv of its output (runs inside the stem kernel)
 
   // device memory

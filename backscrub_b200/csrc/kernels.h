@@ -171,6 +171,19 @@ void launch_bilateral_norm(cudaStream_t s, int B, const uint8_t* in_u8, int mw, 
 // multiple of 16 bytes so the post kernel can fetch patches of it with TMA).
 void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
                          uint8_t* state, uint8_t* ofinal, int opitch);
+// DeepLab: the graph ends with RESIZE_BILINEAR 33x33x21 -> 257x257x21 and the decision is an argmax over the 21 classes of
+// every output pixel.  This variant interpolates the 21 values of a pixel on the fly (the exact expression of the resize
+// kernel) instead of writing and re-reading the 5.5 MB-per-frame tensor.
+void launch_decision_up_iir(cudaStream_t s, int B, const float* low, int ih, int iw, int ld, bool align_corners, bool half_pixel,
+                            int oh, int ow, uint8_t* state, uint8_t* ofinal, int opitch);
+// source coordinate / neighbours of RESIZE_BILINEAR (TF/lite/kernels/internal/reference/resize_bilinear.h:29-57)
+BSB_D void bsb_resize_interp(float value, float scale, bool half_pixel, int in_size, float* scaled, int* lo, int* hi) {
+  *scaled = half_pixel ? (value + 0.5f) * scale - 0.5f : value * scale;
+  const float fl = floorf(*scaled);
+  int l = (int)fl; if (l < 0) l = 0;
+  int h = (int)ceilf(*scaled); if (h > in_size - 1) h = in_size - 1;
+  *lo = l; *hi = h;
+}
 
 // lib/libbackscrub.cc:366-371 + app/deepseg.cc:108-134,87-106 fused:
 // mask = blur5x5(resize(ofinal(out_roi) -> roi)) inside roidim, 255 outside;
@@ -242,6 +255,7 @@ bool ensure_dyn_smem(const void* func, size_t bytes);
 // results, only which bit-identical kernel variant runs.  Defaults are the measured-best choices.
 struct Tuning {
   int pw_variant = 0;      // launch_pointwise: 0 heuristics, 2 classic tiles, 3/4/8 register-tiled, 5 row-streaming, 16/32/64 classic N tile
+  int dec_up = 1;          // DeepLab: final 33 -> 257 resize folded into the argmax decision kernel
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel

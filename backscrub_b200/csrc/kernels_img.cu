@@ -224,6 +224,51 @@ void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* mod
   count_launch();
 }
 
+// DeepLab: RESIZE_BILINEAR (33x33x21 -> 257x257x21) + argmax + IIR in one pass.  One thread = one output pixel; the four
+// neighbours and weights are those of k_resize_bilinear, the value of class i is formed with the same expression
+// (-fmad=false: every product and sum rounds separately), the argmax scans the classes in order with a strict >.
+__global__ void __launch_bounds__(128) k_decision_up_iir(int B, const float* low, int ih, int iw, int ld, float hs, float ws, bool half_pixel,
+                                                         int oh, int ow, uint8_t* state, uint8_t* ofinal, int opitch, int oframe) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= oh * ow) return;
+  const int y = n / ow, x = n - y * ow;
+  float fy, fx; int y0, y1, x0, x1;
+  bsb_resize_interp((float)y, hs, half_pixel, ih, &fy, &y0, &y1);
+  bsb_resize_interp((float)x, ws, half_pixel, iw, &fx, &x0, &x1);
+  const float dy = fy - (float)y0, dx = fx - (float)x0;
+  const float wy0 = 1.f - dy, wx0 = 1.f - dx;
+  const int o00 = (y0 * iw + x0) * ld, o10 = (y1 * iw + x0) * ld, o01 = (y0 * iw + x1) * ld, o11 = (y1 * iw + x1) * ld;
+  const int opos = y * opitch + x;
+  unsigned st = state[n];
+  for (int b = 0; b < B; ++b) {
+    const float* f = low + (size_t)b * ih * iw * ld;
+    float maxval = -10000.f; int maxpos = 0;
+#pragma unroll 7
+    for (int i = 0; i < 21; ++i) {
+      const float a = __ldg(f + o00 + i) * wy0 * wx0;
+      const float bb = __ldg(f + o10 + i) * dy * wx0;
+      const float d = __ldg(f + o01 + i) * wy0 * dx;
+      const float e = __ldg(f + o11 + i) * dy * dx;
+      const float v = ((a + bb) + d) + e;
+      if (v > maxval) { maxval = v; maxpos = i; }
+    }
+    const unsigned val = (maxpos == 15) ? 0u : 255u;
+    st = (val & 0xE0u) | (st >> 3);
+    ofinal[(size_t)b * oframe + opos] = (uint8_t)st;
+  }
+  state[n] = (uint8_t)st;
+}
+
+void launch_decision_up_iir(cudaStream_t s, int B, const float* low, int ih, int iw, int ld, bool align_corners, bool half_pixel,
+                            int oh, int ow, uint8_t* state, uint8_t* ofinal, int opitch) {
+  float hs = (float)ih / (float)oh, ws = (float)iw / (float)ow;
+  if (align_corners && oh > 1) hs = (float)(ih - 1) / (float)(oh - 1);
+  if (align_corners && ow > 1) ws = (float)(iw - 1) / (float)(ow - 1);
+  BSB_LAUNCH(k_decision_up_iir, dim3((unsigned)ceil_div(oh * ow, 128)), dim3(128), 0, s, B, low, ih, iw, ld, hs, ws, half_pixel, oh, ow, state,
+             ofinal, opitch, oh * opitch);
+  count_launch();
+}
+
 // ---------------------------------------------------------------------------
 // Fused post stage: mask upsample (cv::resize 8UC1) + cv::blur 5x5 (REFLECT_101 inside the
 // ROI) + alpha_blend + optional RGB->YUYV + optional mask store.

@@ -691,9 +691,11 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
 // Whole-plane variant for the 33x33 atrous layers of DeepLab / BodyPix (stride 1, 3x3, any dilation): one block owns
 // 16 channels of one frame, stages that 33x33x16 slice in shared memory once (every input byte is read from L2/HBM
 // exactly once, where the strip kernel re-reads each pixel up to nine times through L2) and produces all its outputs
-// from there.  Tap order and the skipping of out-of-image taps are those of the oracle.
-// NOT YET MEASURED on hardware: opt-in through BSB_DW_PLANE=1 until a B200 run decides.
-constexpr int DWP_CS = 16;
+// from there.  A thread owns 4 channels of FOUR vertically adjacent output pixels: the nine weight vectors sit in
+// registers, the four accumulation chains are independent (the first version — one pixel per thread, 180 instructions per
+// output with a 9-deep dependent LDS -> FFMA chain — ran at 1 TB/s of L2 traffic, profiles/r2_launch_shares_deeplab_bodypix.txt).
+// Tap order and the skipping of out-of-image taps are those of the oracle.
+constexpr int DWP_CS = 16, DWP_R = 4;
 __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   BSB_DYN_SMEM(smem_raw);
   float* plane = reinterpret_cast<float*>(smem_raw);           // [ih*iw][16]
@@ -707,26 +709,39 @@ __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   }
   for (int i = threadIdx.x; i < 9 * DWP_CS; i += blockDim.x) ws[i] = __ldg(a.w + (size_t)(i / DWP_CS) * a.c + c0 + (i % DWP_CS));
   __syncthreads();
-  for (int i = threadIdx.x; i < a.oh * a.ow * (DWP_CS / 4); i += blockDim.x) {
-    const int p = i >> 2, q = i & 3;
-    const int oy = p / a.ow, ox = p - oy * a.ow;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int q = threadIdx.x & 3, ch = c0 + 4 * q;
+  float4 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4*>(ws + t * DWP_CS + 4 * q);
+  const int row_groups = (a.oh + DWP_R - 1) / DWP_R;
+  for (int p = threadIdx.x >> 2; p < row_groups * a.ow; p += blockDim.x >> 2) {
+    const int rg = p / a.ow, ox = p - rg * a.ow, oy0 = rg * DWP_R;
+    float4 acc[DWP_R];
+#pragma unroll
+    for (int j = 0; j < DWP_R; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ixs[3]; bool vx[3];
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx) { ixs[fx] = ox - a.pl + a.dw * fx; vx[fx] = ixs[fx] >= 0 && ixs[fx] < a.iw; }
 #pragma unroll
     for (int fy = 0; fy < 3; ++fy) {
-      const int iy = oy - a.pt + a.dh * fy;
-      if (iy < 0 || iy >= a.ih) continue;
 #pragma unroll
-      for (int fx = 0; fx < 3; ++fx) {
-        const int ix = ox - a.pl + a.dw * fx;
-        if (ix < 0 || ix >= a.iw) continue;
-        fma4(acc, *reinterpret_cast<const float4*>(plane + (iy * a.iw + ix) * DWP_CS + 4 * q),
-             *reinterpret_cast<const float4*>(ws + (fy * 3 + fx) * DWP_CS + 4 * q));
+      for (int j = 0; j < DWP_R; ++j) {
+        const int iy = oy0 + j - a.pt + a.dh * fy;
+        if (iy < 0 || iy >= a.ih) continue;                  // (rows past the image: their outputs are never stored)
+        const float* rowp = plane + (size_t)iy * a.iw * DWP_CS + 4 * q;
+#pragma unroll
+        for (int fx = 0; fx < 3; ++fx)
+          if (vx[fx]) fma4(acc[j], *reinterpret_cast<const float4*>(rowp + ixs[fx] * DWP_CS), w[fy * 3 + fx]);
       }
     }
-    const size_t pix = (size_t)b * a.oh * a.ow + p;
-    const int ch = c0 + 4 * q;
-    *reinterpret_cast<float4*>(a.out + pix * a.ld_out + ch) = make_float4(epilogue(acc.x, ch, pix, a.e), epilogue(acc.y, ch + 1, pix, a.e),
-                                                                        epilogue(acc.z, ch + 2, pix, a.e), epilogue(acc.w, ch + 3, pix, a.e));
+#pragma unroll
+    for (int j = 0; j < DWP_R; ++j) {
+      const int oy = oy0 + j;
+      if (oy >= a.oh) break;
+      const size_t pix = (size_t)b * a.oh * a.ow + (size_t)oy * a.ow + ox;
+      *reinterpret_cast<float4*>(a.out + pix * a.ld_out + ch) = make_float4(epilogue(acc[j].x, ch, pix, a.e), epilogue(acc[j].y, ch + 1, pix, a.e),
+                                                                          epilogue(acc[j].z, ch + 2, pix, a.e), epilogue(acc[j].w, ch + 3, pix, a.e));
+    }
   }
 }
 
@@ -1066,13 +1081,7 @@ void launch_mb_block(cudaStream_t s, int B, const MbBlockArgs& a) {
 // ---------------------------------------------------------------------------
 // RESIZE_BILINEAR, float, NHWC.  One thread = one output pixel x 4 channels.
 // ---------------------------------------------------------------------------
-BSB_D void interp(float value, float scale, bool half_pixel, int in_size, float* scaled, int* lo, int* hi) {
-  *scaled = half_pixel ? (value + 0.5f) * scale - 0.5f : value * scale;
-  const float fl = floorf(*scaled);
-  int l = (int)fl; if (l < 0) l = 0;
-  int h = (int)ceilf(*scaled); if (h > in_size - 1) h = in_size - 1;
-  *lo = l; *hi = h;
-}
+#define interp bsb_resize_interp
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_resize_bilinear(const float* in, int B, int ih, int iw, int c, int ld_in,

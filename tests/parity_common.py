@@ -441,6 +441,8 @@ def check_fusion_switches(lib, key, n=2):
     for b in range(n):
         assert np.array_equal(base[b].view(np.uint32), m.invoke(x[b])[0].view(np.uint32)), f"{key}: frame {b} differs from the oracle"
     defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 0}
+    if key == "deeplab":
+        defaults = {b"dec_up": 1, b"dw_plane": 1}       # final resize folded into the argmax kernel; whole-plane atrous depthwise
     for sw, dflt in defaults.items():
         try:
             assert lib.bsb_set_tuning(sw, 1 - dflt)

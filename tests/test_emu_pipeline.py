@@ -60,7 +60,7 @@ def test_chain_kernel(lib, key):
     pc.check_chain(lib, key, n=2)
 
 
-@pytest.mark.parametrize("key", ["meet_lite", "mlkit"])
+@pytest.mark.parametrize("key", ["meet_lite", "mlkit", "deeplab"])
 def test_fusion_switches(lib, key):
     pc.check_fusion_switches(lib, key, n=2)
 

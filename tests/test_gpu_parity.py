@@ -83,7 +83,7 @@ def test_chain_kernel(lib, key, n):
     pc.check_chain(lib, key, n=n)
 
 
-@pytest.mark.parametrize("key", ["meet_full", "meet_lite", "mlkit", "bodypix"])
+@pytest.mark.parametrize("key", ["meet_full", "meet_lite", "mlkit", "bodypix", "deeplab"])
 def test_fusion_switches(lib, key):
     pc.check_fusion_switches(lib, key, n=3)
 
