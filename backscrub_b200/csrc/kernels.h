@@ -255,6 +255,7 @@ bool ensure_dyn_smem(const void* func, size_t bytes);
 // results, only which bit-identical kernel variant runs.  Defaults are the measured-best choices.
 struct Tuning {
   int pw_variant = 0;      // launch_pointwise: 0 heuristics, 2 classic tiles, 3/4/8 register-tiled, 5 row-streaming, 16/32/64 classic N tile
+  int dw_px = 1;           // small depthwise layers: row-batched loads (k_depthwise_px) instead of the generic tap loop
   int dec_up = 1;          // DeepLab: final 33 -> 257 resize folded into the argmax decision kernel
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it

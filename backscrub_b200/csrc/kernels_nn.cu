@@ -638,6 +638,49 @@ BSB_D void fma4(float4& acc, const float4& v, const float4& w) {
   acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
 }
 
+// One output pixel x 4 channels per thread, like k_depthwise<4>, for the layers too small for the strip kernel to fill the
+// GPU — but the KS loads of a kernel row are issued together (and all the rows are unrolled), where the generic kernel
+// waits for each tap's load before it even computes the next address (taps behind `continue`s): on these small,
+// latency-bound layers memory-level parallelism per thread is what counts.  Same (fy, fx) accumulation order; out-of-image
+// taps are skipped.
+template <int KS>
+__global__ void __launch_bounds__(256) k_depthwise_px(DWArgs a) {
+  const int groups = a.c / 4;
+  const long total = (long)a.B * a.oh * a.ow * groups;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % groups) * 4;
+  const long pix = idx / groups;
+  const int ox = (int)(pix % a.ow);
+  const int oy = (int)((pix / a.ow) % a.oh);
+  const int b = (int)(pix / ((long)a.ow * a.oh));
+  const float* inb = a.in + (size_t)b * a.ih * a.iw * a.ld_in + c0;
+  const int iy0 = oy * a.sh - a.pt, ix0 = ox * a.sw - a.pl;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int fy = 0; fy < KS; ++fy) {
+    const int iy = iy0 + a.dh * fy;
+    const bool vy = iy >= 0 && iy < a.ih;
+    const float* rowp = inb + (size_t)(vy ? iy : 0) * a.iw * a.ld_in;
+    float4 v[KS], w[KS];
+    bool ok[KS];
+#pragma unroll
+    for (int fx = 0; fx < KS; ++fx) {
+      const int ix = ix0 + a.dw * fx;
+      ok[fx] = vy && ix >= 0 && ix < a.iw;
+      v[fx] = ok[fx] ? __ldg(reinterpret_cast<const float4*>(rowp + (size_t)ix * a.ld_in)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      w[fx] = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(fy * KS + fx) * a.c + c0));
+    }
+#pragma unroll
+    for (int fx = 0; fx < KS; ++fx)
+      if (ok[fx]) fma4(acc, v[fx], w[fx]);
+  }
+  float* op = a.out + (size_t)pix * a.ld_out + c0;
+  *reinterpret_cast<float4*>(op) = make_float4(epilogue(acc.x, c0, (size_t)pix, a.e), epilogue(acc.y, c0 + 1, (size_t)pix, a.e),
+                                               epilogue(acc.z, c0 + 2, (size_t)pix, a.e), epilogue(acc.w, c0 + 3, (size_t)pix, a.e));
+}
+
+
 template <int KS, int S, int D = 1>   // D = dilation (DeepLab / BodyPix atrous layers): taps sit D pixels apart
 __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
   constexpr int CNT = 3 * S + (KS - 1) * D + 1;
@@ -703,11 +746,23 @@ __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   const int c0 = blockIdx.x * DWP_CS, b = blockIdx.y;
   const int hw = a.ih * a.iw;
   const float* inb = a.in + (size_t)b * hw * a.ld_in + c0;
+  // asynchronous 16-byte copies straight into shared memory (LDGSTS): all ~17 copies of a thread are in flight together.
+  // The first version went through registers one load at a time and ran at the latency of a single outstanding load per
+  // thread: 1 TB/s of L2 traffic for a kernel that does nothing but move 2 x 67 MB (run r2u).
   for (int i = threadIdx.x; i < hw * (DWP_CS / 4); i += blockDim.x) {
     const int p = i >> 2, q = i & 3;
+#if defined(BSB_EMU)
     *reinterpret_cast<float4*>(plane + p * DWP_CS + 4 * q) = __ldg(reinterpret_cast<const float4*>(inb + (size_t)p * a.ld_in + 4 * q));
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(plane + p * DWP_CS + 4 * q)),
+                 "l"(inb + (size_t)p * a.ld_in + 4 * q) : "memory");
+#endif
   }
   for (int i = threadIdx.x; i < 9 * DWP_CS; i += blockDim.x) ws[i] = __ldg(a.w + (size_t)(i / DWP_CS) * a.c + c0 + (i % DWP_CS));
+#if !defined(BSB_EMU)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
   __syncthreads();
   const int q = threadIdx.x & 3, ch = c0 + 4 * q;
   float4 w[9];
@@ -774,6 +829,12 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
     }
   }
   const long total = (long)B * oh * ow * (vec ? c / 4 : c);
+  if (vec && kh == kw && (kh == 3 || kh == 5) && tuning().dw_px) {
+    if (kh == 3) BSB_LAUNCH(k_depthwise_px<3>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
+    else BSB_LAUNCH(k_depthwise_px<5>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
+    count_launch();
+    return;
+  }
   if (vec) BSB_LAUNCH(k_depthwise<4>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
   else BSB_LAUNCH(k_depthwise<1>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
   count_launch();
