@@ -739,6 +739,11 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
 // output with a 9-deep dependent LDS -> FFMA chain — ran at 1 TB/s of L2 traffic, profiles/r2_launch_shares_deeplab_bodypix.txt).
 // Tap order and the skipping of out-of-image taps are those of the oracle.
 constexpr int DWP_CS = 16, DWP_R = 4;
+// RELU6_ONLY: the epilogue is bias + RELU6 and nothing else (every atrous layer of DeepLab and BodyPix): the four bias
+// values of the thread's channels are loaded once and the activation is a compile-time constant, where the generic
+// epilogue re-loads the bias and walks two activation switches and a residual test per value (25 % of the kernel's
+// instructions and 40 % of its stall samples, profiles/r2_ncu_k_depthwise_plane.txt).
+template <bool RELU6_ONLY>
 __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   BSB_DYN_SMEM(smem_raw);
   float* plane = reinterpret_cast<float*>(smem_raw);           // [ih*iw][16]
@@ -768,6 +773,8 @@ __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   float4 w[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4*>(ws + t * DWP_CS + 4 * q);
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (RELU6_ONLY && a.e.bias) bias4 = make_float4(__ldg(a.e.bias + ch), __ldg(a.e.bias + ch + 1), __ldg(a.e.bias + ch + 2), __ldg(a.e.bias + ch + 3));
   const int row_groups = (a.oh + DWP_R - 1) / DWP_R;
   for (int p = threadIdx.x >> 2; p < row_groups * a.ow; p += blockDim.x >> 2) {
     const int rg = p / a.ow, ox = p - rg * a.ow, oy0 = rg * DWP_R;
@@ -794,8 +801,15 @@ __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
       const int oy = oy0 + j;
       if (oy >= a.oh) break;
       const size_t pix = (size_t)b * a.oh * a.ow + (size_t)oy * a.ow + ox;
-      *reinterpret_cast<float4*>(a.out + pix * a.ld_out + ch) = make_float4(epilogue(acc[j].x, ch, pix, a.e), epilogue(acc[j].y, ch + 1, pix, a.e),
-                                                                          epilogue(acc[j].z, ch + 2, pix, a.e), epilogue(acc[j].w, ch + 3, pix, a.e));
+      float4 r;
+      if (RELU6_ONLY) {
+        r = make_float4(bsb_act(acc[j].x + bias4.x, ACT_RELU6), bsb_act(acc[j].y + bias4.y, ACT_RELU6), bsb_act(acc[j].z + bias4.z, ACT_RELU6),
+                        bsb_act(acc[j].w + bias4.w, ACT_RELU6));
+      } else {
+        r = make_float4(epilogue(acc[j].x, ch, pix, a.e), epilogue(acc[j].y, ch + 1, pix, a.e), epilogue(acc[j].z, ch + 2, pix, a.e),
+                        epilogue(acc[j].w, ch + 3, pix, a.e));
+      }
+      *reinterpret_cast<float4*>(a.out + pix * a.ld_out + ch) = r;
     }
   }
 }
@@ -808,8 +822,11 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
   const size_t plane_smem = ((size_t)ih * iw + 9) * DWP_CS * sizeof(float);
   if (tuning().dw_plane && (dil_h > 1 || dil_w > 1) && (c % DWP_CS == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && kh == 3 && kw == 3 &&
       stride_h == 1 && stride_w == 1 && oh == ih && ow == iw && plane_smem <= 100 * 1024 &&
-      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane), plane_smem)) {
-    BSB_LAUNCH(k_depthwise_plane, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<true>), plane_smem) &&
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<false>), plane_smem)) {
+    const bool relu6_only = !e.residual && ((e.act1 == ACT_RELU6 && e.act2 == ACT_NONE) || (e.act1 == ACT_NONE && e.act2 == ACT_RELU6));
+    if (relu6_only) BSB_LAUNCH(k_depthwise_plane<true>, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
+    else BSB_LAUNCH(k_depthwise_plane<false>, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
     count_launch();
     return;
   }
