@@ -657,6 +657,8 @@ int bsb_set_tuning(const char* name, int value) {
   if (n == "pw_variant") t.pw_variant = value;
   else if (n == "dw_plane") t.dw_plane = value;
   else if (n == "dec_up") t.dec_up = value;
+  else if (n == "dec_par") t.dec_par = value;
+  else if (n == "epi_static") t.epi_static = value;
   else if (n == "dw_px") t.dw_px = value;
   else if (n == "post_tma") t.post_tma = value;
   else if (n == "cnn_chain") t.cnn_chain = value;

@@ -257,6 +257,8 @@ struct Tuning {
   int pw_variant = 0;      // launch_pointwise: 0 heuristics, 2 classic tiles, 3/4/8 register-tiled, 5 row-streaming, 16/32/64 classic N tile
   int dw_px = 1;           // small depthwise layers: row-batched loads (k_depthwise_px) instead of the generic tap loop
   int dec_up = 1;          // DeepLab: final 33 -> 257 resize folded into the argmax decision kernel
+  int epi_static = 1;      // compile-time epilogues (bias preloaded, activation fixed) for the common combinations; 0 = the generic run-time epilogue everywhere
+  int dec_par = 1;         // decision + temporal smoother: frames in parallel (a block = 32 pixels x all frames) instead of one thread per pixel
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel
@@ -269,7 +271,7 @@ struct Tuning {
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)
   int cnn_chain = 1;       // one kernel for the low-resolution middle of the MobileNetV3-style graphs (kernels_chain.cu)
   int sub_batch_mb = 0;    // engine: wide-layer segments run in frame groups whose largest tensor is <= this many MB (0 = off; measured slower, run r2t)
-  int post_tile = 64;      // k_post_tma: tile width (64: eight CTAs per SM, 128: four)
+  int post_tile = 0;       // k_post_tma: tile width (64: eight CTAs per SM, 128: four; 0 = by frame size: 128 from 2560 pixels wide)
   int post_wide = 1;       // k_post_fast: 256-bit sector-aligned accesses
   int post_l1 = 1;         // k_post_fast: frame loads allocate in L1
 };

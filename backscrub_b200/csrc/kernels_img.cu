@@ -216,9 +216,54 @@ __global__ void __launch_bounds__(128) k_decision_iir(int model_type, int B, con
   state[n] = (uint8_t)st;
 }
 
+// Frame-parallel form of the same stage.  The 3-tap state is a finite window: unrolling
+//   st_b = (val_b & 0xE0) | (st_{b-1} >> 3)
+// gives st_b = E0*d_b | 1C*d_{b-1} | 03*d_{b-2} for b >= 2, st_1 = E0*d_1 | 1C*d_0 | (s >> 6), st_0 = E0*d_0 | (s >> 3)
+// (s = the state the previous call left, any byte; d = 1 where val = 255), so nothing but the three latest decisions
+// is carried from frame to frame.  k_decision_iir walks the B frames of a pixel in ONE thread — 36 864 threads for the
+// Meet output however large the batch is, 12 % of the GPU's thread slots, 0.4 TB/s (profiles/r2_launch_shares_meet720_b256.txt:
+// 195 us per 256-frame launch).  Here a block owns 32 pixels x all B frames: its eight warps take the frames round-robin,
+// park the decisions in shared memory ([B][32] bytes) and, after one barrier, each thread assembles the state bytes of
+// its frames from three of them.  The block that owns a pixel is the only one that touches its state byte: read before
+// the barrier, written (by the owner of frame B-1) after it.
+constexpr int DEC_PX = 32, DEC_WARPS = 8;
+
+BSB_D void decision_window_store(const uint8_t* d, int tx, int ty, int B, unsigned s_in, uint8_t* state_px, uint8_t* ofinal_px, int oframe) {
+  for (int b = ty; b < B; b += DEC_WARPS) {
+    unsigned st = d[b * DEC_PX + tx] ? 0xE0u : 0u;
+    if (b >= 1) st |= d[(b - 1) * DEC_PX + tx] ? 0x1Cu : 0u; else st |= s_in >> 3;
+    if (b >= 2) st |= d[(b - 2) * DEC_PX + tx] ? 0x03u : 0u; else if (b == 1) st |= s_in >> 6;
+    ofinal_px[(size_t)b * oframe] = (uint8_t)st;
+    if (b == B - 1) *state_px = (uint8_t)st;
+  }
+}
+
+__global__ void __launch_bounds__(DEC_PX * DEC_WARPS) k_decision_par(int model_type, int B, const float* out_f, int npix, int oc,
+                                                                     uint8_t* state, uint8_t* ofinal, int ow, int opitch, int oframe) {
+  BSB_DYN_SMEM(smem_raw);
+  uint8_t* d = reinterpret_cast<uint8_t*>(smem_raw);               // [B][32] decisions
+  const int tx = threadIdx.x % DEC_PX, ty = threadIdx.x / DEC_PX;
+  const int n = blockIdx.x * DEC_PX + tx;
+  const bool valid = n < npix;
+  const unsigned s_in = valid ? state[n] : 0u;
+  if (valid) {
+#pragma unroll 4
+    for (int b = ty; b < B; b += DEC_WARPS) d[b * DEC_PX + tx] = (uint8_t)decide(model_type, out_f + ((size_t)b * npix + n) * oc);
+  }
+  __syncthreads();
+  if (!valid) return;
+  decision_window_store(d, tx, ty, B, s_in, state + n, ofinal + (n / ow) * opitch + (n % ow), oframe);
+}
+
 void launch_decision_iir(cudaStream_t s, int model_type, int B, const float* model_out, int oh, int ow, int oc,
                          uint8_t* state, uint8_t* ofinal, int opitch) {
   const int npix = oh * ow;
+  if (tuning().dec_par && (size_t)B * DEC_PX <= 48 * 1024) {
+    BSB_LAUNCH(k_decision_par, dim3((unsigned)ceil_div(npix, DEC_PX)), dim3(DEC_PX * DEC_WARPS), (size_t)B * DEC_PX, s, model_type, B, model_out,
+               npix, oc, state, ofinal, ow, opitch, oh * opitch);
+    count_launch();
+    return;
+  }
   BSB_LAUNCH(k_decision_iir, dim3((unsigned)ceil_div(npix, 128)), dim3(128), 0, s, model_type, B, model_out, npix, oc, state, ofinal,
              ow, opitch, oh * opitch);
   count_launch();
@@ -259,11 +304,54 @@ __global__ void __launch_bounds__(128) k_decision_up_iir(int B, const float* low
   state[n] = (uint8_t)st;
 }
 
+// frame-parallel form (see k_decision_par): a block = 32 output pixels x all B frames
+__global__ void __launch_bounds__(DEC_PX * DEC_WARPS) k_decision_up_par(int B, const float* low, int ih, int iw, int ld, float hs, float ws, bool half_pixel,
+                                                                        int oh, int ow, uint8_t* state, uint8_t* ofinal, int opitch, int oframe) {
+  BSB_DYN_SMEM(smem_raw);
+  uint8_t* d = reinterpret_cast<uint8_t*>(smem_raw);
+  const int tx = threadIdx.x % DEC_PX, ty = threadIdx.x / DEC_PX;
+  const int n = blockIdx.x * DEC_PX + tx;
+  const bool valid = n < oh * ow;
+  const unsigned s_in = valid ? state[n] : 0u;
+  const int y = valid ? n / ow : 0, x = valid ? n - y * ow : 0;
+  if (valid) {
+    float fy, fx; int y0, y1, x0, x1;
+    bsb_resize_interp((float)y, hs, half_pixel, ih, &fy, &y0, &y1);
+    bsb_resize_interp((float)x, ws, half_pixel, iw, &fx, &x0, &x1);
+    const float dy = fy - (float)y0, dx = fx - (float)x0;
+    const float wy0 = 1.f - dy, wx0 = 1.f - dx;
+    const int o00 = (y0 * iw + x0) * ld, o10 = (y1 * iw + x0) * ld, o01 = (y0 * iw + x1) * ld, o11 = (y1 * iw + x1) * ld;
+    for (int b = ty; b < B; b += DEC_WARPS) {
+      const float* f = low + (size_t)b * ih * iw * ld;
+      float maxval = -10000.f; int maxpos = 0;
+#pragma unroll 7
+      for (int i = 0; i < 21; ++i) {
+        const float a = __ldg(f + o00 + i) * wy0 * wx0;
+        const float bb = __ldg(f + o10 + i) * dy * wx0;
+        const float dd = __ldg(f + o01 + i) * wy0 * dx;
+        const float e = __ldg(f + o11 + i) * dy * dx;
+        const float v = ((a + bb) + dd) + e;
+        if (v > maxval) { maxval = v; maxpos = i; }
+      }
+      d[b * DEC_PX + tx] = (maxpos == 15) ? 0 : 1;
+    }
+  }
+  __syncthreads();
+  if (!valid) return;
+  decision_window_store(d, tx, ty, B, s_in, state + n, ofinal + y * opitch + x, oframe);
+}
+
 void launch_decision_up_iir(cudaStream_t s, int B, const float* low, int ih, int iw, int ld, bool align_corners, bool half_pixel,
                             int oh, int ow, uint8_t* state, uint8_t* ofinal, int opitch) {
   float hs = (float)ih / (float)oh, ws = (float)iw / (float)ow;
   if (align_corners && oh > 1) hs = (float)(ih - 1) / (float)(oh - 1);
   if (align_corners && ow > 1) ws = (float)(iw - 1) / (float)(ow - 1);
+  if (tuning().dec_par && (size_t)B * DEC_PX <= 48 * 1024) {
+    BSB_LAUNCH(k_decision_up_par, dim3((unsigned)ceil_div(oh * ow, DEC_PX)), dim3(DEC_PX * DEC_WARPS), (size_t)B * DEC_PX, s, B, low, ih, iw, ld, hs, ws,
+               half_pixel, oh, ow, state, ofinal, opitch, oh * opitch);
+    count_launch();
+    return;
+  }
   BSB_LAUNCH(k_decision_up_iir, dim3((unsigned)ceil_div(oh * ow, 128)), dim3(128), 0, s, B, low, ih, iw, ld, hs, ws, half_pixel, oh, ow, state,
              ofinal, opitch, oh * opitch);
   count_launch();

@@ -55,6 +55,50 @@ BSB_D float epilogue(float total, int ch, size_t pix, const EpiDev& e) {
   return v;
 }
 
+// Compile-time epilogue.  The generic one above costs ~25 instructions per value (a bias load from global memory at the
+// very end of the kernel, two activation switches, a residual test): 40 % of the instructions of the 16 -> 16 1x1 conv of
+// the Meet graph and 45 % of its stall samples (profiles/r2_ncu_meet_hires_kernels.txt).  MODE < 0: that generic path.
+// MODE >= 0: value = act(acc + bias) with act = MODE & 7 fixed at compile time and the bias preloaded by the caller
+// (before its main loop); MODE & 8: + residual, no activation after it.  Same operations in the same order as the generic
+// path for these combinations (a missing bias is + 0.f there and here), so the bits are unchanged.
+template <int MODE>
+BSB_D float epilogue_m(float total, float bias, int ch, size_t pix, const EpiDev& e) {
+  if (MODE < 0) return epilogue(total, ch, pix, e);
+  float v = bsb_act(total + bias, MODE & 7);
+  if (MODE & 8) v = v + __ldg(e.residual + pix * (size_t)e.ld_res + ch);
+  return v;
+}
+template <int MODE>
+BSB_D float4 epilogue_bias4(const EpiDev& e, int ch0, int N) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODE >= 0 && e.bias) {
+    if (ch0 + 3 < N) { b.x = __ldg(e.bias + ch0); b.y = __ldg(e.bias + ch0 + 1); b.z = __ldg(e.bias + ch0 + 2); b.w = __ldg(e.bias + ch0 + 3); }
+    else { if (ch0 < N) b.x = __ldg(e.bias + ch0); if (ch0 + 1 < N) b.y = __ldg(e.bias + ch0 + 1); if (ch0 + 2 < N) b.z = __ldg(e.bias + ch0 + 2); }
+  }
+  return b;
+}
+// the combinations the five bundled graphs use outside the chain kernel; anything else runs the generic path
+static int epi_mode(const Epilogue& e) {
+  if (!tuning().epi_static) return -1;
+  int act;
+  if (e.act1 == ACT_NONE) act = e.act2; else if (e.act2 == ACT_NONE) act = e.act1; else return -1;
+  int mode;
+  if (!e.residual) mode = act; else if (e.act3 == ACT_NONE) mode = 8 | act; else return -1;
+  return (mode == 0 || mode == 1 || mode == 3 || mode == 4 || mode == 8 || mode == 11) ? mode : -1;
+}
+template <int M> struct EpiTag { static constexpr int value = M; };
+template <class F> static void epi_dispatch(int mode, F&& f) {
+  switch (mode) {
+    case 0: f(EpiTag<0>{}); break;
+    case 1: f(EpiTag<1>{}); break;
+    case 3: f(EpiTag<3>{}); break;
+    case 4: f(EpiTag<4>{}); break;
+    case 8: f(EpiTag<8>{}); break;
+    case 11: f(EpiTag<11>{}); break;
+    default: f(EpiTag<-1>{}); break;
+  }
+}
+
 // four adjacent channels of one row, as a real call: keeps the 32/64-output epilogue of the register-tiled
 // kernel from being unrolled into tens of thousands of instructions
 BSB_D_NOINLINE float4 epilogue4(float4 v, int ch, size_t pix, const EpiDev& e) {
@@ -142,12 +186,15 @@ struct StemArgs {
   const float* w2; float* out2; int ld_out2; EpiDev e2;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
   BSB_DYN_SMEM(smem_raw);
-  float* ws = reinterpret_cast<float*>(smem_raw);     // [kh][kw][3][16]
+  float* ws = reinterpret_cast<float*>(smem_raw);     // [kh][kw][3][16] | [16][16] second stage | [16] bias
   const int wcount = a.kh * a.kw * 3 * 16;
   for (int i = threadIdx.x; i < wcount; i += blockDim.x) ws[i] = __ldg(a.w + i);
   if (a.w2) for (int i = threadIdx.x; i < 256; i += blockDim.x) ws[wcount + i] = __ldg(a.w2 + i);
+  float* bs = ws + wcount + 256;
+  if (MODE >= 0 && threadIdx.x < 16) bs[threadIdx.x] = a.e.bias ? __ldg(a.e.bias + threadIdx.x) : 0.f;
   __syncthreads();
   const long total = (long)a.B * a.oh * a.ow;
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,8 +230,10 @@ __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
   float4 r[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
-    r[q] = valid ? make_float4(epilogue(acc[4 * q], 4 * q, (size_t)pix, a.e), epilogue(acc[4 * q + 1], 4 * q + 1, (size_t)pix, a.e),
-                               epilogue(acc[4 * q + 2], 4 * q + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], 4 * q + 3, (size_t)pix, a.e))
+    r[q] = valid ? make_float4(epilogue_m<MODE>(acc[4 * q], MODE >= 0 ? bs[4 * q] : 0.f, 4 * q, (size_t)pix, a.e),
+                               epilogue_m<MODE>(acc[4 * q + 1], MODE >= 0 ? bs[4 * q + 1] : 0.f, 4 * q + 1, (size_t)pix, a.e),
+                               epilogue_m<MODE>(acc[4 * q + 2], MODE >= 0 ? bs[4 * q + 2] : 0.f, 4 * q + 2, (size_t)pix, a.e),
+                               epilogue_m<MODE>(acc[4 * q + 3], MODE >= 0 ? bs[4 * q + 3] : 0.f, 4 * q + 3, (size_t)pix, a.e))
                  : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 r2[4];
   if (a.w2) {
@@ -255,7 +304,10 @@ void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw,
   StemArgs a{in_u8, w_t, out, B, ih, iw, kh, kw, stride_h, stride_w, pad_t, pad_l, oh, ow, ld_out, scale, offset, to_dev(e),
              w2_kn, out2, ld_out2, e2 ? to_dev(*e2) : EpiDev{nullptr, nullptr, 0, 0, 0, 0}};
   const long total = (long)B * oh * ow;
-  BSB_LAUNCH(k_stem_u8, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * ((size_t)kh * kw * 48 + (w2_kn ? 256 : 0)), s, a);
+  epi_dispatch(epi_mode(e), [&](auto tag) {
+    auto k = k_stem_u8<decltype(tag)::value>;
+    BSB_LAUNCH(k, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * ((size_t)kh * kw * 48 + 256 + 16), s, a);
+  });
   count_launch();
 }
 
@@ -271,7 +323,7 @@ struct PWArgs {
   EpiDev e;
 };
 
-template <int BN, int TM>
+template <int BN, int TM, int MODE>
 __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
   constexpr int BK = 16;
   constexpr int CT = BN / 4;          // column threads
@@ -286,6 +338,12 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
   float acc[TM][4];
 #pragma unroll
   for (int i = 0; i < TM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  const float4 bias4 = epilogue_bias4<MODE>(a.e, n0 + tx * 4, a.N);
+  // frame of a row (for the per-frame operand scale) without a division per element: the tile starts in frame f0 and,
+  // when a frame has at least BM rows, crosses at most one frame boundary
+  const int f0 = a.in_scale ? m0 / a.rows_per_frame : 0;
+  const int fnext = (f0 + 1) * a.rows_per_frame;
+  const bool two_frames = a.rows_per_frame >= BM;
 
   for (int k0 = 0; k0 < a.K; k0 += BK) {
     // ---- stage A tile (BM x BK) transposed into As[k][m] ----
@@ -303,7 +361,8 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
           for (int j = 0; j < 4; ++j) if (gk + j < a.K) v[j] = __ldg(ap + j);
         }
         if (a.in_scale) {
-          const float* sp = a.in_scale + (size_t)(gm / a.rows_per_frame) * a.K + gk;
+          const int fr = two_frames ? f0 + (gm >= fnext ? 1 : 0) : gm / a.rows_per_frame;
+          const float* sp = a.in_scale + (size_t)fr * a.K + gk;
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (gk + j < a.K) v[j] = v[j] * __ldg(sp + j);
         }
@@ -346,15 +405,16 @@ __global__ void __launch_bounds__(256) k_pointwise(PWArgs a) {
     if (gm >= a.M) continue;
     float* op = a.out + (size_t)gm * a.ld_out;
     const int ch0 = n0 + tx * 4;
+    const float bj[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
     if (vec_o && ch0 + 3 < a.N) {      // one 16-byte store per row segment instead of four strided scalar stores
-      *reinterpret_cast<float4*>(op + ch0) = make_float4(epilogue(acc[i][0], ch0, (size_t)gm, a.e), epilogue(acc[i][1], ch0 + 1, (size_t)gm, a.e),
-                                                         epilogue(acc[i][2], ch0 + 2, (size_t)gm, a.e), epilogue(acc[i][3], ch0 + 3, (size_t)gm, a.e));
+      *reinterpret_cast<float4*>(op + ch0) = make_float4(epilogue_m<MODE>(acc[i][0], bj[0], ch0, (size_t)gm, a.e), epilogue_m<MODE>(acc[i][1], bj[1], ch0 + 1, (size_t)gm, a.e),
+                                                         epilogue_m<MODE>(acc[i][2], bj[2], ch0 + 2, (size_t)gm, a.e), epilogue_m<MODE>(acc[i][3], bj[3], ch0 + 3, (size_t)gm, a.e));
       continue;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ch = ch0 + j;
-      if (ch < a.N) op[ch] = epilogue(acc[i][j], ch, (size_t)gm, a.e);
+      if (ch < a.N) op[ch] = epilogue_m<MODE>(acc[i][j], bj[j], ch, (size_t)gm, a.e);
     }
   }
 }
@@ -482,6 +542,7 @@ __global__ void __launch_bounds__(256, TN == 8 ? 2 : 3) k_pointwise_tile(PWArgs 
 // the whole weight matrix sits in shared memory; a thread owns 4 output channels of one
 // pixel and walks K in ascending order (float4 loads of the pixel row are shared by the
 // CT threads of that pixel through the L1 broadcast path).  Memory-bound by design.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
   BSB_DYN_SMEM(smem_raw);
   float* Ws = reinterpret_cast<float*>(smem_raw);            // [K][n4]
@@ -492,6 +553,7 @@ __global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
   const int tx = threadIdx.x % ct, tr = threadIdx.x / ct;
   if (tr >= rows_per_block) return;
   const int n0 = tx * 4;
+  const float4 bias4 = epilogue_bias4<MODE>(a.e, n0, a.N);
   for (long gm = (long)blockIdx.x * rows_per_block + tr; gm < a.M; gm += (long)gridDim.x * rows_per_block) {
     const float* ap = a.A + (size_t)gm * a.ld_a;
     const float* sp = a.in_scale ? a.in_scale + (size_t)((unsigned)gm / (unsigned)a.rows_per_frame) * a.K : nullptr;
@@ -510,15 +572,15 @@ __global__ void __launch_bounds__(256) k_pointwise_rows(PWArgs a, int ct) {
       }
     }
     float* op = a.out + (size_t)gm * a.ld_out + n0;
-    const float r0 = epilogue(acc0, n0, (size_t)gm, a.e);
+    const float r0 = epilogue_m<MODE>(acc0, bias4.x, n0, (size_t)gm, a.e);
     if (n0 + 3 < a.N && (a.ld_out & 3) == 0) {
-      *reinterpret_cast<float4*>(op) = make_float4(r0, epilogue(acc1, n0 + 1, (size_t)gm, a.e), epilogue(acc2, n0 + 2, (size_t)gm, a.e),
-                                                   epilogue(acc3, n0 + 3, (size_t)gm, a.e));
+      *reinterpret_cast<float4*>(op) = make_float4(r0, epilogue_m<MODE>(acc1, bias4.y, n0 + 1, (size_t)gm, a.e), epilogue_m<MODE>(acc2, bias4.z, n0 + 2, (size_t)gm, a.e),
+                                                   epilogue_m<MODE>(acc3, bias4.w, n0 + 3, (size_t)gm, a.e));
     } else {
       op[0] = r0;
-      if (n0 + 1 < a.N) op[1] = epilogue(acc1, n0 + 1, (size_t)gm, a.e);
-      if (n0 + 2 < a.N) op[2] = epilogue(acc2, n0 + 2, (size_t)gm, a.e);
-      if (n0 + 3 < a.N) op[3] = epilogue(acc3, n0 + 3, (size_t)gm, a.e);
+      if (n0 + 1 < a.N) op[1] = epilogue_m<MODE>(acc1, bias4.y, n0 + 1, (size_t)gm, a.e);
+      if (n0 + 2 < a.N) op[2] = epilogue_m<MODE>(acc2, bias4.z, n0 + 2, (size_t)gm, a.e);
+      if (n0 + 3 < a.N) op[3] = epilogue_m<MODE>(acc3, bias4.w, n0 + 3, (size_t)gm, a.e);
     }
   }
 }
@@ -556,7 +618,10 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
     const int ct = n4 / 4, rows_per_block = 256 / ct;
     long blocks = ((long)M + rows_per_block - 1) / rows_per_block;
     if (blocks > 148L * 16) blocks = 148L * 16;             // grid-stride: a few waves of 148 SMs
-    BSB_LAUNCH(k_pointwise_rows, dim3((unsigned)blocks), dim3(256), sizeof(float) * (size_t)K * n4, s, a, ct);
+    epi_dispatch(epi_mode(e), [&](auto tag) {
+      auto k = k_pointwise_rows<decltype(tag)::value>;
+      BSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), sizeof(float) * (size_t)K * n4, s, a, ct);
+    });
     count_launch();
     return;
   }
@@ -571,9 +636,12 @@ void launch_pointwise(cudaStream_t s, int M, int K, int N, const float* A, int l
   const bool small = (long)ceil_div(M, rt * 4) * ceil_div(N, bn) < 2 * 148;
   const int bm = small ? rt : rt * 4;
   dim3 grid((unsigned)ceil_div(M, bm), (unsigned)ceil_div(N, bn));
-  if (bn == 64) { if (small) { auto k = k_pointwise<64, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<64, 4>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
-  else if (bn == 32) { if (small) { auto k = k_pointwise<32, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<32, 4>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
-  else { if (small) { auto k = k_pointwise<16, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<16, 4>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+  epi_dispatch(epi_mode(e), [&](auto tag) {
+    constexpr int MD = decltype(tag)::value;
+    if (bn == 64) { if (small) { auto k = k_pointwise<64, 1, MD>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<64, 4, MD>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+    else if (bn == 32) { if (small) { auto k = k_pointwise<32, 1, MD>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<32, 4, MD>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+    else { if (small) { auto k = k_pointwise<16, 1, MD>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_pointwise<16, 4, MD>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+  });
   count_launch();
 }
 
@@ -643,7 +711,7 @@ BSB_D void fma4(float4& acc, const float4& v, const float4& w) {
 // waits for each tap's load before it even computes the next address (taps behind `continue`s): on these small,
 // latency-bound layers memory-level parallelism per thread is what counts.  Same (fy, fx) accumulation order; out-of-image
 // taps are skipped.
-template <int KS>
+template <int KS, int MODE>
 __global__ void __launch_bounds__(256) k_depthwise_px(DWArgs a) {
   const int groups = a.c / 4;
   const long total = (long)a.B * a.oh * a.ow * groups;
@@ -656,6 +724,7 @@ __global__ void __launch_bounds__(256) k_depthwise_px(DWArgs a) {
   const int b = (int)(pix / ((long)a.ow * a.oh));
   const float* inb = a.in + (size_t)b * a.ih * a.iw * a.ld_in + c0;
   const int iy0 = oy * a.sh - a.pt, ix0 = ox * a.sw - a.pl;
+  const float4 bias4 = epilogue_bias4<MODE>(a.e, c0, a.c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int fy = 0; fy < KS; ++fy) {
@@ -676,12 +745,12 @@ __global__ void __launch_bounds__(256) k_depthwise_px(DWArgs a) {
       if (ok[fx]) fma4(acc, v[fx], w[fx]);
   }
   float* op = a.out + (size_t)pix * a.ld_out + c0;
-  *reinterpret_cast<float4*>(op) = make_float4(epilogue(acc.x, c0, (size_t)pix, a.e), epilogue(acc.y, c0 + 1, (size_t)pix, a.e),
-                                               epilogue(acc.z, c0 + 2, (size_t)pix, a.e), epilogue(acc.w, c0 + 3, (size_t)pix, a.e));
+  *reinterpret_cast<float4*>(op) = make_float4(epilogue_m<MODE>(acc.x, bias4.x, c0, (size_t)pix, a.e), epilogue_m<MODE>(acc.y, bias4.y, c0 + 1, (size_t)pix, a.e),
+                                               epilogue_m<MODE>(acc.z, bias4.z, c0 + 2, (size_t)pix, a.e), epilogue_m<MODE>(acc.w, bias4.w, c0 + 3, (size_t)pix, a.e));
 }
 
 
-template <int KS, int S, int D = 1>   // D = dilation (DeepLab / BodyPix atrous layers): taps sit D pixels apart
+template <int KS, int S, int D, int MODE>   // D = dilation (DeepLab / BodyPix atrous layers): taps sit D pixels apart
 __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
   constexpr int CNT = 3 * S + (KS - 1) * D + 1;
   const int groups = a.c / 4, strips = (a.ow + 3) / 4;
@@ -694,6 +763,7 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
   const int oy = (int)(t % a.oh);
   const int b = (int)(t / a.oh);
   const float* inb = a.in + (size_t)b * a.ih * a.iw * a.ld_in + c0;
+  const float4 bias4 = epilogue_bias4<MODE>(a.e, c0, a.c);
   float4 acc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -726,8 +796,8 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
     if (ox >= a.ow) break;
     const size_t pix = ((size_t)b * a.oh + oy) * a.ow + ox;
     float* op = a.out + pix * a.ld_out + c0;
-    *reinterpret_cast<float4*>(op) = make_float4(epilogue(acc[j].x, c0, pix, a.e), epilogue(acc[j].y, c0 + 1, pix, a.e),
-                                                 epilogue(acc[j].z, c0 + 2, pix, a.e), epilogue(acc[j].w, c0 + 3, pix, a.e));
+    *reinterpret_cast<float4*>(op) = make_float4(epilogue_m<MODE>(acc[j].x, bias4.x, c0, pix, a.e), epilogue_m<MODE>(acc[j].y, bias4.y, c0 + 1, pix, a.e),
+                                                 epilogue_m<MODE>(acc[j].z, bias4.z, c0 + 2, pix, a.e), epilogue_m<MODE>(acc[j].w, bias4.w, c0 + 3, pix, a.e));
   }
 }
 
@@ -835,20 +905,26 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
     const long nthreads = (long)B * oh * ((ow + 3) / 4) * (c / 4);
     if (nthreads >= 148L * 1024) {   // enough strips to fill the GPU; small layers keep one pixel per thread
     const dim3 grid((unsigned)((nthreads + 127) / 128)), block(128);
-    if (atrous && dil_h == 2) { auto k = k_depthwise_strip<3, 1, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
-    else if (atrous) { auto k = k_depthwise_strip<3, 1, 4>; BSB_LAUNCH(k, grid, block, 0, s, a); }
-    else if (kh == 3 && stride_h == 1) { auto k = k_depthwise_strip<3, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
-    else if (kh == 3) { auto k = k_depthwise_strip<3, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
-    else if (stride_h == 1) { auto k = k_depthwise_strip<5, 1>; BSB_LAUNCH(k, grid, block, 0, s, a); }
-    else { auto k = k_depthwise_strip<5, 2>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    epi_dispatch(epi_mode(e), [&](auto tag) {
+      constexpr int MD = decltype(tag)::value;
+      if (atrous && dil_h == 2) { auto k = k_depthwise_strip<3, 1, 2, MD>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+      else if (atrous) { auto k = k_depthwise_strip<3, 1, 4, MD>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+      else if (kh == 3 && stride_h == 1) { auto k = k_depthwise_strip<3, 1, 1, MD>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+      else if (kh == 3) { auto k = k_depthwise_strip<3, 2, 1, MD>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+      else if (stride_h == 1) { auto k = k_depthwise_strip<5, 1, 1, MD>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+      else { auto k = k_depthwise_strip<5, 2, 1, MD>; BSB_LAUNCH(k, grid, block, 0, s, a); }
+    });
     count_launch();
     return;
     }
   }
   const long total = (long)B * oh * ow * (vec ? c / 4 : c);
   if (vec && kh == kw && (kh == 3 || kh == 5) && tuning().dw_px) {
-    if (kh == 3) BSB_LAUNCH(k_depthwise_px<3>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
-    else BSB_LAUNCH(k_depthwise_px<5>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a);
+    epi_dispatch(epi_mode(e), [&](auto tag) {
+      constexpr int MD = decltype(tag)::value;
+      if (kh == 3) { auto k = k_depthwise_px<3, MD>; BSB_LAUNCH(k, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a); }
+      else { auto k = k_depthwise_px<5, MD>; BSB_LAUNCH(k, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, a); }
+    });
     count_launch();
     return;
   }
@@ -1216,7 +1292,7 @@ struct UpPwArgs {
   EpiDev e;
 };
 
-template <int NQ>     // output channel quads per thread; a pixel is shared by n4 / (4 * NQ) threads
+template <int NQ, int MODE>     // output channel quads per thread; a pixel is shared by n4 / (4 * NQ) threads
 __global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a, int groups) {
   BSB_DYN_SMEM(smem_raw);
   float* Ws = reinterpret_cast<float*>(smem_raw);            // [K][n4]
@@ -1243,6 +1319,12 @@ __global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a, int groups) {
   float acc[NQ * 4];
 #pragma unroll
   for (int n = 0; n < NQ * 4; ++n) acc[n] = 0.f;
+  float4 bias4[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) bias4[q] = epilogue_bias4<MODE>(a.e, nbase + 4 * q, a.N);
+  // (unrolled so that the 16 loads of four k steps are in flight together: with one step at a time the 128-deep layer
+  //  spent 64 % of its stall samples waiting for them, profiles/r2_ncu_meet_hires_kernels.txt)
+#pragma unroll 4
   for (int k = 0; k < a.K; k += 4) {
     const float4 v00 = __ldg(reinterpret_cast<const float4*>(p00 + k)), v10 = __ldg(reinterpret_cast<const float4*>(p10 + k));
     const float4 v01 = __ldg(reinterpret_cast<const float4*>(p01 + k)), v11 = __ldg(reinterpret_cast<const float4*>(p11 + k));
@@ -1266,12 +1348,13 @@ __global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a, int groups) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int n0 = nbase + 4 * q;
+    const float bj[4] = {bias4[q].x, bias4[q].y, bias4[q].z, bias4[q].w};
     if (n0 + 3 < a.N) {
-      *reinterpret_cast<float4*>(op + n0) = make_float4(epilogue(acc[4 * q], n0, (size_t)pix, a.e), epilogue(acc[4 * q + 1], n0 + 1, (size_t)pix, a.e),
-                                                        epilogue(acc[4 * q + 2], n0 + 2, (size_t)pix, a.e), epilogue(acc[4 * q + 3], n0 + 3, (size_t)pix, a.e));
+      *reinterpret_cast<float4*>(op + n0) = make_float4(epilogue_m<MODE>(acc[4 * q], bj[0], n0, (size_t)pix, a.e), epilogue_m<MODE>(acc[4 * q + 1], bj[1], n0 + 1, (size_t)pix, a.e),
+                                                        epilogue_m<MODE>(acc[4 * q + 2], bj[2], n0 + 2, (size_t)pix, a.e), epilogue_m<MODE>(acc[4 * q + 3], bj[3], n0 + 3, (size_t)pix, a.e));
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (n0 + j < a.N) op[n0 + j] = epilogue(acc[4 * q + j], n0 + j, (size_t)pix, a.e);
+      for (int j = 0; j < 4; ++j) if (n0 + j < a.N) op[n0 + j] = epilogue_m<MODE>(acc[4 * q + j], bj[j], n0 + j, (size_t)pix, a.e);
     }
   }
 }
@@ -1295,13 +1378,15 @@ void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, 
   while (nq > 1 && (nq % 2 == 0 || nq % 3 == 0) && pixels * (quads / nq) < 148L * 2048) nq = (nq % 2 == 0) ? nq / 2 : nq / 3;
   const int groups = quads / nq;
   const dim3 grid((unsigned)((pixels * groups + 127) / 128)), block(128);
+  // (the five graphs only ever put a plain bias behind this op: one specialised instance per NQ, generic otherwise)
+  const bool plain = epi_mode(e) == 0;
   switch (nq) {
-    case 1: BSB_LAUNCH(k_upsample_pw<1>, grid, block, smem, s, a, groups); break;
-    case 2: BSB_LAUNCH(k_upsample_pw<2>, grid, block, smem, s, a, groups); break;
-    case 3: BSB_LAUNCH(k_upsample_pw<3>, grid, block, smem, s, a, groups); break;
-    case 4: BSB_LAUNCH(k_upsample_pw<4>, grid, block, smem, s, a, groups); break;
-    case 5: BSB_LAUNCH(k_upsample_pw<5>, grid, block, smem, s, a, groups); break;
-    default: BSB_LAUNCH(k_upsample_pw<6>, grid, block, smem, s, a, groups); break;
+    case 1: if (plain) { auto k = k_upsample_pw<1, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<1, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
+    case 2: if (plain) { auto k = k_upsample_pw<2, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<2, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
+    case 3: if (plain) { auto k = k_upsample_pw<3, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<3, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
+    case 4: if (plain) { auto k = k_upsample_pw<4, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<4, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
+    case 5: if (plain) { auto k = k_upsample_pw<5, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<5, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
+    default: if (plain) { auto k = k_upsample_pw<6, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<6, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
   }
   count_launch();
 }

@@ -366,7 +366,14 @@ static bool build_post_maps(const PostArgs& a, PostMaps* tm, int TW) {
   return ok;
 }
 
-static int post_tile_width() { return tuning().post_tile == 128 ? 128 : 64; }
+// measured (profiles/r2_post_tile_ab.txt): 64-wide tiles (eight CTAs per SM) win at 720p, 60.9 vs 65.6 us per 32-frame launch;
+// at 3840x2160, where > 95 % of the tiles are pure copies, 128-wide tiles halve the per-CTA fixed cost: 136.7 vs 140.2 us
+// per 8-frame launch (0.81 vs 0.79 of the measured HBM peak)
+static int post_tile_width(const PostArgs& a) {
+  const int t = tuning().post_tile;
+  if (t == 64 || t == 128) return t;
+  return a.W >= 2560 ? 128 : 64;
+}
 
 static bool post_tma_shape_ok(const PostArgs& a) {
   if (!tuning().post_tma || !encode_fn()) return false;
@@ -381,14 +388,14 @@ static bool post_tma_shape_ok(const PostArgs& a) {
   if (!(a.out || a.yuyv || a.mask) || !al16(a.ofinal) || a.opitch % 16) return false;
   if (a.ow > 32000 || a.oh > 32000 || a.roi_w < 8 || a.roi_h < 8) return false;
   const double scale_y = (double)a.out_h / (double)a.roi_h, scale_x = (double)a.out_w / (double)a.roi_w;
-  const int tw = post_tile_width();
+  const int tw = post_tile_width(a);
   if ((int)(PF_UH * scale_y) + 3 > PT_RMAX || (int)((tw + 4) * scale_x) + 4 > (tw == 128 ? PtL<128>::PCOLS : PtL<64>::PCOLS)) return false;
   return true;
 }
 
 bool post_tma_eligible(const PostArgs& a) {
   PostMaps tm;
-  return post_tma_shape_ok(a) && build_post_maps(a, &tm, post_tile_width());
+  return post_tma_shape_ok(a) && build_post_maps(a, &tm, post_tile_width(a));
 }
 
 template <bool IN_YUYV, int TW>
@@ -402,7 +409,7 @@ static bool launch_post_tma_t(cudaStream_t s, const PostMaps& tm, const PostArgs
 
 bool launch_post_tma(cudaStream_t s, const PostArgs& a) {
   PostMaps tm;
-  const int tw = post_tile_width();
+  const int tw = post_tile_width(a);
   if (!post_tma_shape_ok(a) || !build_post_maps(a, &tm, tw)) return false;
   const PostTmaCfg cfg{a.out ? 1 : 0, a.yuyv ? 1 : 0, a.mask ? 1 : 0, a.bg_yuyv ? 1 : 0};
   bool ok;

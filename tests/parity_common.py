@@ -443,6 +443,8 @@ def check_fusion_switches(lib, key, n=2):
     defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 0}
     if key == "deeplab":
         defaults = {b"dec_up": 1, b"dw_plane": 1}       # final resize folded into the argmax kernel; whole-plane atrous depthwise
+    defaults[b"epi_static"] = 1                          # compile-time epilogues vs the generic run-time one
+    defaults[b"dec_par"] = 1                             # frame-parallel decision + smoother vs one thread per pixel
     for sw, dflt in defaults.items():
         try:
             assert lib.bsb_set_tuning(sw, 1 - dflt)

@@ -65,6 +65,12 @@ def test_fusion_switches(lib, key):
     pc.check_fusion_switches(lib, key, n=2)
 
 
+def test_decision_window_across_calls(lib):
+    """11 frames in calls of 4 + 4 + 3: the frame-parallel decision kernel rebuilds each state byte from the three latest
+    decisions, the first two frames of a call from the state byte the previous call left (lib/libbackscrub.cc:314-361)."""
+    pc.check_pipeline(lib, "meet_lite", 320, 240, n_frames=11, batch=4)
+
+
 def test_sub_batched_segments(lib):
     pc.check_sub_batch(lib, "deeplab", n=3)
 
