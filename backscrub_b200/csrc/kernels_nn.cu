@@ -1423,17 +1423,25 @@ struct HeadArgs {
 };
 constexpr int HD_TW = 32, HD_TH = 8, HD_SW = HD_TW + 2, HD_SH = HD_TH + 2;
 
-template <int C>
+// FAST: no activation on the 1x1, bias + RELU6 on the depthwise, plain residual add, no activation on the transposed
+// conv — what the three decoder stages of the Meet / MLKit graphs are — fixed at compile time; anything else takes the
+// run-time switches.  A pixel's channels sit C + 4 floats apart in shared memory: with a stride of C (64 / 96 bytes) the
+// 16-byte accesses of neighbouring lanes fell on two / four bank groups (4-way conflicts on every tap load and store).
+template <int C, bool FAST>
 __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
-  __shared__ __align__(16) float ts[HD_SH * HD_SW * C];
+  constexpr int CP = C + 4;
+  __shared__ __align__(16) float ts[HD_SH * HD_SW * CP];
   __shared__ __align__(16) float wps[C * C];
   __shared__ __align__(16) float wds[9 * C];
   __shared__ __align__(16) float wts[2 * 4 * C];
+  __shared__ __align__(16) float bps[C], bds[C], bts[4];
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * HD_TW, y0 = blockIdx.y * HD_TH, b = blockIdx.z;
   for (int i = tid; i < C * C; i += 256) wps[i] = __ldg(a.wp + i);
   for (int i = tid; i < 9 * C; i += 256) wds[i] = __ldg(a.wd + i);
   if (a.wt) for (int i = tid; i < a.oc * 4 * C; i += 256) wts[i] = __ldg(a.wt + i);
+  if (tid < C) { bps[tid] = a.bp ? __ldg(a.bp + tid) : 0.f; bds[tid] = a.bd ? __ldg(a.bd + tid) : 0.f; }
+  if (tid < 4) bts[tid] = (a.wt && tid < a.oc) ? __ldg(a.bt + tid) : 0.f;
   __syncthreads();
   const float* xb = a.x + (size_t)b * a.h * a.w * a.ld_x;
   const float* ab = a.add ? a.add + (size_t)b * a.h * a.w * a.ld_add : nullptr;
@@ -1444,27 +1452,49 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
     const int gy = y0 + sy - 1, gx = x0 + sx - 1;
     if (gy < 0 || gy >= a.h || gx < 0 || gx >= a.w) continue;          // never read: phase B skips out-of-image taps
     const size_t pix = (size_t)gy * a.w + gx;
+    float4 xv[C / 4];
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) xv[k] = __ldg(reinterpret_cast<const float4*>(xb + pix * a.ld_x + 4 * k));
+    if (svb) {
+#pragma unroll
+      for (int k = 0; k < C / 4; ++k) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(svb + 4 * k));
+        xv[k].x = xv[k].x * sc.x; xv[k].y = xv[k].y * sc.y; xv[k].z = xv[k].z * sc.z; xv[k].w = xv[k].w * sc.w;
+      }
+    }
+    if (ab) {
+#pragma unroll
+      for (int k = 0; k < C / 4; ++k) {
+        const float4 ad = __ldg(reinterpret_cast<const float4*>(ab + pix * a.ld_add + 4 * k));
+        xv[k].x = xv[k].x + ad.x; xv[k].y = xv[k].y + ad.y; xv[k].z = xv[k].z + ad.z; xv[k].w = xv[k].w + ad.w;
+      }
+    }
     float acc[C];
 #pragma unroll
     for (int n = 0; n < C; ++n) acc[n] = 0.f;
 #pragma unroll
-    for (int k = 0; k < C; k += 4) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(xb + pix * a.ld_x + k));
-      if (svb) { const float4 sc = __ldg(reinterpret_cast<const float4*>(svb + k)); v.x = v.x * sc.x; v.y = v.y * sc.y; v.z = v.z * sc.z; v.w = v.w * sc.w; }
-      if (ab) { const float4 ad = __ldg(reinterpret_cast<const float4*>(ab + pix * a.ld_add + k)); v.x = v.x + ad.x; v.y = v.y + ad.y; v.z = v.z + ad.z; v.w = v.w + ad.w; }
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < C / 4; ++k) {
+      const float vv[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wps + (k + j) * C + 4 * q);
+          const float4 w4 = *reinterpret_cast<const float4*>(wps + (4 * k + j) * C + 4 * q);
           acc[4 * q] = fmaf(vv[j], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(vv[j], w4.y, acc[4 * q + 1]);
           acc[4 * q + 2] = fmaf(vv[j], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(vv[j], w4.w, acc[4 * q + 3]);
         }
     }
-    float* tp = ts + (size_t)i * C;
+    float* tp = ts + (size_t)i * CP;
 #pragma unroll
-    for (int n = 0; n < C; ++n) tp[n] = bsb_act(bsb_act(acc[n] + (a.bp ? __ldg(a.bp + n) : 0.f), a.actp1), a.actp2);
+    for (int q = 0; q < C / 4; ++q) {
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = acc[4 * q + j] + bps[4 * q + j];
+        r[j] = FAST ? v : bsb_act(bsb_act(v, a.actp1), a.actp2);
+      }
+      *reinterpret_cast<float4*>(tp + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
+    }
   }
   __syncthreads();
   // ---- B: depthwise 3x3 + residual (+ transposed conv) ----
@@ -1482,18 +1512,23 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
     for (int fx = 0; fx < 3; ++fx) {
       const int ix = gx - a.pl + fx;
       if (ix < 0 || ix >= a.w) continue;
-      const float* tp = ts + (size_t)((iy - y0 + 1) * HD_SW + (ix - x0 + 1)) * C;
+      const float* tp = ts + (size_t)((iy - y0 + 1) * HD_SW + (ix - x0 + 1)) * CP;
       const float* wp = wds + (fy * 3 + fx) * C;
 #pragma unroll
-      for (int c = 0; c < C; ++c) u[c] = fmaf(tp[c], wp[c], u[c]);
+      for (int q = 0; q < C / 4; ++q) {
+        const float4 t4 = *reinterpret_cast<const float4*>(tp + 4 * q), w4 = *reinterpret_cast<const float4*>(wp + 4 * q);
+        u[4 * q] = fmaf(t4.x, w4.x, u[4 * q]); u[4 * q + 1] = fmaf(t4.y, w4.y, u[4 * q + 1]);
+        u[4 * q + 2] = fmaf(t4.z, w4.z, u[4 * q + 2]); u[4 * q + 3] = fmaf(t4.w, w4.w, u[4 * q + 3]);
+      }
     }
   }
   {
-    const float* tc = ts + (size_t)((ly + 1) * HD_SW + lx + 1) * C;
+    const float* tc = ts + (size_t)((ly + 1) * HD_SW + lx + 1) * CP;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float d = bsb_act(bsb_act(u[c] + (a.bd ? __ldg(a.bd + c) : 0.f), a.actd1), a.actd2);
-      u[c] = bsb_act(d + tc[c], a.actr);                      // ADD(t, act(dw(t))): the planner folded it as residual of the depthwise step
+      const float v = u[c] + bds[c];
+      const float d = FAST ? bsb_act(v, ACT_RELU6) : bsb_act(bsb_act(v, a.actd1), a.actd2);
+      u[c] = FAST ? d + tc[c] : bsb_act(d + tc[c], a.actr);    // ADD(t, act(dw(t))): the planner folded it as residual of the depthwise step
     }
   }
   if (!a.wt) {
@@ -1513,10 +1548,10 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
         r[fx][o] = 0.f;
         if (o >= a.oc) continue;
         const float* wq = wts + ((o * 2 + fy) * 2 + fx) * C;
-        float acc = __ldg(a.bt + o);
+        float acc = bts[o];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc = fmaf(u[c], wq[c], acc);
-        r[fx][o] = bsb_act(acc, a.actt);
+        r[fx][o] = FAST ? acc : bsb_act(acc, a.actt);
       }
     float* op = a.out + (((size_t)b * oh + 2 * gy + fy) * ow + 2 * gx) * a.oc;
     if (a.oc == 2) *reinterpret_cast<float4*>(op) = make_float4(r[0][0], r[0][1], r[1][0], r[1][1]);
@@ -1536,8 +1571,10 @@ void launch_head(cudaStream_t s, int C, const float* x, int ld_x, const float* s
                  const float* wt, const float* bt, int oc, int actt, float* out, int ld_out, int B, int h, int w, int pt, int pl) {
   HeadArgs a{x, ld_x, sv, add, ld_add, wp, bp, actp1, actp2, wd, bd, actd1, actd2, actr, wt, bt, oc, actt, out, ld_out, B, h, w, pt, pl};
   const dim3 grid((unsigned)ceil_div(w, HD_TW), (unsigned)ceil_div(h, HD_TH), (unsigned)B);
-  if (C == 16) BSB_LAUNCH(k_head<16>, grid, dim3(256), 0, s, a);
-  else BSB_LAUNCH(k_head<24>, grid, dim3(256), 0, s, a);
+  const bool relu6_dw = (actd1 == ACT_NONE && actd2 == ACT_RELU6) || (actd1 == ACT_RELU6 && actd2 == ACT_NONE);
+  const bool fast = actp1 == ACT_NONE && actp2 == ACT_NONE && relu6_dw && actr == ACT_NONE && (!wt || actt == ACT_NONE);
+  if (C == 16) { if (fast) { auto k = k_head<16, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_head<16, false>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+  else { if (fast) { auto k = k_head<24, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_head<24, false>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
   count_launch();
 }
 

@@ -130,7 +130,7 @@ def test_4k_bodypix(lib):                     # BASELINE config 5 geometry (docu
     pc.check_pipeline(lib, "bodypix", 3840, 2160, n_frames=1)
 
 
-@pytest.mark.parametrize("key,W,H,n,batch", [("meet", 1280, 720, 27, 10), ("mlkit", 640, 480, 11, 4), ("deeplab", 640, 480, 7, 3)])
+@pytest.mark.parametrize("key,W,H,n,batch", [("meet_full", 1280, 720, 27, 10), ("mlkit", 640, 480, 11, 4), ("deeplab", 640, 480, 7, 3)])
 def test_decision_window_across_calls(lib, key, W, H, n, batch):
     """Frame-parallel decision + temporal smoother (k_decision_par / k_decision_up_par): batches longer than the eight
     frame lanes of a block, and the state byte carried from call to call (27 frames in calls of 10 + 10 + 7, ...)."""
