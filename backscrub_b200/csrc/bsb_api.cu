@@ -1,4 +1,5 @@
 // backscrub_b200/csrc/bsb_api.cu — extern "C" entry points declared in include/backscrub_b200.h.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -20,6 +21,11 @@ struct bsb_ctx {
   Engine* eng = nullptr;
   bsb::Callbacks cb;
   void* jpeg_state = nullptr;      // nvjpegJpegState_t of this context (MJPG ingest), created on first use
+  // copy / compute overlap inside one host-buffer call (bsb_composite_yuyv): two copy streams and per-chunk events
+  static constexpr int kMaxChunks = 16;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+  bool pipe_ready = false;
 };
 
 namespace {
@@ -141,6 +147,11 @@ bsb_ctx* bsb_maskgen_new(const char* modelname, size_t threads, size_t width, si
 void bsb_maskgen_delete(bsb_ctx* ctx) {
   if (!ctx) return;
   bsb_jpeg_release(ctx);
+  if (ctx->pipe_ready && ctx->eng && cudaSetDevice(ctx->eng->device()) == cudaSuccess) {
+    for (int i = 0; i < bsb_ctx::kMaxChunks; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  }
   delete ctx->eng;
   delete ctx;
 }
@@ -283,6 +294,55 @@ int bsb_composite_yuyv(bsb_ctx* ctx, int n_frames, const uint8_t* yuyv_frames, s
   if (!yuyv_frames || in_stride < npix * 2) { report(cbp, "error: invalid frame"); return 0; }
   if (out_yuyv && (e->out_w() & 1)) { report(cbp, "error: YUYV output needs an even width"); return 0; }
   API_CUDA(cudaSetDevice(e->device()));
+  // ---- chunked, overlapped form: H2D of chunk c+1, the graph of chunk c and D2H of chunk c-1 run at the same time on
+  //      three streams (the temporal smoother's state simply carries from chunk to chunk on the compute stream).  A
+  //      single-stream caller no longer pays copy + compute + copy back to back (app/deepseg.cc does exactly that:
+  //      cap.read -> CalcMask -> write); results are identical, only the schedule changes ----
+  const int chunk = bsb::tuning().e2e_chunk;
+  if (chunk > 0 && n_frames >= 2 * chunk && (n_frames + chunk - 1) / chunk <= bsb_ctx::kMaxChunks) {
+    if (!ctx->pipe_ready) {
+      API_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+      API_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+      for (int i = 0; i < bsb_ctx::kMaxChunks; ++i) {
+        API_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        API_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      }
+      ctx->pipe_ready = true;
+    }
+    const int nchunks = (n_frames + chunk - 1) / chunk;
+    for (int c = 0; c < nchunks; ++c) {
+      const int b0 = c * chunk, nb = std::min(chunk, n_frames - b0);
+      if (in_stride == npix * 2) API_CUDA(cudaMemcpyAsync(e->d_yuyv_in() + (size_t)b0 * npix * 2, yuyv_frames + (size_t)b0 * in_stride, npix * 2 * nb, cudaMemcpyHostToDevice, ctx->s_in));
+      else for (int b = b0; b < b0 + nb; ++b)
+        API_CUDA(cudaMemcpyAsync(e->d_yuyv_in() + (size_t)b * npix * 2, yuyv_frames + (size_t)b * in_stride, npix * 2, cudaMemcpyHostToDevice, ctx->s_in));
+      API_CUDA(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    }
+    std::string perr;
+    for (int c = 0; c < nchunks; ++c) {
+      const int b0 = c * chunk, nb = std::min(chunk, n_frames - b0);
+      API_CUDA(cudaStreamWaitEvent(e->stream(), ctx->ev_in[c], 0));
+      if (!e->run_yuyv(nb, e->d_yuyv_in() + (size_t)b0 * npix * 2, out ? e->d_out() + (size_t)b0 * obytes : nullptr, obytes, out_yuyv ? e->d_yuyv() + (size_t)b0 * opix * 2 : nullptr, opix * 2,
+                       out_mask ? e->d_mask() + (size_t)b0 * npix : nullptr, npix, &perr)) {
+        cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(e->stream()); cudaStreamSynchronize(ctx->s_out);
+        report(cbp, "error: failed to process video frame: " + perr); return 0;
+      }
+      API_CUDA(cudaEventRecord(ctx->ev_done[c], e->stream()));
+      API_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
+      if (out) for (int b = b0; b < b0 + nb; ++b)
+        API_CUDA(cudaMemcpyAsync(out + (size_t)b * out_stride, e->d_out() + (size_t)b * obytes, obytes, cudaMemcpyDeviceToHost, ctx->s_out));
+      if (out_yuyv) {
+        if (yuyv_stride == opix * 2) API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b0 * yuyv_stride, e->d_yuyv() + (size_t)b0 * opix * 2, opix * 2 * nb, cudaMemcpyDeviceToHost, ctx->s_out));
+        else for (int b = b0; b < b0 + nb; ++b)
+          API_CUDA(cudaMemcpyAsync(out_yuyv + (size_t)b * yuyv_stride, e->d_yuyv() + (size_t)b * opix * 2, opix * 2, cudaMemcpyDeviceToHost, ctx->s_out));
+      }
+      if (out_mask) for (int b = b0; b < b0 + nb; ++b)
+        API_CUDA(cudaMemcpyAsync(out_mask + (size_t)b * mask_stride, e->d_mask() + (size_t)b * npix, npix, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    API_CUDA(cudaStreamSynchronize(ctx->s_out));
+    API_CUDA(cudaStreamSynchronize(e->stream()));
+    API_CUDA(cudaGetLastError());
+    return 1;
+  }
   if (in_stride == npix * 2) API_CUDA(cudaMemcpyAsync(e->d_yuyv_in(), yuyv_frames, npix * 2 * n_frames, cudaMemcpyHostToDevice, e->stream()));
   else for (int b = 0; b < n_frames; ++b)
     API_CUDA(cudaMemcpyAsync(e->d_yuyv_in() + b * npix * 2, yuyv_frames + (size_t)b * in_stride, npix * 2, cudaMemcpyHostToDevice, e->stream()));
@@ -658,6 +718,7 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "dw_plane") t.dw_plane = value;
   else if (n == "dec_up") t.dec_up = value;
   else if (n == "dec_par") t.dec_par = value;
+  else if (n == "e2e_chunk") t.e2e_chunk = value;
   else if (n == "epi_static") t.epi_static = value;
   else if (n == "dw_px") t.dw_px = value;
   else if (n == "post_tma") t.post_tma = value;

@@ -258,6 +258,7 @@ struct Tuning {
   int dw_px = 1;           // small depthwise layers: row-batched loads (k_depthwise_px) instead of the generic tap loop
   int dec_up = 1;          // DeepLab: final 33 -> 257 resize folded into the argmax decision kernel
   int epi_static = 1;      // compile-time epilogues (bias preloaded, activation fixed) for the common combinations; 0 = the generic run-time epilogue everywhere
+  int e2e_chunk = 8;       // bsb_composite_yuyv (host buffers): frames per chunk of the copy / compute overlap (0 = one serial H2D -> graph -> D2H)
   int dec_par = 1;         // decision + temporal smoother: frames in parallel (a block = 32 pixels x all frames) instead of one thread per pixel
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it

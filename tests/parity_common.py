@@ -124,6 +124,36 @@ def check_yuyv_ingest(lib, key="meet_lite", W=640, H=480, n=2):
     g.close()
 
 
+def check_overlapped_host_call(lib, key="meet_lite", W=640, H=480, n=19, oracle_frames=(0, 1, 8, 9, 18)):
+    """bsb_composite_yuyv with enough frames to take the chunked, copy/compute-overlapped schedule (chunks of 8 + 8 + 3 on
+    three streams) must return exactly what the serial schedule (e2e_chunk = 0) returns — the temporal smoother's state
+    carries across the chunk borders — over two consecutive calls, and both must equal the oracle."""
+    bg = synth.background()
+    bgr = np.stack([synth.frame(W, H, t=t) for t in range(n)])
+    yuyv_in = np.stack([po.convert_rgb_to_yuyv(f) for f in bgr])
+    res = {}
+    try:
+        for chunk in (0, 8):
+            assert lib.bsb_set_tuning(b"e2e_chunk", chunk)
+            g = api.MaskGen(lib, model_path(key), W, H, max_batch=n)
+            g.set_background(bg)
+            first = g.composite_yuyv(yuyv_in)
+            second = g.composite_yuyv(yuyv_in[::-1].copy())        # state carried from the first call
+            res[chunk] = (first, second)
+            g.close()
+    finally:
+        lib.bsb_set_tuning(b"e2e_chunk", 8)
+    for call in range(2):
+        for a, b, what in zip(res[0][call], res[8][call], ("composite", "YUYV", "mask")):
+            assert np.array_equal(a, b), f"{key}: overlapped schedule changes the {what} (call {call})"
+    o = po.MaskGen(model_path(key), W, H)
+    out, yuyv, mask = res[8][0]
+    for b in range(n):
+        ro, ry, rm = o.composite(po.yuyv_to_bgr(yuyv_in[b]), bg)
+        if b in oracle_frames:
+            assert np.array_equal(mask[b], rm) and np.array_equal(out[b], ro) and np.array_equal(yuyv[b], ry), b
+
+
 def check_mask_only_and_callbacks(lib, key="mlkit", W=640, H=480):
     """bs_maskgen_process semantics: callbacks fire in order once per call; mask aliases
     context storage; consecutive calls advance the IIR like the oracle."""

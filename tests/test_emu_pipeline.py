@@ -152,3 +152,8 @@ def test_depthwise_plane_and_strips():
                              capture_output=True, text=True, timeout=900)
         assert out.returncode == 0 and "plane ok" in out.stdout, out.stderr[-2000:]
         assert ("k_depthwise_plane" in out.stderr) == (v == "1")
+
+
+def test_overlapped_host_call_on_the_emulator(lib):
+    """the chunked schedule of bsb_composite_yuyv (the emulator runs its three streams in program order)"""
+    pc.check_overlapped_host_call(lib, "meet_lite", 320, 240, n=17, oracle_frames=(0, 8, 16))

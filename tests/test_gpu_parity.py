@@ -130,6 +130,10 @@ def test_4k_bodypix(lib):                     # BASELINE config 5 geometry (docu
     pc.check_pipeline(lib, "bodypix", 3840, 2160, n_frames=1)
 
 
+def test_overlapped_host_call(lib):
+    pc.check_overlapped_host_call(lib, "meet_full", 1280, 720, n=19)
+
+
 @pytest.mark.parametrize("key,W,H,n,batch", [("meet_full", 1280, 720, 27, 10), ("mlkit", 640, 480, 11, 4), ("deeplab", 640, 480, 7, 3)])
 def test_decision_window_across_calls(lib, key, W, H, n, batch):
     """Frame-parallel decision + temporal smoother (k_decision_par / k_decision_up_par): batches longer than the eight
