@@ -718,6 +718,9 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "dw_plane") t.dw_plane = value;
   else if (n == "dec_up") t.dec_up = value;
   else if (n == "dec_par") t.dec_par = value;
+  else if (n == "stem_x2") t.stem_x2 = value;
+  else if (n == "dw_plane_cs") t.dw_plane_cs = value;
+  else if (n == "up_staged") t.up_staged = value;
   else if (n == "e2e_chunk") t.e2e_chunk = value;
   else if (n == "epi_static") t.epi_static = value;
   else if (n == "dw_px") t.dw_px = value;

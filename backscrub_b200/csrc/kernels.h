@@ -258,9 +258,12 @@ struct Tuning {
   int dw_px = 1;           // small depthwise layers: row-batched loads (k_depthwise_px) instead of the generic tap loop
   int dec_up = 1;          // DeepLab: final 33 -> 257 resize folded into the argmax decision kernel
   int epi_static = 1;      // compile-time epilogues (bias preloaded, activation fixed) for the common combinations; 0 = the generic run-time epilogue everywhere
-  int e2e_chunk = 8;       // bsb_composite_yuyv (host buffers): frames per chunk of the copy / compute overlap (0 = one serial H2D -> graph -> D2H)
+  int up_staged = 1;       // resize + 1x1: interpolated operand rows built once per pixel in shared memory when a pixel is shared by several threads
+  int stem_x2 = 1;         // stem conv: two adjacent output pixels per thread (3x3 stride 2, even width), shared weight loads
+  int e2e_chunk = 16;      // bsb_composite_yuyv (host buffers): frames per chunk of the copy / compute overlap (0 = one serial H2D -> graph -> D2H)
   int dec_par = 1;         // decision + temporal smoother: frames in parallel (a block = 32 pixels x all frames) instead of one thread per pixel
   int dw_plane = 1;        // whole-plane depthwise kernel for the 33x33 atrous layers
+  int dw_plane_cs = 16;    // ... channels per block (16: 70 KB of shared memory per 33x33 plane, 3 blocks per SM; 8: 35 KB, 6 blocks)
   int post_tma = 1;        // TMA-staged post kernel where the geometry allows it
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel
   int tc_min_k = 16;       // smallest input depth of a 1x1 conv that goes to the tensor cores (with BSB_FLAG_TENSOR_CORES)

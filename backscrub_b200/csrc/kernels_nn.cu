@@ -297,6 +297,84 @@ __global__ void __launch_bounds__(128) k_stem_u8(StemArgs a) {
   }
 }
 
+// Two horizontally adjacent output pixels per thread (3x3, stride 2, even output width, packed 16-channel output — the
+// stems of the Meet / MLKit graphs).  The one-pixel kernel above issues 108 LDS.128 of weights and 27 byte loads behind
+// bounds tests per 432 fmaf; here the weight vectors are shared by the two pixels (108 LDS.128 per 864 fmaf), the 3 x 5
+// input window (one shared column) is fetched up front with predicated loads, all in flight together, and out-of-image
+// taps enter as +0 instead of being skipped: fmaf(+0, w, acc) leaves an accumulator that started at +0 unchanged bit
+// for bit, so each output still sees exactly the oracle's (fy, fx, c) chain.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_stem_u8_x2(StemArgs a) {
+  __shared__ __align__(16) float ws[27 * 16];           // [3][3][3][16]
+  __shared__ __align__(16) float bs[16];
+  __shared__ float4 stage[8 * 129];
+  for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) ws[i] = __ldg(a.w + i);
+  if (threadIdx.x < 16) bs[threadIdx.x] = a.e.bias ? __ldg(a.e.bias + threadIdx.x) : 0.f;
+  __syncthreads();
+  const long total = (long)a.B * a.oh * a.ow;           // even: ow is even
+  const long blk0 = (long)blockIdx.x * 256;
+  const long pix = blk0 + 2 * threadIdx.x;              // this thread's pixels: pix, pix + 1 (same row)
+  const bool valid = pix < total;
+  float acc[2][16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) { acc[0][o] = 0.f; acc[1][o] = 0.f; }
+  if (valid) {
+    const int ox = (int)(pix % a.ow), oy = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
+    const uint8_t* inb = a.in + (size_t)b * a.ih * a.iw * 3;
+    const int iy0 = oy * 2 - a.pt, ix0 = ox * 2 - a.pl;
+    float v[3][5][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = iy0 + r;
+      const bool vy = iy >= 0 && iy < a.ih;
+#pragma unroll
+      for (int c5 = 0; c5 < 5; ++c5) {
+        const int ix = ix0 + c5;
+        const bool ok = vy && ix >= 0 && ix < a.iw;
+        const uint8_t* ip = inb + ((size_t)(ok ? iy : 0) * a.iw + (ok ? ix : 0)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[r][c5][c] = ok ? fmaf((float)ip[c], a.scale, a.offset) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy)
+#pragma unroll
+      for (int fx = 0; fx < 3; ++fx)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* wp = ws + ((fy * 3 + fx) * 3 + c) * 16;
+          const float v0 = v[fy][fx][c], v1 = v[fy][fx + 2][c];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + q * 4);
+            acc[0][4 * q] = fmaf(v0, w4.x, acc[0][4 * q]); acc[0][4 * q + 1] = fmaf(v0, w4.y, acc[0][4 * q + 1]);
+            acc[0][4 * q + 2] = fmaf(v0, w4.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(v0, w4.w, acc[0][4 * q + 3]);
+            acc[1][4 * q] = fmaf(v1, w4.x, acc[1][4 * q]); acc[1][4 * q + 1] = fmaf(v1, w4.y, acc[1][4 * q + 1]);
+            acc[1][4 * q + 2] = fmaf(v1, w4.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(v1, w4.w, acc[1][4 * q + 3]);
+          }
+        }
+  }
+  // the block's 256 pixels x 16 channels are 16 KB of contiguous output: transpose through shared memory so that a warp
+  // writes 512 contiguous bytes per store instruction
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      stage[(p * 4 + q) * 129 + threadIdx.x] =
+          valid ? make_float4(epilogue_m<MODE>(acc[p][4 * q], MODE >= 0 ? bs[4 * q] : 0.f, 4 * q, (size_t)(pix + p), a.e),
+                              epilogue_m<MODE>(acc[p][4 * q + 1], MODE >= 0 ? bs[4 * q + 1] : 0.f, 4 * q + 1, (size_t)(pix + p), a.e),
+                              epilogue_m<MODE>(acc[p][4 * q + 2], MODE >= 0 ? bs[4 * q + 2] : 0.f, 4 * q + 2, (size_t)(pix + p), a.e),
+                              epilogue_m<MODE>(acc[p][4 * q + 3], MODE >= 0 ? bs[4 * q + 3] : 0.f, 4 * q + 3, (size_t)(pix + p), a.e))
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(a.out + (size_t)blk0 * 16);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = it * 128 + threadIdx.x;                 // float4 index inside the block's output: thread j / 8, its k-th vector j % 8
+    if (blk0 + (j >> 2) < total) dst[j] = stage[(j & 7) * 129 + (j >> 3)];
+  }
+}
+
 void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw, float scale, float offset,
                     const float* w_t, int kh, int kw, int stride_h, int stride_w, int pad_t, int pad_l,
                     float* out, int oh, int ow, int ld_out, const Epilogue& e,
@@ -304,6 +382,15 @@ void launch_stem_u8(cudaStream_t s, int B, const uint8_t* in_u8, int ih, int iw,
   StemArgs a{in_u8, w_t, out, B, ih, iw, kh, kw, stride_h, stride_w, pad_t, pad_l, oh, ow, ld_out, scale, offset, to_dev(e),
              w2_kn, out2, ld_out2, e2 ? to_dev(*e2) : EpiDev{nullptr, nullptr, 0, 0, 0, 0}};
   const long total = (long)B * oh * ow;
+  if (tuning().stem_x2 && !w2_kn && kh == 3 && kw == 3 && stride_h == 2 && stride_w == 2 && (ow & 1) == 0 && ld_out == 16 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    epi_dispatch(epi_mode(e), [&](auto tag) {
+      auto k = k_stem_u8_x2<decltype(tag)::value>;
+      BSB_LAUNCH(k, dim3((unsigned)((total + 255) / 256)), dim3(128), 0, s, a);
+    });
+    count_launch();
+    return;
+  }
   epi_dispatch(epi_mode(e), [&](auto tag) {
     auto k = k_stem_u8<decltype(tag)::value>;
     BSB_LAUNCH(k, dim3((unsigned)((total + 127) / 128)), dim3(128), sizeof(float) * ((size_t)kh * kw * 48 + 256 + 16), s, a);
@@ -808,13 +895,14 @@ __global__ void __launch_bounds__(128) k_depthwise_strip(DWArgs a) {
 // registers, the four accumulation chains are independent (the first version — one pixel per thread, 180 instructions per
 // output with a 9-deep dependent LDS -> FFMA chain — ran at 1 TB/s of L2 traffic, profiles/r2_launch_shares_deeplab_bodypix.txt).
 // Tap order and the skipping of out-of-image taps are those of the oracle.
-constexpr int DWP_CS = 16, DWP_R = 4;
+constexpr int DWP_R = 4;     // (channels per block: template parameter DWP_CS, 16 or 8 — 70 KB or 35 KB of shared memory for a 33x33 plane)
 // RELU6_ONLY: the epilogue is bias + RELU6 and nothing else (every atrous layer of DeepLab and BodyPix): the four bias
 // values of the thread's channels are loaded once and the activation is a compile-time constant, where the generic
 // epilogue re-loads the bias and walks two activation switches and a residual test per value (25 % of the kernel's
 // instructions and 40 % of its stall samples, profiles/r2_ncu_k_depthwise_plane.txt).
-template <bool RELU6_ONLY>
+template <bool RELU6_ONLY, int DWP_CS>
 __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
+  constexpr int QN = DWP_CS / 4;                               // float4 quads per pixel of the slice
   BSB_DYN_SMEM(smem_raw);
   float* plane = reinterpret_cast<float*>(smem_raw);           // [ih*iw][16]
   float* ws = plane + (size_t)a.ih * a.iw * DWP_CS;             // [9][16]
@@ -825,7 +913,7 @@ __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   // The first version went through registers one load at a time and ran at the latency of a single outstanding load per
   // thread: 1 TB/s of L2 traffic for a kernel that does nothing but move 2 x 67 MB (run r2u).
   for (int i = threadIdx.x; i < hw * (DWP_CS / 4); i += blockDim.x) {
-    const int p = i >> 2, q = i & 3;
+    const int p = i / QN, q = i % QN;
 #if defined(BSB_EMU)
     *reinterpret_cast<float4*>(plane + p * DWP_CS + 4 * q) = __ldg(reinterpret_cast<const float4*>(inb + (size_t)p * a.ld_in + 4 * q));
 #else
@@ -839,14 +927,14 @@ __global__ void __launch_bounds__(256) k_depthwise_plane(DWArgs a) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
   __syncthreads();
-  const int q = threadIdx.x & 3, ch = c0 + 4 * q;
+  const int q = threadIdx.x % QN, ch = c0 + 4 * q;
   float4 w[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4*>(ws + t * DWP_CS + 4 * q);
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (RELU6_ONLY && a.e.bias) bias4 = make_float4(__ldg(a.e.bias + ch), __ldg(a.e.bias + ch + 1), __ldg(a.e.bias + ch + 2), __ldg(a.e.bias + ch + 3));
   const int row_groups = (a.oh + DWP_R - 1) / DWP_R;
-  for (int p = threadIdx.x >> 2; p < row_groups * a.ow; p += blockDim.x >> 2) {
+  for (int p = threadIdx.x / QN; p < row_groups * a.ow; p += blockDim.x / QN) {
     const int rg = p / a.ow, ox = p - rg * a.ow, oy0 = rg * DWP_R;
     float4 acc[DWP_R];
 #pragma unroll
@@ -889,14 +977,23 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
                       int pad_t, int pad_l, float* out, int oh, int ow, int ld_out, const Epilogue& e) {
   DWArgs a{in, w, out, B, ih, iw, c, ld_in, kh, kw, stride_h, stride_w, dil_h, dil_w, pad_t, pad_l, oh, ow, ld_out, to_dev(e)};
   const bool vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0);
-  const size_t plane_smem = ((size_t)ih * iw + 9) * DWP_CS * sizeof(float);
-  if (tuning().dw_plane && (dil_h > 1 || dil_w > 1) && (c % DWP_CS == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && kh == 3 && kw == 3 &&
+  const int cs = tuning().dw_plane_cs == 8 ? 8 : 16;
+  const size_t plane_smem = ((size_t)ih * iw + 9) * cs * sizeof(float);
+  if (tuning().dw_plane && (dil_h > 1 || dil_w > 1) && (c % cs == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && kh == 3 && kw == 3 &&
       stride_h == 1 && stride_w == 1 && oh == ih && ow == iw && plane_smem <= 100 * 1024 &&
-      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<true>), plane_smem) &&
-      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<false>), plane_smem)) {
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<true, 16>), plane_smem) &&
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<false, 16>), plane_smem) &&
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<true, 8>), plane_smem) &&
+      ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<false, 8>), plane_smem)) {
     const bool relu6_only = !e.residual && ((e.act1 == ACT_RELU6 && e.act2 == ACT_NONE) || (e.act1 == ACT_NONE && e.act2 == ACT_RELU6));
-    if (relu6_only) BSB_LAUNCH(k_depthwise_plane<true>, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
-    else BSB_LAUNCH(k_depthwise_plane<false>, dim3((unsigned)(c / DWP_CS), (unsigned)B), dim3(256), plane_smem, s, a);
+    const dim3 pgrid((unsigned)(c / cs), (unsigned)B);
+    if (cs == 16) {
+      if (relu6_only) { auto k = k_depthwise_plane<true, 16>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
+      else { auto k = k_depthwise_plane<false, 16>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
+    } else {
+      if (relu6_only) { auto k = k_depthwise_plane<true, 8>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
+      else { auto k = k_depthwise_plane<false, 8>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
+    }
     count_launch();
     return;
   }
@@ -1359,6 +1456,90 @@ __global__ void __launch_bounds__(128) k_upsample_pw(UpPwArgs a, int groups) {
   }
 }
 
+// Staged form for pixels that are shared by several threads (groups > 1: few output quads per thread so that small
+// layers still fill the GPU): the kernel above recomputes the interpolated operand — 4 loads and 44 flops per 4 input
+// channels — in every one of the pixel's threads, 6 times over for the 128 -> 24 layer of the Meet decoder, where it was
+// 2/3 of the instructions and the layer ran at 0.8 TB/s of L2 traffic (profiles/r2_launch_shares_meet720_b256_final.txt).
+// Here a block owns PB = 128 / groups pixels: its threads first build the interpolated rows once ([PB][K + 4] floats in
+// shared memory; thread (pixel, g) takes the float4 chunks g, g + groups, ...), then run the k-ascending fmaf chains from
+// there.  The interpolated value is formed by the same expression, so the bits are those of the unstaged kernel.
+template <int NQ, int MODE>
+__global__ void __launch_bounds__(128) k_upsample_pw_staged(UpPwArgs a, int groups) {
+  BSB_DYN_SMEM(smem_raw);
+  float* Ws = reinterpret_cast<float*>(smem_raw);            // [K][n4]
+  float* As = Ws + (size_t)a.K * a.n4;                        // [PB][K + 4]
+  const int lda = a.K + 4;
+  for (int i = threadIdx.x * 4; i < a.K * a.n4; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(Ws + i) = __ldg(reinterpret_cast<const float4*>(a.w + i));
+  const int PB = 128 / groups;
+  const int lp = threadIdx.x / groups, grp = threadIdx.x - lp * groups;
+  const long pix = (long)blockIdx.x * PB + lp;
+  const bool valid = lp < PB && pix < (long)a.B * a.oh * a.ow;
+  if (valid) {
+    const int x = (int)(pix % a.ow), y = (int)((pix / a.ow) % a.oh), b = (int)(pix / ((long)a.ow * a.oh));
+    float fy, fx; int y0, y1, x0, x1;
+    interp((float)y, a.hs, a.half_pixel, a.ih, &fy, &y0, &y1);
+    interp((float)x, a.ws, a.half_pixel, a.iw, &fx, &x0, &x1);
+    const float dy = fy - (float)y0, dx = fx - (float)x0;
+    const float wy0 = 1.f - dy, wx0 = 1.f - dx;
+    const float* inb = a.in + (size_t)b * a.ih * a.iw * a.ld_in;
+    const float* p00 = inb + ((size_t)y0 * a.iw + x0) * a.ld_in;
+    const float* p10 = inb + ((size_t)y1 * a.iw + x0) * a.ld_in;
+    const float* p01 = inb + ((size_t)y0 * a.iw + x1) * a.ld_in;
+    const float* p11 = inb + ((size_t)y1 * a.iw + x1) * a.ld_in;
+    float* arow = As + (size_t)lp * lda;
+#pragma unroll 2
+    for (int k = 4 * grp; k < a.K; k += 4 * groups) {
+      const float4 v00 = __ldg(reinterpret_cast<const float4*>(p00 + k)), v10 = __ldg(reinterpret_cast<const float4*>(p10 + k));
+      const float4 v01 = __ldg(reinterpret_cast<const float4*>(p01 + k)), v11 = __ldg(reinterpret_cast<const float4*>(p11 + k));
+      float4 r;
+      r.x = ((v00.x * wy0 * wx0 + v10.x * dy * wx0) + v01.x * wy0 * dx) + v11.x * dy * dx;
+      r.y = ((v00.y * wy0 * wx0 + v10.y * dy * wx0) + v01.y * wy0 * dx) + v11.y * dy * dx;
+      r.z = ((v00.z * wy0 * wx0 + v10.z * dy * wx0) + v01.z * wy0 * dx) + v11.z * dy * dx;
+      r.w = ((v00.w * wy0 * wx0 + v10.w * dy * wx0) + v01.w * wy0 * dx) + v11.w * dy * dx;
+      *reinterpret_cast<float4*>(arow + k) = r;
+    }
+  }
+  __syncthreads();
+  if (!valid) return;
+  const int nbase = grp * NQ * 4;
+  float acc[NQ * 4];
+#pragma unroll
+  for (int n = 0; n < NQ * 4; ++n) acc[n] = 0.f;
+  float4 bias4[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) bias4[q] = epilogue_bias4<MODE>(a.e, nbase + 4 * q, a.N);
+  const float* arow = As + (size_t)lp * lda;
+#pragma unroll 4
+  for (int k = 0; k < a.K; k += 4) {
+    const float4 r4 = *reinterpret_cast<const float4*>(arow + k);
+    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* wr = Ws + (size_t)(k + j) * a.n4 + nbase;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * q);
+        acc[4 * q] = fmaf(r[j], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(r[j], w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(r[j], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(r[j], w4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  float* op = a.out + (size_t)pix * a.ld_out;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int n0 = nbase + 4 * q;
+    const float bj[4] = {bias4[q].x, bias4[q].y, bias4[q].z, bias4[q].w};
+    if (n0 + 3 < a.N) {
+      *reinterpret_cast<float4*>(op + n0) = make_float4(epilogue_m<MODE>(acc[4 * q], bj[0], n0, (size_t)pix, a.e), epilogue_m<MODE>(acc[4 * q + 1], bj[1], n0 + 1, (size_t)pix, a.e),
+                                                        epilogue_m<MODE>(acc[4 * q + 2], bj[2], n0 + 2, (size_t)pix, a.e), epilogue_m<MODE>(acc[4 * q + 3], bj[3], n0 + 3, (size_t)pix, a.e));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (n0 + j < a.N) op[n0 + j] = epilogue_m<MODE>(acc[4 * q + j], bj[j], n0 + j, (size_t)pix, a.e);
+    }
+  }
+}
+
 bool upsample_pw_supported(int K, int N, int n4, int ld_in, int ld_out) {
   return K % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && n4 % 4 == 0 && n4 >= 4 && n4 <= 24 && N <= n4 && (size_t)K * n4 * 4 <= 48 * 1024;
 }
@@ -1380,6 +1561,18 @@ void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, 
   const dim3 grid((unsigned)((pixels * groups + 127) / 128)), block(128);
   // (the five graphs only ever put a plain bias behind this op: one specialised instance per NQ, generic otherwise)
   const bool plain = epi_mode(e) == 0;
+  const size_t smem_staged = smem + sizeof(float) * (size_t)(128 / groups) * (K + 4);
+  if (tuning().up_staged && groups > 1 && nq <= 3 && smem_staged <= 48 * 1024) {
+    const int PB = 128 / groups;
+    const dim3 sgrid((unsigned)((pixels + PB - 1) / PB));
+    switch (nq) {
+      case 1: if (plain) { auto k = k_upsample_pw_staged<1, 0>; BSB_LAUNCH(k, sgrid, block, smem_staged, s, a, groups); } else { auto k = k_upsample_pw_staged<1, -1>; BSB_LAUNCH(k, sgrid, block, smem_staged, s, a, groups); } break;
+      case 2: if (plain) { auto k = k_upsample_pw_staged<2, 0>; BSB_LAUNCH(k, sgrid, block, smem_staged, s, a, groups); } else { auto k = k_upsample_pw_staged<2, -1>; BSB_LAUNCH(k, sgrid, block, smem_staged, s, a, groups); } break;
+      default: if (plain) { auto k = k_upsample_pw_staged<3, 0>; BSB_LAUNCH(k, sgrid, block, smem_staged, s, a, groups); } else { auto k = k_upsample_pw_staged<3, -1>; BSB_LAUNCH(k, sgrid, block, smem_staged, s, a, groups); } break;
+    }
+    count_launch();
+    return;
+  }
   switch (nq) {
     case 1: if (plain) { auto k = k_upsample_pw<1, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<1, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
     case 2: if (plain) { auto k = k_upsample_pw<2, 0>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } else { auto k = k_upsample_pw<2, -1>; BSB_LAUNCH(k, grid, block, smem, s, a, groups); } break;
@@ -1427,8 +1620,12 @@ constexpr int HD_TW = 32, HD_TH = 8, HD_SW = HD_TW + 2, HD_SH = HD_TH + 2;
 // conv — what the three decoder stages of the Meet / MLKit graphs are — fixed at compile time; anything else takes the
 // run-time switches.  A pixel's channels sit C + 4 floats apart in shared memory: with a stride of C (64 / 96 bytes) the
 // 16-byte accesses of neighbouring lanes fell on two / four bank groups (4-way conflicts on every tap load and store).
-template <int C, bool FAST>
+// CFG 1: Meet (1x1 none, depthwise RELU6, transposed conv none); CFG 2: MLKit (RELU, RELU, LOGISTIC); CFG 0: run time.
+template <int CFG> struct HeadCfg { static constexpr int P = CFG == 1 ? ACT_NONE : ACT_RELU, D = CFG == 1 ? ACT_RELU6 : ACT_RELU, T = CFG == 1 ? ACT_NONE : ACT_LOGISTIC; };
+template <int C, int CFG>
 __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+  constexpr bool FAST = CFG != 0;
+  using HC = HeadCfg<CFG>;
   constexpr int CP = C + 4;
   __shared__ __align__(16) float ts[HD_SH * HD_SW * CP];
   __shared__ __align__(16) float wps[C * C];
@@ -1491,7 +1688,7 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float v = acc[4 * q + j] + bps[4 * q + j];
-        r[j] = FAST ? v : bsb_act(bsb_act(v, a.actp1), a.actp2);
+        r[j] = FAST ? bsb_act(v, HC::P) : bsb_act(bsb_act(v, a.actp1), a.actp2);
       }
       *reinterpret_cast<float4*>(tp + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
     }
@@ -1527,7 +1724,7 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float v = u[c] + bds[c];
-      const float d = FAST ? bsb_act(v, ACT_RELU6) : bsb_act(bsb_act(v, a.actd1), a.actd2);
+      const float d = FAST ? bsb_act(v, HC::D) : bsb_act(bsb_act(v, a.actd1), a.actd2);
       u[c] = FAST ? d + tc[c] : bsb_act(d + tc[c], a.actr);    // ADD(t, act(dw(t))): the planner folded it as residual of the depthwise step
     }
   }
@@ -1551,7 +1748,7 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
         float acc = bts[o];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc = fmaf(u[c], wq[c], acc);
-        r[fx][o] = FAST ? acc : bsb_act(acc, a.actt);
+        r[fx][o] = FAST ? bsb_act(acc, HC::T) : bsb_act(acc, a.actt);
       }
     float* op = a.out + (((size_t)b * oh + 2 * gy + fy) * ow + 2 * gx) * a.oc;
     if (a.oc == 2) *reinterpret_cast<float4*>(op) = make_float4(r[0][0], r[0][1], r[1][0], r[1][1]);
@@ -1571,10 +1768,19 @@ void launch_head(cudaStream_t s, int C, const float* x, int ld_x, const float* s
                  const float* wt, const float* bt, int oc, int actt, float* out, int ld_out, int B, int h, int w, int pt, int pl) {
   HeadArgs a{x, ld_x, sv, add, ld_add, wp, bp, actp1, actp2, wd, bd, actd1, actd2, actr, wt, bt, oc, actt, out, ld_out, B, h, w, pt, pl};
   const dim3 grid((unsigned)ceil_div(w, HD_TW), (unsigned)ceil_div(h, HD_TH), (unsigned)B);
-  const bool relu6_dw = (actd1 == ACT_NONE && actd2 == ACT_RELU6) || (actd1 == ACT_RELU6 && actd2 == ACT_NONE);
-  const bool fast = actp1 == ACT_NONE && actp2 == ACT_NONE && relu6_dw && actr == ACT_NONE && (!wt || actt == ACT_NONE);
-  if (C == 16) { if (fast) { auto k = k_head<16, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_head<16, false>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
-  else { if (fast) { auto k = k_head<24, true>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } else { auto k = k_head<24, false>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); } }
+  auto one = [](int a1, int a2, int want) { return (a1 == ACT_NONE && a2 == want) || (a1 == want && a2 == ACT_NONE); };
+  int cfg = 0;
+  if (actr == ACT_NONE && one(actp1, actp2, ACT_NONE) && one(actd1, actd2, ACT_RELU6) && (!wt || actt == ACT_NONE)) cfg = 1;
+  else if (actr == ACT_NONE && one(actp1, actp2, ACT_RELU) && one(actd1, actd2, ACT_RELU) && (!wt || actt == ACT_LOGISTIC)) cfg = 2;
+  if (C == 16) {
+    if (cfg == 1) { auto k = k_head<16, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else if (cfg == 2) { auto k = k_head<16, 2>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else { auto k = k_head<16, 0>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+  } else {
+    if (cfg == 1) { auto k = k_head<24, 1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else if (cfg == 2) { auto k = k_head<24, 2>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+    else { auto k = k_head<24, 0>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+  }
   count_launch();
 }
 

@@ -142,7 +142,7 @@ def check_overlapped_host_call(lib, key="meet_lite", W=640, H=480, n=19, oracle_
             res[chunk] = (first, second)
             g.close()
     finally:
-        lib.bsb_set_tuning(b"e2e_chunk", 8)
+        lib.bsb_set_tuning(b"e2e_chunk", 16)
     for call in range(2):
         for a, b, what in zip(res[0][call], res[8][call], ("composite", "YUYV", "mask")):
             assert np.array_equal(a, b), f"{key}: overlapped schedule changes the {what} (call {call})"
@@ -473,6 +473,9 @@ def check_fusion_switches(lib, key, n=2):
     defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 0}
     if key == "deeplab":
         defaults = {b"dec_up": 1, b"dw_plane": 1}       # final resize folded into the argmax kernel; whole-plane atrous depthwise
+    if key != "deeplab":
+        defaults[b"up_staged"] = 1                       # resize + 1x1: staged interpolated rows
+        defaults[b"stem_x2"] = 1                         # two output pixels per thread in the stem conv
     defaults[b"epi_static"] = 1                          # compile-time epilogues vs the generic run-time one
     defaults[b"dec_par"] = 1                             # frame-parallel decision + smoother vs one thread per pixel
     for sw, dflt in defaults.items():
