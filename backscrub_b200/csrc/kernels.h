@@ -268,8 +268,8 @@ struct Tuning {
   int tc_variant = 2;      // tensor-core pointwise kernel: 2 = warp-specialised TMA-fed persistent kernel, 1 = the round-1 kernel
   int tc_min_k = 16;       // smallest input depth of a 1x1 conv that goes to the tensor cores (with BSB_FLAG_TENSOR_CORES)
   int tc_mask_hi = 0;      // tensor-core kernel: clear the low mantissa bits of A explicitly instead of relying on the hardware truncation
-  int head = 0;            // decoder stages (1x1 -> depthwise 3x3 + residual [-> transposed conv]) in one kernel (measured: no faster
-                           // alone, 7 % slower with 8 streams in flight, run r2n; off)
+  int head = 1;            // decoder stages (1x1 -> depthwise 3x3 + residual [-> transposed conv]) in one kernel (k_head: with the padded
+                           // shared-memory stride and compile-time activations 93.7 -> 100.0 k frames/s on Meet 720p, 57.5 -> 63.1 k on MLKit, run s2g)
   int up_pw = 1;           // fuse RESIZE_BILINEAR into the 1x1 conv that consumes it
   int stem_pw = 0;         // run the 16 -> 16 1x1 conv that follows the stem inside the stem kernel (measured slower: 78.9 vs 40 + 30 us; off)
   int pool_merge = 1;      // global pool + SE tail in one launch (last block per frame runs the tail)

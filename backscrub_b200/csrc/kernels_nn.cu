@@ -987,12 +987,13 @@ void launch_depthwise(cudaStream_t s, int B, const float* in, int ih, int iw, in
       ensure_dyn_smem(reinterpret_cast<const void*>(k_depthwise_plane<false, 8>), plane_smem)) {
     const bool relu6_only = !e.residual && ((e.act1 == ACT_RELU6 && e.act2 == ACT_NONE) || (e.act1 == ACT_NONE && e.act2 == ACT_RELU6));
     const dim3 pgrid((unsigned)(c / cs), (unsigned)B);
+    // (local names keep "k_depthwise_plane" in the emulator's launch trace)
     if (cs == 16) {
-      if (relu6_only) { auto k = k_depthwise_plane<true, 16>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
-      else { auto k = k_depthwise_plane<false, 16>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
+      if (relu6_only) { auto k_depthwise_plane_r16 = k_depthwise_plane<true, 16>; BSB_LAUNCH(k_depthwise_plane_r16, pgrid, dim3(256), plane_smem, s, a); }
+      else { auto k_depthwise_plane_g16 = k_depthwise_plane<false, 16>; BSB_LAUNCH(k_depthwise_plane_g16, pgrid, dim3(256), plane_smem, s, a); }
     } else {
-      if (relu6_only) { auto k = k_depthwise_plane<true, 8>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
-      else { auto k = k_depthwise_plane<false, 8>; BSB_LAUNCH(k, pgrid, dim3(256), plane_smem, s, a); }
+      if (relu6_only) { auto k_depthwise_plane_r8 = k_depthwise_plane<true, 8>; BSB_LAUNCH(k_depthwise_plane_r8, pgrid, dim3(256), plane_smem, s, a); }
+      else { auto k_depthwise_plane_g8 = k_depthwise_plane<false, 8>; BSB_LAUNCH(k_depthwise_plane_g8, pgrid, dim3(256), plane_smem, s, a); }
     }
     count_launch();
     return;

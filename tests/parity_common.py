@@ -470,7 +470,7 @@ def check_fusion_switches(lib, key, n=2):
     g.close()
     for b in range(n):
         assert np.array_equal(base[b].view(np.uint32), m.invoke(x[b])[0].view(np.uint32)), f"{key}: frame {b} differs from the oracle"
-    defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 0}
+    defaults = {b"stem_pw": 0, b"pool_merge": 1, b"cnn_chain": 1, b"up_pw": 1, b"head": 1}
     if key == "deeplab":
         defaults = {b"dec_up": 1, b"dw_plane": 1}       # final resize folded into the argmax kernel; whole-plane atrous depthwise
     if key != "deeplab":
