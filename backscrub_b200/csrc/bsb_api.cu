@@ -719,6 +719,7 @@ int bsb_set_tuning(const char* name, int value) {
   else if (n == "dec_up") t.dec_up = value;
   else if (n == "dec_par") t.dec_par = value;
   else if (n == "stem_x2") t.stem_x2 = value;
+  else if (n == "pw_dws2") t.pw_dws2 = value;
   else if (n == "dw_plane_cs") t.dw_plane_cs = value;
   else if (n == "up_staged") t.up_staged = value;
   else if (n == "e2e_chunk") t.e2e_chunk = value;

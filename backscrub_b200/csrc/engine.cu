@@ -443,6 +443,8 @@ bool Engine::plan(std::string* err) {
   if (tuning().cnn_chain && !(flags_ & (1u | 8u))) detect_chain();
   // ---- decoder stages (1x1 -> depthwise + residual [-> transposed conv]) as one kernel each ----
   if (tuning().head && !(flags_ & (1u | 8u))) detect_heads();
+  // ---- encoder entry (16 -> 16 1x1 -> depthwise 3x3 stride 2) as one kernel ----
+  if (tuning().pw_dws2 && !tuning().stem_pw && !(flags_ & (1u | 8u))) detect_pw_dws2();
   find_segments();
   dec_up_step_ = -1;
   if (tuning().dec_up && model_type_ == MODEL_DEEPLAB && !(flags_ & 1u) && !steps_.empty()) {
@@ -574,6 +576,27 @@ void Engine::detect_heads() {
     if (hp.has_t) tinfo_[D.out].materialized = false;
     const size_t n_erase = hp.has_t ? 3 : 2;
     steps_.erase(steps_.begin() + i, steps_.begin() + i + n_erase);
+    steps_.insert(steps_.begin() + i, h);
+  }
+}
+
+void Engine::detect_pw_dws2() {
+  auto reads = [&](const Step& r, int t) { return r.in == t || r.in2 == t || r.scale == t || r.in_add == t || r.residual == t; };
+  for (size_t i = 0; i + 1 < steps_.size(); ++i) {
+    const Step& P = steps_[i]; const Step& D = steps_[i + 1];
+    if (P.kind != Step::PW || P.use_tc || P.up_from >= 0 || P.residual >= 0 || P.scale >= 0 || P.in_add >= 0 || P.K != 16 || P.N != 16 || P.n4 != 16) continue;
+    if (D.kind != Step::DW || D.in != P.out || D.residual >= 0 || D.kh != 3 || D.kw != 3 || D.sh != 2 || D.sw != 2 || D.dh != 1 || D.dw != 1) continue;
+    if ((P.act1 != ACT_NONE && P.act2 != ACT_NONE) || (D.act1 != ACT_NONE && D.act2 != ACT_NONE)) continue;
+    if (tinfo_[D.out].c != 16 || P.out == g_.output || D.out == g_.output) continue;
+    bool only_d = true;                                         // the 1x1 output must be private to the depthwise step
+    for (size_t k = 0; k < steps_.size(); ++k) if (k != i + 1 && reads(steps_[k], P.out)) only_d = false;
+    if (!only_d || !pw_dws2_supported(P.K, P.N, tinfo_[P.in].ld, tinfo_[D.out].ld)) continue;
+    HeadPlan hp; hp.p = P; hp.d = D; hp.s2 = true;
+    Step h; h.kind = Step::HEAD; h.op_index = P.op_index; h.in = P.in; h.out = D.out;
+    h.block = (int)heads_.size();
+    heads_.push_back(hp);
+    tinfo_[P.out].materialized = false;
+    steps_.erase(steps_.begin() + i, steps_.begin() + i + 2);
     steps_.insert(steps_.begin() + i, h);
   }
 }
@@ -1018,6 +1041,12 @@ void Engine::run_step(size_t si, int n, bool from_u8, bool* first_p, bool* skip_
       case Step::HEAD: {
         const HeadPlan& hp = heads_[st.block];
         const Step& P = hp.p; const Step& D = hp.d; const Step& T = hp.t;
+        if (hp.s2) {
+          launch_pw_dws2(stream_, tptr(P.in), I.ld, wblob_ + P.w_off, P.has_bias ? wblob_ + P.b_off : nullptr, P.act1 != ACT_NONE ? P.act1 : P.act2,
+                         wblob_ + D.w_off, D.has_bias ? wblob_ + D.b_off : nullptr, D.act1 != ACT_NONE ? D.act1 : D.act2,
+                         tptr(st.out), O.ld, n, I.h, I.w, O.h, O.w, D.pt, D.pl);
+          break;
+        }
         launch_head(stream_, P.N, tptr(P.in), I.ld, P.scale >= 0 ? tptr(P.scale) : nullptr, P.in_add >= 0 ? tptr(P.in_add) : nullptr,
                     P.in_add >= 0 ? tinfo_[P.in_add].ld : 0, wblob_ + P.w_off, P.has_bias ? wblob_ + P.b_off : nullptr, P.act1, P.act2,
                     wblob_ + D.w_off, D.has_bias ? wblob_ + D.b_off : nullptr, D.act1, D.act2, D.act3,

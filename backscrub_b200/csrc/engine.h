@@ -202,9 +202,10 @@ class Engine {
   std::vector<ChainPlan> chains_;
   bool detect_chain();
   // decoder stage run by one kernel (k_head): 1x1 conv -> depthwise 3x3 + residual [-> transposed conv]
-  struct HeadPlan { Step p, d, t; bool has_t = false; };
+  struct HeadPlan { Step p, d, t; bool has_t = false; bool s2 = false; };   // s2: 1x1 + stride-2 depthwise (k_pw_dws2), else a decoder stage (k_head)
   std::vector<HeadPlan> heads_;
   void detect_heads();
+  void detect_pw_dws2();
   std::vector<float> wblob_h_;
   size_t arena_elems_ = 0;
   bool tc_enabled_ = false, uses_tc_ = false;   // tensor-core 1x1 convs allowed / actually planned for at least one layer

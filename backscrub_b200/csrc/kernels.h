@@ -127,6 +127,9 @@ void launch_upsample_pw(cudaStream_t s, int B, const float* in, int ih, int iw, 
 
 // Decoder stage in one kernel: 1x1 conv (optional SE scale / skip add on its operand) -> depthwise 3x3 + residual of its
 // own input -> optionally Convolution2DTransposeBias k2 s2.  C = 16 or 24.  Same arithmetic per output as the stand-alone kernels.
+bool pw_dws2_supported(int K, int N, int ld_x, int ld_out);
+void launch_pw_dws2(cudaStream_t s, const float* x, int ld_x, const float* wp, const float* bp, int actp, const float* wd, const float* bd, int actd,
+                    float* out, int ld_out, int B, int ih, int iw, int oh, int ow, int pt, int pl);
 bool head_supported(int C, int ld_x, int ld_add, int ld_out, int oc, bool tconv);
 void launch_head(cudaStream_t s, int C, const float* x, int ld_x, const float* sv, const float* add, int ld_add,
                  const float* wp, const float* bp, int actp1, int actp2, const float* wd, const float* bd, int actd1, int actd2, int actr,
@@ -258,6 +261,7 @@ struct Tuning {
   int dw_px = 1;           // small depthwise layers: row-batched loads (k_depthwise_px) instead of the generic tap loop
   int dec_up = 1;          // DeepLab: final 33 -> 257 resize folded into the argmax decision kernel
   int epi_static = 1;      // compile-time epilogues (bias preloaded, activation fixed) for the common combinations; 0 = the generic run-time epilogue everywhere
+  int pw_dws2 = 1;         // 16 -> 16 1x1 conv + the stride-2 depthwise 3x3 that consumes it in one kernel (the 1x1's output is never materialised)
   int up_staged = 1;       // resize + 1x1: interpolated operand rows built once per pixel in shared memory when a pixel is shared by several threads
   int stem_x2 = 1;         // stem conv: two adjacent output pixels per thread (3x3 stride 2, even width), shared weight loads
   int e2e_chunk = 16;      // bsb_composite_yuyv (host buffers): frames per chunk of the copy / compute overlap (0 = one serial H2D -> graph -> D2H)

@@ -1757,6 +1757,113 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Encoder entry of the MobileNetV3-style graphs in one kernel (16 channels):
+//     t   = act_p( x . Wp + bp )                       1x1 conv on the stem's output (72x128 / 128x128 pixels)
+//     out = act_d( dw3x3 stride 2 (t) + bd )           depthwise 3x3, stride 2
+// The 1x1's output — the largest activation of the graph — is never written or re-read: one CTA = a 16 x 8 tile of the
+// depthwise OUTPUT; phase A computes t on the 33 x 17 input pixels the tile needs into shared memory (a pixel and its 16
+// channels per thread, k-ascending fmaf chains, as the stand-alone 1x1 kernel), phase B = a thread per output pixel and
+// 8 channels: 9 taps in (fy, fx) order from shared memory, out-of-image taps skipped.  (Pixels shared by neighbouring
+// tiles — one row and one column in 17 x 33 — are computed twice; each value is still the one chain of the oracle.)
+// ---------------------------------------------------------------------------
+struct PwDwArgs {
+  const float* x; int ld_x; const float* wp; const float* bp; int actp;     // [16][16]
+  const float* wd; const float* bd; int actd;                                 // [3][3][16]
+  float* out; int ld_out;
+  int B, ih, iw, oh, ow, pt, pl;
+};
+constexpr int PD_TW = 16, PD_TH = 8, PD_SW = 2 * PD_TW + 1, PD_SH = 2 * PD_TH + 1, PD_C = 16, PD_CP = PD_C + 4;
+
+template <int ACTP, int ACTD>     // -1: run-time activation code
+__global__ void __launch_bounds__(256) k_pw_dws2(PwDwArgs a) {
+  __shared__ __align__(16) float ts[PD_SH * PD_SW * PD_CP];
+  __shared__ __align__(16) float wps[PD_C * PD_C];
+  __shared__ __align__(16) float wds[9 * PD_C];
+  __shared__ __align__(16) float bps[PD_C], bds[PD_C];
+  const int tid = threadIdx.x;
+  const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH, b = blockIdx.z;
+  const int ix0 = ox0 * 2 - a.pl, iy0 = oy0 * 2 - a.pt;         // input pixel of the tile's shared-memory origin
+  for (int i = tid; i < PD_C * PD_C; i += 256) wps[i] = __ldg(a.wp + i);
+  for (int i = tid; i < 9 * PD_C; i += 256) wds[i] = __ldg(a.wd + i);
+  if (tid < PD_C) { bps[tid] = a.bp ? __ldg(a.bp + tid) : 0.f; bds[tid] = a.bd ? __ldg(a.bd + tid) : 0.f; }
+  __syncthreads();
+  const float* xb = a.x + (size_t)b * a.ih * a.iw * a.ld_x;
+  // ---- A: t on the (2 TH + 1) x (2 TW + 1) input window ----
+  for (int i = tid; i < PD_SH * PD_SW; i += 256) {
+    const int sy = i / PD_SW, sx = i - sy * PD_SW;
+    const int gy = iy0 + sy, gx = ix0 + sx;
+    if (gy < 0 || gy >= a.ih || gx < 0 || gx >= a.iw) continue;          // never read: phase B skips out-of-image taps
+    const float* xp = xb + ((size_t)gy * a.iw + gx) * a.ld_x;
+    float4 xv[PD_C / 4];
+#pragma unroll
+    for (int k = 0; k < PD_C / 4; ++k) xv[k] = __ldg(reinterpret_cast<const float4*>(xp + 4 * k));
+    float acc[PD_C];
+#pragma unroll
+    for (int n = 0; n < PD_C; ++n) acc[n] = 0.f;
+#pragma unroll
+    for (int k = 0; k < PD_C / 4; ++k) {
+      const float vv[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < PD_C / 4; ++q) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wps + (4 * k + j) * PD_C + 4 * q);
+          acc[4 * q] = fmaf(vv[j], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(vv[j], w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(vv[j], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(vv[j], w4.w, acc[4 * q + 3]);
+        }
+    }
+    float* tp = ts + (size_t)i * PD_CP;
+#pragma unroll
+    for (int q = 0; q < PD_C / 4; ++q) {
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = bsb_act(acc[4 * q + j] + bps[4 * q + j], ACTP >= 0 ? ACTP : a.actp);
+      *reinterpret_cast<float4*>(tp + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+  __syncthreads();
+  // ---- B: depthwise 3x3 stride 2: thread = output pixel x 8 channels ----
+  const int half = tid & 1, lp = tid >> 1;
+  const int lx = lp % PD_TW, ly = lp / PD_TW;
+  const int ox = ox0 + lx, oy = oy0 + ly;
+  if (ox >= a.ow || oy >= a.oh) return;
+  const int c0 = half * 8;
+  float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+    const int iy = oy * 2 - a.pt + fy;
+    if (iy < 0 || iy >= a.ih) continue;
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx) {
+      const int ix = ox * 2 - a.pl + fx;
+      if (ix < 0 || ix >= a.iw) continue;
+      const float* tp = ts + (size_t)((2 * ly + fy) * PD_SW + (2 * lx + fx)) * PD_CP + c0;
+      const float* wp = wds + (fy * 3 + fx) * PD_C + c0;
+      const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+      u0.x = fmaf(t0.x, w0.x, u0.x); u0.y = fmaf(t0.y, w0.y, u0.y); u0.z = fmaf(t0.z, w0.z, u0.z); u0.w = fmaf(t0.w, w0.w, u0.w);
+      u1.x = fmaf(t1.x, w1.x, u1.x); u1.y = fmaf(t1.y, w1.y, u1.y); u1.z = fmaf(t1.z, w1.z, u1.z); u1.w = fmaf(t1.w, w1.w, u1.w);
+    }
+  }
+  const int ad = ACTD >= 0 ? ACTD : a.actd;
+  float* op = a.out + (((size_t)b * a.oh + oy) * a.ow + ox) * a.ld_out + c0;
+  *reinterpret_cast<float4*>(op) = make_float4(bsb_act(u0.x + bds[c0], ad), bsb_act(u0.y + bds[c0 + 1], ad), bsb_act(u0.z + bds[c0 + 2], ad), bsb_act(u0.w + bds[c0 + 3], ad));
+  *reinterpret_cast<float4*>(op + 4) = make_float4(bsb_act(u1.x + bds[c0 + 4], ad), bsb_act(u1.y + bds[c0 + 5], ad), bsb_act(u1.z + bds[c0 + 6], ad), bsb_act(u1.w + bds[c0 + 7], ad));
+}
+
+bool pw_dws2_supported(int K, int N, int ld_x, int ld_out) { return K == PD_C && N == PD_C && ld_x % 4 == 0 && ld_out % 4 == 0; }
+
+void launch_pw_dws2(cudaStream_t s, const float* x, int ld_x, const float* wp, const float* bp, int actp, const float* wd, const float* bd, int actd,
+                    float* out, int ld_out, int B, int ih, int iw, int oh, int ow, int pt, int pl) {
+  PwDwArgs a{x, ld_x, wp, bp, actp, wd, bd, actd, out, ld_out, B, ih, iw, oh, ow, pt, pl};
+  const dim3 grid((unsigned)ceil_div(ow, PD_TW), (unsigned)ceil_div(oh, PD_TH), (unsigned)B);
+  if (actp == ACT_RELU6 && actd == ACT_RELU6) { auto k = k_pw_dws2<ACT_RELU6, ACT_RELU6>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+  else if (actp == ACT_RELU && actd == ACT_RELU) { auto k = k_pw_dws2<ACT_RELU, ACT_RELU>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+  else { auto k = k_pw_dws2<-1, -1>; BSB_LAUNCH(k, grid, dim3(256), 0, s, a); }
+  count_launch();
+}
+
 bool head_supported(int C, int ld_x, int ld_add, int ld_out, int oc, bool tconv) {
   if (C != 16 && C != 24) return false;
   if (ld_x % 4 || ld_add % 4) return false;

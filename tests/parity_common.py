@@ -474,6 +474,7 @@ def check_fusion_switches(lib, key, n=2):
     if key == "deeplab":
         defaults = {b"dec_up": 1, b"dw_plane": 1}       # final resize folded into the argmax kernel; whole-plane atrous depthwise
     if key != "deeplab":
+        defaults[b"pw_dws2"] = 1                         # 1x1 + stride-2 depthwise in one kernel
         defaults[b"up_staged"] = 1                       # resize + 1x1: staged interpolated rows
         defaults[b"stem_x2"] = 1                         # two output pixels per thread in the stem conv
     defaults[b"epi_static"] = 1                          # compile-time epilogues vs the generic run-time one
