@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--e2e-hugepages", action="store_true", help="end-to-end staging buffers on 2 MB transparent huge pages + cudaHostRegister instead of cudaHostAlloc")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs (parsed.configs)")
     ap.add_argument("--frames", default="person", choices=["person", "noise", "const"], help="synthetic stream kind (SURVEY 8d)")
-    ap.add_argument("--launches-per-step", type=int, default=4, help="graph launches per stream per timed step (lengthens the timed window)")
+    ap.add_argument("--launches-per-step", type=int, default=20, help="graph launches per stream per timed step (lengthens the timed window)")
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="bsb_set_tuning switch (A/B runs): pw_variant, dw_plane, post_tma, ...")
     return ap.parse_args()
 
