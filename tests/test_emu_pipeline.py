@@ -72,7 +72,7 @@ def test_decision_window_across_calls(lib):
 
 
 def test_sub_batched_segments(lib):
-    pc.check_sub_batch(lib, "deeplab", n=3)
+    pc.check_sub_batch(lib, "deeplab", n=3, mbs=(0, 8))      # (the one-frame-per-group case runs in the GPU suite)
 
 
 def test_infer_batch(lib):
