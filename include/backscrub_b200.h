@@ -250,9 +250,12 @@ BSB_API int bsb_uses_tensor_cores(bsb_ctx* ctx);
 /* algorithmic FLOPs of one CNN frame (2*MAC) */
 BSB_API double bsb_model_flops(bsb_ctx* ctx);
 /* Process-wide measurement switches of the kernel launchers (A/B runs in bench.py / tools/): they select between
- * bit-identical kernel variants and never change results.  Names: "pw_variant", "dw_plane", "post_tma", "cnn_chain",
- * "post_wide", "post_l1".  Set them before creating contexts (captured CUDA graphs keep the variant they were captured with).
- * Returns 1, or 0 for an unknown name. */
+ * bit-identical kernel variants / schedules and never change results.  Names (defaults in csrc/kernels.h, struct Tuning):
+ * planner fusions "cnn_chain", "pool_merge", "up_pw", "up_staged", "head", "pw_dws2", "stem_pw", "stem_x2", "dec_up", "sub_batch_mb";
+ * kernel variants "pw_variant", "dw_px", "dw_plane", "dw_plane_cs", "epi_static", "dec_par", "tc_variant", "tc_min_k", "tc_mask_hi";
+ * post stage "post_tma", "post_tile" (0 = by frame size), "post_wide", "post_l1"; host-buffer calls "e2e_chunk" (frames per
+ * overlapped chunk of bsb_composite_yuyv, 0 = serial).  Set them before creating contexts (plans and captured CUDA graphs
+ * keep the variant they were built with).  Returns 1, or 0 for an unknown name. */
 BSB_API int bsb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus
